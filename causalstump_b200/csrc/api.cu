@@ -1,0 +1,1004 @@
+// C-ABI of libcausalstump_b200.so (declared in include/cs_b200.h): host orchestration of
+// the device-resident fit.  One translation unit; compiled by nvcc for sm_100a only
+// (tests/emu compiles the same file with -DCS_EMU for index-logic unit tests).
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <string>
+#include <vector>
+
+#include "../../include/cs_b200.h"
+#include "dense.cuh"
+#include "kernels.cuh"
+#include "predict.cuh"
+
+using csdense::DenseEngine;
+using csdense::g_launches;
+using csk::EvalScalars;
+using csk::Layout;
+using csk::LoopState;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define RT(call)                                                                              \
+  do {                                                                                        \
+    int e__ = (call);                                                                         \
+    if (e__ != 0) return fail(e__ == 2 ? CS_ERR_NOMEM : CS_ERR_CUDA, "%s failed: %s (%s:%d)", \
+                              #call, rt::err_str(e__), __FILE__, __LINE__);                   \
+  } while (0)
+
+#define KCHECK()                                                                                      \
+  do {                                                                                                \
+    int e__ = rt::last_error();                                                                       \
+    if (e__ != 0) return fail(CS_ERR_CUDA, "kernel launch failed: %s (%s:%d)", rt::err_str(e__),     \
+                              __FILE__, __LINE__);                                                    \
+  } while (0)
+
+static int need_device() {
+  int n = 0;
+  if (rt::device_count(&n) != 0 || n <= 0)
+    return fail(CS_ERR_NODEVICE, "no CUDA device available: libcausalstump_b200 has no CPU fallback");
+  return 0;
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------
+static __global__ void fill_kernel(double* p, long long n, double v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// identity padding of an np x np matrix whose leading n x n block holds data
+static __global__ void pad_identity_kernel(double* A, long long ld, int n, int np) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)np * np;
+  if (idx >= total) return;
+  const int r = (int)(idx % np), c = (int)(idx / np);
+  if (r >= n || c >= n) A[(long long)c * ld + r] = (r == c) ? 1.0 : 0.0;
+}
+
+static __global__ void add_noise_diag_kernel(double* A, long long ld, int n, const double* w, double esig) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (i < n) A[(long long)i * ld + i] += esig / w[i];
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) rt::dev_free(p); }
+  int alloc(size_t bytes) { return rt::dev_malloc(&p, bytes); }
+  double* d() const { return static_cast<double*>(p); }
+};
+
+// host (ld = rows) -> device (ld = ldd) column-major upload with zero padding
+static int upload_matrix(double* dst, long long ldd, int rows_pad, int cols_pad, const double* src, int rows,
+                         int cols, cudaStream_t st) {
+  int e;
+  if ((e = rt::memset0(dst, sizeof(double) * (size_t)ldd * cols_pad, st))) return e;
+  (void)rows_pad;
+#ifdef CS_EMU
+  for (int c = 0; c < cols; ++c) std::memcpy(dst + (size_t)c * ldd, src + (size_t)c * rows, sizeof(double) * rows);
+  return 0;
+#else
+  return (int)cudaMemcpy2DAsync(dst, sizeof(double) * ldd, src, sizeof(double) * rows, sizeof(double) * rows, cols,
+                                cudaMemcpyHostToDevice, st);
+#endif
+}
+
+static int download_matrix(double* dst, int rows, int cols, const double* src, long long lds, cudaStream_t st) {
+#ifdef CS_EMU
+  for (int c = 0; c < cols; ++c) std::memcpy(dst + (size_t)c * rows, src + (size_t)c * lds, sizeof(double) * rows);
+  return 0;
+#else
+  return (int)cudaMemcpy2DAsync(dst, sizeof(double) * rows, src, sizeof(double) * lds, sizeof(double) * rows, cols,
+                                cudaMemcpyDeviceToHost, st);
+#endif
+}
+
+static int upload_vector(double* dst, int npad, const double* src, int n, double padval, cudaStream_t st) {
+  int e;
+  if (npad > n) {
+    auto k = fill_kernel;
+    ++g_launches;
+    CS_LAUNCH(k, (npad + 255) / 256, 256, 0, st, dst, (long long)npad, padval);
+  }
+  if ((e = rt::h2d(dst, src, sizeof(double) * n, st))) return e;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// the fit handle
+// ------------------------------------------------------------------------------------
+struct cs_fit {
+  cs_fit_config cfg{};
+  Layout lay{};
+  int n = 0, p = 0, np = 0, nblk = 0;  // np: padded to the dense tile; nblk = np / 64
+  cudaStream_t st{};
+  DenseEngine eng;
+  double *X = nullptr, *y = nullptr, *z = nullptr, *w = nullptr, *ones = nullptr;
+  double *params = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr;
+  double *alpha = nullptr, *u = nullptr, *s = nullptr;
+  double* mv_part = nullptr;
+  int nsplit = 1, cols_per_split = 0;
+  double* gpart = nullptr;
+  int ncta_grad = 1;
+  double* kal_part = nullptr;
+  EvalScalars* sc = nullptr;
+  LoopState* ls = nullptr;
+  double* trace = nullptr;
+  int trace_cap = 0;
+  double* flush = nullptr;
+  size_t flush_bytes = 0;
+  cudaEvent_t ev[16]{};
+  bool ev_ok = false;
+  std::vector<void*> allocs;
+
+  int dalloc(void** ptr, size_t bytes) {
+    int e = rt::dev_malloc(ptr, bytes);
+    if (e == 0) allocs.push_back(*ptr);
+    return e;
+  }
+};
+
+static int split_plan(int row_blocks, int cols, int* nsplit, int* cols_per_split) {
+  int target = 4 * rt::sm_count();
+  int ns = (target + row_blocks - 1) / row_blocks;
+  const int cblocks = cols / csk::TB;
+  if (ns > cblocks) ns = cblocks;
+  if (ns < 1) ns = 1;
+  int cps = ((cblocks + ns - 1) / ns) * csk::TB;
+  ns = (cols + cps - 1) / cps;
+  *nsplit = ns;
+  *cols_per_split = cps;
+  return 0;
+}
+
+static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
+  const int n = f->n, np = f->np, p = f->p;
+  cudaStream_t st = f->st;
+  const long long ld = np;
+  int ph = 0;
+  if (phase_ev) rt::event_record(phase_ev[ph++], st);
+  {  // K1
+    auto k = csk::gram_train_kernel;
+    ++g_launches;
+    CS_LAUNCH(k, csg::lower_tiles(f->nblk), csk::ETH, csk::gram_smem_bytes(p), st, f->X, ld, f->z, f->w, f->params,
+              f->lay, n, f->eng.G, ld, skip);
+  }
+  if (phase_ev) rt::event_record(phase_ev[ph++], st);
+  f->eng.set_status_max(st, skip);
+  f->eng.run_seq(f->eng.potrf, st, skip);
+  if (phase_ev) rt::event_record(phase_ev[ph++], st);
+  f->eng.run_seq(f->eng.trtri, st, skip);
+  if (phase_ev) rt::event_record(phase_ev[ph++], st);
+  f->eng.run_seq(f->eng.xtx, st, skip);
+  if (phase_ev) rt::event_record(phase_ev[ph++], st);
+  {  // alpha, u, s
+    auto k = csk::matvec_kernel<3>;
+    ++g_launches;
+    CS_LAUNCH(k, dim3(f->nblk, f->nsplit), csk::ETH, 0, st, f->eng.C, ld, f->cols_per_split, np, f->y, f->y, f->ones,
+              f->params + f->lay.i_mu(), f->mv_part, ld, 3 * ld, skip);
+    auto k2 = csk::scalars_kernel;
+    ++g_launches;
+    CS_LAUNCH(k2, 1, csk::ETH, 0, st, f->mv_part, f->nsplit, ld, 3 * ld, n, np, f->y, f->params, f->lay,
+              f->eng.logdet_part, f->eng.N, f->alpha, f->u, f->s, f->sc, skip);
+  }
+  if (phase_ev) rt::event_record(phase_ev[ph++], st);
+  {  // K3 / K4
+    auto k = csk::grad_trace_kernel<false>;
+    ++g_launches;
+    CS_LAUNCH(k, f->ncta_grad, csk::ETH, csk::grad_smem_bytes(p), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
+              f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)nullptr,
+              (const double*)nullptr, (const double*)nullptr, skip);
+  }
+  if (phase_ev) rt::event_record(phase_ev[ph++], st);
+  {
+    auto k = csk::finalize_kernel;
+    ++g_launches;
+    CS_LAUNCH(k, 1, csk::ETH, 0, st, f->gpart, f->ncta_grad, f->kal_part, ld, f->nblk, f->eng.C, ld, f->alpha, f->y,
+              f->w, f->params, f->lay, n, f->sc, f->grad, skip);
+  }
+  if (phase_ev) rt::event_record(phase_ev[ph++], st);
+  return 0;
+}
+
+extern "C" {
+
+int cs_version(void) { return 100; }
+const char* cs_last_error(void) { return g_err.c_str(); }
+int cs_device_count(void) {
+  int n = 0;
+  if (rt::device_count(&n) != 0) return 0;
+  return n;
+}
+int cs_set_device(int device) {
+  if (need_device()) return CS_ERR_NODEVICE;
+  RT(rt::set_device(device));
+  return 0;
+}
+long long cs_launch_count(void) { return g_launches; }
+
+int cs_fit_create(const cs_fit_config* cfg, int n, int p, const double* y, const double* X, const double* z,
+                  const double* w, const double* init_params, cs_fit** out) {
+  if (!cfg || !y || !X || !z || !init_params || !out) return fail(CS_ERR_ARG, "cs_fit_create: null argument");
+  if (n < 1 || p < 1) return fail(CS_ERR_ARG, "cs_fit_create: n and p must be positive");
+  if (p > CS_MAX_P) return fail(CS_ERR_UNSUPPORTED, "cs_fit_create: p=%d exceeds CS_MAX_P=%d", p, CS_MAX_P);
+  if (cfg->kind != CS_GP && cfg->kind != CS_TP) return fail(CS_ERR_ARG, "cs_fit_create: bad kind");
+  if (cfg->optim < 0 || cfg->optim > 2) return fail(CS_ERR_ARG, "cs_fit_create: bad optimizer");
+  if (need_device()) return CS_ERR_NODEVICE;
+  int tile = cfg->tile ? cfg->tile : csdense::pick_tile(n);
+  if (tile != 64 && tile != 128) return fail(CS_ERR_ARG, "cs_fit_create: tile must be 0, 64 or 128");
+  cs_fit* f = new cs_fit();
+  *out = nullptr;
+  f->cfg = *cfg;
+  f->cfg.tile = tile;
+  f->lay.kind = cfg->kind;
+  f->lay.p = p;
+  f->n = n;
+  f->p = p;
+  auto bail = [&](int code) { cs_fit_destroy(f); return code; };
+  if (rt::stream_create(&f->st)) return bail(fail(CS_ERR_CUDA, "stream create failed"));
+  if (int e = f->eng.init(n, tile)) return bail(fail(e == 2 ? CS_ERR_NOMEM : CS_ERR_CUDA, "dense engine init failed: %s", rt::err_str(e)));
+  const int np = f->eng.np;
+  f->np = np;
+  f->nblk = np / csk::TB;
+  const int NP = f->lay.np();
+  const size_t vb = sizeof(double) * np;
+#define DA(ptr, bytes) if (f->dalloc((void**)&(ptr), (bytes))) return bail(fail(CS_ERR_NOMEM, "device allocation failed"))
+  DA(f->X, vb * p); DA(f->y, vb); DA(f->z, vb); DA(f->w, vb); DA(f->ones, vb);
+  DA(f->params, sizeof(double) * NP); DA(f->grad, sizeof(double) * NP);
+  DA(f->m, sizeof(double) * NP); DA(f->v, sizeof(double) * NP);
+  DA(f->alpha, vb); DA(f->u, vb); DA(f->s, vb);
+  split_plan(f->nblk, np, &f->nsplit, &f->cols_per_split);
+  DA(f->mv_part, vb * 3 * f->nsplit);
+  f->ncta_grad = std::min(csg::lower_tiles(f->nblk), rt::sm_count());
+  DA(f->gpart, sizeof(double) * (2 * p + 2) * f->ncta_grad);
+  DA(f->kal_part, vb * f->nblk);
+  DA(f->sc, sizeof(EvalScalars)); DA(f->ls, sizeof(LoopState));
+#undef DA
+  cudaStream_t st = f->st;
+  const size_t mb = sizeof(double) * (size_t)np * np;
+  if (rt::memset0(f->eng.G, mb, st) || rt::memset0(f->eng.X, mb, st) || rt::memset0(f->eng.C, mb, st))
+    return bail(fail(CS_ERR_CUDA, "memset failed"));
+  if (upload_matrix(f->X, np, np, p, X, n, p, st)) return bail(fail(CS_ERR_CUDA, "upload X failed"));
+  if (upload_vector(f->y, np, y, n, 0.0, st) || upload_vector(f->z, np, z, n, 0.0, st))
+    return bail(fail(CS_ERR_CUDA, "upload y/z failed"));
+  {
+    auto k = fill_kernel;
+    ++g_launches;
+    CS_LAUNCH(k, (np + 255) / 256, 256, 0, st, f->ones, (long long)np, 1.0);
+    if (w) { if (upload_vector(f->w, np, w, n, 1.0, st)) return bail(fail(CS_ERR_CUDA, "upload w failed")); }
+    else { ++g_launches; CS_LAUNCH(k, (np + 255) / 256, 256, 0, st, f->w, (long long)np, 1.0); }
+  }
+  if (rt::h2d(f->params, init_params, sizeof(double) * NP, st)) return bail(fail(CS_ERR_CUDA, "upload params failed"));
+  if (rt::memset0(f->m, sizeof(double) * NP, st) || rt::memset0(f->v, sizeof(double) * NP, st) ||
+      rt::memset0(f->grad, sizeof(double) * NP, st) || rt::memset0(f->sc, sizeof(EvalScalars), st) ||
+      rt::memset0(f->ls, sizeof(LoopState), st))
+    return bail(fail(CS_ERR_CUDA, "memset failed"));
+  { auto k = csk::gram_train_kernel; CS_SET_SMEM(k, csk::gram_smem_bytes(csk::PMAX)); }
+  { auto k = csk::gram_cross_kernel; CS_SET_SMEM(k, csk::gram_smem_bytes(csk::PMAX)); }
+  { auto k = csk::grad_trace_kernel<false>; CS_SET_SMEM(k, csk::grad_smem_bytes(csk::PMAX)); }
+  { auto k = csk::grad_trace_kernel<true>; CS_SET_SMEM(k, csk::grad_smem_bytes(csk::PMAX)); }
+  { auto k = csp::gram_sum_kernel; CS_SET_SMEM(k, csk::gram_smem_bytes(csk::PMAX)); }
+  for (int i = 0; i < 16; ++i)
+    if (rt::event_create(&f->ev[i])) return bail(fail(CS_ERR_CUDA, "event create failed"));
+  f->ev_ok = true;
+  if (rt::stream_sync(st)) return bail(fail(CS_ERR_CUDA, "fit create sync failed: %s", rt::err_str(rt::last_error())));
+  *out = f;
+  return 0;
+}
+
+void cs_fit_destroy(cs_fit* f) {
+  if (!f) return;
+  rt::stream_sync(f->st);
+  for (void* p : f->allocs) rt::dev_free(p);
+  if (f->trace) rt::dev_free(f->trace);
+  if (f->flush) rt::dev_free(f->flush);
+  f->eng.destroy();
+  if (f->ev_ok) for (int i = 0; i < 16; ++i) rt::event_destroy(f->ev[i]);
+  rt::stream_destroy(f->st);
+  delete f;
+}
+
+int cs_fit_nparam(const cs_fit* f) { return f ? f->lay.np() : CS_ERR_ARG; }
+
+int cs_fit_set_params(cs_fit* f, const double* params) {
+  if (!f || !params) return fail(CS_ERR_ARG, "cs_fit_set_params: null argument");
+  RT(rt::h2d(f->params, params, sizeof(double) * f->lay.np(), f->st));
+  RT(rt::stream_sync(f->st));
+  return 0;
+}
+
+int cs_fit_get_params(cs_fit* f, double* params) {
+  if (!f || !params) return fail(CS_ERR_ARG, "cs_fit_get_params: null argument");
+  RT(rt::d2h(params, f->params, sizeof(double) * f->lay.np(), f->st));
+  RT(rt::stream_sync(f->st));
+  return 0;
+}
+
+int cs_fit_reset_optimizer(cs_fit* f) {
+  if (!f) return fail(CS_ERR_ARG, "null handle");
+  RT(rt::memset0(f->m, sizeof(double) * f->lay.np(), f->st));
+  RT(rt::memset0(f->v, sizeof(double) * f->lay.np(), f->st));
+  return 0;
+}
+
+int cs_fit_eval_async(cs_fit* f) {
+  if (!f) return fail(CS_ERR_ARG, "null handle");
+  fit_enqueue_eval(f, nullptr, nullptr);
+  KCHECK();
+  return 0;
+}
+
+int cs_fit_sync(cs_fit* f) {
+  if (!f) return fail(CS_ERR_ARG, "null handle");
+  RT(rt::stream_sync(f->st));
+  return 0;
+}
+
+static int read_status(cs_fit* f) {
+  int status = 0;
+  RT(rt::d2h(&status, f->eng.status, sizeof(int), f->st));
+  RT(rt::stream_sync(f->st));
+  if (status != 0x7fffffff && status > 0) {
+    fail(status, "inv_sympd(): matrix is singular or not positive definite (pivot %d)", status);
+    return status;
+  }
+  return 0;
+}
+
+int cs_fit_fetch(cs_fit* f, double* grad, double* stats, double* mu_solution) {
+  if (!f) return fail(CS_ERR_ARG, "null handle");
+  EvalScalars h{};
+  RT(rt::d2h(&h, f->sc, sizeof h, f->st));
+  if (grad) RT(rt::d2h(grad, f->grad, sizeof(double) * f->lay.np(), f->st));
+  RT(rt::stream_sync(f->st));
+  if (stats) { stats[0] = h.stats[0]; stats[1] = h.stats[1]; }
+  if (mu_solution) *mu_solution = h.mu_sol;
+  return read_status(f);
+}
+
+int cs_fit_eval(cs_fit* f, const double* params, double* grad, double* stats, double* mu_solution) {
+  if (!f) return fail(CS_ERR_ARG, "null handle");
+  if (params) RT(rt::h2d(f->params, params, sizeof(double) * f->lay.np(), f->st));
+  int e = cs_fit_eval_async(f);
+  if (e) return e;
+  return cs_fit_fetch(f, grad, stats, mu_solution);
+}
+
+int cs_fit_run(cs_fit* f, int maxiter, double tol, int* iters, double* stats_trace) {
+  if (!f) return fail(CS_ERR_ARG, "null handle");
+  if (maxiter < 1) return fail(CS_ERR_ARG, "cs_fit_run: maxiter must be >= 1");
+  cudaStream_t st = f->st;
+  const int cap = 2 * (maxiter + 2);
+  if (f->trace_cap < cap) {
+    if (f->trace) rt::dev_free(f->trace);
+    f->trace = nullptr;
+    RT(rt::dev_malloc((void**)&f->trace, sizeof(double) * cap));
+    f->trace_cap = cap;
+  }
+  RT(rt::memset0(f->trace, sizeof(double) * cap, st));
+  LoopState h{};
+  h.it = 1; h.done = 0; h.iters = 0; h.maxiter = maxiter; h.tol = tol; h.prev_lml = 0.0;  // stats[,1] = 0 (R/main.R:77)
+  RT(rt::h2d(f->ls, &h, sizeof h, st));
+  int chunk = f->cfg.chunk;
+  if (chunk <= 0) {
+    // keep each poll interval around a few milliseconds of device work
+    const double flops = (double)f->np * f->np * f->np;
+    chunk = (int)std::max(1.0, std::min(64.0, 2.0e9 / std::max(flops, 1.0)));
+  }
+  int launched = 0;
+  while (launched < maxiter) {
+    const int todo = std::min(chunk, maxiter - launched);
+    for (int i = 0; i < todo; ++i) {
+      fit_enqueue_eval(f, &f->ls->done, nullptr);
+      auto k = csk::loop_step_kernel;
+      ++g_launches;
+      CS_LAUNCH(k, 1, 64, 0, st, f->cfg.optim, f->lay, f->cfg.lr, f->cfg.beta1, f->cfg.beta2, f->cfg.eps,
+                f->cfg.momentum, f->m, f->v, f->grad, f->params, f->sc, f->ls, f->trace);
+    }
+    launched += todo;
+    KCHECK();
+    RT(rt::d2h(&h, f->ls, sizeof h, st));
+    RT(rt::stream_sync(st));
+    int stt = 0;
+    RT(rt::d2h(&stt, f->eng.status, sizeof(int), st));
+    RT(rt::stream_sync(st));
+    if (stt != 0x7fffffff && stt > 0)
+      return fail(stt, "inv_sympd(): matrix is singular or not positive definite (pivot %d) at iteration %d", stt,
+                  h.it - 1);
+    if (h.done) break;
+  }
+  const int it = h.done ? h.iters : maxiter;
+  // final get_train_stats with the final parameters (R/main.R:88)
+  fit_enqueue_eval(f, nullptr, nullptr);
+  KCHECK();
+  double st2[2];
+  int e = cs_fit_fetch(f, nullptr, st2, nullptr);
+  if (e) return e;
+  if (iters) *iters = it;
+  if (stats_trace) {
+    RT(rt::d2h(stats_trace, f->trace, sizeof(double) * cap, st));
+    RT(rt::stream_sync(st));
+    stats_trace[2 * (it + 1) + 0] = st2[0];
+    stats_trace[2 * (it + 1) + 1] = st2[1];
+  }
+  return 0;
+}
+
+int cs_fit_get_matrices(cs_fit* f, double* Kmat, double* Km, double* Ka, double* invK) {
+  if (!f) return fail(CS_ERR_ARG, "null handle");
+  const int n = f->n, np = f->np;
+  cudaStream_t st = f->st;
+  if (Kmat || Km || Ka) {
+    DevBuf bK, bM, bA;
+    const size_t mb = sizeof(double) * (size_t)np * np;
+    if (Kmat && bK.alloc(mb)) return fail(CS_ERR_NOMEM, "alloc failed");
+    if (Km && bM.alloc(mb)) return fail(CS_ERR_NOMEM, "alloc failed");
+    if (Ka && bA.alloc(mb)) return fail(CS_ERR_NOMEM, "alloc failed");
+    auto k = csk::gram_cross_kernel;
+    ++g_launches;
+    CS_LAUNCH(k, dim3(f->nblk, f->nblk), csk::ETH, csk::gram_smem_bytes(f->p), st, f->X, (long long)np, f->z, n, f->X,
+              (long long)np, f->z, n, f->params, f->lay, bK.d(), bM.d(), bA.d(), (long long)np);
+    KCHECK();
+    if (Kmat) RT(download_matrix(Kmat, n, n, bK.d(), np, st));
+    if (Km) RT(download_matrix(Km, n, n, bM.d(), np, st));
+    if (Ka) RT(download_matrix(Ka, n, n, bA.d(), np, st));
+    RT(rt::stream_sync(st));
+  }
+  if (invK) {
+    RT(download_matrix(invK, n, n, f->eng.C, np, st));
+    RT(rt::stream_sync(st));
+  }
+  return 0;
+}
+
+int cs_fit_event_record(cs_fit* f, int slot) {
+  if (!f || slot < 0 || slot >= 16) return fail(CS_ERR_ARG, "bad event slot");
+  RT(rt::event_record(f->ev[slot], f->st));
+  return 0;
+}
+
+int cs_fit_event_elapsed_ms(cs_fit* f, int a, int b, float* ms) {
+  if (!f || !ms || a < 0 || a >= 16 || b < 0 || b >= 16) return fail(CS_ERR_ARG, "bad event slot");
+  RT(rt::event_sync(f->ev[b]));
+  RT(rt::event_elapsed(ms, f->ev[a], f->ev[b]));
+  return 0;
+}
+
+int cs_fit_eval_profile(cs_fit* f, float phase_ms[CS_NPHASE]) {
+  if (!f || !phase_ms) return fail(CS_ERR_ARG, "null argument");
+  fit_enqueue_eval(f, nullptr, f->ev);
+  KCHECK();
+  RT(rt::stream_sync(f->st));
+  for (int i = 0; i < CS_NPHASE; ++i) RT(rt::event_elapsed(&phase_ms[i], f->ev[i], f->ev[i + 1]));
+  return read_status(f);
+}
+
+int cs_flush_l2(cs_fit* f) {
+  if (!f) return fail(CS_ERR_ARG, "null handle");
+  const size_t bytes = (size_t)256 << 20;  // 256 MiB > 126 MB L2
+  if (!f->flush) {
+    RT(rt::dev_malloc((void**)&f->flush, bytes));
+    f->flush_bytes = bytes;
+  }
+  RT(rt::memset0(f->flush, f->flush_bytes, f->st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// predict / treatment
+// ------------------------------------------------------------------------------------
+struct CrossWork {
+  DevBuf X2, z2, Kc, V, part, q, tmp, cov;
+  int n2 = 0, n2p = 0, nsplit = 1, cps = 0;
+};
+
+// shared by cs_predict (use_m = 1, z2 given) and cs_treat (use_m = 0, z2 = 1, Ka only)
+static int cross_common(cs_fit* f, CrossWork& W, int n2, const double* X2, const double* z2, bool treat,
+                        double* map, double* var_diag, double add_sigma, double add_const, double* cov_out) {
+  const int n = f->n, np = f->np, p = f->p, tile = f->eng.tile;
+  cudaStream_t st = f->st;
+  const int n2p = round_up(n2, tile);
+  W.n2 = n2; W.n2p = n2p;
+  const size_t vb2 = sizeof(double) * n2p;
+  if (W.X2.alloc(vb2 * p) || W.z2.alloc(vb2) || W.Kc.alloc(vb2 * np) || W.V.alloc(vb2 * np) || W.q.alloc(vb2) ||
+      W.tmp.alloc(vb2))
+    return fail(CS_ERR_NOMEM, "predict workspace allocation failed");
+  RT(upload_matrix(W.X2.d(), n2p, n2p, p, X2, n2, p, st));
+  if (treat) {
+    auto k = fill_kernel;
+    ++g_launches;
+    CS_LAUNCH(k, (n2p + 255) / 256, 256, 0, st, W.z2.d(), (long long)n2p, 1.0);
+  } else {
+    RT(upload_vector(W.z2.d(), n2p, z2, n2, 0.0, st));
+  }
+  const int rb2 = n2p / csk::TB;
+  {  // K_xX (or Ka_xX) : n2p x np
+    auto k = csk::gram_cross_kernel;
+    ++g_launches;
+    double* nul = nullptr;
+    CS_LAUNCH(k, dim3(rb2, f->nblk), csk::ETH, csk::gram_smem_bytes(p), st, W.X2.d(), (long long)n2p, W.z2.d(), n2, f->X,
+              (long long)np, f->z, n, f->params, f->lay, treat ? nul : W.Kc.d(), nul, treat ? W.Kc.d() : nul,
+              (long long)n2p);
+  }
+  split_plan(rb2, np, &W.nsplit, &W.cps);
+  if (W.part.alloc(vb2 * W.nsplit)) return fail(CS_ERR_NOMEM, "predict workspace allocation failed");
+  {  // map = Kc * alpha (+ mu)
+    auto k = csk::matvec_kernel<1>;
+    ++g_launches;
+    const double* nul = nullptr;
+    CS_LAUNCH(k, dim3(rb2, W.nsplit), csk::ETH, 0, st, W.Kc.d(), (long long)n2p, W.cps, np, f->alpha, nul, nul, nul,
+              W.part.d(), (long long)n2p, (long long)n2p, (const int*)nullptr);
+    auto k2 = csp::reduce_parts_kernel;
+    ++g_launches;
+    CS_LAUNCH(k2, (n2p + 255) / 256, 256, 0, st, W.part.d(), W.nsplit, (long long)n2p, n2p,
+              treat ? nul : (const double*)(f->params + f->lay.i_mu()), W.tmp.d());
+    if (map) RT(rt::d2h(map, W.tmp.d(), sizeof(double) * n2, st));
+  }
+  {  // V = Kc * K^-1  (NT GEMM on the DMMA path; K^-1 is full symmetric)
+    csg::GemmProblem P = DenseEngine::mk(W.Kc.d(), n2p, f->eng.C, np, W.V.d(), n2p, n2p / tile, np / tile, np,
+                                         csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0);
+    DevBuf dP;
+    if (dP.alloc(sizeof P)) return fail(CS_ERR_NOMEM, "alloc failed");
+    RT(rt::h2d(dP.p, &P, sizeof P, st));
+    csdense::launch_gemm(tile, csdense::GK_NT, (const csg::GemmProblem*)dP.p, 1, P.ntiles, st);
+    // q_i = sum_k V[i,k] Kc[i,k]
+    auto k = csp::rowdot_kernel;
+    ++g_launches;
+    CS_LAUNCH(k, dim3(rb2, W.nsplit), csk::ETH, 0, st, W.V.d(), W.Kc.d(), (long long)n2p, W.cps, np, W.part.d(),
+              (long long)n2p);
+    auto k2 = csp::reduce_parts_kernel;
+    ++g_launches;
+    CS_LAUNCH(k2, (n2p + 255) / 256, 256, 0, st, W.part.d(), W.nsplit, (long long)n2p, n2p, (const double*)nullptr,
+              W.q.d());
+    auto k3 = csp::var_diag_kernel;
+    ++g_launches;
+    CS_LAUNCH(k3, (n2p + 255) / 256, 256, 0, st, W.q.d(), W.z2.d(), f->params, f->lay, treat ? 0 : 1, add_sigma,
+              add_const, n2, W.tmp.d());
+    if (var_diag) RT(rt::d2h(var_diag, W.tmp.d(), sizeof(double) * n2, st));
+    RT(rt::stream_sync(st));  // dP must outlive the launch
+  }
+  if (cov_out) {
+    if (W.cov.alloc(vb2 * n2p)) return fail(CS_ERR_NOMEM, "cov allocation failed");
+    auto k = csk::gram_cross_kernel;
+    ++g_launches;
+    double* nul = nullptr;
+    CS_LAUNCH(k, dim3(rb2, rb2), csk::ETH, csk::gram_smem_bytes(p), st, W.X2.d(), (long long)n2p, W.z2.d(), n2,
+              W.X2.d(), (long long)n2p, W.z2.d(), n2, f->params, f->lay, treat ? nul : W.cov.d(), nul,
+              treat ? W.cov.d() : nul, (long long)n2p);
+    csg::GemmProblem P = DenseEngine::mk(W.V.d(), n2p, W.Kc.d(), n2p, W.cov.d(), n2p, n2p / tile, n2p / tile, np,
+                                         csg::KM_FULL, csg::ORD_COL, 0, -1.0, 1.0);
+    DevBuf dP;
+    if (dP.alloc(sizeof P)) return fail(CS_ERR_NOMEM, "alloc failed");
+    RT(rt::h2d(dP.p, &P, sizeof P, st));
+    csdense::launch_gemm(tile, csdense::GK_NT, (const csg::GemmProblem*)dP.p, 1, P.ntiles, st);
+    auto k2 = csp::cov_diag_kernel;
+    ++g_launches;
+    CS_LAUNCH(k2, (n2p + 255) / 256, 256, 0, st, W.cov.d(), (long long)n2p, n2, n2p, f->params, f->lay, add_sigma,
+              add_const);
+    RT(download_matrix(cov_out, n2, n2, W.cov.d(), n2p, st));
+    RT(rt::stream_sync(st));
+  }
+  KCHECK();
+  return 0;
+}
+
+int cs_predict(cs_fit* f, int n2, const double* X2, const double* z2, double* map, double* var_diag, double* cov) {
+  if (!f || !X2 || !z2 || n2 < 1) return fail(CS_ERR_ARG, "cs_predict: bad argument");
+  CrossWork W;
+  int e = cross_common(f, W, n2, X2, z2, false, map, var_diag, 1.0, 0.0, cov);
+  if (e) return e;
+  RT(rt::stream_sync(f->st));
+  return 0;
+}
+
+int cs_treat(cs_fit* f, int n2, const double* X2, double cov_jitter, double* map, double* var_diag, double* ate,
+             double* ate_var, double* cov) {
+  if (!f || !X2 || n2 < 1) return fail(CS_ERR_ARG, "cs_treat: bad argument");
+  CrossWork W;
+  std::vector<double> hmap(n2);
+  int e = cross_common(f, W, n2, X2, nullptr, true, hmap.data(), var_diag, 0.0, cov_jitter, cov);
+  if (e) return e;
+  cudaStream_t st = f->st;
+  const int np = f->np, n2p = W.n2p, p = f->p;
+  RT(rt::stream_sync(st));
+  if (map) std::copy(hmap.begin(), hmap.end(), map);
+  if (ate) {
+    double s = 0.0;
+    for (int i = 0; i < n2; ++i) s += hmap[i];
+    *ate = s / n2;  // mean(map), R/kernel_GP_SE_class.R:96
+  }
+  if (ate_var) {
+    // sum(cov) = sum(Ka_xx) - c' K^-1 c,  c_j = sum_i Ka_xX[i,j]   (no n2 x n2 temporaries)
+    DevBuf c, t, part, scal, gs;
+    const int rb2 = n2p / csk::TB;
+    int ns = 1, cps = 0;
+    split_plan(f->nblk, np, &ns, &cps);
+    if (c.alloc(sizeof(double) * np) || t.alloc(sizeof(double) * np) || part.alloc(sizeof(double) * np * ns) ||
+        scal.alloc(sizeof(double) * 2) || gs.alloc(sizeof(double) * rb2 * rb2))
+      return fail(CS_ERR_NOMEM, "alloc failed");
+    auto k = csp::colsum_kernel;
+    ++g_launches;
+    CS_LAUNCH(k, (np * 32 + 255) / 256, 256, 0, st, W.Kc.d(), (long long)n2p, n2, np, c.d());
+    auto k2 = csk::matvec_kernel<1>;
+    ++g_launches;
+    const double* nul = nullptr;
+    CS_LAUNCH(k2, dim3(f->nblk, ns), csk::ETH, 0, st, f->eng.C, (long long)np, cps, np, c.d(), nul, nul, nul, part.d(),
+              (long long)np, (long long)np, (const int*)nullptr);
+    auto k3 = csp::reduce_parts_kernel;
+    ++g_launches;
+    CS_LAUNCH(k3, (np + 255) / 256, 256, 0, st, part.d(), ns, (long long)np, np, nul, t.d());
+    auto k4 = csp::dot_kernel;
+    ++g_launches;
+    CS_LAUNCH(k4, 1, csk::ETH, 0, st, c.d(), t.d(), f->n, scal.d());
+    auto k5 = csp::gram_sum_kernel;
+    ++g_launches;
+    CS_LAUNCH(k5, dim3(rb2, rb2), csk::ETH, csk::gram_smem_bytes(p), st, W.X2.d(), (long long)n2p, n2, f->params, f->lay,
+              gs.d());
+    ++g_launches;
+    CS_LAUNCH(k4, 1, csk::ETH, 0, st, gs.d(), nul, rb2 * rb2, scal.d() + 1);
+    KCHECK();
+    double h[2];
+    RT(rt::d2h(h, scal.d(), sizeof h, st));
+    RT(rt::stream_sync(st));
+    const double dn = (double)f->n;
+    *ate_var = (h[1] - h[0] + cov_jitter * n2) / (dn * dn);  // R/kernel_GP_SE_class.R:101 (training n)
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// Student-t posterior sampler
+// ------------------------------------------------------------------------------------
+int cs_tp_sample(int n2, const double* cov, double df, int nsampling, unsigned long long seed, double* U,
+                 double* ate_U) {
+  if (n2 < 1 || !cov || !U || !(df > 0.0) || nsampling < 1) return fail(CS_ERR_ARG, "cs_tp_sample: bad argument");
+  if (need_device()) return CS_ERR_NODEVICE;
+  const int NS = 1000, NSP = csp::SORT_N;            // N_sample (R/kernel_TP_SE_class.R:86) padded to 1024
+  const int rank = (int)std::floor(NS * 0.90) - 1;   // 900th order statistic, 1-based in R (:90)
+  const int nrep = (nsampling + NS - 1) / NS;        // :88
+  DenseEngine eng;
+  const int tile = csdense::pick_tile(n2);
+  if (int e = eng.init(n2, tile)) { eng.destroy(); return fail(e == 2 ? CS_ERR_NOMEM : CS_ERR_CUDA, "engine init failed"); }
+  struct Guard { DenseEngine& e; ~Guard() { e.destroy(); } } guard{eng};
+  cudaStream_t st = 0;
+  const int np = eng.np;
+  RT(upload_matrix(eng.G, np, np, np, cov, n2, n2, st));
+  {
+    auto k = pad_identity_kernel;
+    ++g_launches;
+    const long long tot = (long long)np * np;
+    CS_LAUNCH(k, (unsigned)((tot + 255) / 256), 256, 0, st, eng.G, (long long)np, n2, np);
+  }
+  eng.factor(st);
+  KCHECK();
+  int status = 0;
+  RT(rt::d2h(&status, eng.status, sizeof(int), st));
+  RT(rt::stream_sync(st));
+  if (status != 0x7fffffff && status > 0) return fail(status, "rmvt: covariance not positive definite (pivot %d)", status);
+  DevBuf Z, Y, scale, Ud, rm, au, dP;
+  if (Z.alloc(sizeof(double) * NSP * np) || Y.alloc(sizeof(double) * NSP * np) || scale.alloc(sizeof(double) * NSP) ||
+      Ud.alloc(sizeof(double) * np) || rm.alloc(sizeof(double) * NSP) || au.alloc(sizeof(double)) ||
+      dP.alloc(sizeof(csg::GemmProblem)))
+    return fail(CS_ERR_NOMEM, "sampler allocation failed");
+  RT(rt::memset0(Ud.d(), sizeof(double) * np, st));
+  RT(rt::memset0(au.d(), sizeof(double), st));
+  // Y[s,i] = sum_k Z[s,k] L[i,k]   (NT)
+  csg::GemmProblem P = DenseEngine::mk(Z.d(), NSP, eng.G, np, Y.d(), NSP, NSP / tile, np / tile, np, csg::KM_FULL,
+                                       csg::ORD_COL, 0, 1.0, 0.0);
+  RT(rt::h2d(dP.p, &P, sizeof P, st));
+  for (int r = 0; r < nrep; ++r) {
+    auto k = csp::normal_fill_kernel;
+    const long long npair = ((long long)NSP * np + 1) / 2;
+    ++g_launches;
+    CS_LAUNCH(k, (unsigned)((npair + 255) / 256), 256, 0, st, Z.d(), (long long)NSP, NSP, np, seed, (unsigned)r);
+    auto k2 = csp::chi2_scale_kernel;
+    ++g_launches;
+    CS_LAUNCH(k2, (NSP + 255) / 256, 256, 0, st, scale.d(), NSP, df, seed, (unsigned)r);
+    csdense::launch_gemm(tile, csdense::GK_NT, (const csg::GemmProblem*)dP.p, 1, P.ntiles, st);
+    auto k3 = csp::order_stat_kernel;
+    ++g_launches;
+    CS_LAUNCH(k3, n2, 512, 0, st, Y.d(), (long long)NSP, scale.d(), NS, rank, 1.0 / nrep, Ud.d());
+    if (ate_U) {
+      auto k4 = csp::rowmean_kernel;
+      ++g_launches;
+      CS_LAUNCH(k4, (NSP + 255) / 256, 256, 0, st, Y.d(), (long long)NSP, NSP, n2, rm.d());
+      ++g_launches;
+      CS_LAUNCH(k3, 1, 512, 0, st, rm.d(), (long long)NSP, scale.d(), NS, rank, 1.0 / nrep, au.d());
+    }
+  }
+  KCHECK();
+  RT(rt::d2h(U, Ud.d(), sizeof(double) * n2, st));
+  if (ate_U) RT(rt::d2h(ate_U, au.d(), sizeof(double), st));
+  RT(rt::stream_sync(st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// stateless mirrors of the registered routines
+// ------------------------------------------------------------------------------------
+int cs_kernmat(int n1, int n2, int p, const double* X1, const double* X2, const double* Z1, const double* Z2,
+               const double* Lm, const double* La, double lambdam, double lambda_a, double* K, double* Km,
+               double* Ka) {
+  if (n1 < 1 || n2 < 1 || p < 1 || !X1 || !X2 || !Z1 || !Z2 || !Lm || !La) return fail(CS_ERR_ARG, "cs_kernmat: bad argument");
+  if (p > CS_MAX_P) return fail(CS_ERR_UNSUPPORTED, "cs_kernmat: p=%d exceeds CS_MAX_P=%d", p, CS_MAX_P);
+  if (need_device()) return CS_ERR_NODEVICE;
+  cudaStream_t st = 0;
+  const int n1p = round_up(n1, csk::TB), n2p = round_up(n2, csk::TB);
+  Layout lay{CS_GP, p};
+  std::vector<double> hp(lay.np(), 0.0);
+  hp[lay.i_lm()] = lambdam;
+  hp[lay.i_la()] = lambda_a;
+  for (int i = 0; i < p; ++i) { hp[lay.i_Lm() + i] = Lm[i]; hp[lay.i_La() + i] = La[i]; }
+  DevBuf dX1, dX2, dZ1, dZ2, dP, dK, dM, dA;
+  const size_t mb = sizeof(double) * (size_t)n1p * n2p;
+  if (dX1.alloc(sizeof(double) * n1p * p) || dX2.alloc(sizeof(double) * n2p * p) || dZ1.alloc(sizeof(double) * n1p) ||
+      dZ2.alloc(sizeof(double) * n2p) || dP.alloc(sizeof(double) * hp.size()) || (K && dK.alloc(mb)) ||
+      (Km && dM.alloc(mb)) || (Ka && dA.alloc(mb)))
+    return fail(CS_ERR_NOMEM, "cs_kernmat: allocation failed");
+  RT(upload_matrix(dX1.d(), n1p, n1p, p, X1, n1, p, st));
+  RT(upload_matrix(dX2.d(), n2p, n2p, p, X2, n2, p, st));
+  RT(upload_vector(dZ1.d(), n1p, Z1, n1, 0.0, st));
+  RT(upload_vector(dZ2.d(), n2p, Z2, n2, 0.0, st));
+  RT(rt::h2d(dP.p, hp.data(), sizeof(double) * hp.size(), st));
+  auto k = csk::gram_cross_kernel;
+  CS_SET_SMEM(k, csk::gram_smem_bytes(csk::PMAX));
+  ++g_launches;
+  CS_LAUNCH(k, dim3(n1p / csk::TB, n2p / csk::TB), csk::ETH, csk::gram_smem_bytes(p), st, dX1.d(), (long long)n1p,
+            dZ1.d(), n1, dX2.d(), (long long)n2p, dZ2.d(), n2, dP.d(), lay, dK.d(), dM.d(), dA.d(), (long long)n1p);
+  KCHECK();
+  if (K) RT(download_matrix(K, n1, n2, dK.d(), n1p, st));
+  if (Km) RT(download_matrix(Km, n1, n2, dM.d(), n1p, st));
+  if (Ka) RT(download_matrix(Ka, n1, n2, dA.d(), n1p, st));
+  RT(rt::stream_sync(st));
+  return 0;
+}
+
+static int engine_status(DenseEngine& eng, cudaStream_t st) {
+  int status = 0;
+  RT(rt::d2h(&status, eng.status, sizeof(int), st));
+  RT(rt::stream_sync(st));
+  if (status != 0x7fffffff && status > 0)
+    return fail(status, "inv_sympd(): matrix is singular or not positive definite (pivot %d)", status);
+  return 0;
+}
+
+static int engine_logdet(DenseEngine& eng, cudaStream_t st, double* out) {
+  std::vector<double> h(eng.N);
+  RT(rt::d2h(h.data(), eng.logdet_part, sizeof(double) * eng.N, st));
+  RT(rt::stream_sync(st));
+  double s = 0.0;
+  for (double v : h) s += v;
+  *out = 2.0 * s;
+  return 0;
+}
+
+int cs_invkernel(int n, const double* w, const double* K, double sigma, double* invK, double* logdet) {
+  if (n < 1 || !K || !invK) return fail(CS_ERR_ARG, "cs_invkernel: bad argument");
+  if (need_device()) return CS_ERR_NODEVICE;
+  DenseEngine eng;
+  if (int e = eng.init(n, csdense::pick_tile(n))) { eng.destroy(); return fail(e == 2 ? CS_ERR_NOMEM : CS_ERR_CUDA, "engine init failed"); }
+  struct Guard { DenseEngine& e; ~Guard() { e.destroy(); } } guard{eng};
+  cudaStream_t st = 0;
+  const int np = eng.np;
+  DevBuf dw;
+  if (dw.alloc(sizeof(double) * np)) return fail(CS_ERR_NOMEM, "alloc failed");
+  RT(upload_matrix(eng.G, np, np, np, K, n, n, st));
+  if (w) RT(upload_vector(dw.d(), np, w, n, 1.0, st));
+  else { auto k = fill_kernel; ++g_launches; CS_LAUNCH(k, (np + 255) / 256, 256, 0, st, dw.d(), (long long)np, 1.0); }
+  {
+    auto k = pad_identity_kernel;
+    const long long tot = (long long)np * np;
+    ++g_launches;
+    CS_LAUNCH(k, (unsigned)((tot + 255) / 256), 256, 0, st, eng.G, (long long)np, n, np);
+    auto k2 = add_noise_diag_kernel;
+    ++g_launches;
+    CS_LAUNCH(k2, (n + 255) / 256, 256, 0, st, eng.G, (long long)np, n, dw.d(), std::exp(sigma));  // :55
+  }
+  eng.factor(st);
+  eng.invert(st);
+  KCHECK();
+  if (int e = engine_status(eng, st)) return e;
+  RT(download_matrix(invK, n, n, eng.C, np, st));
+  RT(rt::stream_sync(st));
+  if (logdet) return engine_logdet(eng, st, logdet);
+  return 0;
+}
+
+int cs_mu_solution(int n, const double* y, const double* invK, double* mu) {
+  if (n < 1 || !y || !invK || !mu) return fail(CS_ERR_ARG, "cs_mu_solution: bad argument");
+  if (need_device()) return CS_ERR_NODEVICE;
+  cudaStream_t st = 0;
+  const int np = round_up(n, csk::TB), nb = np / csk::TB;
+  int ns = 1, cps = 0;
+  split_plan(nb, np, &ns, &cps);
+  DevBuf dA, dy, d1, part, out;
+  if (dA.alloc(sizeof(double) * (size_t)np * np) || dy.alloc(sizeof(double) * np) || d1.alloc(sizeof(double) * np) ||
+      part.alloc(sizeof(double) * np * 2 * ns) || out.alloc(sizeof(double)))
+    return fail(CS_ERR_NOMEM, "alloc failed");
+  RT(upload_matrix(dA.d(), np, np, np, invK, n, n, st));
+  RT(upload_vector(dy.d(), np, y, n, 0.0, st));
+  {
+    auto k = fill_kernel; ++g_launches;
+    CS_LAUNCH(k, (np + 255) / 256, 256, 0, st, d1.d(), (long long)np, 1.0);
+    auto k2 = csk::matvec_kernel<2>; ++g_launches;
+    const double* nul = nullptr;
+    CS_LAUNCH(k2, dim3(nb, ns), csk::ETH, 0, st, dA.d(), (long long)np, cps, np, dy.d(), d1.d(), nul, nul, part.d(),
+              (long long)np, (long long)(2 * np), (const int*)nullptr);
+    auto k3 = csk::mu_solution_kernel; ++g_launches;
+    CS_LAUNCH(k3, 1, csk::ETH, 0, st, part.d(), ns, (long long)np, (long long)(2 * np), n, out.d());
+  }
+  KCHECK();
+  RT(rt::d2h(mu, out.p, sizeof(double), st));
+  RT(rt::stream_sync(st));
+  return 0;
+}
+
+// grad / stats mirrors share one implementation: a temporary fit handle whose K^-1 is
+// either computed (invK == NULL) or uploaded as given.
+static int grad_stats_common(int kind, int n, int p, const double* y, const double* X, const double* z,
+                             const double* w, const double* Kmat, const double* Km, const double* Ka,
+                             const double* invK, const double* params, double* grad, double* stats) {
+  cs_fit_config cfg{};
+  cfg.kind = kind; cfg.optim = CS_OPT_NADAM; cfg.lr = 0.0; cfg.beta1 = 0.9; cfg.beta2 = 0.999; cfg.eps = 1e-8;
+  cs_fit* f = nullptr;
+  int e = cs_fit_create(&cfg, n, p, y, X, z, w, params, &f);
+  if (e) return e;
+  struct Guard { cs_fit* f; ~Guard() { cs_fit_destroy(f); } } guard{f};
+  if (!invK) {
+    if (Kmat || Km || Ka) return fail(CS_ERR_ARG, "Kmat/Km/Ka given without invK");
+    return cs_fit_eval(f, nullptr, grad, stats, nullptr);
+  }
+  cudaStream_t st = f->st;
+  const int np = f->np;
+  const long long ld = np;
+  // the given inverse: full copy in C for the traces, lower copy in G to obtain log det(invK)
+  RT(upload_matrix(f->eng.C, np, np, np, invK, n, n, st));
+  RT(upload_matrix(f->eng.G, np, np, np, invK, n, n, st));
+  {
+    auto k = pad_identity_kernel;
+    const long long tot = (long long)np * np;
+    ++g_launches; CS_LAUNCH(k, (unsigned)((tot + 255) / 256), 256, 0, st, f->eng.C, ld, n, np);
+    ++g_launches; CS_LAUNCH(k, (unsigned)((tot + 255) / 256), 256, 0, st, f->eng.G, ld, n, np);
+  }
+  f->eng.factor(st);  // logdet_part now holds log det(invK)/2 per block; sign flipped below
+  DevBuf dK, dM, dA;
+  const size_t mb = sizeof(double) * (size_t)np * np;
+  const bool from_mem = Kmat && Km && Ka;
+  if ((Kmat || Km || Ka) && !from_mem) return fail(CS_ERR_ARG, "Kmat, Km and Ka must be given together");
+  if (from_mem) {
+    if (dK.alloc(mb) || dM.alloc(mb) || dA.alloc(mb)) return fail(CS_ERR_NOMEM, "alloc failed");
+    RT(upload_matrix(dK.d(), np, np, np, Kmat, n, n, st));
+    RT(upload_matrix(dM.d(), np, np, np, Km, n, n, st));
+    RT(upload_matrix(dA.d(), np, np, np, Ka, n, n, st));
+  }
+  {
+    auto kneg = csk::negate_kernel;
+    ++g_launches; CS_LAUNCH(kneg, 1, 256, 0, st, f->eng.logdet_part, f->eng.N);
+    auto k = csk::matvec_kernel<3>;
+    ++g_launches;
+    CS_LAUNCH(k, dim3(f->nblk, f->nsplit), csk::ETH, 0, st, f->eng.C, ld, f->cols_per_split, np, f->y, f->y, f->ones,
+              f->params + f->lay.i_mu(), f->mv_part, ld, 3 * ld, (const int*)nullptr);
+    auto k2 = csk::scalars_kernel;
+    ++g_launches;
+    CS_LAUNCH(k2, 1, csk::ETH, 0, st, f->mv_part, f->nsplit, ld, 3 * ld, n, np, f->y, f->params, f->lay,
+              f->eng.logdet_part, f->eng.N, f->alpha, f->u, f->s, f->sc, (const int*)nullptr);
+    ++g_launches;
+    if (from_mem) {
+      auto k3 = csk::grad_trace_kernel<true>;
+      CS_LAUNCH(k3, f->ncta_grad, csk::ETH, csk::grad_smem_bytes(p), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
+                f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)dK.d(), (const double*)dM.d(),
+                (const double*)dA.d(), (const int*)nullptr);
+    } else {
+      auto k3 = csk::grad_trace_kernel<false>;
+      CS_LAUNCH(k3, f->ncta_grad, csk::ETH, csk::grad_smem_bytes(p), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
+                f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)nullptr,
+                (const double*)nullptr, (const double*)nullptr, (const int*)nullptr);
+    }
+    auto k4 = csk::finalize_kernel;
+    ++g_launches;
+    CS_LAUNCH(k4, 1, csk::ETH, 0, st, f->gpart, f->ncta_grad, f->kal_part, ld, f->nblk, f->eng.C, ld, f->alpha, f->y,
+              f->w, f->params, f->lay, n, f->sc, f->grad, (const int*)nullptr);
+  }
+  KCHECK();
+  return cs_fit_fetch(f, grad, stats, nullptr);
+}
+
+int cs_grad(int kind, int n, int p, const double* y, const double* X, const double* z, const double* w,
+            const double* Kmat, const double* Km, const double* Ka, const double* invK, const double* params,
+            double* grad, double* stats) {
+  if (!y || !X || !z || !params) return fail(CS_ERR_ARG, "cs_grad: null argument");
+  return grad_stats_common(kind, n, p, y, X, z, w, Kmat, Km, Ka, invK, params, grad, stats);
+}
+
+int cs_stats(int kind, int n, const double* y, const double* Kmat, const double* invK, double mu, double nu,
+             double* stats) {
+  if (n < 1 || !y || !Kmat || !invK || !stats) return fail(CS_ERR_ARG, "cs_stats: bad argument");
+  if (need_device()) return CS_ERR_NODEVICE;
+  DenseEngine eng;
+  if (int e = eng.init(n, csdense::pick_tile(n))) { eng.destroy(); return fail(e == 2 ? CS_ERR_NOMEM : CS_ERR_CUDA, "engine init failed"); }
+  struct Guard { DenseEngine& e; ~Guard() { e.destroy(); } } guard{eng};
+  cudaStream_t st = 0;
+  const int np = eng.np, nb = np / csk::TB;
+  const long long ld = np;
+  int ns = 1, cps = 0;
+  split_plan(nb, np, &ns, &cps);
+  DevBuf dy, dmu, part, alpha, kal, out;
+  if (dy.alloc(sizeof(double) * np) || dmu.alloc(sizeof(double)) || part.alloc(sizeof(double) * np * ns) ||
+      alpha.alloc(sizeof(double) * np) || kal.alloc(sizeof(double) * np) || out.alloc(sizeof(double) * 2))
+    return fail(CS_ERR_NOMEM, "alloc failed");
+  RT(upload_vector(dy.d(), np, y, n, 0.0, st));
+  RT(rt::h2d(dmu.p, &mu, sizeof(double), st));
+  RT(upload_matrix(eng.C, np, np, np, invK, n, n, st));
+  RT(upload_matrix(eng.G, np, np, np, invK, n, n, st));
+  {
+    auto k = pad_identity_kernel;
+    const long long tot = (long long)np * np;
+    ++g_launches; CS_LAUNCH(k, (unsigned)((tot + 255) / 256), 256, 0, st, eng.G, ld, n, np);
+  }
+  eng.factor(st);
+  const double* nul = nullptr;
+  auto mv = csk::matvec_kernel<1>;
+  auto rp = csp::reduce_parts_kernel;
+  ++g_launches;  // alpha = invK (y - mu); padded rows of C are zero, padded alpha is discarded below
+  CS_LAUNCH(mv, dim3(nb, ns), csk::ETH, 0, st, eng.C, ld, cps, np, dy.d(), nul, nul, (const double*)dmu.d(), part.d(), ld,
+            ld, (const int*)nullptr);
+  ++g_launches;
+  CS_LAUNCH(rp, (np + 255) / 256, 256, 0, st, part.d(), ns, ld, n, nul, alpha.d());
+  if (np > n) { auto kf = fill_kernel; ++g_launches; CS_LAUNCH(kf, (np - n + 255) / 256, 256, 0, st, alpha.d() + n, (long long)(np - n), 0.0); }
+  RT(upload_matrix(eng.C, np, np, np, Kmat, n, n, st));  // reuse C for Kmat (stream-ordered after the mat-vec)
+  ++g_launches;
+  CS_LAUNCH(mv, dim3(nb, ns), csk::ETH, 0, st, eng.C, ld, cps, np, alpha.d(), nul, nul, nul, part.d(), ld, ld,
+            (const int*)nullptr);
+  ++g_launches;
+  CS_LAUNCH(rp, (np + 255) / 256, 256, 0, st, part.d(), ns, ld, n, nul, kal.d());
+  auto ks = csk::stats_only_kernel;
+  ++g_launches;
+  CS_LAUNCH(ks, 1, csk::ETH, 0, st, kind, n, (const double*)dy.d(), (const double*)alpha.d(), (const double*)kal.d(),
+            (const double*)eng.logdet_part, eng.N, mu, nu, out.d());
+  KCHECK();
+  if (int e = engine_status(eng, st)) return e;
+  RT(rt::d2h(stats, out.p, sizeof(double) * 2, st));
+  RT(rt::stream_sync(st));
+  return 0;
+}
+
+int cs_opt_step(int optim, int nparam, double iter, double lr, double beta1, double beta2, double eps, double* m,
+                double* v, const double* grad, double* para) {
+  if (nparam < 1 || !m || !grad || !para) return fail(CS_ERR_ARG, "cs_opt_step: null argument");
+  if (optim != CS_OPT_NESTEROV && !v) return fail(CS_ERR_ARG, "cs_opt_step: v required for Adam/Nadam");
+  if (need_device()) return CS_ERR_NODEVICE;
+  cudaStream_t st = 0;
+  DevBuf dm, dv, dg, dp;
+  const size_t b = sizeof(double) * nparam;
+  if (dm.alloc(b) || dv.alloc(b) || dg.alloc(b) || dp.alloc(b)) return fail(CS_ERR_NOMEM, "alloc failed");
+  RT(rt::h2d(dm.p, m, b, st));
+  if (v) RT(rt::h2d(dv.p, v, b, st)); else RT(rt::memset0(dv.p, b, st));
+  RT(rt::h2d(dg.p, grad, b, st));
+  RT(rt::h2d(dp.p, para, b, st));
+  auto k = csk::opt_step_kernel;
+  ++g_launches;
+  CS_LAUNCH(k, 1, 32, 0, st, optim, nparam, iter, lr, beta1, beta2, eps, /*momentum=*/beta1, dm.d(), dv.d(),
+            (const double*)dg.d(), dp.d());
+  KCHECK();
+  RT(rt::d2h(m, dm.p, b, st));
+  if (v) RT(rt::d2h(v, dv.p, b, st));
+  RT(rt::d2h(para, dp.p, b, st));
+  RT(rt::stream_sync(st));
+  return 0;
+}
+
+}  // extern "C"

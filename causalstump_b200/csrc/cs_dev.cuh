@@ -1,0 +1,80 @@
+// Device primitives for sm_100a: FP64 tensor-core MMA (DMMA.8x8x4), cp.async staging,
+// warp reductions.  Under CS_EMU (tests only) each primitive has a behavioural model.
+#pragma once
+#include "cs_rt.h"
+
+namespace csd {
+
+// D(8x8) += A(8x4,row) * B(4x8,col), fp64.  Fragment ownership (PTX ISA, mma.m8n8k4.f64):
+//   a : A[lane>>2][lane&3]        b : B[lane&3][lane>>2]
+//   c[i] : C[lane>>2][2*(lane&3)+i]
+__device__ __forceinline__ void dmma8x8x4(double (&c)[2], double a, double b) {
+#ifdef CS_EMU
+  int par = emu::next_parity();
+  double* slot = static_cast<double*>(emu::xch_slot(par, emu::lane()));
+  slot[0] = a; slot[1] = b;
+  emu::barrier_warp();
+  const int g = emu::lane() >> 2, t = emu::lane() & 3;
+  for (int i = 0; i < 2; ++i) {
+    const int col = 2 * t + i;
+    double s = c[i];
+    for (int k = 0; k < 4; ++k) {
+      const double av = static_cast<double*>(emu::xch_slot(par, g * 4 + k))[0];
+      const double bv = static_cast<double*>(emu::xch_slot(par, col * 4 + k))[1];
+      s = std::fma(av, bv, s);
+    }
+    c[i] = s;
+  }
+#else
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+#endif
+}
+
+// 16-byte global -> shared asynchronous copy (LDGSTS).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+#ifdef CS_EMU
+  std::memcpy(smem_dst, gmem_src, 16);
+#else
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef CS_EMU
+  asm volatile("cp.async.commit_group;\n" ::);
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef CS_EMU
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+#endif
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic block-wide sum; result valid in thread 0 (and returned to all after sync).
+// `red` must hold >= 32 doubles of shared memory.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (wid == 0) {
+    r = (lane < nw) ? red[lane] : 0.0;
+    r = warp_sum(r);
+    if (lane == 0) red[0] = r;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+}  // namespace csd

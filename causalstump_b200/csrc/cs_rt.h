@@ -1,0 +1,83 @@
+// Runtime shim: the product build (nvcc, sm_100a) talks to the CUDA runtime directly.
+// With -DCS_EMU (g++, tests/emu only) the same sources run on the SIMT emulator so the
+// kernels' index logic can be unit-tested without a GPU.  There is no CPU fallback in
+// the product library: CS_EMU is never defined by causalstump_b200/csrc/build.py.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#ifdef CS_EMU
+#include "emu.h"
+typedef int cudaStream_t;
+typedef int cudaEvent_t;
+typedef int cudaError_t;
+#define cudaSuccess 0
+#define CS_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::dyn_smem)
+#define CS_LAUNCH(kfn, grid, block, smem, stream, ...) \
+  emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kfn(__VA_ARGS__); })
+#define CS_SET_SMEM(kfn, bytes) ((void)0)
+namespace rt {
+inline int check(int e, const char*, int) { return e; }
+inline int dev_malloc(void** p, size_t bytes) { *p = std::malloc(bytes ? bytes : 1); return *p ? 0 : 2; }
+inline int dev_free(void* p) { std::free(p); return 0; }
+inline int h2d(void* d, const void* h, size_t b, cudaStream_t) { std::memcpy(d, h, b); return 0; }
+inline int d2h(void* h, const void* d, size_t b, cudaStream_t) { std::memcpy(h, d, b); return 0; }
+inline int d2d(void* d, const void* s, size_t b, cudaStream_t) { std::memmove(d, s, b); return 0; }
+inline int memset0(void* d, size_t b, cudaStream_t) { std::memset(d, 0, b); return 0; }
+inline int stream_create(cudaStream_t* s) { *s = 0; return 0; }
+inline int stream_destroy(cudaStream_t) { return 0; }
+inline int stream_sync(cudaStream_t) { return 0; }
+inline int event_create(cudaEvent_t* e) { *e = 0; return 0; }
+inline int event_destroy(cudaEvent_t) { return 0; }
+inline int event_record(cudaEvent_t, cudaStream_t) { return 0; }
+inline int event_sync(cudaEvent_t) { return 0; }
+inline int stream_wait_event(cudaStream_t, cudaEvent_t) { return 0; }
+inline int event_elapsed(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
+inline int last_error() { return 0; }
+inline const char* err_str(int) { return "emu"; }
+inline int device_count(int* n) { *n = 1; return 0; }
+inline int set_device(int) { return 0; }
+inline int sm_count() { return 4; }
+inline int host_alloc(void** p, size_t b) { *p = std::malloc(b ? b : 1); return *p ? 0 : 2; }
+inline int host_free(void* p) { std::free(p); return 0; }
+}  // namespace rt
+#else
+#include <cuda_runtime.h>
+#define CS_DYN_SMEM(T, name) \
+  extern __shared__ __align__(16) unsigned char cs_dyn_smem_raw[]; \
+  T* name = reinterpret_cast<T*>(cs_dyn_smem_raw)
+#define CS_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define CS_SET_SMEM(kfn, bytes) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+namespace rt {
+inline int dev_malloc(void** p, size_t bytes) { return (int)cudaMalloc(p, bytes ? bytes : 1); }
+inline int dev_free(void* p) { return (int)cudaFree(p); }
+inline int h2d(void* d, const void* h, size_t b, cudaStream_t s) { return (int)cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, s); }
+inline int d2h(void* h, const void* d, size_t b, cudaStream_t s) { return (int)cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, s); }
+inline int d2d(void* d, const void* s_, size_t b, cudaStream_t s) { return (int)cudaMemcpyAsync(d, s_, b, cudaMemcpyDeviceToDevice, s); }
+inline int memset0(void* d, size_t b, cudaStream_t s) { return (int)cudaMemsetAsync(d, 0, b, s); }
+inline int stream_create(cudaStream_t* s) { return (int)cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); }
+inline int stream_destroy(cudaStream_t s) { return (int)cudaStreamDestroy(s); }
+inline int stream_sync(cudaStream_t s) { return (int)cudaStreamSynchronize(s); }
+inline int event_create(cudaEvent_t* e) { return (int)cudaEventCreate(e); }
+inline int event_destroy(cudaEvent_t e) { return (int)cudaEventDestroy(e); }
+inline int event_record(cudaEvent_t e, cudaStream_t s) { return (int)cudaEventRecord(e, s); }
+inline int event_sync(cudaEvent_t e) { return (int)cudaEventSynchronize(e); }
+inline int stream_wait_event(cudaStream_t s, cudaEvent_t e) { return (int)cudaStreamWaitEvent(s, e, 0); }
+inline int event_elapsed(float* ms, cudaEvent_t a, cudaEvent_t b) { return (int)cudaEventElapsedTime(ms, a, b); }
+inline int last_error() { return (int)cudaGetLastError(); }
+inline const char* err_str(int e) { return cudaGetErrorString((cudaError_t)e); }
+inline int device_count(int* n) { return (int)cudaGetDeviceCount(n); }
+inline int set_device(int d) { return (int)cudaSetDevice(d); }
+inline int sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  return n;
+}
+inline int host_alloc(void** p, size_t b) { return (int)cudaMallocHost(p, b ? b : 1); }
+inline int host_free(void* p) { return (int)cudaFreeHost(p); }
+}  // namespace rt
+#endif

@@ -1,0 +1,199 @@
+// Structured FP64 tile GEMM on the DMMA.8x8x4 tensor path (sm_100a), used for every
+// dense contraction of the fit: Cholesky trailing updates, the panel multiply by the
+// inverted diagonal block, the recursive triangular inverse, K^-1 = X^T X, and the
+// predict / treatment cross products.  One launch executes a *group* of problems; each
+// CTA owns one TILE x TILE output tile and walks its own k-range (triangular operands
+// are skipped at tile granularity; the opposite triangle is stored as explicit zeros so
+// correctness never depends on the skipping).
+//
+// Operand staging: cp.async (LDGSTS) 16-byte copies into a NSTAGE-deep padded
+// shared-memory ring; pads (+4 doubles) make every fragment LDS.64 conflict-free.
+// All matrices are column-major fp64 (the R / Armadillo layout of the reference).
+#pragma once
+#include "cs_dev.cuh"
+
+namespace csg {
+
+enum KMode { KM_FULL = 0, KM_GE_J = 1, KM_LE_I = 2, KM_GE_I = 3 };
+enum TileOrder { ORD_COL = 0, ORD_ROW_DESC = 1, ORD_LOWER = 2 };
+
+struct GemmProblem {
+  const double* A;  // element (i,k): AK ? A[k + i*lda] : A[i + k*lda]
+  const double* B;  // element (j,k): BK ? B[k + j*ldb] : B[j + k*ldb]
+  double* C;        // element (i,j): C[i + j*ldc]
+  long long lda, ldb, ldc;
+  int mt, nt;       // tiles along m / n
+  int K;            // k extent in elements (multiple of GEMM_BK)
+  int kmode;        // KMode, in units of TILE
+  int order;        // TileOrder; ORD_LOWER enumerates only I >= J (mt == nt)
+  int mirror;       // also store C(j,i) = C(i,j)
+  int tile_base;    // first linear tile id of this problem inside the launch
+  int ntiles;
+  double alpha, beta;  // C = beta*C + alpha*acc   (beta in {0,1})
+};
+
+constexpr int GEMM_BK = 16;
+constexpr int GEMM_PAD = 4;
+constexpr int GEMM_STAGES = 4;
+
+__host__ __device__ inline int lower_tiles(int n) { return n * (n + 1) / 2; }
+
+__host__ __device__ inline void decode_tile(int order, int mt, int nt, int t, int& I, int& J) {
+  if (order == ORD_COL) {
+    J = t / mt; I = t - J * mt;
+  } else if (order == ORD_ROW_DESC) {
+    int r = t / nt; I = mt - 1 - r; J = t - r * nt;
+  } else {
+    int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((long long)(i + 1) * (i + 2) / 2 <= t) ++i;
+    while ((long long)i * (i + 1) / 2 > t) --i;
+    I = i; J = t - i * (i + 1) / 2;
+  }
+}
+
+__host__ __device__ inline void tile_krange(int kmode, int K, int TILE, int I, int J, int& kbeg, int& kend) {
+  kbeg = 0; kend = K;
+  if (kmode == KM_GE_J) kbeg = J * TILE;
+  else if (kmode == KM_GE_I) kbeg = I * TILE;
+  else if (kmode == KM_LE_I) kend = (I + 1) * TILE;
+  if (kend > K) kend = K;
+  if (kbeg > kend) kbeg = kend;
+}
+
+template <int TILE, bool KMAJ>
+struct OperandSmem {
+  // m-major: [BK][TILE+PAD]   k-major: [TILE][BK+PAD]
+  static constexpr int LD = KMAJ ? (GEMM_BK + GEMM_PAD) : (TILE + GEMM_PAD);
+  static constexpr int SIZE = KMAJ ? TILE * LD : GEMM_BK * LD;
+};
+
+template <int TILE, int WM, int WN>
+struct GemmCfg {
+  static constexpr int THREADS = WM * WN * 32;
+  static constexpr int WTM = TILE / WM, WTN = TILE / WN;
+  static constexpr int FM = WTM / 8, FN = WTN / 8;
+};
+
+template <int TILE, bool AK, bool BK_>
+constexpr int gemm_smem_bytes() {
+  return GEMM_STAGES * (OperandSmem<TILE, AK>::SIZE + OperandSmem<TILE, BK_>::SIZE) * (int)sizeof(double);
+}
+
+// copy one TILE x GEMM_BK operand chunk into a stage buffer
+template <int TILE, bool KMAJ, int THREADS>
+__device__ __forceinline__ void load_operand(double* __restrict__ s, const double* __restrict__ g, long long ld,
+                                             int row0, int k0, int tid) {
+  using S = OperandSmem<TILE, KMAJ>;
+  constexpr int NCOPY = TILE * GEMM_BK / 2;
+  static_assert(NCOPY % THREADS == 0, "copy count must divide");
+#pragma unroll
+  for (int it = 0; it < NCOPY / THREADS; ++it) {
+    const int idx = tid + it * THREADS;
+    if (KMAJ) {
+      const int i = idx / (GEMM_BK / 2), kc = idx - i * (GEMM_BK / 2);
+      csd::cp_async16(s + i * S::LD + 2 * kc, g + (long long)(row0 + i) * ld + k0 + 2 * kc);
+    } else {
+      const int kk = idx / (TILE / 2), ic = idx - kk * (TILE / 2);
+      csd::cp_async16(s + kk * S::LD + 2 * ic, g + (long long)(k0 + kk) * ld + row0 + 2 * ic);
+    }
+  }
+}
+
+template <int TILE, int WM, int WN, bool AK, bool BK_>
+__global__ void __launch_bounds__(WM * WN * 32)
+gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  using Cfg = GemmCfg<TILE, WM, WN>;
+  using SA = OperandSmem<TILE, AK>;
+  using SB = OperandSmem<TILE, BK_>;
+  constexpr int FM = Cfg::FM, FN = Cfg::FN;
+  CS_DYN_SMEM(double, smem);
+  double* sA = smem;
+  double* sB = smem + GEMM_STAGES * SA::SIZE;
+
+  const int tid = threadIdx.x;
+  // locate the problem this CTA belongs to (uniform across the CTA)
+  int pi = 0;
+  const int bt = (int)blockIdx.x;
+  while (pi + 1 < nprob && bt >= probs[pi + 1].tile_base) ++pi;
+  const GemmProblem P = probs[pi];
+  int I, J;
+  decode_tile(P.order, P.mt, P.nt, bt - P.tile_base, I, J);
+  int kbeg, kend;
+  tile_krange(P.kmode, P.K, TILE, I, J, kbeg, kend);
+  const int nchunks = (kend - kbeg) / GEMM_BK;
+  const int i0 = I * TILE, j0 = J * TILE;
+
+  const int lane = tid & 31, wid = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (wid % WM) * Cfg::WTM, wn = (wid / WM) * Cfg::WTN;
+
+  double acc[FM][FN][2];
+#pragma unroll
+  for (int a = 0; a < FM; ++a)
+#pragma unroll
+    for (int b = 0; b < FN; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+
+  // prologue
+#pragma unroll
+  for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+    if (s < nchunks) {
+      load_operand<TILE, AK, Cfg::THREADS>(sA + s * SA::SIZE, P.A, P.lda, i0, kbeg + s * GEMM_BK, tid);
+      load_operand<TILE, BK_, Cfg::THREADS>(sB + s * SB::SIZE, P.B, P.ldb, j0, kbeg + s * GEMM_BK, tid);
+    }
+    csd::cp_async_commit();
+  }
+
+  for (int c = 0; c < nchunks; ++c) {
+    csd::cp_async_wait<GEMM_STAGES - 2>();
+    __syncthreads();
+    {
+      const int cn = c + GEMM_STAGES - 1;
+      if (cn < nchunks) {
+        const int sn = cn % GEMM_STAGES;
+        load_operand<TILE, AK, Cfg::THREADS>(sA + sn * SA::SIZE, P.A, P.lda, i0, kbeg + cn * GEMM_BK, tid);
+        load_operand<TILE, BK_, Cfg::THREADS>(sB + sn * SB::SIZE, P.B, P.ldb, j0, kbeg + cn * GEMM_BK, tid);
+      }
+      csd::cp_async_commit();
+    }
+    const double* a_s = sA + (c % GEMM_STAGES) * SA::SIZE;
+    const double* b_s = sB + (c % GEMM_STAGES) * SB::SIZE;
+#pragma unroll
+    for (int kk = 0; kk < GEMM_BK; kk += 4) {
+      double af[FM], bf[FN];
+#pragma unroll
+      for (int a = 0; a < FM; ++a)
+        af[a] = AK ? a_s[(wm + a * 8 + g) * SA::LD + kk + t] : a_s[(kk + t) * SA::LD + wm + a * 8 + g];
+#pragma unroll
+      for (int b = 0; b < FN; ++b)
+        bf[b] = BK_ ? b_s[(wn + b * 8 + g) * SB::LD + kk + t] : b_s[(kk + t) * SB::LD + wn + b * 8 + g];
+#pragma unroll
+      for (int a = 0; a < FM; ++a)
+#pragma unroll
+        for (int b = 0; b < FN; ++b) csd::dmma8x8x4(acc[a][b], af[a], bf[b]);
+    }
+  }
+  csd::cp_async_wait<0>();
+
+  // epilogue: C = beta*C + alpha*acc (+ mirrored store)
+  const double alpha = P.alpha, beta = P.beta;
+#pragma unroll
+  for (int a = 0; a < FM; ++a) {
+    const long long r = i0 + wm + a * 8 + g;
+#pragma unroll
+    for (int b = 0; b < FN; ++b) {
+      const long long cc = j0 + wn + b * 8 + 2 * t;
+      double* p0 = P.C + r + cc * P.ldc;
+      double* p1 = p0 + P.ldc;
+      double v0 = alpha * acc[a][b][0], v1 = alpha * acc[a][b][1];
+      if (beta != 0.0) { v0 += beta * (*p0); v1 += beta * (*p1); }
+      *p0 = v0; *p1 = v1;
+      if (P.mirror && I != J) {
+        double* q = P.C + cc + r * P.ldc;  // (cc, r) and (cc+1, r) are adjacent
+        q[0] = v0; q[1] = v1;
+      }
+    }
+  }
+}
+
+}  // namespace csg

@@ -1,0 +1,590 @@
+// Gram (K1), K^-1 mat-vec, fused trace-gradient (K3/K4), finalize and optimizer (K5)
+// kernels of the GP / Student-t-process fit.  Reference arithmetic:
+//   kernmat_{GP,TP}_SE_cpp   /root/reference/src/kernel_GP_SE_cpp.cpp:72-140, kernel_TP_SE_cpp.cpp:46-90
+//   grad_{GP,TP}_SE_cpp      kernel_GP_SE_cpp.cpp:143-202 (+ :8-44), kernel_TP_SE_cpp.cpp:100-163
+//   mu_solution_cpp          kernel_GP_SE_cpp.cpp:61-70
+//   Adam/Nadam/Nesterov_cpp  optimizer_cpp.cpp:9-63
+// All matrices column-major fp64.  Vectors are padded to np (multiple of 64).
+#pragma once
+#include "cs_dev.cuh"
+
+namespace csk {
+
+constexpr int TB = 64;        // tile edge of the element-wise kernels
+constexpr int ETH = 256;      // threads per CTA (16 x 16, 4 x 4 entries each)
+constexpr int PMAX = 40;      // max covariates supported by the fused gradient kernel
+
+enum Kind { KIND_GP = 0, KIND_TP = 1 };
+enum Optim { OPT_ADAM = 0, OPT_NADAM = 1, OPT_NESTEROV = 2 };
+
+// flat parameter vector layout = reference list order
+//   GP: sigma, lambdam, lambdaa, Lm[p], La[p], mu          (R/kernel_GP_SE_class.R:13-19)
+//   TP: sigma, lambdam, nu, lambda0, Lm[p], La[p], mu      (R/kernel_TP_SE_class.R:14-21)
+struct Layout {
+  int kind, p;
+  __host__ __device__ int base() const { return kind == KIND_TP ? 4 : 3; }
+  __host__ __device__ int i_sigma() const { return 0; }
+  __host__ __device__ int i_lm() const { return 1; }
+  __host__ __device__ int i_nu() const { return 2; }                       // TP only
+  __host__ __device__ int i_la() const { return kind == KIND_TP ? 3 : 2; }  // lambdaa / lambda0
+  __host__ __device__ int i_Lm() const { return base(); }
+  __host__ __device__ int i_La() const { return base() + p; }
+  __host__ __device__ int i_mu() const { return base() + 2 * p; }
+  __host__ __device__ int np() const { return base() + 2 * p + 1; }
+};
+
+// device-resident scalars of one evaluation
+struct EvalScalars {
+  double M;        // ybar' alpha
+  double sum_alpha, sum_u, sum_s;
+  double coef;     // 1 (GP) or TP_adjust (kernel_TP_SE_cpp.cpp:122)
+  double logdet;   // log det K_n
+  double mu_sol;   // 0.5 * sum(K^-1 y) / sum(K^-1)      (quirk Q1)
+  double stats[2]; // squared residual, LML
+};
+
+// device-resident optimisation-loop state
+struct LoopState {
+  int it;          // next iteration number (1-based)
+  int done;        // 1 once converged or maxiter reached
+  int iters;       // iterations performed when done
+  int maxiter;
+  double tol;
+  double prev_lml; // stats[2, iter] of the previous iteration (0 before the first)
+};
+
+// ---------------------------------------------------------------------------------
+// shared micro-tile: thread (tx,ty) owns rows tx+16a, cols ty+16b (a,b = 0..3) of a 64x64 tile
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void load_x_tile(double* __restrict__ xs, const double* __restrict__ X, long long ldx,
+                                            int row0, int p, int tid) {
+  for (int idx = tid; idx < p * TB; idx += ETH) {
+    const int i = idx / TB, r = idx - i * TB;
+    xs[idx] = X[(long long)i * ldx + row0 + r];
+  }
+}
+
+// exponents sm = sum_i a_i d_i^2, sa = sum_i b_i d_i^2 for the 4x4 micro-tile
+__device__ __forceinline__ void sqdist_4x4(const double* __restrict__ xr, const double* __restrict__ xc,
+                                           const double* __restrict__ ea, const double* __restrict__ eb, int p,
+                                           int tx, int ty, double (&sm)[4][4], double (&sa)[4][4]) {
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { sm[a][b] = 0.0; sa[a][b] = 0.0; }
+  for (int i = 0; i < p; ++i) {
+    double xa[4], xb[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) xa[a] = xr[i * TB + tx + 16 * a];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) xb[b] = xc[i * TB + ty + 16 * b];
+    const double ai = ea[i], bi = eb[i];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const double d = xa[a] - xb[b];
+        const double d2 = d * d;
+        sm[a][b] = fma(d2, ai, sm[a][b]);
+        sa[a][b] = fma(d2, bi, sa[a][b]);
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// K1: training Gram K_n = Km + Ka + diag(exp(sigma)/w), lower tiles, identity padding.
+// ---------------------------------------------------------------------------------
+inline int gram_smem_bytes(int p) { return (2 * p * TB + 2 * PMAX + 3 * TB) * (int)sizeof(double); }
+
+__global__ void __launch_bounds__(ETH)
+gram_train_kernel(const double* __restrict__ X, long long ldx, const double* __restrict__ z,
+                  const double* __restrict__ w, const double* __restrict__ params, Layout lay, int n,
+                  double* __restrict__ G, long long ldg, const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  CS_DYN_SMEM(double, sm_);
+  const int p = lay.p;
+  double* xr = sm_;
+  double* xc = xr + p * TB;
+  double* ea = xc + p * TB;
+  double* eb = ea + PMAX;
+  double* zr = eb + PMAX;
+  double* zc = zr + TB;
+  double* wr = zc + TB;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  // lower-triangular tile enumeration
+  const int t = (int)blockIdx.x;
+  int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((long long)(I + 1) * (I + 2) / 2 <= t) ++I;
+  while ((long long)I * (I + 1) / 2 > t) --I;
+  const int J = t - I * (I + 1) / 2;
+  const int r0 = I * TB, c0 = J * TB;
+  load_x_tile(xr, X, ldx, r0, p, tid);
+  load_x_tile(xc, X, ldx, c0, p, tid);
+  if (tid < p) { ea[tid] = exp(-params[lay.i_Lm() + tid]); eb[tid] = exp(-params[lay.i_La() + tid]); }
+  if (tid < TB) { zr[tid] = z[r0 + tid]; zc[tid] = z[c0 + tid]; wr[tid] = w[r0 + tid]; }
+  __syncthreads();
+  const double lam_m = params[lay.i_lm()], lam_a = params[lay.i_la()];
+  const double esig = exp(params[lay.i_sigma()]);
+  double sm[4][4], sa[4][4];
+  sqdist_4x4(xr, xc, ea, eb, p, tx, ty, sm, sa);
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int cl = ty + 16 * b, gc = c0 + cl;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int rl = tx + 16 * a, gr = r0 + rl;
+      double v;
+      if (gr >= n || gc >= n) v = (gr == gc) ? 1.0 : 0.0;
+      else if (gr < gc) v = 0.0;
+      else {
+        const double km = exp(lam_m - sm[a][b]);
+        const double ka = exp(lam_a - sa[a][b]) * zr[rl] * zc[cl];
+        v = km + ka;
+        if (gr == gc) v += esig / wr[rl];
+      }
+      G[(long long)gc * ldg + gr] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// cross Gram (kernmat_*_SE_cpp with X1 != X2): K, Km, Ka (any may be null), n1 x n2,
+// rows padded to ld; entries outside (n1,n2) are written as 0.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ETH)
+gram_cross_kernel(const double* __restrict__ X1, long long ldx1, const double* __restrict__ z1, int n1,
+                  const double* __restrict__ X2, long long ldx2, const double* __restrict__ z2, int n2,
+                  const double* __restrict__ params, Layout lay, double* __restrict__ K, double* __restrict__ Km,
+                  double* __restrict__ Ka, long long ldk) {
+  CS_DYN_SMEM(double, sm_);
+  const int p = lay.p;
+  double* xr = sm_;
+  double* xc = xr + p * TB;
+  double* ea = xc + p * TB;
+  double* eb = ea + PMAX;
+  double* zr = eb + PMAX;
+  double* zc = zr + TB;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int r0 = (int)blockIdx.x * TB, c0 = (int)blockIdx.y * TB;
+  load_x_tile(xr, X1, ldx1, r0, p, tid);
+  load_x_tile(xc, X2, ldx2, c0, p, tid);
+  if (tid < p) { ea[tid] = exp(-params[lay.i_Lm() + tid]); eb[tid] = exp(-params[lay.i_La() + tid]); }
+  if (tid < TB) { zr[tid] = z1[r0 + tid]; zc[tid] = z2[c0 + tid]; }
+  __syncthreads();
+  const double lam_m = params[lay.i_lm()], lam_a = params[lay.i_la()];
+  double sm[4][4], sa[4][4];
+  sqdist_4x4(xr, xc, ea, eb, p, tx, ty, sm, sa);
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int cl = ty + 16 * b, gc = c0 + cl;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int rl = tx + 16 * a, gr = r0 + rl;
+      double km = 0.0, ka = 0.0;
+      if (gr < n1 && gc < n2) {
+        km = exp(lam_m - sm[a][b]);
+        ka = exp(lam_a - sa[a][b]) * zr[rl] * zc[cl];
+      }
+      const long long o = (long long)gc * ldk + gr;
+      if (K) K[o] = km + ka;
+      if (Km) Km[o] = km;
+      if (Ka) Ka[o] = ka;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Mat-vec panel: out_part[split][k][r] = sum_{c in split} A[r,c] * v_k[c], k < NV.
+// A is rows x cols column-major (ld), rows/cols multiples of 64; CTA = 64 rows x 4 lanes.
+// ---------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(ETH)
+matvec_kernel(const double* __restrict__ A, long long ld, int cols_per_split, int cols,
+              const double* __restrict__ v0, const double* __restrict__ v1, const double* __restrict__ v2,
+              const double* __restrict__ shift0, double* __restrict__ out_part, long long out_stride_k,
+              long long out_stride_split, const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  __shared__ double red[3][4][TB];
+  const double sh = shift0 ? *shift0 : 0.0;  // v0 is used as (v0 - *shift0): ybar = y - mu
+  const int tid = threadIdx.x, rl = tid & 63, cl = tid >> 6;
+  const int r = (int)blockIdx.x * TB + rl;
+  const int cbeg = (int)blockIdx.y * cols_per_split;
+  int cend = cbeg + cols_per_split;
+  if (cend > cols) cend = cols;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int c = cbeg + cl; c < cend; c += 4) {
+    const double a = A[(long long)c * ld + r];
+    s0 = fma(a, v0[c] - sh, s0);
+    if (NV > 1) s1 = fma(a, v1[c], s1);
+    if (NV > 2) s2 = fma(a, v2[c], s2);
+  }
+  red[0][cl][rl] = s0;
+  if (NV > 1) red[1][cl][rl] = s1;
+  if (NV > 2) red[2][cl][rl] = s2;
+  __syncthreads();
+  if (tid < TB) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const double s = (red[k][0][tid] + red[k][1][tid]) + (red[k][2][tid] + red[k][3][tid]);
+      out_part[(long long)blockIdx.y * out_stride_split + k * out_stride_k + (int)blockIdx.x * TB + tid] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// After the K^-1 mat-vec: alpha = K^-1 (y - mu), u = K^-1 y, s = K^-1 1 (reduced over
+// splits), then the scalars M, sums, TP coefficient, log det and the closed-form mu.
+// One CTA.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ETH)
+scalars_kernel(const double* __restrict__ mv_part, int nsplit, long long stride_k, long long stride_split, int n,
+               int npad, const double* __restrict__ y, const double* __restrict__ params, Layout lay,
+               const double* __restrict__ logdet_part, int nblk, double* __restrict__ alpha,
+               double* __restrict__ u, double* __restrict__ s, EvalScalars* __restrict__ sc,
+               const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  __shared__ double red[32];
+  const int tid = threadIdx.x;
+  const double mu = params[lay.i_mu()];
+  double M = 0.0, sa = 0.0, su = 0.0, ss = 0.0;
+  for (int r = tid; r < npad; r += ETH) {
+    double a = 0.0, uu = 0.0, s1 = 0.0;
+    if (r < n) {
+      for (int k = 0; k < nsplit; ++k) {
+        const double* base = mv_part + (long long)k * stride_split + r;
+        a += base[0];
+        uu += base[stride_k];
+        s1 += base[2 * stride_k];
+      }
+      M = fma(y[r] - mu, a, M);
+      sa += a; su += uu; ss += s1;
+    }
+    alpha[r] = a; u[r] = uu; s[r] = s1;
+  }
+  M = csd::block_sum(M, red);
+  sa = csd::block_sum(sa, red);
+  su = csd::block_sum(su, red);
+  ss = csd::block_sum(ss, red);
+  double ld = 0.0;
+  for (int b = tid; b < nblk; b += ETH) ld += logdet_part[b];
+  ld = csd::block_sum(ld, red);
+  if (tid == 0) {
+    sc->M = M; sc->sum_alpha = sa; sc->sum_u = su; sc->sum_s = ss;
+    sc->logdet = 2.0 * ld;
+    sc->mu_sol = 0.5 * su / ss;  // kernel_GP_SE_cpp.cpp:64
+    double coef = 1.0;
+    if (lay.kind == KIND_TP) {
+      const double nu = exp(params[lay.i_nu()]);
+      const double lambda0 = exp(params[lay.i_la()]);
+      coef = (nu + (double)n) / ((nu + M) * lambda0);  // kernel_TP_SE_cpp.cpp:122
+    }
+    sc->coef = coef;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// K3/K4: fused trace gradients.  T = K^-1 - coef * alpha alpha^T is formed per entry,
+// Km / Ka / the per-dimension d^2 are recomputed from X, nothing n x n is materialised.
+// Persistent CTAs walk the lower 64x64 tiles (off-diagonal tiles weigh 2).  Per CTA:
+//   gpart[cta][0]        = sum T .* Km
+//   gpart[cta][1]        = sum T .* Ka
+//   gpart[cta][2+i]      = sum T .* Km .* d_i^2
+//   gpart[cta][2+p+i]    = sum T .* Ka .* d_i^2
+// and K*alpha row partials go to kal_part[slot][row] (each slot/row written exactly once).
+// ---------------------------------------------------------------------------------
+inline int grad_smem_bytes(int p) {
+  return ((2 * p + 2) * ETH + 2 * p * TB + 2 * PMAX + 6 * TB + 8 * TB + 32) * (int)sizeof(double);
+}
+
+template <bool FROM_MEM>
+__global__ void __launch_bounds__(ETH)
+grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __restrict__ z,
+                  const double* __restrict__ params, Layout lay, int n, int nblk,
+                  const double* __restrict__ Cinv, long long ldc, const double* __restrict__ alpha,
+                  const EvalScalars* __restrict__ sc, double* __restrict__ gpart, double* __restrict__ kal_part,
+                  long long kal_stride, const double* __restrict__ Kmat_in, const double* __restrict__ Km_in,
+                  const double* __restrict__ Ka_in, const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  CS_DYN_SMEM(double, sm_);
+  const int p = lay.p;
+  const int nacc = 2 * p + 2;
+  double* acc = sm_;                    // [nacc][ETH]
+  double* xr = acc + nacc * ETH;        // [p][TB]
+  double* xc = xr + p * TB;
+  double* ea = xc + p * TB;
+  double* eb = ea + PMAX;
+  double* zr = eb + PMAX;
+  double* zc = zr + TB;
+  double* ar = zc + TB;                 // alpha rows
+  double* ac = ar + TB;                 // alpha cols
+  double* rsum = ac + TB;               // [TB] row sums final
+  double* csum = rsum + TB;             // [TB] col sums final
+  double* rred = csum + TB;             // [8][TB]
+  double* red = rred + 8 * TB;          // [32]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, wid = tid >> 5;
+  for (int k = 0; k < nacc; ++k) acc[k * ETH + tid] = 0.0;
+  if (tid < p) { ea[tid] = exp(-params[lay.i_Lm() + tid]); eb[tid] = exp(-params[lay.i_La() + tid]); }
+  const double lam_m = params[lay.i_lm()], lam_a = params[lay.i_la()];
+  const double coef = sc->coef;
+  const int ntiles = nblk * (nblk + 1) / 2;
+
+  for (int t = (int)blockIdx.x; t < ntiles; t += (int)gridDim.x) {
+    int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((long long)(I + 1) * (I + 2) / 2 <= t) ++I;
+    while ((long long)I * (I + 1) / 2 > t) --I;
+    const int J = t - I * (I + 1) / 2;
+    const int r0 = I * TB, c0 = J * TB;
+    const double wgt = (I == J) ? 1.0 : 2.0;
+    __syncthreads();  // previous tile fully consumed
+    load_x_tile(xr, X, ldx, r0, p, tid);
+    load_x_tile(xc, X, ldx, c0, p, tid);
+    if (tid < TB) { zr[tid] = z[r0 + tid]; zc[tid] = z[c0 + tid]; ar[tid] = alpha[r0 + tid]; ac[tid] = alpha[c0 + tid]; }
+    __syncthreads();
+    double km[4][4], ka[4][4];
+    if (!FROM_MEM) sqdist_4x4(xr, xc, ea, eb, p, tx, ty, km, ka);
+    double rs[4] = {0.0, 0.0, 0.0, 0.0}, cs[4] = {0.0, 0.0, 0.0, 0.0};
+    double tm = 0.0, ta = 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int cl = ty + 16 * b, gc = c0 + cl;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int rl = tx + 16 * a, gr = r0 + rl;
+        double vkm = 0.0, vka = 0.0, T = 0.0, kfull = 0.0;
+        if (gr < n && gc < n) {
+          if (FROM_MEM) {  // matrices exactly as passed to grad_*_SE_cpp
+            vkm = Km_in[(long long)gc * ldc + gr];
+            vka = Ka_in[(long long)gc * ldc + gr];
+            kfull = Kmat_in[(long long)gc * ldc + gr];
+          } else {
+            vkm = exp(lam_m - km[a][b]);
+            vka = exp(lam_a - ka[a][b]) * zr[rl] * zc[cl];
+            kfull = vkm + vka;
+          }
+          T = Cinv[(long long)gc * ldc + gr] - coef * ar[rl] * ac[cl];
+        }
+        rs[a] = fma(kfull, ac[cl], rs[a]);
+        cs[b] = fma(kfull, ar[rl], cs[b]);
+        km[a][b] = T * vkm;  // T .* Km
+        ka[a][b] = T * vka;  // T .* Ka
+        tm += km[a][b];
+        ta += ka[a][b];
+      }
+    }
+    acc[0 * ETH + tid] += wgt * tm;
+    acc[1 * ETH + tid] += wgt * ta;
+    for (int i = 0; i < p; ++i) {
+      double xa[4], xb[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) xa[a] = xr[i * TB + tx + 16 * a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) xb[b] = xc[i * TB + ty + 16 * b];
+      double gm = 0.0, ga = 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const double d = xa[a] - xb[b];
+          const double d2 = d * d;
+          gm = fma(km[a][b], d2, gm);
+          ga = fma(ka[a][b], d2, ga);
+        }
+      acc[(2 + i) * ETH + tid] += wgt * gm;
+      acc[(2 + p + i) * ETH + tid] += wgt * ga;
+    }
+    // K*alpha partials: rows (reduce over ty) and columns (reduce over tx)
+#pragma unroll
+    for (int a = 0; a < 4; ++a) rs[a] += __shfl_xor_sync(0xffffffffu, rs[a], 16);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      double v = cs[b];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      cs[b] = v;
+    }
+    if (lane < 16) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) rred[wid * TB + tx + 16 * a] = rs[a];
+    }
+    if (tx == 0) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) csum[ty + 16 * b] = cs[b];
+    }
+    __syncthreads();
+    if (tid < TB) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) sacc += rred[w8 * TB + tid];
+      kal_part[(long long)J * kal_stride + r0 + tid] = sacc;
+      if (I != J) kal_part[(long long)I * kal_stride + c0 + tid] = csum[tid];
+    }
+  }
+  __syncthreads();
+  for (int k = 0; k < nacc; ++k) {
+    const double v = csd::block_sum(acc[k * ETH + tid], red);
+    if (tid == 0) gpart[(long long)blockIdx.x * nacc + k] = v;
+  }
+  (void)rsum;
+}
+
+// ---------------------------------------------------------------------------------
+// Finalize: gradients in parameter order, stats = (squared residual, LML), mu solution.
+// One CTA.  grad_*_SE_cpp :161-198 / TP :127-159.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ETH)
+finalize_kernel(const double* __restrict__ gpart, int ncta, const double* __restrict__ kal_part,
+                long long kal_stride, int nblk, const double* __restrict__ Cinv, long long ldc,
+                const double* __restrict__ alpha, const double* __restrict__ y, const double* __restrict__ w,
+                const double* __restrict__ params, Layout lay, int n, EvalScalars* __restrict__ sc,
+                double* __restrict__ grad, const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  __shared__ double red[32];
+  __shared__ double gsum[2 * PMAX + 2];
+  const int tid = threadIdx.x;
+  const int p = lay.p, nacc = 2 * p + 2;
+  // deterministic reduction over CTAs
+  for (int k = tid; k < nacc; k += ETH) {
+    double s = 0.0;
+    for (int c = 0; c < ncta; ++c) s += gpart[(long long)c * nacc + k];
+    gsum[k] = s;
+  }
+  const double coef = sc->coef;
+  const double mu = params[lay.i_mu()];
+  const double esig = exp(params[lay.i_sigma()]);
+  double tsig = 0.0, res = 0.0;
+  for (int r = tid; r < n; r += ETH) {
+    const double T = Cinv[(long long)r * ldc + r] - coef * alpha[r] * alpha[r];
+    tsig = fma(T, esig / w[r], tsig);
+    double ka = 0.0;
+    for (int b = 0; b < nblk; ++b) ka += kal_part[(long long)b * kal_stride + r];
+    const double e = y[r] - (ka + mu);
+    res = fma(e, e, res);
+  }
+  tsig = csd::block_sum(tsig, red);
+  res = csd::block_sum(res, red);
+  __syncthreads();
+  if (tid < p) {
+    grad[lay.i_Lm() + tid] = -0.5 * exp(-params[lay.i_Lm() + tid]) * gsum[2 + tid];
+    grad[lay.i_La() + tid] = -0.5 * exp(-params[lay.i_La() + tid]) * gsum[2 + p + tid];
+  }
+  if (tid == 0) {
+    grad[lay.i_sigma()] = -0.5 * tsig;
+    grad[lay.i_lm()] = -0.5 * gsum[0];
+    grad[lay.i_la()] = -0.5 * gsum[1];
+    grad[lay.i_mu()] = coef * sc->sum_alpha;
+    const double dn = (double)n;
+    double lml;
+    if (lay.kind == KIND_TP) {
+      grad[lay.i_nu()] = 0.0;
+      const double nu = exp(params[lay.i_nu()]);
+      lml = lgamma(0.5 * (nu + dn)) - lgamma(0.5 * nu) -
+            0.5 * (dn * log(nu * 3.14159265358979323846) + sc->logdet + (nu + dn) * log(1.0 + sc->M / nu));
+    } else {
+      lml = -0.5 * (dn * log(2.0 * 3.14159265358979323846) + sc->logdet + sc->M);
+    }
+    sc->stats[0] = res;
+    sc->stats[1] = lml;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// K5: optimizer step on the flat vectors (one warp), closed-form mu overwrite, trace
+// append and the device-side stopping rule of R/main.R:79-84.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void opt_update(int optim, int i, double iter, double lr, double b1, double b2,
+                                           double eps, double momentum, double* m, double* v,
+                                           const double* grad, double* para) {
+  const double g = grad[i];
+  if (optim == OPT_NESTEROV) {
+    const double nu_old = m[i];
+    m[i] = momentum * nu_old + lr * g;  // optimizer_cpp.cpp:19
+    para[i] = para[i] + nu_old;         // :20 (old velocity, quirk Q3)
+  } else {
+    const double mn = b1 * m[i] + (1.0 - b1) * g;      // :39 / :57
+    const double vn = b2 * v[i] + (1.0 - b2) * g * g;  // :40 / :58
+    m[i] = mn; v[i] = vn;
+    const double num = (optim == OPT_NADAM) ? (b1 * mn + (1.0 - b1) * g) : mn;
+    para[i] = para[i] + lr * (num / (1.0 - pow(b1, iter))) / (sqrt(vn / (1.0 - pow(b2, iter))) + eps);  // :41 / :59
+  }
+}
+
+__global__ void opt_step_kernel(int optim, int nparam, double iter, double lr, double b1, double b2, double eps,
+                                double momentum, double* m, double* v, const double* grad, double* para) {
+  for (int i = threadIdx.x; i < nparam; i += blockDim.x)
+    opt_update(optim, i, iter, lr, b1, b2, eps, momentum, m, v, grad, para);
+}
+
+__global__ void loop_step_kernel(int optim, Layout lay, double lr, double b1, double b2, double eps, double momentum,
+                                 double* m, double* v, const double* grad, double* para, EvalScalars* sc,
+                                 LoopState* ls, double* trace) {
+  if (ls->done) return;
+  const int it = ls->it;
+  const int nparam = lay.np();
+  for (int i = threadIdx.x; i < nparam; i += blockDim.x)
+    opt_update(optim, i, (double)it, lr, b1, b2, eps, momentum, m, v, grad, para);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    para[lay.i_mu()] = sc->mu_sol;  // mean_solution overrides the optimizer's mu (quirk Q1)
+    trace[2 * it + 0] = sc->stats[0];
+    trace[2 * it + 1] = sc->stats[1];
+    const double change = fabs(sc->stats[1] - ls->prev_lml);
+    ls->prev_lml = sc->stats[1];
+    int done = 0;
+    if (change < ls->tol && it > 3) done = 1;  // R/main.R:82-83
+    if (it >= ls->maxiter) done = 1;
+    if (done) { ls->iters = it; ls->done = 1; }
+    ls->it = it + 1;
+  }
+}
+
+__global__ void negate_kernel(double* v, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] = -v[i];
+}
+
+// stats_*_SE (kernel_GP_SE_cpp.cpp:204-227, kernel_TP_SE_cpp.cpp:165-192) from alpha = invK*ybar
+// and kal = Kmat*alpha; logdet_part holds log det(invK)/2 per block.  One CTA.
+__global__ void __launch_bounds__(ETH)
+stats_only_kernel(int kind, int n, const double* __restrict__ y, const double* __restrict__ alpha,
+                  const double* __restrict__ kal, const double* __restrict__ logdet_part, int nblk, double mu,
+                  double nu, double* __restrict__ stats) {
+  __shared__ double red[32];
+  double M = 0.0, res = 0.0, ld = 0.0;
+  for (int r = threadIdx.x; r < n; r += ETH) {
+    M = fma(y[r] - mu, alpha[r], M);
+    const double e = y[r] - (kal[r] + mu);
+    res = fma(e, e, res);
+  }
+  for (int b = threadIdx.x; b < nblk; b += ETH) ld += logdet_part[b];
+  M = csd::block_sum(M, red);
+  res = csd::block_sum(res, red);
+  ld = csd::block_sum(ld, red);
+  if (threadIdx.x == 0) {
+    const double val = 2.0 * ld;  // log det of the INVERSE (:223)
+    const double dn = (double)n;
+    stats[0] = res;
+    if (kind == KIND_TP)
+      stats[1] = lgamma(0.5 * (nu + dn)) - lgamma(0.5 * nu) -
+                 0.5 * (dn * log(nu * 3.14159265358979323846) - val + (nu + dn) * log(1.0 + M / nu));
+    else
+      stats[1] = -0.5 * (dn * log(2.0 * 3.14159265358979323846) - val + M);
+  }
+}
+
+// mu <- closed-form solution (used by the stateless mirror of mu_solution_cpp)
+__global__ void mu_solution_kernel(const double* __restrict__ mv_part, int nsplit, long long stride_k,
+                                   long long stride_split, int n, double* __restrict__ out) {
+  __shared__ double red[32];
+  double su = 0.0, ss = 0.0;
+  for (int r = threadIdx.x; r < n; r += blockDim.x)
+    for (int k = 0; k < nsplit; ++k) {
+      su += mv_part[(long long)k * stride_split + r];
+      ss += mv_part[(long long)k * stride_split + stride_k + r];
+    }
+  su = csd::block_sum(su, red);
+  ss = csd::block_sum(ss, red);
+  if (threadIdx.x == 0) out[0] = 0.5 * su / ss;
+}
+
+}  // namespace csk

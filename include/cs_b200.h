@@ -1,0 +1,173 @@
+/* cs_b200.h -- C ABI of libcausalstump_b200.so
+ *
+ * B200-native (sm_100a) replacement for the RcppArmadillo hot path of
+ * mazphilip/CausalStump.  This header is the drop-in boundary: every entry point
+ * names the reference interface it replaces (file:line under /root/reference).
+ * The reference's boundary is R's .Call into 11 registered routines
+ * (src/RcppExports.cpp:187-205, R/RcppExports.R:4-46); INTEGRATION.md shows the
+ * Rcpp / .Call glue that binds them to the functions below.
+ *
+ * Conventions
+ *   - all matrices column-major fp64 (R / Armadillo layout), all pointers HOST memory
+ *     unless stated otherwise; nothing is retained across stateless calls
+ *   - return value: 0 = OK; >0 = matrix not positive definite, value is the 1-based
+ *     failing pivot (LAPACK dpotrf `info`, what makes arma::inv_sympd throw at
+ *     src/kernel_GP_SE_cpp.cpp:56); <0 = CS_ERR_* below, text in cs_last_error()
+ *   - flat parameter vector = the reference's list order
+ *       GP (kind 0): sigma, lambdam, lambdaa, Lm[p], La[p], mu        (2p+4)
+ *       TP (kind 1): sigma, lambdam, nu, lambda0, Lm[p], La[p], mu    (2p+5)
+ *     gradients use the same layout (clone(parameters), kernel_GP_SE_cpp.cpp:145)
+ *   - there is NO CPU fallback: every call needs a CUDA device and fails with
+ *     CS_ERR_NODEVICE otherwise
+ */
+#ifndef CS_B200_H
+#define CS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CS_GP 0
+#define CS_TP 1
+
+#define CS_OPT_ADAM 0
+#define CS_OPT_NADAM 1
+#define CS_OPT_NESTEROV 2 /* "GD" is Nesterov with momentum 0 (R/main.R:68-70) */
+
+#define CS_ERR_ARG (-1)
+#define CS_ERR_CUDA (-2)
+#define CS_ERR_NOMEM (-3)
+#define CS_ERR_NODEVICE (-4)
+#define CS_ERR_UNSUPPORTED (-5)
+
+#define CS_MAX_P 40
+
+typedef struct cs_fit cs_fit; /* opaque device-resident fit handle */
+
+/* mirrors the arguments of CausalStump() (R/main.R:35) that reach the native code */
+typedef struct cs_fit_config {
+  int kind;        /* CS_GP / CS_TP          <- prior=                              */
+  int optim;       /* CS_OPT_*               <- myoptim=                            */
+  double lr;       /* learning_rate                                                 */
+  double beta1;    /* beta1                                                         */
+  double beta2;    /* beta2                                                         */
+  double eps;      /* 1e-8, hard-coded at R/optimizer_classes.R:23,44               */
+  double momentum; /* momentum (Nesterov / GD)                                      */
+  int tile;        /* 0 = auto; 64 or 128 selects the dense tile edge               */
+  int chunk;       /* optimizer iterations enqueued between host polls (0 = auto)   */
+} cs_fit_config;
+
+/* ---- library / device ---------------------------------------------------------- */
+int cs_version(void);
+const char* cs_last_error(void);
+int cs_device_count(void);
+int cs_set_device(int device);
+
+/* ---- stateless mirrors of the 11 registered routines --------------------------- */
+
+/* kernmat_GP_SE_cpp (src/kernel_GP_SE_cpp.cpp:72-140) and kernmat_TP_SE_cpp
+ * (src/kernel_TP_SE_cpp.cpp:46-90; lambda_a carries lambda0).  X1 n1 x p, X2 n2 x p,
+ * outputs n1 x n2; any of K/Km/Ka may be NULL. */
+int cs_kernmat(int n1, int n2, int p, const double* X1, const double* X2, const double* Z1, const double* Z2,
+               const double* Lm, const double* La, double lambdam, double lambda_a, double* K, double* Km,
+               double* Ka);
+
+/* invkernel_cpp (src/kernel_GP_SE_cpp.cpp:46-59): invK = inv_sympd(K + diag(exp(sigma)/w)).
+ * logdet (nullable) receives log det of the noisy matrix. */
+int cs_invkernel(int n, const double* w, const double* K, double sigma, double* invK, double* logdet);
+
+/* mu_solution_cpp (src/kernel_GP_SE_cpp.cpp:61-70) */
+int cs_mu_solution(int n, const double* y, const double* invK, double* mu);
+
+/* grad_GP_SE_cpp (src/kernel_GP_SE_cpp.cpp:143-202) / grad_TP_SE_cpp
+ * (src/kernel_TP_SE_cpp.cpp:100-163), same arguments in the same order.
+ *   invK == NULL : Gram, Cholesky and inverse are computed on the device from
+ *                  (X, z, w, params) -- the fast path; Kmat/Km/Ka must be NULL too.
+ *   invK != NULL : used exactly as passed (log det taken from a Cholesky of it, the
+ *                  reference uses an LU of it, :197).  Kmat/Km/Ka either all NULL
+ *                  (recomputed from X, z, params -- they are pure functions of those at
+ *                  every reference call site, R/kernel_GP_SE_class.R:50) or all given
+ *                  (then read from memory exactly like the reference).
+ * grad has the parameter layout; stats[2] = (squared residual, log marginal likelihood). */
+int cs_grad(int kind, int n, int p, const double* y, const double* X, const double* z, const double* w,
+            const double* Kmat, const double* Km, const double* Ka, const double* invK, const double* params,
+            double* grad, double* stats);
+
+/* stats_GP_SE (src/kernel_GP_SE_cpp.cpp:204-227) / stats_TP_SE (kernel_TP_SE_cpp.cpp:165-192):
+ * mu = parameters$mu; nu = exp(parameters$nu) (TP only). */
+int cs_stats(int kind, int n, const double* y, const double* Kmat, const double* invK, double mu, double nu,
+             double* stats);
+
+/* Adam_cpp / Nadam_cpp / Nesterov_cpp (src/optimizer_cpp.cpp:46-63, 28-44, 9-26) on flat
+ * vectors of length nparam.  For Nesterov `m` is the velocity `nu`, `v` is unused and
+ * beta1 carries the momentum.  Updates m, v, para in place. */
+int cs_opt_step(int optim, int nparam, double iter, double lr, double beta1, double beta2, double eps, double* m,
+                double* v, const double* grad, double* para);
+
+/* ---- stateful fast path: KernelClass_*_SE + the loop of R/main.R:79-88 ---------- */
+
+/* Uploads y, X (n x p), z, w once; init_params as produced by parainit
+ * (R/kernel_GP_SE_class.R:10-22 / R/kernel_TP_SE_class.R:11-22). */
+int cs_fit_create(const cs_fit_config* cfg, int n, int p, const double* y, const double* X, const double* z,
+                  const double* w, const double* init_params, cs_fit** out);
+void cs_fit_destroy(cs_fit* f);
+int cs_fit_nparam(const cs_fit* f);
+
+/* One "LML + gradient evaluation" (SURVEY.md 8d): Gram -> Cholesky -> inverse -> fused
+ * trace gradients -> LML/stats -> closed-form mu.  params NULL = current parameters.
+ * No parameter update.  Outputs nullable. */
+int cs_fit_eval(cs_fit* f, const double* params, double* grad, double* stats, double* mu_solution);
+
+/* Same evaluation, device-resident: enqueue only (no host copies, no sync). */
+int cs_fit_eval_async(cs_fit* f);
+int cs_fit_sync(cs_fit* f);
+int cs_fit_fetch(cs_fit* f, double* grad, double* stats, double* mu_solution);
+
+/* The optimisation loop of R/main.R:79-88 entirely on the device: para_update per
+ * iteration (gradient, optimizer step, closed-form mu, stopping rule |dLML| < tol &&
+ * iter > 3), then the final get_train_stats.  stats_trace (nullable) is 2 x (maxiter+2)
+ * column-major like `stats` in R/main.R:77; *iters receives the last iteration run. */
+int cs_fit_run(cs_fit* f, int maxiter, double tol, int* iters, double* stats_trace);
+
+int cs_fit_get_params(cs_fit* f, double* params);
+int cs_fit_set_params(cs_fit* f, const double* params);
+/* Reset optimizer moments (initOpt, R/optimizer_classes.R:29-33) */
+int cs_fit_reset_optimizer(cs_fit* f);
+/* RefClass fields Kmat, Km, Ka, invKmatn (n x n each, nullable) for the CURRENT
+ * parameters as left by the last eval / run. */
+int cs_fit_get_matrices(cs_fit* f, double* Kmat, double* Km, double* Ka, double* invK);
+
+/* KernelClass_*_SE$predict (R/kernel_GP_SE_class.R:74-85, R/kernel_TP_SE_class.R:72-94):
+ * map[n2] = K_xX K^-1 (y-mu) + mu, var_diag[n2] = diag(cov), cov (nullable, n2 x n2)
+ * = K_xx - K_xX K^-1 K_xX' + exp(sigma) I.  Normalised scale. */
+int cs_predict(cs_fit* f, int n2, const double* X2, const double* z2, double* map, double* var_diag, double* cov);
+
+/* KernelClass_*_SE$predict_treat (R/kernel_GP_SE_class.R:86-105, R/kernel_TP_SE_class.R:95-125):
+ * treatment-interaction block with z2 = 1.  ate = mean(map); ate_var = sum(cov)/n^2 with
+ * the TRAINING n (quirk Q8).  cov_jitter is added to diag(cov) (1e-6 for TP, :110). */
+int cs_treat(cs_fit* f, int n2, const double* X2, double cov_jitter, double* map, double* var_diag, double* ate,
+             double* ate_var, double* cov);
+
+/* mvnfast::rmvt + per-column order statistic (R/kernel_TP_SE_class.R:84-93, 112-124) on
+ * the device: N_rep = ceil(nsampling/1000) rounds of 1000 multivariate-t draws with
+ * scale `cov` (n2 x n2) and df degrees of freedom; U[n2] = mean over rounds of the 900th
+ * order statistic per column, *ate_U likewise for the row means (nullable). */
+int cs_tp_sample(int n2, const double* cov, double df, int nsampling, unsigned long long seed, double* U,
+                 double* ate_U);
+
+/* ---- measurement helpers (bench.py) -------------------------------------------- */
+/* CUDA events on the handle's stream; slots 0..15 */
+int cs_fit_event_record(cs_fit* f, int slot);
+int cs_fit_event_elapsed_ms(cs_fit* f, int slot_a, int slot_b, float* ms);
+/* per-phase device time of one evaluation: gram, potrf, trtri, xtx, matvec, grad, final */
+#define CS_NPHASE 7
+int cs_fit_eval_profile(cs_fit* f, float phase_ms[CS_NPHASE]);
+/* kernels launched by this library since load (claimed launch count for bench.py) */
+long long cs_launch_count(void);
+/* write `bytes` of device memory (> L2) to flush the cache between timed iterations */
+int cs_flush_l2(cs_fit* f);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CS_B200_H */
