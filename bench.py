@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- fp64 LML+gradient evals/sec at n=8192, p=25 (BASELINE.json metric i) plus
+Hill-sim replicate fits/hour (metric ii) as an extra object.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one LML+gradient evaluation of the GP on one Hill-(2011)-shaped synthetic
+batch: Gram -> Cholesky -> inverse -> fused trace gradients -> LML / stats
+-> closed-form mu.  `value` is device-resident throughput (inputs already in HBM);
+`e2e` goes through the C ABI with host buffers (pinned-staged H2D of y, X, z, w and the
+parameters, D2H of gradient + stats every step).  N > 1 runs one replica per GPU
+("replicas only", no collective on the data path).
+
+--impl reference times the CPU restatement of the reference (oracle/, kind "port": R and
+RcppArmadillo are not available) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_METRIC, P_METRIC = 8192, 25
+METRIC = "fp64 LML+gradient evals/sec at n=8192,p=25"
+UNIT = "evals/s"
+
+
+def make_inputs(n, p, replicate, kind="GP"):
+    """Hill-shaped synthetic data, reference normalisation and reference initial
+    hyper-parameters (R/kernel_GP_SE_class.R:13-19).  Host prep, not on the timed path."""
+    from causalstump_b200 import hill
+    from causalstump_b200.main import KernelClass_GP_SE, KernelClass_TP_SE, norm_variables
+    from causalstump_b200 import rcpp_exports as rx
+    d = hill.hill_surface_b(n=n, p=p, replicate=replicate)
+    nr = norm_variables(d["y"], d["X"])
+    y, X, z = np.ascontiguousarray(nr["y"]), np.asfortranarray(nr["X"]), np.ascontiguousarray(d["z"])
+    draws = hill.restart_draws(replicate, 0, prior=(kind == "TP"))
+    K = KernelClass_GP_SE(p, np.ones(n)) if kind == "GP" else KernelClass_TP_SE(p, np.ones(n))
+    if kind == "GP":
+        K.parainit(y, draws)
+    else:
+        K.parainit(y, 2000, draws)
+    return dict(y=y, X=X, z=z, w=np.ones(n), params=rx.pack(K.parameters), raw=d, moments=nr["moments"], par=K.parameters)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        top = sorted(sm)[len(sm) // 2:]  # samples under load = upper half
+        return {"sm_mhz": float(np.median(top)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU side: the oracle on a bounded sample of the same workload
+# ------------------------------------------------------------------------------------------
+def cpu_eval_seconds(inp, budget_s):
+    """Reference-faithful CPU cost of ONE n=8192 evaluation, from a bounded sample:
+    the O(p n^2) element-wise passes are timed on a few of the p dimensions at full n
+    and scaled by p/dims; the LAPACK part (dpotrf + dpotri + mirror, dgetrf of the
+    inverse, mat-vecs) is timed at n_s <= n and scaled by (n/n_s)^3.  Returns
+    (seconds, description)."""
+    from oracle import causalstump_oracle as o
+    from scipy.linalg import lapack
+    y, X, z, w, par = inp["y"], inp["X"], inp["z"], inp["w"], inp["par"]
+    n, p = X.shape
+    t_all0 = time.perf_counter()
+    # --- Gram passes (kernmat_GP_SE_cpp :105-134) on dg dims
+    dg = 2 if budget_s < 20 else 4
+    sub = dict(par); sub["Lm"] = par["Lm"][:dg]; sub["La"] = par["La"][:dg]
+    t0 = time.perf_counter()
+    Kl = o.kernmat_GP_SE_cpp(X[:, :dg], X[:, :dg], z, z, sub)
+    t_gram_dims = time.perf_counter() - t0
+    # split fixed part (final exp pass) from per-dim part with a second, 1-dim measurement
+    sub1 = dict(par); sub1["Lm"] = par["Lm"][:1]; sub1["La"] = par["La"][:1]
+    t0 = time.perf_counter()
+    o.kernmat_GP_SE_cpp(X[:, :1], X[:, :1], z, z, sub1)
+    t_gram_1 = time.perf_counter() - t0
+    per_dim = max((t_gram_dims - t_gram_1) / (dg - 1), 0.0)
+    t_gram = t_gram_1 + per_dim * (p - 1)
+    # --- dense LAPACK part at n_s
+    ns = n
+    while ns > 1024 and 6.0 * (ns / 4096.0) ** 3 > 0.45 * budget_s:
+        ns //= 2
+    A = np.array(Kl["Kmat"][:ns, :ns], order="F")
+    A[np.diag_indices(ns)] += 1.0
+    t0 = time.perf_counter()
+    inv = o.inv_sympd(A)
+    o.log_det(inv)
+    t_dense = (time.perf_counter() - t0) * (n / ns) ** 3
+    # --- gradient passes (evid_scale_gradients :28-41) on dgr dims at full n
+    dgr = 1 if budget_s < 20 else 2
+    T = Kl["Km"]  # any dense n x n stand-in for tmpK: the passes are data-independent
+    t0 = time.perf_counter()
+    o.evid_scale_gradients(X[:, :dgr], T, Kl["Km"], Kl["Ka"], dict(Lm=par["Lm"][:dgr], La=par["La"][:dgr]))
+    t_grad = (time.perf_counter() - t0) * (p / dgr)
+    # --- the remaining n^2 passes of grad_GP_SE_cpp (:158-198): alpha, outer product, 3 traces, K alpha
+    ybar = y - par["mu"]
+    t0 = time.perf_counter()
+    alpha = T @ ybar
+    tmpK = T - np.outer(alpha, alpha)
+    o.evid_grad(tmpK, Kl["Km"]); o.evid_grad(tmpK, Kl["Ka"]); o.evid_grad(tmpK, np.diag(1.0 / w))
+    (Kl["Kmat"] @ alpha).sum()
+    t_rest = time.perf_counter() - t0
+    total = t_gram + t_dense + t_grad + t_rest
+    desc = ("oracle (NumPy + SciPy-OpenBLAS restatement of the reference), n=%d p=%d: Gram passes timed on %d of %d dims, "
+            "lengthscale-gradient passes on %d of %d dims (scaled by p/dims), inv_sympd+log_det timed at n_s=%d "
+            "(scaled by (n/n_s)^3), remaining n^2 passes in full; %.1f s of CPU work"
+            % (n, p, dg, p, dgr, p, ns, time.perf_counter() - t_all0))
+    return total, desc
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        ths = [i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"]
+        if ths:
+            return int(max(ths))
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    total_steps = args.steps + args.warmup
+    budget = max(6.0, min(30.0, 150.0 / max(total_steps, 1)))
+    inp = make_inputs(N_METRIC, P_METRIC, 0)
+    secs = []
+    desc = ""
+    for i in range(total_steps):
+        s, desc = cpu_eval_seconds(inp, budget)
+        if i >= args.warmup:
+            secs.append(s)
+    ms = 1e3 * float(np.mean(secs))
+    value = 1e3 / ms
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": "Hill-(2011)-shaped synthetic n=8192 p=25, GP (prior=FALSE), one LML+gradient evaluation per step",
+                   "n": N_METRIC, "p": P_METRIC},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------
+def measure_fp64_peak(torch, dev):
+    """cuBLAS DGEMM 8192^3 burst (best of 5) -- the FP64 denominator MEASURED_PEAKS.json lacks."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    c = torch.empty(n, n, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize(dev)
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b, out=c); e1.record()
+        torch.cuda.synchronize(dev)
+        best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def measure_fits(lib, rank, world, nfit):
+    """Metric ii: one 'fit' = CausalStump() on a 672 x 25 training split to the reference's
+    stopping rule (maxiter=3000, tol=1e-1, lr=.01, Nadam; test/sec5-3_Hill2011.R:344-345)
+    + predict on 747 + treatment on 672 and 75.  Returns (seconds, fits, iterations)."""
+    import causalstump_b200 as cb
+    from causalstump_b200 import hill
+    t0 = time.perf_counter()
+    iters = []
+    for k in range(nfit):
+        rep = rank * nfit + k
+        d = hill.hill_surface_b(n=747, p=25, replicate=rep)
+        rng = np.random.default_rng(565 + 5 * rep)
+        test = rng.choice(747, 75, replace=False)
+        tr = np.setdiff1d(np.arange(747), test)
+        fit = cb.CausalStump(d["y"][tr], d["X"][tr], d["z"][tr], maxiter=3000, tol=1e-1, learning_rate=0.01,
+                             myoptim="Nadam", init_draws=hill.restart_draws(rep, 0), verbose=False)
+        cb.predict(fit, X=d["X"], z=d["z"])
+        cb.treatment(fit, X=d["X"][tr])
+        cb.treatment(fit, X=d["X"][test])
+        iters.append(fit.iters)
+    return time.perf_counter() - t0, nfit, iters
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from causalstump_b200 import _lib
+    lib = _lib.load()
+    lib.require_device()
+    lib.check(lib.dll.cs_set_device(local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    inp = make_inputs(N_METRIC, P_METRIC, rank)  # one replicate per rank (weak scaling)
+    fit = _lib.Fit(lib, _lib.CS_GP, inp["y"], inp["X"], inp["z"], inp["w"], inp["params"])
+    n, p = N_METRIC, P_METRIC
+    K, W = args.steps, max(args.warmup, 0)
+
+    # ---- device-resident throughput (`value`) ----
+    for _ in range(max(W, 3)):
+        fit.eval_async()
+    fit.sync()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    l0 = lib.launch_count()
+    fit.event_record(0)
+    for _ in range(K):
+        fit.eval_async()
+    fit.event_record(1)
+    fit.sync()
+    barrier()
+    launches = lib.launch_count() - l0
+    ms_total = max_over_ranks(fit.event_elapsed_ms(0, 1))
+    clk = clocks.stop()
+    g, st, mu = fit.fetch()
+    assert np.isfinite(st).all() and np.isfinite(g).all(), "non-finite evaluation"
+    ms_step = ms_total / K
+    value = world * K / (ms_total * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers (`e2e`) ----
+    h2d = 8 * (n * (p + 3) + len(inp["params"]))
+    d2h = 8 * (len(inp["params"]) + 2 + 9) + 4
+    for _ in range(2):
+        fit.set_data(inp["y"], inp["X"], inp["z"], inp["w"]); fit.eval(inp["params"])
+    barrier()
+    t0 = time.perf_counter()
+    fit.event_record(2)
+    for _ in range(K):
+        fit.set_data(inp["y"], inp["X"], inp["z"], inp["w"])
+        fit.eval(inp["params"])
+    fit.event_record(3)
+    fit.sync()
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    e2e_s = max_over_ranks(max(e2e_wall, fit.event_elapsed_ms(2, 3) * 1e-3))
+    e2e = {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+
+    # ---- per-phase device times and the roofline of the dominant kernel ----
+    phases = None
+    for _ in range(3):
+        ph = fit.eval_profile()
+        phases = ph if phases is None else {k: min(phases[k], ph[k]) for k in ph}
+    line_extra = {}
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        fp64_peak = measure_fp64_peak(torch, dev)
+        npad = n
+        f_xtx = npad ** 3 / 3.0
+        xtx_tflops = f_xtx / (phases["xtx"] * 1e-3) / 1e12
+        dense_ms = phases["potrf"] + phases["trtri"] + phases["xtx"]
+        dense_tflops = float(npad) ** 3 / (dense_ms * 1e-3) / 1e12
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        line_extra["roofline"] = {
+            "kernel": "csg::gemm_kernel<128,2,4,true,true> (K^-1 = X^T X, one launch, DMMA.8x8x4)",
+            "bound": "tensor", "achieved": xtx_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": xtx_tflops / fp64_peak, "traffic": None,
+            "peak_source": "cuBLAS DGEMM 8192^3 fp64 burst measured live in this run (MEASURED_PEAKS.json has no fp64 entry)",
+            "flops_per_launch": f_xtx, "ms_per_launch": phases["xtx"],
+        }
+        line_extra["roofline_dense_path"] = {
+            "what": "Cholesky + triangular inverse + X^T X (n^3 algorithmic flops, %d launches)" % 0,
+            "bound": "tensor", "achieved": dense_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": dense_tflops / fp64_peak, "ms": dense_ms,
+        }
+        b_gram = 8.0 * n * n / 2 + 8.0 * n * (p + 2)   # lower triangle written once
+        b_grad = 8.0 * n * n / 2 + 8.0 * n * (p + 3)   # lower triangle of K^-1 read once
+        line_extra["roofline_elementwise"] = {
+            "gram": {"bound": "hbm", "achieved": b_gram / (phases["gram"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": b_gram / (phases["gram"] * 1e-3) / 1e9 / hbm_peak, "ms": phases["gram"],
+                     "fp64_tflops": (n * n / 2.0) * (6 * p + 6) / (phases["gram"] * 1e-3) / 1e12},
+            "grad": {"bound": "hbm", "achieved": b_grad / (phases["grad"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": b_grad / (phases["grad"] * 1e-3) / 1e9 / hbm_peak, "ms": phases["grad"],
+                     "fp64_tflops": (n * n / 2.0) * (10 * p + 12) / (phases["grad"] * 1e-3) / 1e12},
+            "note": "at p=25 both kernels are FP64-issue-bound, not HBM-bound (SURVEY.md 8d)",
+        }
+        line_extra["phases_ms"] = phases
+        # ---- CPU baseline on the host cores (rank 0, N=1 only) ----
+        if world == 1 and not args.no_cpu:
+            secs, desc = cpu_eval_seconds(inp, 25.0)
+            line_extra["cpu_baseline"] = {"value": 1.0 / secs, "unit": UNIT, "cores": host_threads(), "kind": "port",
+                                          "sample": desc}
+    fit.close()
+
+    # ---- metric ii: replicate fits/hour (extra object) ----
+    fits_obj = None
+    if not args.no_fits:
+        nfit = args.fits
+        barrier()
+        secs, nf, iters = measure_fits(lib, rank, world, nfit)
+        secs = max_over_ranks(secs)
+        if dist is not None:
+            all_it = [None] * world
+            dist.all_gather_object(all_it, iters)
+            iters = [i for sub in all_it for i in sub]
+        fits_obj = {"value": world * nf / secs * 3600.0, "unit": "fits/hour", "fits": world * nf,
+                    "iterations_mean": float(np.mean(iters)),
+                    "what": "CausalStump() on 672x25 Hill split to the reference stopping rule + predict(747) + treatment(672, 75)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "Hill-(2011)-shaped synthetic n=8192 p=25, GP (prior=FALSE), one LML+gradient evaluation per step; one replica per GPU",
+                       "n": n, "p": p, "l2": "working set 3 x 512 MiB per evaluation, larger than the 126 MB L2 (no flush needed)",
+                       "parallelism": "replicas x%d, no collective" % world},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "lml": float(st[1]),
+        }
+        line.update(line_extra)
+        if fits_obj:
+            line["fits"] = fits_obj
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--fits", type=int, default=3, help="replicate fits per GPU for the fits/hour object")
+    ap.add_argument("--no-fits", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    return run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -60,6 +60,7 @@ _SIGS = {
     "cs_fit_sync": (C.c_int, [C.c_void_p]),
     "cs_fit_fetch": (C.c_int, [C.c_void_p, dp, dp, dp]),
     "cs_fit_run": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_int), dp]),
+    "cs_fit_set_data": (C.c_int, [C.c_void_p, dp, dp, dp, dp]),
     "cs_fit_get_params": (C.c_int, [C.c_void_p, dp]),
     "cs_fit_set_params": (C.c_int, [C.c_void_p, dp]),
     "cs_fit_reset_optimizer": (C.c_int, [C.c_void_p]),
@@ -239,6 +240,13 @@ class Fit:
 
     def set_params(self, params):
         self.lib.check(self.lib.dll.cs_fit_set_params(self.h, _ptr(_f64(params))))
+
+    def set_data(self, y, X, z, w=None):
+        y, z = _f64(y), _f64(z)
+        X = _f64(X if np.ndim(X) > 1 else np.asarray(X)[:, None])
+        assert X.shape == (self.n, self.p) and len(y) == self.n
+        w = None if w is None else _f64(w)
+        self.lib.check(self.lib.dll.cs_fit_set_data(self.h, _ptr(y), _ptr(X), _ptr(z), _ptr(w)))
 
     def reset_optimizer(self):
         self.lib.check(self.lib.dll.cs_fit_reset_optimizer(self.h))

