@@ -135,6 +135,8 @@ struct cs_fit {
   double* gpart = nullptr;
   int ncta_grad = 1;
   double* kal_part = nullptr;
+  double* rs_part = nullptr;
+  int nrs = 1;
   EvalScalars* sc = nullptr;
   LoopState* ls = nullptr;
   double* trace = nullptr;
@@ -143,6 +145,9 @@ struct cs_fit {
   size_t flush_bytes = 0;
   double* pinned = nullptr;
   size_t pinned_bytes = 0;
+  rt::graph_exec_t iter_graph{};   // one captured optimizer iteration
+  bool graph_ok = false, graph_tried = false;
+  long long launches_per_iter = 0;
   cudaEvent_t ev[16]{};
   bool ev_ok = false;
   std::vector<void*> allocs;
@@ -207,10 +212,14 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
   }
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
   {
+    auto k0 = csk::rowstats_kernel;
+    ++g_launches;
+    CS_LAUNCH(k0, f->nrs, csk::ETH, 0, st, f->kal_part, ld, f->nblk, f->eng.C, ld, f->alpha, f->y, f->w, f->params,
+              f->lay, n, f->sc, f->rs_part, skip);
     auto k = csk::finalize_kernel;
     ++g_launches;
-    CS_LAUNCH(k, 1, csk::ETH, 0, st, f->gpart, f->ncta_grad, f->kal_part, ld, f->nblk, f->eng.C, ld, f->alpha, f->y,
-              f->w, f->params, f->lay, n, f->sc, f->grad, skip);
+    CS_LAUNCH(k, 1, csk::ETH, 0, st, f->gpart, f->ncta_grad, f->rs_part, f->nrs, f->params, f->lay, n, f->sc, f->grad,
+              skip);
   }
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
   return 0;
@@ -268,6 +277,8 @@ int cs_fit_create(const cs_fit_config* cfg, int n, int p, const double* y, const
   f->ncta_grad = std::min(csg::lower_tiles(f->nblk), rt::sm_count());
   DA(f->gpart, sizeof(double) * (2 * p + 2) * f->ncta_grad);
   DA(f->kal_part, vb * f->nblk);
+  f->nrs = (np + csk::ETH - 1) / csk::ETH;
+  DA(f->rs_part, sizeof(double) * 2 * f->nrs);
   DA(f->sc, sizeof(EvalScalars)); DA(f->ls, sizeof(LoopState));
 #undef DA
   cudaStream_t st = f->st;
@@ -309,6 +320,7 @@ void cs_fit_destroy(cs_fit* f) {
   if (f->trace) rt::dev_free(f->trace);
   if (f->flush) rt::dev_free(f->flush);
   if (f->pinned) rt::host_free(f->pinned);
+  if (f->graph_ok) rt::graph_destroy(f->iter_graph);
   f->eng.destroy();
   if (f->ev_ok) for (int i = 0; i < 16; ++i) rt::event_destroy(f->ev[i]);
   rt::stream_destroy(f->st);
@@ -339,6 +351,7 @@ int cs_fit_set_data(cs_fit* f, const double* y, const double* X, const double* z
   const size_t need = sizeof(double) * (size_t)n * (p + 3);
   if (f->pinned_bytes < need) {
     if (f->pinned) rt::host_free(f->pinned);
+  if (f->graph_ok) rt::graph_destroy(f->iter_graph);
     f->pinned = nullptr;
     RT(rt::host_alloc((void**)&f->pinned, need));
     f->pinned_bytes = need;
@@ -417,6 +430,8 @@ int cs_fit_run(cs_fit* f, int maxiter, double tol, int* iters, double* stats_tra
     f->trace = nullptr;
     RT(rt::dev_malloc((void**)&f->trace, sizeof(double) * cap));
     f->trace_cap = cap;
+    if (f->graph_ok) { rt::graph_destroy(f->iter_graph); f->graph_ok = false; }  // graph holds the old pointer
+    f->graph_tried = false;
   }
   RT(rt::memset0(f->trace, sizeof(double) * cap, st));
   LoopState h{};
@@ -428,15 +443,33 @@ int cs_fit_run(cs_fit* f, int maxiter, double tol, int* iters, double* stats_tra
     const double flops = (double)f->np * f->np * f->np;
     chunk = (int)std::max(1.0, std::min(64.0, 2.0e9 / std::max(flops, 1.0)));
   }
+  auto enqueue_iteration = [&]() {
+    fit_enqueue_eval(f, &f->ls->done, nullptr);
+    auto k = csk::loop_step_kernel;
+    ++g_launches;
+    CS_LAUNCH(k, 1, 64, 0, st, f->cfg.optim, f->lay, f->cfg.lr, f->cfg.beta1, f->cfg.beta2, f->cfg.eps,
+              f->cfg.momentum, f->m, f->v, f->grad, f->params, f->sc, f->ls, f->trace);
+  };
+  if (!f->graph_tried && f->cfg.use_graph >= 0) {
+    f->graph_tried = true;
+    const long long l0 = g_launches;
+    if (rt::graph_begin(st) == 0) {
+      enqueue_iteration();
+      f->graph_ok = (rt::graph_end(st, &f->iter_graph) == 0);
+      f->launches_per_iter = g_launches - l0;
+      g_launches = l0;  // captured, not executed
+    }
+  }
   int launched = 0;
   while (launched < maxiter) {
     const int todo = std::min(chunk, maxiter - launched);
     for (int i = 0; i < todo; ++i) {
-      fit_enqueue_eval(f, &f->ls->done, nullptr);
-      auto k = csk::loop_step_kernel;
-      ++g_launches;
-      CS_LAUNCH(k, 1, 64, 0, st, f->cfg.optim, f->lay, f->cfg.lr, f->cfg.beta1, f->cfg.beta2, f->cfg.eps,
-                f->cfg.momentum, f->m, f->v, f->grad, f->params, f->sc, f->ls, f->trace);
+      if (f->graph_ok) {
+        if (rt::graph_launch(f->iter_graph, st) != 0) return fail(CS_ERR_CUDA, "graph launch failed: %s", rt::err_str(rt::last_error()));
+        g_launches += f->launches_per_iter;
+      } else {
+        enqueue_iteration();
+      }
     }
     launched += todo;
     KCHECK();
@@ -937,10 +970,14 @@ static int grad_stats_common(int kind, int n, int p, const double* y, const doub
                 f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)nullptr,
                 (const double*)nullptr, (const double*)nullptr, (const int*)nullptr);
     }
+    auto k40 = csk::rowstats_kernel;
+    ++g_launches;
+    CS_LAUNCH(k40, f->nrs, csk::ETH, 0, st, f->kal_part, ld, f->nblk, f->eng.C, ld, f->alpha, f->y, f->w, f->params,
+              f->lay, n, f->sc, f->rs_part, (const int*)nullptr);
     auto k4 = csk::finalize_kernel;
     ++g_launches;
-    CS_LAUNCH(k4, 1, csk::ETH, 0, st, f->gpart, f->ncta_grad, f->kal_part, ld, f->nblk, f->eng.C, ld, f->alpha, f->y,
-              f->w, f->params, f->lay, n, f->sc, f->grad, (const int*)nullptr);
+    CS_LAUNCH(k4, 1, csk::ETH, 0, st, f->gpart, f->ncta_grad, f->rs_part, f->nrs, f->params, f->lay, n, f->sc,
+              f->grad, (const int*)nullptr);
   }
   KCHECK();
   return cs_fit_fetch(f, grad, stats, nullptr);

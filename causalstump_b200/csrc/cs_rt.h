@@ -28,6 +28,8 @@ inline int d2h(void* h, const void* d, size_t b, cudaStream_t) { std::memcpy(h, 
 inline int d2d(void* d, const void* s, size_t b, cudaStream_t) { std::memmove(d, s, b); return 0; }
 inline int memset0(void* d, size_t b, cudaStream_t) { std::memset(d, 0, b); return 0; }
 inline int stream_create(cudaStream_t* s) { *s = 0; return 0; }
+inline int stream_create_low(cudaStream_t* s) { *s = 0; return 0; }
+inline int event_create_fast(cudaEvent_t* e) { *e = 0; return 0; }
 inline int stream_destroy(cudaStream_t) { return 0; }
 inline int stream_sync(cudaStream_t) { return 0; }
 inline int event_create(cudaEvent_t* e) { *e = 0; return 0; }
@@ -43,6 +45,11 @@ inline int set_device(int) { return 0; }
 inline int sm_count() { return 4; }
 inline int host_alloc(void** p, size_t b) { *p = std::malloc(b ? b : 1); return *p ? 0 : 2; }
 inline int host_free(void* p) { std::free(p); return 0; }
+typedef int graph_exec_t;
+inline int graph_begin(cudaStream_t) { return 1; }  // no graphs on the emulator: eager launches
+inline int graph_end(cudaStream_t, graph_exec_t*) { return 1; }
+inline int graph_launch(graph_exec_t, cudaStream_t) { return 1; }
+inline int graph_destroy(graph_exec_t) { return 0; }
 }  // namespace rt
 #else
 #include <cuda_runtime.h>
@@ -58,7 +65,19 @@ inline int h2d(void* d, const void* h, size_t b, cudaStream_t s) { return (int)c
 inline int d2h(void* h, const void* d, size_t b, cudaStream_t s) { return (int)cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, s); }
 inline int d2d(void* d, const void* s_, size_t b, cudaStream_t s) { return (int)cudaMemcpyAsync(d, s_, b, cudaMemcpyDeviceToDevice, s); }
 inline int memset0(void* d, size_t b, cudaStream_t s) { return (int)cudaMemsetAsync(d, 0, b, s); }
-inline int stream_create(cudaStream_t* s) { return (int)cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); }
+// main streams carry the latency-bound critical path: highest priority; auxiliary streams
+// (bulk trailing updates) lowest, so critical-path CTAs take the next free SM slot.
+inline int stream_create(cudaStream_t* s) {
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  return (int)cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, hi);
+}
+inline int stream_create_low(cudaStream_t* s) {
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  return (int)cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, lo);
+}
+inline int event_create_fast(cudaEvent_t* e) { return (int)cudaEventCreateWithFlags(e, cudaEventDisableTiming); }
 inline int stream_destroy(cudaStream_t s) { return (int)cudaStreamDestroy(s); }
 inline int stream_sync(cudaStream_t s) { return (int)cudaStreamSynchronize(s); }
 inline int event_create(cudaEvent_t* e) { return (int)cudaEventCreate(e); }
@@ -79,5 +98,20 @@ inline int sm_count() {
 }
 inline int host_alloc(void** p, size_t b) { return (int)cudaMallocHost(p, b ? b : 1); }
 inline int host_free(void* p) { return (int)cudaFreeHost(p); }
+// CUDA graphs: one optimizer iteration (all its launches, both streams) is captured once
+// and replayed, removing per-launch CPU cost from latency-bound small-n fits.
+typedef cudaGraphExec_t graph_exec_t;
+inline int graph_begin(cudaStream_t s) { return (int)cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal); }
+inline int graph_end(cudaStream_t s, graph_exec_t* exec) {
+  cudaGraph_t g = nullptr;
+  int e = (int)cudaStreamEndCapture(s, &g);
+  if (e != 0 || g == nullptr) { cudaGetLastError(); return e ? e : 1; }
+  e = (int)cudaGraphInstantiate(exec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != 0) cudaGetLastError();
+  return e;
+}
+inline int graph_launch(graph_exec_t exec, cudaStream_t s) { return (int)cudaGraphLaunch(exec, s); }
+inline int graph_destroy(graph_exec_t exec) { return (int)cudaGraphExecDestroy(exec); }
 }  // namespace rt
 #endif

@@ -24,84 +24,144 @@ using csg::GemmProblem;
 constexpr int LEAF_THREADS = 256;
 
 template <int TILE>
-constexpr int leaf_smem_bytes() { return (TILE * (TILE + 1) + 2 * TILE + 32) * (int)sizeof(double); }
+constexpr int leaf_smem_bytes() { return (6 * TILE + 32) * (int)sizeof(double); }
 
+// Register-resident leaf: the TILE x TILE block lives in the register files of a 16 x 16
+// thread grid, cyclically distributed (thread (tx,ty) owns rows tx+16a, columns ty+16b), so
+// the work stays balanced as the factorization shrinks.  Per elimination step only one column
+// (and, for the inverse, one row) crosses shared memory; one barrier per step (double-buffered).
 template <int TILE>
 __global__ void __launch_bounds__(LEAF_THREADS)
 leaf_kernel(double* __restrict__ G, long long ldg, double* __restrict__ X, long long ldx, int blk,
             double* __restrict__ logdet_part, int* __restrict__ status, int n_real,
             const int* __restrict__ skip) {
   if (skip && *skip) return;
-  constexpr int LD = TILE + 1;
-  CS_DYN_SMEM(double, S);
-  double* colbuf = S + TILE * LD;
-  double* rowbuf = colbuf + TILE;  // also holds the pivots during phase 1
-  double* red = rowbuf + TILE;
+  constexpr int NA = TILE / 16;
+  CS_DYN_SMEM(double, sm);
+  double* colbuf = sm;              // [2][TILE]
+  double* rowbuf = sm + 2 * TILE;   // [2][TILE]
+  double* piv = sm + 4 * TILE;      // [TILE]
+  double* dinv = sm + 5 * TILE;     // [TILE]
+  double* red = sm + 6 * TILE;      // [32]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   double* Gt = G + (long long)blk * TILE * (ldg + 1);
   double* Xt = X + (long long)blk * TILE * (ldx + 1);
 
-  for (int idx = tid; idx < TILE * TILE; idx += LEAF_THREADS) {
-    const int r = idx % TILE, c = idx / TILE;
-    S[r + c * LD] = (r >= c) ? Gt[r + c * ldg] : 0.0;
-  }
-  __syncthreads();
+  double reg[NA][NA];
+#pragma unroll
+  for (int b = 0; b < NA; ++b)
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      const int r = tx + 16 * a, c = ty + 16 * b;
+      reg[a][b] = (r >= c) ? Gt[r + c * ldg] : 0.0;
+    }
 
-  // phase 1: right-looking Cholesky, columns kept unscaled (L[r][j] = S[r][j]/sqrt(d_j))
+  // ---- phase 1: right-looking Cholesky; columns stay unscaled (L[r][j] = S[r][j] / sqrt(d_j)) ----
   for (int j = 0; j < TILE; ++j) {
-    double d = S[j + j * LD];
+    double* buf = colbuf + (j & 1) * TILE;
+    const int bj = j >> 4, tj = j & 15;
+    if (ty == tj) {
+#pragma unroll
+      for (int b = 0; b < NA; ++b)
+        if (b == bj) {
+#pragma unroll
+          for (int a = 0; a < NA; ++a) buf[tx + 16 * a] = reg[a][b];
+        }
+    }
+    __syncthreads();
+    double d = buf[j];
     if (!(d > 0.0)) {
       const int gidx = blk * TILE + j;
       if (tid == 0 && gidx < n_real) atomicMin(status, gidx + 1);  // LAPACK-style 1-based info
       d = 1.0;
     }
-    if (tid == 0) rowbuf[j] = d;
+    if (tid == 0) piv[j] = d;
     const double invd = 1.0 / d;
-    for (int c = j + 1 + ((ty - (j + 1)) & 15); c < TILE; c += 16) {
-      const double scj = S[c + j * LD] * invd;
-      for (int r = c + ((tx - c) & 15); r < TILE; r += 16) S[r + c * LD] -= S[r + j * LD] * scj;
-    }
-    __syncthreads();
-  }
-  // scale columns, emit L, accumulate 0.5*log(d) = log(L_jj)
-  double ld_local = 0.0;
-  for (int idx = tid; idx < TILE * TILE; idx += LEAF_THREADS) {
-    const int r = idx % TILE, c = idx / TILE;
-    double v = 0.0;
-    if (r >= c) {
-      const double sq = sqrt(rowbuf[c]);
-      v = (r == c) ? sq : S[r + c * LD] / sq;
-      if (r == c) ld_local += log(sq);
-    }
-    S[r + c * LD] = v;
-    Gt[r + c * ldg] = v;
-  }
-  const double ldsum = csd::block_sum(ld_local, red);  // contains __syncthreads
-  if (tid == 0) logdet_part[blk] = ldsum;
-
-  // phase 2: in-place inverse of the lower-triangular factor (row-by-row, rank-1 updates)
-  for (int i = 0; i < TILE; ++i) {
-    const double xii = 1.0 / S[i + i * LD];
-    if (tid < TILE) {
-      if (tid > i) colbuf[tid] = S[tid + i * LD];
-      if (tid < i) rowbuf[tid] = -xii * S[i + tid * LD];
-      if (tid == i) rowbuf[tid] = xii;
-    }
-    __syncthreads();
-    if (tid <= i) S[i + tid * LD] = rowbuf[tid];
-    for (int jj = ty; jj <= i; jj += 16) {
-      const double xv = rowbuf[jj];
-      for (int r = i + 1 + ((tx - (i + 1)) & 15); r < TILE; r += 16) {
-        const double prev = (jj == i) ? 0.0 : S[r + jj * LD];
-        S[r + jj * LD] = prev + colbuf[r] * xv;
+    double cr[NA], cc[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) cr[a] = buf[tx + 16 * a];
+#pragma unroll
+    for (int b = 0; b < NA; ++b) cc[b] = buf[ty + 16 * b] * invd;
+#pragma unroll
+    for (int b = 0; b < NA; ++b) {
+      if (b > bj || (b == bj && ty > tj)) {  // column c = ty + 16 b > j
+#pragma unroll
+        for (int a = b; a < NA; ++a) reg[a][b] -= cr[a] * cc[b];
       }
     }
+  }
+  __syncthreads();
+  // scale the columns, emit L (explicit zeros above the diagonal), 1/L_cc, log det
+#pragma unroll
+  for (int b = 0; b < NA; ++b) {
+    const int c = ty + 16 * b;
+    const double sq = sqrt(piv[c]);
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      const int r = tx + 16 * a;
+      double v = 0.0;
+      if (r == c) { v = sq; dinv[c] = 1.0 / sq; }
+      else if (r > c) v = reg[a][b] / sq;
+      reg[a][b] = v;
+      Gt[r + c * ldg] = v;
+    }
+  }
+  const double ldsum = csd::block_sum(tid < TILE ? 0.5 * log(piv[tid < TILE ? tid : 0]) : 0.0, red);
+  if (tid == 0) logdet_part[blk] = ldsum;  // block_sum ends with a barrier: dinv is visible
+
+  // ---- phase 2: in-place inverse X = L^-1, row by row with rank-1 updates of the rows below ----
+  for (int i = 0; i < TILE; ++i) {
+    double* cbuf = colbuf + (i & 1) * TILE;
+    double* rbuf = rowbuf + (i & 1) * TILE;
+    const int bi = i >> 4, ti = i & 15;
+    const double xii = dinv[i];
+    if (tx == ti) {  // owners of row i finalise X[i][c], c <= i
+#pragma unroll
+      for (int a = 0; a < NA; ++a)
+        if (a == bi) {
+#pragma unroll
+          for (int b = 0; b <= a; ++b) {
+            const int c = ty + 16 * b;
+            if (c <= i) {
+              const double v = (c == i) ? xii : -xii * reg[a][b];
+              reg[a][b] = v;
+              rbuf[c] = v;
+            }
+          }
+        }
+    }
+    if (ty == ti) {  // owners of column i publish L[r][i], r > i
+#pragma unroll
+      for (int b = 0; b < NA; ++b)
+        if (b == bi) {
+#pragma unroll
+          for (int a = b; a < NA; ++a) {
+            const int r = tx + 16 * a;
+            if (r > i) cbuf[r] = reg[a][b];
+          }
+        }
+    }
     __syncthreads();
+#pragma unroll
+    for (int b = 0; b < NA; ++b) {
+      const int c = ty + 16 * b;
+      if (c <= i) {
+        const double xv = rbuf[c];
+#pragma unroll
+        for (int a = b; a < NA; ++a) {
+          const int r = tx + 16 * a;
+          if (r > i) reg[a][b] = ((c == i) ? 0.0 : reg[a][b]) + cbuf[r] * xv;
+        }
+      }
+    }
   }
-  for (int idx = tid; idx < TILE * TILE; idx += LEAF_THREADS) {
-    const int r = idx % TILE, c = idx / TILE;
-    Xt[r + c * ldx] = (r >= c) ? S[r + c * LD] : 0.0;
-  }
+#pragma unroll
+  for (int b = 0; b < NA; ++b)
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      const int r = tx + 16 * a, c = ty + 16 * b;
+      Xt[r + c * ldx] = (r >= c) ? reg[a][b] : 0.0;
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -111,13 +171,17 @@ enum GemmKind { GK_NT = 0, GK_NN = 1, GK_TN = 2 };
 
 static long long g_launches = 0;  // kernels launched by this library (claimed count for bench.py)
 
+enum OpType { OP_GEMM = 0, OP_LEAF = 1, OP_RECORD = 2, OP_WAIT = 3 };
+
 struct Launch {
-  int is_leaf;     // 1: leaf_kernel(blk)   0: gemm group
+  int is_leaf;     // OpType (1: leaf_kernel(blk), 0: gemm group, 2/3: event record / wait)
   int blk;         // leaf block index
   int kind;        // GemmKind
   int first_prob;  // index into the problem array
   int nprob;
   int ntiles;
+  int stream;      // 0: main (critical path, high priority)   1: auxiliary (bulk updates)
+  int ev;          // event index for OP_RECORD / OP_WAIT
 };
 
 inline int pick_tile(int n) { return n <= 1536 ? 64 : 128; }
@@ -164,6 +228,11 @@ struct DenseEngine {
   GemmProblem* d_probs = nullptr;
   std::vector<GemmProblem> probs;
   std::vector<Launch> potrf, trtri, xtx;
+  int panel_blocks = 4;             // outer panel width in blocks
+  int n_events = 0;
+  std::vector<cudaEvent_t> events;
+  cudaStream_t aux{};
+  bool aux_ok = false;
 
   static GemmProblem mk(const double* A, long long lda, const double* B, long long ldb, double* C, long long ldc,
                         int mt, int nt, int K, int kmode, int order, int mirror, double alpha, double beta) {
@@ -178,7 +247,7 @@ struct DenseEngine {
   void add_group(std::vector<Launch>& seq, int kind, std::vector<GemmProblem>& group) {
     if (group.empty()) return;
     Launch L{};
-    L.is_leaf = 0; L.kind = kind; L.first_prob = (int)probs.size(); L.nprob = (int)group.size();
+    L.is_leaf = OP_GEMM; L.kind = kind; L.first_prob = (int)probs.size(); L.nprob = (int)group.size();
     int base = 0;
     for (auto& p : group) { p.tile_base = base; base += p.ntiles; probs.push_back(p); }
     L.ntiles = base;
@@ -209,19 +278,61 @@ struct DenseEngine {
     const long long ld = np;
     const long long T = tile;
     std::vector<GemmProblem> grp;
-    // --- blocked right-looking Cholesky ---
-    for (int k = 0; k < N; ++k) {
-      Launch L{}; L.is_leaf = 1; L.blk = k; potrf.push_back(L);
-      const int m = N - k - 1;
-      if (m <= 0) continue;
-      double* panel = G + (k + 1) * T + k * T * ld;
-      // L21 = A21 * X_kk^T   (NT, in place)
-      grp.push_back(mk(panel, ld, X + k * T * (ld + 1), ld, panel, ld, m, 1, tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
+    // --- two-level blocked right-looking Cholesky with one-panel look-ahead ---
+    // Outer panels of W blocks.  Inside a panel: leaf -> panel multiply -> update of the
+    // panel's remaining columns (k = TILE).  After a panel: trailing update with
+    // k = W*TILE, split into U1 (the next panel's columns, main stream) and U2 (the rest,
+    // auxiliary stream) so the next panel's latency-bound chain overlaps the bulk update.
+    const int W = panel_blocks;
+    int npanel = 0, last_aux_ev = -1;
+    for (int p0 = 0; p0 < N; p0 += W, ++npanel) {
+      const int p1 = std::min(p0 + W, N);
+      for (int k = p0; k < p1; ++k) {
+        Launch L{}; L.is_leaf = OP_LEAF; L.blk = k; potrf.push_back(L);
+        const int m = N - k - 1;
+        if (m <= 0) continue;
+        double* panel = G + (k + 1) * T + k * T * ld;
+        // L21 = A21 * X_kk^T   (NT, in place)
+        grp.push_back(mk(panel, ld, X + k * T * (ld + 1), ld, panel, ld, m, 1, tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
+        add_group(potrf, GK_NT, grp);
+        // inner update: columns k+1 .. p1-1 of the current panel (lower part + rectangle below)
+        const int nc = p1 - 1 - k;
+        if (nc > 0) {
+          grp.push_back(mk(panel, ld, panel, ld, G + (k + 1) * T * (ld + 1), ld, nc, nc, tile, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
+          const int mr = N - p1;
+          if (mr > 0)
+            grp.push_back(mk(G + p1 * T + k * T * ld, ld, panel, ld, G + p1 * T + (k + 1) * T * ld, ld, mr, nc, tile,
+                             csg::KM_FULL, csg::ORD_COL, 0, -1.0, 1.0));
+          add_group(potrf, GK_NT, grp);
+        }
+      }
+      const int mt = N - p1;  // trailing blocks
+      if (mt <= 0) continue;
+      const int kw = (p1 - p0) * tile;
+      double* pan = G + p1 * T + p0 * T * ld;  // rows >= p1 of the finished panel
+      const int n1 = std::min(W, mt);          // next panel's block columns
+      { Launch R{}; R.is_leaf = OP_RECORD; R.stream = 0; R.ev = 2 * npanel; potrf.push_back(R); }
+      if (npanel > 0) { Launch Wt{}; Wt.is_leaf = OP_WAIT; Wt.stream = 0; Wt.ev = 2 * (npanel - 1) + 1; potrf.push_back(Wt); }
+      // U1: columns [p1, p1+n1): lower part + rectangle below (main stream)
+      grp.push_back(mk(pan, ld, pan, ld, G + p1 * T * (ld + 1), ld, n1, n1, kw, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
+      if (mt > n1)
+        grp.push_back(mk(pan + n1 * T, ld, pan, ld, G + (p1 + n1) * T + p1 * T * ld, ld, mt - n1, n1, kw, csg::KM_FULL,
+                         csg::ORD_COL, 0, -1.0, 1.0));
       add_group(potrf, GK_NT, grp);
-      // A22 -= L21 L21^T   (NT, lower tiles only)
-      grp.push_back(mk(panel, ld, panel, ld, G + (k + 1) * T * (ld + 1), ld, m, m, tile, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
-      add_group(potrf, GK_NT, grp);
+      // U2: everything to the right of the next panel (auxiliary stream)
+      if (mt > n1) {
+        { Launch Wt{}; Wt.is_leaf = OP_WAIT; Wt.stream = 1; Wt.ev = 2 * npanel; potrf.push_back(Wt); }
+        grp.push_back(mk(pan + n1 * T, ld, pan + n1 * T, ld, G + (p1 + n1) * T * (ld + 1), ld, mt - n1, mt - n1, kw,
+                         csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
+        add_group(potrf, GK_NT, grp);
+        potrf.back().stream = 1;
+      }
+      { Launch R{}; R.is_leaf = OP_RECORD; R.stream = 1; R.ev = 2 * npanel + 1; potrf.push_back(R); }
+      last_aux_ev = 2 * npanel + 1;
     }
+    // the main stream rejoins the auxiliary stream before anything reads the factor
+    if (last_aux_ev >= 0) { Launch Wt{}; Wt.is_leaf = OP_WAIT; Wt.stream = 0; Wt.ev = last_aux_ev; potrf.push_back(Wt); }
+    n_events = 2 * npanel + 2;
     // --- recursive triangular inverse, batched by tree height ---
     std::vector<Node> nodes;
     const int hmax = build_tree(0, N, nodes);
@@ -245,6 +356,11 @@ struct DenseEngine {
     grp.push_back(mk(X, ld, X, ld, C, ld, N, N, np, csg::KM_GE_I, csg::ORD_LOWER, 1, 1.0, 0.0));
     add_group(xtx, GK_TN, grp);
 
+    if ((e = rt::stream_create_low(&aux))) return e;
+    aux_ok = true;
+    events.resize(n_events);
+    for (int i = 0; i < n_events; ++i)
+      if ((e = rt::event_create_fast(&events[i]))) return e;
     if ((e = rt::dev_malloc((void**)&d_probs, sizeof(GemmProblem) * probs.size()))) return e;
     if ((e = rt::h2d(d_probs, probs.data(), sizeof(GemmProblem) * probs.size(), 0))) return e;
     if ((e = rt::stream_sync(0))) return e;
@@ -254,17 +370,25 @@ struct DenseEngine {
   void destroy() {
     rt::dev_free(G); rt::dev_free(X); rt::dev_free(C); rt::dev_free(logdet_part); rt::dev_free(status);
     rt::dev_free(d_probs);
+    for (auto& ev : events) rt::event_destroy(ev);
+    events.clear();
+    if (aux_ok) { rt::stream_sync(aux); rt::stream_destroy(aux); aux_ok = false; }
     G = X = C = logdet_part = nullptr; status = nullptr; d_probs = nullptr;
   }
 
   void run_seq(const std::vector<Launch>& seq, cudaStream_t st, const int* skip = nullptr) {
     for (const Launch& L : seq) {
-      if (L.is_leaf) {
+      cudaStream_t s = L.stream ? aux : st;
+      if (L.is_leaf == OP_LEAF) {
         ++g_launches;
-        if (tile == 128) { auto k = leaf_kernel<128>; CS_LAUNCH(k, 1, LEAF_THREADS, leaf_smem_bytes<128>(), st, G, (long long)np, X, (long long)np, L.blk, logdet_part, status, n, skip); }
-        else { auto k = leaf_kernel<64>; CS_LAUNCH(k, 1, LEAF_THREADS, leaf_smem_bytes<64>(), st, G, (long long)np, X, (long long)np, L.blk, logdet_part, status, n, skip); }
+        if (tile == 128) { auto k = leaf_kernel<128>; CS_LAUNCH(k, 1, LEAF_THREADS, leaf_smem_bytes<128>(), s, G, (long long)np, X, (long long)np, L.blk, logdet_part, status, n, skip); }
+        else { auto k = leaf_kernel<64>; CS_LAUNCH(k, 1, LEAF_THREADS, leaf_smem_bytes<64>(), s, G, (long long)np, X, (long long)np, L.blk, logdet_part, status, n, skip); }
+      } else if (L.is_leaf == OP_RECORD) {
+        rt::event_record(events[L.ev], s);
+      } else if (L.is_leaf == OP_WAIT) {
+        rt::stream_wait_event(s, events[L.ev]);
       } else {
-        launch_gemm(tile, L.kind, d_probs + L.first_prob, L.nprob, L.ntiles, st, skip);
+        launch_gemm(tile, L.kind, d_probs + L.first_prob, L.nprob, L.ntiles, s, skip);
       }
     }
   }

@@ -60,11 +60,11 @@ __host__ __device__ inline void tile_krange(int kmode, int K, int TILE, int I, i
   if (kbeg > kend) kbeg = kend;
 }
 
-template <int TILE, bool KMAJ>
+template <int TILE, bool KMAJ, int KC = GEMM_BK>
 struct OperandSmem {
-  // m-major: [BK][TILE+PAD]   k-major: [TILE][BK+PAD]
-  static constexpr int LD = KMAJ ? (GEMM_BK + GEMM_PAD) : (TILE + GEMM_PAD);
-  static constexpr int SIZE = KMAJ ? TILE * LD : GEMM_BK * LD;
+  // m-major: [KC][TILE+PAD]   k-major: [TILE][KC+PAD]
+  static constexpr int LD = KMAJ ? (KC + GEMM_PAD) : (TILE + GEMM_PAD);
+  static constexpr int SIZE = KMAJ ? TILE * LD : KC * LD;
 };
 
 template <int TILE, int WM, int WN>
@@ -74,23 +74,23 @@ struct GemmCfg {
   static constexpr int FM = WTM / 8, FN = WTN / 8;
 };
 
-template <int TILE, bool AK, bool BK_>
+template <int TILE, bool AK, bool BK_, int KC = GEMM_BK, int NS = GEMM_STAGES>
 constexpr int gemm_smem_bytes() {
-  return GEMM_STAGES * (OperandSmem<TILE, AK>::SIZE + OperandSmem<TILE, BK_>::SIZE) * (int)sizeof(double);
+  return NS * (OperandSmem<TILE, AK, KC>::SIZE + OperandSmem<TILE, BK_, KC>::SIZE) * (int)sizeof(double);
 }
 
 // copy one TILE x GEMM_BK operand chunk into a stage buffer
-template <int TILE, bool KMAJ, int THREADS>
+template <int TILE, bool KMAJ, int THREADS, int KC>
 __device__ __forceinline__ void load_operand(double* __restrict__ s, const double* __restrict__ g, long long ld,
                                              int row0, int k0, int tid) {
-  using S = OperandSmem<TILE, KMAJ>;
-  constexpr int NCOPY = TILE * GEMM_BK / 2;
+  using S = OperandSmem<TILE, KMAJ, KC>;
+  constexpr int NCOPY = TILE * KC / 2;
   static_assert(NCOPY % THREADS == 0, "copy count must divide");
 #pragma unroll
   for (int it = 0; it < NCOPY / THREADS; ++it) {
     const int idx = tid + it * THREADS;
     if (KMAJ) {
-      const int i = idx / (GEMM_BK / 2), kc = idx - i * (GEMM_BK / 2);
+      const int i = idx / (KC / 2), kc = idx - i * (KC / 2);
       csd::cp_async16(s + i * S::LD + 2 * kc, g + (long long)(row0 + i) * ld + k0 + 2 * kc);
     } else {
       const int kk = idx / (TILE / 2), ic = idx - kk * (TILE / 2);
@@ -99,17 +99,17 @@ __device__ __forceinline__ void load_operand(double* __restrict__ s, const doubl
   }
 }
 
-template <int TILE, int WM, int WN, bool AK, bool BK_>
+template <int TILE, int WM, int WN, bool AK, bool BK_, int KC = GEMM_BK, int NS = GEMM_STAGES>
 __global__ void __launch_bounds__(WM * WN * 32)
 gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restrict__ skip) {
   if (skip && *skip) return;
   using Cfg = GemmCfg<TILE, WM, WN>;
-  using SA = OperandSmem<TILE, AK>;
-  using SB = OperandSmem<TILE, BK_>;
+  using SA = OperandSmem<TILE, AK, KC>;
+  using SB = OperandSmem<TILE, BK_, KC>;
   constexpr int FM = Cfg::FM, FN = Cfg::FN;
   CS_DYN_SMEM(double, smem);
   double* sA = smem;
-  double* sB = smem + GEMM_STAGES * SA::SIZE;
+  double* sB = smem + NS * SA::SIZE;
 
   const int tid = threadIdx.x;
   // locate the problem this CTA belongs to (uniform across the CTA)
@@ -121,45 +121,61 @@ gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restr
   decode_tile(P.order, P.mt, P.nt, bt - P.tile_base, I, J);
   int kbeg, kend;
   tile_krange(P.kmode, P.K, TILE, I, J, kbeg, kend);
-  const int nchunks = (kend - kbeg) / GEMM_BK;
+  const int nchunks = (kend - kbeg) / KC;
   const int i0 = I * TILE, j0 = J * TILE;
 
   const int lane = tid & 31, wid = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wm = (wid % WM) * Cfg::WTM, wn = (wid / WM) * Cfg::WTN;
 
+  // Accumulators start from (beta/alpha)*C so the read of C overlaps the pipeline fill and
+  // the epilogue is store-only:  C = alpha * ((beta/alpha) C + sum_k A B^T).
   double acc[FM][FN][2];
+  if (P.beta != 0.0) {
+    const double sc0 = P.beta / P.alpha;
 #pragma unroll
-  for (int a = 0; a < FM; ++a)
+    for (int a = 0; a < FM; ++a) {
+      const long long r = i0 + wm + a * 8 + g;
 #pragma unroll
-    for (int b = 0; b < FN; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+      for (int b = 0; b < FN; ++b) {
+        const double* p0 = P.C + r + (long long)(j0 + wn + b * 8 + 2 * t) * P.ldc;
+        acc[a][b][0] = sc0 * p0[0];
+        acc[a][b][1] = sc0 * p0[P.ldc];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < FM; ++a)
+#pragma unroll
+      for (int b = 0; b < FN; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+  }
 
   // prologue
 #pragma unroll
-  for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+  for (int s = 0; s < NS - 1; ++s) {
     if (s < nchunks) {
-      load_operand<TILE, AK, Cfg::THREADS>(sA + s * SA::SIZE, P.A, P.lda, i0, kbeg + s * GEMM_BK, tid);
-      load_operand<TILE, BK_, Cfg::THREADS>(sB + s * SB::SIZE, P.B, P.ldb, j0, kbeg + s * GEMM_BK, tid);
+      load_operand<TILE, AK, Cfg::THREADS, KC>(sA + s * SA::SIZE, P.A, P.lda, i0, kbeg + s * KC, tid);
+      load_operand<TILE, BK_, Cfg::THREADS, KC>(sB + s * SB::SIZE, P.B, P.ldb, j0, kbeg + s * KC, tid);
     }
     csd::cp_async_commit();
   }
 
   for (int c = 0; c < nchunks; ++c) {
-    csd::cp_async_wait<GEMM_STAGES - 2>();
+    csd::cp_async_wait<NS - 2>();
     __syncthreads();
     {
-      const int cn = c + GEMM_STAGES - 1;
+      const int cn = c + NS - 1;
       if (cn < nchunks) {
-        const int sn = cn % GEMM_STAGES;
-        load_operand<TILE, AK, Cfg::THREADS>(sA + sn * SA::SIZE, P.A, P.lda, i0, kbeg + cn * GEMM_BK, tid);
-        load_operand<TILE, BK_, Cfg::THREADS>(sB + sn * SB::SIZE, P.B, P.ldb, j0, kbeg + cn * GEMM_BK, tid);
+        const int sn = cn % NS;
+        load_operand<TILE, AK, Cfg::THREADS, KC>(sA + sn * SA::SIZE, P.A, P.lda, i0, kbeg + cn * KC, tid);
+        load_operand<TILE, BK_, Cfg::THREADS, KC>(sB + sn * SB::SIZE, P.B, P.ldb, j0, kbeg + cn * KC, tid);
       }
       csd::cp_async_commit();
     }
-    const double* a_s = sA + (c % GEMM_STAGES) * SA::SIZE;
-    const double* b_s = sB + (c % GEMM_STAGES) * SB::SIZE;
+    const double* a_s = sA + (c % NS) * SA::SIZE;
+    const double* b_s = sB + (c % NS) * SB::SIZE;
 #pragma unroll
-    for (int kk = 0; kk < GEMM_BK; kk += 4) {
+    for (int kk = 0; kk < KC; kk += 4) {
       double af[FM], bf[FN];
 #pragma unroll
       for (int a = 0; a < FM; ++a)
@@ -175,8 +191,8 @@ gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restr
   }
   csd::cp_async_wait<0>();
 
-  // epilogue: C = beta*C + alpha*acc (+ mirrored store)
-  const double alpha = P.alpha, beta = P.beta;
+  // epilogue: C = alpha*acc (+ mirrored store)
+  const double alpha = P.alpha;
 #pragma unroll
   for (int a = 0; a < FM; ++a) {
     const long long r = i0 + wm + a * 8 + g;
@@ -185,8 +201,7 @@ gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restr
       const long long cc = j0 + wn + b * 8 + 2 * t;
       double* p0 = P.C + r + cc * P.ldc;
       double* p1 = p0 + P.ldc;
-      double v0 = alpha * acc[a][b][0], v1 = alpha * acc[a][b][1];
-      if (beta != 0.0) { v0 += beta * (*p0); v1 += beta * (*p1); }
+      const double v0 = alpha * acc[a][b][0], v1 = alpha * acc[a][b][1];
       *p0 = v0; *p1 = v1;
       if (P.mirror && I != J) {
         double* q = P.C + cc + r * P.ldc;  // (cc, r) and (cc+1, r) are adjacent

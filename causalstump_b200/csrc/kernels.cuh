@@ -430,13 +430,42 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
 }
 
 // ---------------------------------------------------------------------------------
+// Row statistics (multi-CTA): K*alpha from its per-tile partials, squared residual
+// ||y - (K alpha + mu)||^2 (:192) and the sigma trace sum_i T_ii exp(sigma)/w_i (:162-163),
+// as per-CTA partials rs_part[cta][2] (deterministic two-stage reduction).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ETH)
+rowstats_kernel(const double* __restrict__ kal_part, long long kal_stride, int nblk,
+                const double* __restrict__ Cinv, long long ldc, const double* __restrict__ alpha,
+                const double* __restrict__ y, const double* __restrict__ w, const double* __restrict__ params,
+                Layout lay, int n, const EvalScalars* __restrict__ sc, double* __restrict__ rs_part,
+                const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  __shared__ double red[32];
+  const int r = (int)blockIdx.x * ETH + (int)threadIdx.x;
+  const double coef = sc->coef;
+  const double mu = params[lay.i_mu()];
+  const double esig = exp(params[lay.i_sigma()]);
+  double tsig = 0.0, res = 0.0;
+  if (r < n) {
+    const double T = Cinv[(long long)r * ldc + r] - coef * alpha[r] * alpha[r];
+    tsig = T * (esig / w[r]);
+    double ka = 0.0;
+    for (int b = 0; b < nblk; ++b) ka += kal_part[(long long)b * kal_stride + r];
+    const double e = y[r] - (ka + mu);
+    res = e * e;
+  }
+  tsig = csd::block_sum(tsig, red);
+  res = csd::block_sum(res, red);
+  if (threadIdx.x == 0) { rs_part[2 * blockIdx.x] = tsig; rs_part[2 * blockIdx.x + 1] = res; }
+}
+
+// ---------------------------------------------------------------------------------
 // Finalize: gradients in parameter order, stats = (squared residual, LML), mu solution.
 // One CTA.  grad_*_SE_cpp :161-198 / TP :127-159.
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ETH)
-finalize_kernel(const double* __restrict__ gpart, int ncta, const double* __restrict__ kal_part,
-                long long kal_stride, int nblk, const double* __restrict__ Cinv, long long ldc,
-                const double* __restrict__ alpha, const double* __restrict__ y, const double* __restrict__ w,
+finalize_kernel(const double* __restrict__ gpart, int ncta, const double* __restrict__ rs_part, int nrs,
                 const double* __restrict__ params, Layout lay, int n, EvalScalars* __restrict__ sc,
                 double* __restrict__ grad, const int* __restrict__ skip) {
   if (skip && *skip) return;
@@ -451,17 +480,8 @@ finalize_kernel(const double* __restrict__ gpart, int ncta, const double* __rest
     gsum[k] = s;
   }
   const double coef = sc->coef;
-  const double mu = params[lay.i_mu()];
-  const double esig = exp(params[lay.i_sigma()]);
   double tsig = 0.0, res = 0.0;
-  for (int r = tid; r < n; r += ETH) {
-    const double T = Cinv[(long long)r * ldc + r] - coef * alpha[r] * alpha[r];
-    tsig = fma(T, esig / w[r], tsig);
-    double ka = 0.0;
-    for (int b = 0; b < nblk; ++b) ka += kal_part[(long long)b * kal_stride + r];
-    const double e = y[r] - (ka + mu);
-    res = fma(e, e, res);
-  }
+  for (int c = tid; c < nrs; c += ETH) { tsig += rs_part[2 * c]; res += rs_part[2 * c + 1]; }
   tsig = csd::block_sum(tsig, red);
   res = csd::block_sum(res, red);
   __syncthreads();

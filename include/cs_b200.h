@@ -55,6 +55,7 @@ typedef struct cs_fit_config {
   double momentum; /* momentum (Nesterov / GD)                                      */
   int tile;        /* 0 = auto; 64 or 128 selects the dense tile edge               */
   int chunk;       /* optimizer iterations enqueued between host polls (0 = auto)   */
+  int use_graph;   /* 0 = replay one captured iteration as a CUDA graph; -1 = eager  */
 } cs_fit_config;
 
 /* ---- library / device ---------------------------------------------------------- */

@@ -1,0 +1,104 @@
+// Micro-benchmark for tuning csg::gemm_kernel on a B200 (not part of the product library).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I causalstump_b200/csrc tools/gemm_bench.cu -o tools/gemm_bench
+#include <cstdio>
+#include <vector>
+#include "gemm.cuh"
+using namespace csg;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
+
+__global__ void fill(double* p, size_t n, unsigned seed) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) { unsigned h = (unsigned)i * 2654435761u + seed; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; p[i] = (double)(h & 0xffff) / 65536.0 - 0.5; }
+}
+
+// raw pipe ceilings
+__global__ void dmma_peak(double* out, int iters) {
+  double c[16][2];
+  for (int i = 0; i < 16; ++i) { c[i][0] = 0; c[i][1] = 0; }
+  double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-4;
+  for (int it = 0; it < iters; ++it)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) csd::dmma8x8x4(c[i], a, b);
+  double s = 0; for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void dfma_peak(double* out, int iters) {
+  double c[16];
+  for (int i = 0; i < 16; ++i) c[i] = i;
+  double a = 1.0 + threadIdx.x * 1e-9, b = threadIdx.x * 1e-7;
+  for (int it = 0; it < iters; ++it)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+  double s = 0; for (int i = 0; i < 16; ++i) s += c[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <class F> float time_ms(F f, int reps = 3) {
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  f(); CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int r = 0; r < reps; ++r) { CK(cudaEventRecord(e0)); f(); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms; }
+  CK(cudaGetLastError());
+  return best;
+}
+
+static GemmProblem* dP;
+template <int TILE, int WM, int WN, bool AK, bool BK_, int KC, int NS>
+void run(const char* name, GemmProblem P, double flops) {
+  auto k = gemm_kernel<TILE, WM, WN, AK, BK_, KC, NS>;
+  constexpr int smem = gemm_smem_bytes<TILE, AK, BK_, KC, NS>();
+  if (smem > 227 * 1024) { printf("%-44s skipped (smem %d)\n", name, smem); return; }
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaMemcpy(dP, &P, sizeof P, cudaMemcpyHostToDevice));
+  float ms = time_ms([&] { k<<<P.ntiles, WM * WN * 32, smem>>>(dP, 1, nullptr); });
+  printf("%-44s %8.3f ms  %6.2f TFLOP/s  (smem %d KB, %d thr)\n", name, ms, flops / (ms * 1e-3) / 1e12, smem / 1024, WM * WN * 32);
+}
+
+#define ALLCFG(AK, BK_, P, FL, tag)                                                     \
+  run<128, 2, 4, AK, BK_, 16, 4>(tag " 128 2x4 kc16 s4 (current)", P, FL);           \
+  run<128, 4, 2, AK, BK_, 16, 4>(tag " 128 4x2 kc16 s4", P, FL);                     \
+  run<128, 4, 4, AK, BK_, 16, 4>(tag " 128 4x4 kc16 s4 (512 thr)", P, FL);           \
+  run<128, 2, 4, AK, BK_, 32, 3>(tag " 128 2x4 kc32 s3", P, FL);                     \
+  run<128, 4, 4, AK, BK_, 32, 3>(tag " 128 4x4 kc32 s3 (512 thr)", P, FL);           \
+  run<128, 2, 4, AK, BK_, 16, 3>(tag " 128 2x4 kc16 s3", P, FL);                     \
+  run<128, 2, 4, AK, BK_, 16, 6>(tag " 128 2x4 kc16 s6", P, FL);                     \
+  run<128, 2, 4, AK, BK_, 8, 6>(tag " 128 2x4 kc8 s6", P, FL);                       \
+  run<64, 2, 2, AK, BK_, 16, 4>(tag " 64 2x2 kc16 s4", P, FL);                       \
+  run<64, 2, 2, AK, BK_, 32, 4>(tag " 64 2x2 kc32 s4", P, FL);
+
+int main() {
+  const int n = 8192;
+  const long long ld = n;
+  double *A, *B, *C, *out;
+  CK(cudaMalloc(&A, sizeof(double) * n * n)); CK(cudaMalloc(&B, sizeof(double) * n * n)); CK(cudaMalloc(&C, sizeof(double) * n * n));
+  CK(cudaMalloc(&out, sizeof(double) * 148 * 8 * 256)); CK(cudaMalloc(&dP, sizeof(GemmProblem)));
+  fill<<<(n * (size_t)n + 255) / 256, 256>>>(A, (size_t)n * n, 1); fill<<<(n * (size_t)n + 255) / 256, 256>>>(B, (size_t)n * n, 2);
+  CK(cudaMemset(C, 0, sizeof(double) * n * n));
+  CK(cudaDeviceSynchronize());
+  {  // pipe ceilings: 148*4 CTAs x 256 threads
+    const int iters = 20000, ctas = 148 * 4;
+    float ms = time_ms([&] { dmma_peak<<<ctas, 256>>>(out, iters); });
+    printf("DMMA.8x8x4 register-only peak: %.2f TFLOP/s\n", 2.0 * 256 * 16.0 * iters * ctas * 8 / (ms * 1e-3) / 1e12);
+    ms = time_ms([&] { dfma_peak<<<ctas, 256>>>(out, iters); });
+    printf("DFMA register-only peak:       %.2f TFLOP/s\n", 2.0 * 16.0 * iters * ctas * 256 / (ms * 1e-3) / 1e12);
+  }
+  auto mk = [&](int TILE, int mt, int nt, int K, int kmode, int order, int mirror, double alpha, double beta) {
+    GemmProblem P{}; P.A = A; P.B = B; P.C = C; P.lda = ld; P.ldb = ld; P.ldc = ld; P.mt = mt; P.nt = nt; P.K = K; P.kmode = kmode;
+    P.order = order; P.mirror = mirror; P.alpha = alpha; P.beta = beta; P.tile_base = 0; P.ntiles = order == ORD_LOWER ? lower_tiles(mt) : mt * nt;
+    return P; };
+  printf("\n== TN  K^-1 = X^T X  (n=8192, k >= i, lower + mirror): n^3/3 flops\n");
+  { double fl = (double)n * n * n / 3.0;
+    ALLCFG(true, true, mk(128, 64, 64, n, KM_GE_I, ORD_LOWER, 1, 1.0, 0.0), fl, "TN")
+    run<64, 2, 2, true, true, 16, 4>("TN 64-tile plan 64 2x2 kc16 s4", mk(64, 128, 128, n, KM_GE_I, ORD_LOWER, 1, 1.0, 0.0), fl); }
+  printf("\n== NT  trailing update k=512, 60 block rows lower (beta=1)\n");
+  { double fl = 2.0 * 128 * 128 * 512.0 * lower_tiles(60);
+    ALLCFG(false, false, mk(128, 60, 60, 512, KM_FULL, ORD_LOWER, 0, -1.0, 1.0), fl, "NT512") }
+  printf("\n== NT  trailing update k=128, 60 block rows lower (beta=1)\n");
+  { double fl = 2.0 * 128 * 128 * 128.0 * lower_tiles(60);
+    ALLCFG(false, false, mk(128, 60, 60, 128, KM_FULL, ORD_LOWER, 0, -1.0, 1.0), fl, "NT128") }
+  printf("\n== NN  full 4096^3 (trtri top level shape, k <= i)\n");
+  { double fl = 2.0 * 4096.0 * 4096 * 4096 / 2;
+    ALLCFG(false, true, mk(128, 32, 32, 4096, KM_LE_I, ORD_ROW_DESC, 0, -1.0, 0.0), fl, "NN") }
+  return 0;
+}

@@ -6,6 +6,11 @@ set -u
 mkdir -p gpurun_out
 cd "${GRAFT_REPO_ROOT:-.}"
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > gpurun_out/gpu.csv 2>&1
+if [ -x tools/gemm_bench ] && [ "${SKIP_GEMM_BENCH:-0}" != "1" ]; then
+  timeout 600 tools/gemm_bench > gpurun_out/gemm_bench.txt 2>&1
+  echo "gemm_bench_exit=$?"
+  cat gpurun_out/gemm_bench.txt
+fi
 echo "== pytest -m gpu" | tee gpurun_out/status.txt
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest_exit=$?" | tee -a gpurun_out/status.txt
@@ -33,11 +38,11 @@ if [ "$BE" = "0" ] && [ "${SKIP_NCU:-0}" != "1" ]; then
   echo "== ncu full (dominant kernel)"
   timeout 600 python bench.py --steps 1 --warmup 1 --no-fits --no-cpu > gpurun_out/plain2.log 2>&1 &&
   timeout 1200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-      -k 'regex:gemm_kernel<128, 2, 4, true, true>' -s 1 -c 1 \
+      -k 'regex:gemm_kernel<.int.128, .int.2, .int.4, .bool.1, .bool.1' -s 1 -c 1 \
       -o gpurun_out/prof_xtx -f python bench.py --steps 1 --warmup 1 --no-fits --no-cpu > gpurun_out/ncu_full.log 2>&1
   echo "ncu_full_exit=$?" | tee -a gpurun_out/status.txt
   timeout 1200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-      -k 'regex:gemm_kernel<128, 2, 4, false, false>' -s 3 -c 1 \
+      -k 'regex:gemm_kernel<.int.128, .int.2, .int.4, .bool.0, .bool.0' -s 12 -c 1 \
       -o gpurun_out/prof_syrk -f python bench.py --steps 1 --warmup 1 --no-fits --no-cpu > gpurun_out/ncu_full2.log 2>&1
   echo "ncu_full2_exit=$?" | tee -a gpurun_out/status.txt
 fi
