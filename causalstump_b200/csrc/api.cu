@@ -261,7 +261,7 @@ int cs_fit_create(const cs_fit_config* cfg, int n, int p, const double* y, const
   f->p = p;
   auto bail = [&](int code) { cs_fit_destroy(f); return code; };
   if (rt::stream_create(&f->st)) return bail(fail(CS_ERR_CUDA, "stream create failed"));
-  if (int e = f->eng.init(n, tile)) return bail(fail(e == 2 ? CS_ERR_NOMEM : CS_ERR_CUDA, "dense engine init failed: %s", rt::err_str(e)));
+  if (int e = f->eng.init(n, tile, cfg->gemm_tile)) return bail(fail(e == 2 ? CS_ERR_NOMEM : CS_ERR_CUDA, "dense engine init failed: %s", rt::err_str(e)));
   const int np = f->eng.np;
   f->np = np;
   f->nblk = np / csk::TB;
@@ -571,9 +571,9 @@ struct CrossWork {
 // shared by cs_predict (use_m = 1, z2 given) and cs_treat (use_m = 0, z2 = 1, Ka only)
 static int cross_common(cs_fit* f, CrossWork& W, int n2, const double* X2, const double* z2, bool treat,
                         double* map, double* var_diag, double add_sigma, double add_const, double* cov_out) {
-  const int n = f->n, np = f->np, p = f->p, tile = f->eng.tile;
+  const int n = f->n, np = f->np, p = f->p, tile = f->eng.gt;
   cudaStream_t st = f->st;
-  const int n2p = round_up(n2, tile);
+  const int n2p = round_up(n2, f->eng.tile);
   W.n2 = n2; W.n2p = n2p;
   const size_t vb2 = sizeof(double) * n2p;
   if (W.X2.alloc(vb2 * p) || W.z2.alloc(vb2) || W.Kc.alloc(vb2 * np) || W.V.alloc(vb2 * np) || W.q.alloc(vb2) ||
@@ -759,7 +759,10 @@ int cs_tp_sample(int n2, const double* cov, double df, int nsampling, unsigned l
   RT(rt::memset0(Ud.d(), sizeof(double) * np, st));
   RT(rt::memset0(au.d(), sizeof(double), st));
   // Y[s,i] = sum_k Z[s,k] L[i,k]   (NT)
-  csg::GemmProblem P = DenseEngine::mk(Z.d(), NSP, eng.G, np, Y.d(), NSP, NSP / tile, np / tile, np, csg::KM_FULL,
+  const int gt = eng.gt;
+  // L is lower triangular (k <= j); tiles above the diagonal of G still hold the uploaded
+  // covariance and must never be read: KM_LE_J stops every k-range at the diagonal tile.
+  csg::GemmProblem P = DenseEngine::mk(Z.d(), NSP, eng.G, np, Y.d(), NSP, NSP / gt, np / gt, np, csg::KM_LE_J,
                                        csg::ORD_COL, 0, 1.0, 0.0);
   RT(rt::h2d(dP.p, &P, sizeof P, st));
   for (int r = 0; r < nrep; ++r) {
@@ -770,7 +773,7 @@ int cs_tp_sample(int n2, const double* cov, double df, int nsampling, unsigned l
     auto k2 = csp::chi2_scale_kernel;
     ++g_launches;
     CS_LAUNCH(k2, (NSP + 255) / 256, 256, 0, st, scale.d(), NSP, df, seed, (unsigned)r);
-    csdense::launch_gemm(tile, csdense::GK_NT, (const csg::GemmProblem*)dP.p, 1, P.ntiles, st);
+    csdense::launch_gemm(gt, csdense::GK_NT, (const csg::GemmProblem*)dP.p, 1, P.ntiles, st);
     auto k3 = csp::order_stat_kernel;
     ++g_launches;
     CS_LAUNCH(k3, n2, 512, 0, st, Y.d(), (long long)NSP, scale.d(), NS, rank, 1.0 / nrep, Ud.d());

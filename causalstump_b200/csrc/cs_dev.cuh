@@ -52,6 +52,15 @@ __device__ __forceinline__ void cp_async_wait() {
 #endif
 }
 
+// reciprocal without the slow-path subroutine call of IEEE division
+__device__ __forceinline__ double fast_rcp(double x) {
+#ifdef CS_EMU
+  return 1.0 / x;
+#else
+  return __drcp_rn(x);
+#endif
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

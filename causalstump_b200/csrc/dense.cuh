@@ -57,37 +57,39 @@ leaf_kernel(double* __restrict__ G, long long ldg, double* __restrict__ X, long 
     }
 
   // ---- phase 1: right-looking Cholesky; columns stay unscaled (L[r][j] = S[r][j] / sqrt(d_j)) ----
-  for (int j = 0; j < TILE; ++j) {
-    double* buf = colbuf + (j & 1) * TILE;
-    const int bj = j >> 4, tj = j & 15;
-    if (ty == tj) {
+  // The step loop is split by the 16-column block bj so every register index and loop bound
+  // is a compile-time constant (no predicated-off work as the trailing matrix shrinks).
 #pragma unroll
-      for (int b = 0; b < NA; ++b)
-        if (b == bj) {
+  for (int bj = 0; bj < NA; ++bj) {
+    for (int tj = 0; tj < 16; ++tj) {
+      const int j = 16 * bj + tj;
+      double* buf = colbuf + (j & 1) * TILE;
+      if (ty == tj) {
 #pragma unroll
-          for (int a = 0; a < NA; ++a) buf[tx + 16 * a] = reg[a][b];
-        }
-    }
-    __syncthreads();
-    double d = buf[j];
-    if (!(d > 0.0)) {
-      const int gidx = blk * TILE + j;
-      if (tid == 0 && gidx < n_real) atomicMin(status, gidx + 1);  // LAPACK-style 1-based info
-      d = 1.0;
-    }
-    if (tid == 0) piv[j] = d;
-    const double invd = 1.0 / d;
-    double cr[NA], cc[NA];
+        for (int a = bj; a < NA; ++a) buf[tx + 16 * a] = reg[a][bj];
+      }
+      __syncthreads();
+      double d = buf[j];
+      if (!(d > 0.0)) {
+        const int gidx = blk * TILE + j;
+        if (tid == 0 && gidx < n_real) atomicMin(status, gidx + 1);  // LAPACK-style 1-based info
+        d = 1.0;
+      }
+      if (tid == 0) piv[j] = d;
+      const double invd = csd::fast_rcp(d);
+      double cr[NA], cc[NA];
 #pragma unroll
-    for (int a = 0; a < NA; ++a) cr[a] = buf[tx + 16 * a];
+      for (int a = bj; a < NA; ++a) cr[a] = buf[tx + 16 * a];
 #pragma unroll
-    for (int b = 0; b < NA; ++b) cc[b] = buf[ty + 16 * b] * invd;
+      for (int b = bj; b < NA; ++b) cc[b] = buf[ty + 16 * b] * invd;
+      if (ty > tj) {  // columns of block bj to the right of j
 #pragma unroll
-    for (int b = 0; b < NA; ++b) {
-      if (b > bj || (b == bj && ty > tj)) {  // column c = ty + 16 b > j
+        for (int a = bj; a < NA; ++a) reg[a][bj] -= cr[a] * cc[bj];
+      }
+#pragma unroll
+      for (int b = bj + 1; b < NA; ++b)
 #pragma unroll
         for (int a = b; a < NA; ++a) reg[a][b] -= cr[a] * cc[b];
-      }
     }
   }
   __syncthreads();
@@ -110,48 +112,47 @@ leaf_kernel(double* __restrict__ G, long long ldg, double* __restrict__ X, long 
   if (tid == 0) logdet_part[blk] = ldsum;  // block_sum ends with a barrier: dinv is visible
 
   // ---- phase 2: in-place inverse X = L^-1, row by row with rank-1 updates of the rows below ----
-  for (int i = 0; i < TILE; ++i) {
-    double* cbuf = colbuf + (i & 1) * TILE;
-    double* rbuf = rowbuf + (i & 1) * TILE;
-    const int bi = i >> 4, ti = i & 15;
-    const double xii = dinv[i];
-    if (tx == ti) {  // owners of row i finalise X[i][c], c <= i
 #pragma unroll
-      for (int a = 0; a < NA; ++a)
-        if (a == bi) {
+  for (int bi = 0; bi < NA; ++bi) {
+    for (int ti = 0; ti < 16; ++ti) {
+      const int i = 16 * bi + ti;
+      double* cbuf = colbuf + (i & 1) * TILE;
+      double* rbuf = rowbuf + (i & 1) * TILE;
+      const double xii = dinv[i];
+      if (tx == ti) {  // owners of row i finalise X[i][c], c <= i
 #pragma unroll
-          for (int b = 0; b <= a; ++b) {
-            const int c = ty + 16 * b;
-            if (c <= i) {
-              const double v = (c == i) ? xii : -xii * reg[a][b];
-              reg[a][b] = v;
-              rbuf[c] = v;
-            }
+        for (int b = 0; b <= bi; ++b) {
+          const int c = ty + 16 * b;
+          if (b < bi || ty <= ti) {
+            const double v = (c == i) ? xii : -xii * reg[bi][b];
+            reg[bi][b] = v;
+            rbuf[c] = v;
           }
         }
-    }
-    if (ty == ti) {  // owners of column i publish L[r][i], r > i
+      }
+      if (ty == ti) {  // owners of column i publish L[r][i], r > i
 #pragma unroll
-      for (int b = 0; b < NA; ++b)
-        if (b == bi) {
-#pragma unroll
-          for (int a = b; a < NA; ++a) {
-            const int r = tx + 16 * a;
-            if (r > i) cbuf[r] = reg[a][b];
-          }
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int b = 0; b < NA; ++b) {
-      const int c = ty + 16 * b;
-      if (c <= i) {
-        const double xv = rbuf[c];
-#pragma unroll
-        for (int a = b; a < NA; ++a) {
+        for (int a = bi; a < NA; ++a) {
           const int r = tx + 16 * a;
-          if (r > i) reg[a][b] = ((c == i) ? 0.0 : reg[a][b]) + cbuf[r] * xv;
+          if (a > bi || tx > ti) cbuf[r] = reg[a][bi];
         }
+      }
+      __syncthreads();
+      // columns c < 16*bi (blocks b < bi): rows r > i
+#pragma unroll
+      for (int b = 0; b < bi; ++b) {
+        const double xv = rbuf[ty + 16 * b];
+        if (tx > ti) reg[bi][b] += cbuf[tx + 16 * bi] * xv;
+#pragma unroll
+        for (int a = bi + 1; a < NA; ++a) reg[a][b] += cbuf[tx + 16 * a] * xv;
+      }
+      // block b == bi: columns c <= i
+      if (ty <= ti) {
+        const double xv = rbuf[ty + 16 * bi];
+        const bool is_i = (ty == ti);
+        if (tx > ti) reg[bi][bi] = (is_i ? 0.0 : reg[bi][bi]) + cbuf[tx + 16 * bi] * xv;
+#pragma unroll
+        for (int a = bi + 1; a < NA; ++a) reg[a][bi] = (is_i ? 0.0 : reg[a][bi]) + cbuf[tx + 16 * a] * xv;
       }
     }
   }
@@ -182,6 +183,7 @@ struct Launch {
   int ntiles;
   int stream;      // 0: main (critical path, high priority)   1: auxiliary (bulk updates)
   int ev;          // event index for OP_RECORD / OP_WAIT
+  int gtile;       // CTA tile of this launch (0 = engine default gt)
 };
 
 inline int pick_tile(int n) { return n <= 1536 ? 64 : 128; }
@@ -221,7 +223,8 @@ inline void configure_kernels() {
 }
 
 struct DenseEngine {
-  int n = 0, np = 0, tile = 0, N = 0;
+  int n = 0, np = 0, tile = 0, N = 0;  // tile: block size of the leaf / panel structure
+  int gt = 0, rr = 1;                   // gt: CTA tile of the GEMM kernel, rr = tile / gt
   double *G = nullptr, *X = nullptr, *C = nullptr;  // device, np x np each
   double* logdet_part = nullptr;                     // device, N
   int* status = nullptr;                             // device, 1 (0 = OK, else 1-based failing pivot)
@@ -265,8 +268,10 @@ struct DenseEngine {
   }
 
   // returns 0 or a runtime error code
-  int init(int n_, int tile_) {
+  int init(int n_, int tile_, int gemm_tile = 64) {
     n = n_; tile = tile_; N = (n + tile - 1) / tile; np = N * tile;
+    gt = (gemm_tile == 128 && tile == 128) ? 128 : 64;
+    rr = tile / gt;
     const size_t bytes = (size_t)np * np * sizeof(double);
     int e;
     if ((e = rt::dev_malloc((void**)&G, bytes))) return e;
@@ -295,13 +300,14 @@ struct DenseEngine {
         // L21 = A21 * X_kk^T   (NT, in place)
         grp.push_back(mk(panel, ld, X + k * T * (ld + 1), ld, panel, ld, m, 1, tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
         add_group(potrf, GK_NT, grp);
+        potrf.back().gtile = tile;  // in place: each CTA owns a full block row of the panel
         // inner update: columns k+1 .. p1-1 of the current panel (lower part + rectangle below)
         const int nc = p1 - 1 - k;
         if (nc > 0) {
-          grp.push_back(mk(panel, ld, panel, ld, G + (k + 1) * T * (ld + 1), ld, nc, nc, tile, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
+          grp.push_back(mk(panel, ld, panel, ld, G + (k + 1) * T * (ld + 1), ld, nc * rr, nc * rr, tile, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
           const int mr = N - p1;
           if (mr > 0)
-            grp.push_back(mk(G + p1 * T + k * T * ld, ld, panel, ld, G + p1 * T + (k + 1) * T * ld, ld, mr, nc, tile,
+            grp.push_back(mk(G + p1 * T + k * T * ld, ld, panel, ld, G + p1 * T + (k + 1) * T * ld, ld, mr * rr, nc * rr, tile,
                              csg::KM_FULL, csg::ORD_COL, 0, -1.0, 1.0));
           add_group(potrf, GK_NT, grp);
         }
@@ -314,15 +320,15 @@ struct DenseEngine {
       { Launch R{}; R.is_leaf = OP_RECORD; R.stream = 0; R.ev = 2 * npanel; potrf.push_back(R); }
       if (npanel > 0) { Launch Wt{}; Wt.is_leaf = OP_WAIT; Wt.stream = 0; Wt.ev = 2 * (npanel - 1) + 1; potrf.push_back(Wt); }
       // U1: columns [p1, p1+n1): lower part + rectangle below (main stream)
-      grp.push_back(mk(pan, ld, pan, ld, G + p1 * T * (ld + 1), ld, n1, n1, kw, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
+      grp.push_back(mk(pan, ld, pan, ld, G + p1 * T * (ld + 1), ld, n1 * rr, n1 * rr, kw, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
       if (mt > n1)
-        grp.push_back(mk(pan + n1 * T, ld, pan, ld, G + (p1 + n1) * T + p1 * T * ld, ld, mt - n1, n1, kw, csg::KM_FULL,
+        grp.push_back(mk(pan + n1 * T, ld, pan, ld, G + (p1 + n1) * T + p1 * T * ld, ld, (mt - n1) * rr, n1 * rr, kw, csg::KM_FULL,
                          csg::ORD_COL, 0, -1.0, 1.0));
       add_group(potrf, GK_NT, grp);
       // U2: everything to the right of the next panel (auxiliary stream)
       if (mt > n1) {
         { Launch Wt{}; Wt.is_leaf = OP_WAIT; Wt.stream = 1; Wt.ev = 2 * npanel; potrf.push_back(Wt); }
-        grp.push_back(mk(pan + n1 * T, ld, pan + n1 * T, ld, G + (p1 + n1) * T * (ld + 1), ld, mt - n1, mt - n1, kw,
+        grp.push_back(mk(pan + n1 * T, ld, pan + n1 * T, ld, G + (p1 + n1) * T * (ld + 1), ld, (mt - n1) * rr, (mt - n1) * rr, kw,
                          csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
         add_group(potrf, GK_NT, grp);
         potrf.back().stream = 1;
@@ -343,17 +349,17 @@ struct DenseEngine {
         const int m = nd.hi - nd.mid, q = nd.mid - nd.lo;
         double* Tw = C + nd.mid * T + nd.lo * T * ld;
         // T = L21 * X11      (NN; X11 lower => k >= j)
-        g1.push_back(mk(G + nd.mid * T + nd.lo * T * ld, ld, X + nd.lo * T * (ld + 1), ld, Tw, ld, m, q, q * tile,
+        g1.push_back(mk(G + nd.mid * T + nd.lo * T * ld, ld, X + nd.lo * T * (ld + 1), ld, Tw, ld, m * rr, q * rr, q * tile,
                         csg::KM_GE_J, csg::ORD_COL, 0, 1.0, 0.0));
         // X21 = -X22 * T     (NN; X22 lower => k <= i)
-        g2.push_back(mk(X + nd.mid * T * (ld + 1), ld, Tw, ld, X + nd.mid * T + nd.lo * T * ld, ld, m, q, m * tile,
+        g2.push_back(mk(X + nd.mid * T * (ld + 1), ld, Tw, ld, X + nd.mid * T + nd.lo * T * ld, ld, m * rr, q * rr, m * tile,
                         csg::KM_LE_I, csg::ORD_ROW_DESC, 0, -1.0, 0.0));
       }
       add_group(trtri, GK_NN, g1);
       add_group(trtri, GK_NN, g2);
     }
     // --- K^-1 = X^T X  (TN; k >= max(i,j) = i on lower tiles; mirrored store) ---
-    grp.push_back(mk(X, ld, X, ld, C, ld, N, N, np, csg::KM_GE_I, csg::ORD_LOWER, 1, 1.0, 0.0));
+    grp.push_back(mk(X, ld, X, ld, C, ld, N * rr, N * rr, np, csg::KM_GE_I, csg::ORD_LOWER, 1, 1.0, 0.0));
     add_group(xtx, GK_TN, grp);
 
     if ((e = rt::stream_create_low(&aux))) return e;
@@ -388,7 +394,7 @@ struct DenseEngine {
       } else if (L.is_leaf == OP_WAIT) {
         rt::stream_wait_event(s, events[L.ev]);
       } else {
-        launch_gemm(tile, L.kind, d_probs + L.first_prob, L.nprob, L.ntiles, s, skip);
+        launch_gemm(L.gtile ? L.gtile : gt, L.kind, d_probs + L.first_prob, L.nprob, L.ntiles, s, skip);
       }
     }
   }

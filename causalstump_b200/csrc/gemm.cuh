@@ -14,7 +14,7 @@
 
 namespace csg {
 
-enum KMode { KM_FULL = 0, KM_GE_J = 1, KM_LE_I = 2, KM_GE_I = 3 };
+enum KMode { KM_FULL = 0, KM_GE_J = 1, KM_LE_I = 2, KM_GE_I = 3, KM_LE_J = 4 };
 enum TileOrder { ORD_COL = 0, ORD_ROW_DESC = 1, ORD_LOWER = 2 };
 
 struct GemmProblem {
@@ -56,6 +56,7 @@ __host__ __device__ inline void tile_krange(int kmode, int K, int TILE, int I, i
   if (kmode == KM_GE_J) kbeg = J * TILE;
   else if (kmode == KM_GE_I) kbeg = I * TILE;
   else if (kmode == KM_LE_I) kend = (I + 1) * TILE;
+  else if (kmode == KM_LE_J) kend = (J + 1) * TILE;
   if (kend > K) kend = K;
   if (kbeg > kend) kbeg = kend;
 }

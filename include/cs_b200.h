@@ -56,6 +56,7 @@ typedef struct cs_fit_config {
   int tile;        /* 0 = auto; 64 or 128 selects the dense tile edge               */
   int chunk;       /* optimizer iterations enqueued between host polls (0 = auto)   */
   int use_graph;   /* 0 = replay one captured iteration as a CUDA graph; -1 = eager  */
+  int gemm_tile;   /* 0 / 64 = 64x64 CTA tiles (default); 128 = 128x128 CTA tiles    */
 } cs_fit_config;
 
 /* ---- library / device ---------------------------------------------------------- */

@@ -58,12 +58,13 @@ def test_stateless_mirrors(emulib):
     assert cs.rel(st, o.stats_TP_SE(y, St[0], inv, par)) < 1e-11
 
 
-def test_sampler_distribution(emulib):
+@pytest.mark.parametrize("n2", [24, 100])
+def test_sampler_distribution(emulib, n2):
     from scipy import stats as ss
     rng = np.random.default_rng(5)
-    A = rng.normal(size=(24, 24))
-    cov = A @ A.T / 24 + 0.5 * np.eye(24)
+    A = rng.normal(size=(n2, n2))
+    cov = A @ A.T / n2 + 0.5 * np.eye(n2)
     U, aU = emulib.tp_sample(cov, 6.0, 4000, 11, want_ate=True)
     ref = np.sqrt(np.diag(cov)) * ss.t.ppf(0.9, 6.0)
     assert np.all(np.abs(U / ref - 1.0) < 0.08)
-    assert abs(aU / (np.sqrt(cov.sum()) / 24 * ss.t.ppf(0.9, 6.0)) - 1.0) < 0.08
+    assert abs(aU / (np.sqrt(cov.sum()) / n2 * ss.t.ppf(0.9, 6.0)) - 1.0) < 0.08

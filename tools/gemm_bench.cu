@@ -55,17 +55,17 @@ void run(const char* name, GemmProblem P, double flops) {
   printf("%-44s %8.3f ms  %6.2f TFLOP/s  (smem %d KB, %d thr)\n", name, ms, flops / (ms * 1e-3) / 1e12, smem / 1024, WM * WN * 32);
 }
 
-#define ALLCFG(AK, BK_, P, FL, tag)                                                     \
-  run<128, 2, 4, AK, BK_, 16, 4>(tag " 128 2x4 kc16 s4 (current)", P, FL);           \
-  run<128, 4, 2, AK, BK_, 16, 4>(tag " 128 4x2 kc16 s4", P, FL);                     \
-  run<128, 4, 4, AK, BK_, 16, 4>(tag " 128 4x4 kc16 s4 (512 thr)", P, FL);           \
-  run<128, 2, 4, AK, BK_, 32, 3>(tag " 128 2x4 kc32 s3", P, FL);                     \
-  run<128, 4, 4, AK, BK_, 32, 3>(tag " 128 4x4 kc32 s3 (512 thr)", P, FL);           \
-  run<128, 2, 4, AK, BK_, 16, 3>(tag " 128 2x4 kc16 s3", P, FL);                     \
-  run<128, 2, 4, AK, BK_, 16, 6>(tag " 128 2x4 kc16 s6", P, FL);                     \
-  run<128, 2, 4, AK, BK_, 8, 6>(tag " 128 2x4 kc8 s6", P, FL);                       \
-  run<64, 2, 2, AK, BK_, 16, 4>(tag " 64 2x2 kc16 s4", P, FL);                       \
-  run<64, 2, 2, AK, BK_, 32, 4>(tag " 64 2x2 kc32 s4", P, FL);
+#define ALLCFG(AK, BK_, MK, FL, tag)                                                   \
+  run<128, 2, 4, AK, BK_, 16, 4>(tag " 128 2x4 kc16 s4", MK(128), FL);               \
+  run<128, 2, 4, AK, BK_, 32, 3>(tag " 128 2x4 kc32 s3", MK(128), FL);               \
+  run<64, 2, 2, AK, BK_, 16, 4>(tag " 64 2x2 kc16 s4 (2 CTA/SM)", MK(64), FL);       \
+  run<64, 2, 2, AK, BK_, 16, 3>(tag " 64 2x2 kc16 s3 (3 CTA/SM)", MK(64), FL);       \
+  run<64, 2, 2, AK, BK_, 16, 2>(tag " 64 2x2 kc16 s2 (5 CTA/SM)", MK(64), FL);       \
+  run<64, 2, 2, AK, BK_, 32, 3>(tag " 64 2x2 kc32 s3 (2 CTA/SM)", MK(64), FL);       \
+  run<64, 2, 2, AK, BK_, 32, 2>(tag " 64 2x2 kc32 s2 (3 CTA/SM)", MK(64), FL);       \
+  run<64, 1, 4, AK, BK_, 16, 3>(tag " 64 1x4 kc16 s3", MK(64), FL);                  \
+  run<64, 4, 1, AK, BK_, 16, 3>(tag " 64 4x1 kc16 s3", MK(64), FL);                  \
+  run<64, 2, 4, AK, BK_, 16, 3>(tag " 64 2x4 kc16 s3 (256 thr)", MK(64), FL);
 
 int main() {
   const int n = 8192;
@@ -89,16 +89,23 @@ int main() {
     return P; };
   printf("\n== TN  K^-1 = X^T X  (n=8192, k >= i, lower + mirror): n^3/3 flops\n");
   { double fl = (double)n * n * n / 3.0;
-    ALLCFG(true, true, mk(128, 64, 64, n, KM_GE_I, ORD_LOWER, 1, 1.0, 0.0), fl, "TN")
-    run<64, 2, 2, true, true, 16, 4>("TN 64-tile plan 64 2x2 kc16 s4", mk(64, 128, 128, n, KM_GE_I, ORD_LOWER, 1, 1.0, 0.0), fl); }
-  printf("\n== NT  trailing update k=512, 60 block rows lower (beta=1)\n");
+    auto MK = [&](int T) { return mk(T, n / T, n / T, n, KM_GE_I, ORD_LOWER, 1, 1.0, 0.0); };
+    ALLCFG(true, true, MK, fl, "TN") }
+  printf("\n== NT  trailing update k=512, 7680 rows lower (beta=1)\n");
   { double fl = 2.0 * 128 * 128 * 512.0 * lower_tiles(60);
-    ALLCFG(false, false, mk(128, 60, 60, 512, KM_FULL, ORD_LOWER, 0, -1.0, 1.0), fl, "NT512") }
-  printf("\n== NT  trailing update k=128, 60 block rows lower (beta=1)\n");
-  { double fl = 2.0 * 128 * 128 * 128.0 * lower_tiles(60);
-    ALLCFG(false, false, mk(128, 60, 60, 128, KM_FULL, ORD_LOWER, 0, -1.0, 1.0), fl, "NT128") }
-  printf("\n== NN  full 4096^3 (trtri top level shape, k <= i)\n");
+    auto MK = [&](int T) { return mk(T, 7680 / T, 7680 / T, 512, KM_FULL, ORD_LOWER, 0, -1.0, 1.0); };
+    ALLCFG(false, false, MK, fl, "NT512") }
+  printf("\n== NT  inner update k=128, 7680 x 384 rectangle (beta=1)\n");
+  { double fl = 2.0 * 7680.0 * 384 * 128;
+    auto MK = [&](int T) { return mk(T, 7680 / T, 384 / T, 128, KM_FULL, ORD_COL, 0, -1.0, 1.0); };
+    ALLCFG(false, false, MK, fl, "NT128") }
+  printf("\n== NN  4096^3 (trtri top level shape, k <= i)\n");
   { double fl = 2.0 * 4096.0 * 4096 * 4096 / 2;
-    ALLCFG(false, true, mk(128, 32, 32, 4096, KM_LE_I, ORD_ROW_DESC, 0, -1.0, 0.0), fl, "NN") }
+    auto MK = [&](int T) { return mk(T, 4096 / T, 4096 / T, 4096, KM_LE_I, ORD_ROW_DESC, 0, -1.0, 0.0); };
+    ALLCFG(false, true, MK, fl, "NN") }
+  printf("\n== NN  512^3 x 8 problems is not grouped here; single 512^3 (k <= i)\n");
+  { double fl = 2.0 * 512.0 * 512 * 512 / 2;
+    auto MK = [&](int T) { return mk(T, 512 / T, 512 / T, 512, KM_LE_I, ORD_ROW_DESC, 0, -1.0, 0.0); };
+    ALLCFG(false, true, MK, fl, "NN512") }
   return 0;
 }

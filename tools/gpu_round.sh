@@ -38,12 +38,12 @@ if [ "$BE" = "0" ] && [ "${SKIP_NCU:-0}" != "1" ]; then
   echo "== ncu full (dominant kernel)"
   timeout 600 python bench.py --steps 1 --warmup 1 --no-fits --no-cpu > gpurun_out/plain2.log 2>&1 &&
   timeout 1200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-      -k 'regex:gemm_kernel<.int.128, .int.2, .int.4, .bool.1, .bool.1' -s 1 -c 1 \
+      -k 'regex:gemm_kernel<.int.64, .int.2, .int.2, .bool.1, .bool.1' -s 1 -c 1 \
       -o gpurun_out/prof_xtx -f python bench.py --steps 1 --warmup 1 --no-fits --no-cpu > gpurun_out/ncu_full.log 2>&1
   echo "ncu_full_exit=$?" | tee -a gpurun_out/status.txt
   timeout 1200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-      -k 'regex:gemm_kernel<.int.128, .int.2, .int.4, .bool.0, .bool.0' -s 12 -c 1 \
-      -o gpurun_out/prof_syrk -f python bench.py --steps 1 --warmup 1 --no-fits --no-cpu > gpurun_out/ncu_full2.log 2>&1
+      -k 'regex:leaf_kernel' -s 10 -c 1 \
+      -o gpurun_out/prof_leaf -f python bench.py --steps 1 --warmup 1 --no-fits --no-cpu > gpurun_out/ncu_full2.log 2>&1
   echo "ncu_full2_exit=$?" | tee -a gpurun_out/status.txt
 fi
 cat gpurun_out/status.txt
