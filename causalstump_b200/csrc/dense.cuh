@@ -32,9 +32,10 @@ constexpr int leaf_smem_bytes() { return (6 * TILE + 32) * (int)sizeof(double); 
 // (and, for the inverse, one row) crosses shared memory; one barrier per step (double-buffered).
 template <int TILE>
 __global__ void __launch_bounds__(LEAF_THREADS)
-leaf_kernel(double* __restrict__ G, long long ldg, double* __restrict__ X, long long ldx, int blk,
-            double* __restrict__ logdet_part, int* __restrict__ status, int n_real,
+leaf_kernel(double* __restrict__ Gt, long long ldg, double* __restrict__ Xt, long long ldx, int pivot_base,
+            double* __restrict__ logdet_out, int* __restrict__ status, int n_real,
             const int* __restrict__ skip) {
+  // Gt / Xt point at the diagonal tile; pivot_base is its first global row (for LAPACK `info`)
   if (skip && *skip) return;
   constexpr int NA = TILE / 16;
   CS_DYN_SMEM(double, sm);
@@ -44,8 +45,6 @@ leaf_kernel(double* __restrict__ G, long long ldg, double* __restrict__ X, long 
   double* dinv = sm + 5 * TILE;     // [TILE]
   double* red = sm + 6 * TILE;      // [32]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  double* Gt = G + (long long)blk * TILE * (ldg + 1);
-  double* Xt = X + (long long)blk * TILE * (ldx + 1);
 
   double reg[NA][NA];
 #pragma unroll
@@ -71,7 +70,7 @@ leaf_kernel(double* __restrict__ G, long long ldg, double* __restrict__ X, long 
       __syncthreads();
       double d = buf[j];
       if (!(d > 0.0)) {
-        const int gidx = blk * TILE + j;
+        const int gidx = pivot_base + j;
         if (tid == 0 && gidx < n_real) atomicMin(status, gidx + 1);  // LAPACK-style 1-based info
         d = 1.0;
       }
@@ -109,7 +108,7 @@ leaf_kernel(double* __restrict__ G, long long ldg, double* __restrict__ X, long 
     }
   }
   const double ldsum = csd::block_sum(tid < TILE ? 0.5 * log(piv[tid < TILE ? tid : 0]) : 0.0, red);
-  if (tid == 0) logdet_part[blk] = ldsum;  // block_sum ends with a barrier: dinv is visible
+  if (tid == 0) *logdet_out = ldsum;  // block_sum ends with a barrier: dinv is visible
 
   // ---- phase 2: in-place inverse X = L^-1, row by row with rank-1 updates of the rows below ----
 #pragma unroll
@@ -197,9 +196,11 @@ inline void launch_gemm_t(int kind, const GemmProblem* dprobs, int nprob, int nt
     else if (kind == GK_NN) { auto k = csg::gemm_kernel<128, 2, 4, false, true>; CS_LAUNCH(k, ntiles, 256, (csg::gemm_smem_bytes<128, false, true>()), st, dprobs, nprob, skip); }
     else { auto k = csg::gemm_kernel<128, 2, 4, true, true>; CS_LAUNCH(k, ntiles, 256, (csg::gemm_smem_bytes<128, true, true>()), st, dprobs, nprob, skip); }
   } else {
-    if (kind == GK_NT) { auto k = csg::gemm_kernel<64, 2, 2, false, false>; CS_LAUNCH(k, ntiles, 128, (csg::gemm_smem_bytes<64, false, false>()), st, dprobs, nprob, skip); }
-    else if (kind == GK_NN) { auto k = csg::gemm_kernel<64, 2, 2, false, true>; CS_LAUNCH(k, ntiles, 128, (csg::gemm_smem_bytes<64, false, true>()), st, dprobs, nprob, skip); }
-    else { auto k = csg::gemm_kernel<64, 2, 2, true, true>; CS_LAUNCH(k, ntiles, 128, (csg::gemm_smem_bytes<64, true, true>()), st, dprobs, nprob, skip); }
+    // 64 x 64 CTA tiles, 128 registers/thread: 3-4 CTAs per SM hide the prologue / epilogue
+    // of one tile behind the main loop of another (stage counts from tools/gemm_bench on B200)
+    if (kind == GK_NT) { auto k = csg::gemm_kernel<64, 2, 2, false, false, 16, 3>; CS_LAUNCH(k, ntiles, 128, (csg::gemm_smem_bytes<64, false, false, 16, 3>()), st, dprobs, nprob, skip); }
+    else if (kind == GK_NN) { auto k = csg::gemm_kernel<64, 2, 2, false, true, 16, 3>; CS_LAUNCH(k, ntiles, 128, (csg::gemm_smem_bytes<64, false, true, 16, 3>()), st, dprobs, nprob, skip); }
+    else { auto k = csg::gemm_kernel<64, 2, 2, true, true, 16, 2>; CS_LAUNCH(k, ntiles, 128, (csg::gemm_smem_bytes<64, true, true, 16, 2>()), st, dprobs, nprob, skip); }
   }
 }
 
@@ -215,11 +216,18 @@ inline void configure_kernels() {
   { auto k = csg::gemm_kernel<128, 2, 4, false, false>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<128, false, false>())); }
   { auto k = csg::gemm_kernel<128, 2, 4, false, true>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<128, false, true>())); }
   { auto k = csg::gemm_kernel<128, 2, 4, true, true>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<128, true, true>())); }
-  { auto k = csg::gemm_kernel<64, 2, 2, false, false>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<64, false, false>())); }
-  { auto k = csg::gemm_kernel<64, 2, 2, false, true>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<64, false, true>())); }
-  { auto k = csg::gemm_kernel<64, 2, 2, true, true>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<64, true, true>())); }
+  { auto k = csg::gemm_kernel<64, 2, 2, false, false, 16, 3>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<64, false, false, 16, 3>())); }
+  { auto k = csg::gemm_kernel<64, 2, 2, false, true, 16, 3>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<64, false, true, 16, 3>())); }
+  { auto k = csg::gemm_kernel<64, 2, 2, true, true, 16, 2>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<64, true, true, 16, 2>())); }
   { auto k = leaf_kernel<128>; CS_SET_SMEM(k, leaf_smem_bytes<128>()); }
   { auto k = leaf_kernel<64>; CS_SET_SMEM(k, leaf_smem_bytes<64>()); }
+}
+
+inline void launch_leaf(int tile, double* Gt, long long ldg, double* Xt, long long ldx, int pivot_base,
+                        double* logdet_out, int* status, int n_real, cudaStream_t s, const int* skip) {
+  ++g_launches;
+  if (tile == 128) { auto k = leaf_kernel<128>; CS_LAUNCH(k, 1, LEAF_THREADS, leaf_smem_bytes<128>(), s, Gt, ldg, Xt, ldx, pivot_base, logdet_out, status, n_real, skip); }
+  else { auto k = leaf_kernel<64>; CS_LAUNCH(k, 1, LEAF_THREADS, leaf_smem_bytes<64>(), s, Gt, ldg, Xt, ldx, pivot_base, logdet_out, status, n_real, skip); }
 }
 
 struct DenseEngine {
@@ -386,9 +394,8 @@ struct DenseEngine {
     for (const Launch& L : seq) {
       cudaStream_t s = L.stream ? aux : st;
       if (L.is_leaf == OP_LEAF) {
-        ++g_launches;
-        if (tile == 128) { auto k = leaf_kernel<128>; CS_LAUNCH(k, 1, LEAF_THREADS, leaf_smem_bytes<128>(), s, G, (long long)np, X, (long long)np, L.blk, logdet_part, status, n, skip); }
-        else { auto k = leaf_kernel<64>; CS_LAUNCH(k, 1, LEAF_THREADS, leaf_smem_bytes<64>(), s, G, (long long)np, X, (long long)np, L.blk, logdet_part, status, n, skip); }
+        launch_leaf(tile, G + (long long)L.blk * tile * ((long long)np + 1), np, X + (long long)L.blk * tile * ((long long)np + 1), np,
+                    L.blk * tile, logdet_part + L.blk, status, n, s, skip);
       } else if (L.is_leaf == OP_RECORD) {
         rt::event_record(events[L.ev], s);
       } else if (L.is_leaf == OP_WAIT) {

@@ -30,6 +30,9 @@ struct GemmProblem {
   int tile_base;    // first linear tile id of this problem inside the launch
   int ntiles;
   double alpha, beta;  // C = beta*C + alpha*acc   (beta in {0,1})
+  // Table mode (distributed block-cyclic sweeps): tile t uses element offsets
+  // table[3t] into A, table[3t+1] into B, table[3t+2] into C and the full k-range.
+  const long long* table;
 };
 
 constexpr int GEMM_BK = 16;
@@ -117,11 +120,16 @@ gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restr
   int pi = 0;
   const int bt = (int)blockIdx.x;
   while (pi + 1 < nprob && bt >= probs[pi + 1].tile_base) ++pi;
-  const GemmProblem P = probs[pi];
-  int I, J;
-  decode_tile(P.order, P.mt, P.nt, bt - P.tile_base, I, J);
-  int kbeg, kend;
-  tile_krange(P.kmode, P.K, TILE, I, J, kbeg, kend);
+  GemmProblem P = probs[pi];
+  int I = 0, J = 0;
+  int kbeg = 0, kend = P.K;
+  if (P.table) {
+    const long long* te = P.table + 3LL * (bt - P.tile_base);
+    P.A += te[0]; P.B += te[1]; P.C += te[2];
+  } else {
+    decode_tile(P.order, P.mt, P.nt, bt - P.tile_base, I, J);
+    tile_krange(P.kmode, P.K, TILE, I, J, kbeg, kend);
+  }
   const int nchunks = (kend - kbeg) / KC;
   const int i0 = I * TILE, j0 = J * TILE;
 
