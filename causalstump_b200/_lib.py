@@ -68,6 +68,12 @@ _SIGS = {
     "cs_predict": (C.c_int, [C.c_void_p, C.c_int, dp, dp, dp, dp, dp]),
     "cs_treat": (C.c_int, [C.c_void_p, C.c_int, dp, C.c_double, dp, dp, dp, dp, dp]),
     "cs_tp_sample": (C.c_int, [C.c_int, dp, C.c_double, C.c_int, C.c_ulonglong, dp, dp]),
+    "cs_dist_unique_id": (C.c_int, [C.c_char_p]),
+    "cs_dist_create": (C.c_int, [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_char_p, C.POINTER(C.c_void_p)]),
+    "cs_dist_eval": (C.c_int, [C.c_void_p, dp, dp, dp, dp, C.POINTER(C.c_float)]),
+    "cs_dist_destroy": (None, [C.c_void_p]),
+    "cs_dist_sim_eval": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]),
     "cs_fit_event_record": (C.c_int, [C.c_void_p, C.c_int]),
     "cs_fit_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "cs_fit_eval_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
@@ -178,6 +184,50 @@ class CsLib:
 
     def launch_count(self):
         return int(self.dll.cs_launch_count())
+
+    # -- config 5: distributed evaluation -------------------------------------------------
+    def dist_sim_eval(self, kind, y, X, z, w, params, P, Q, T=128):
+        """All P*Q ranks in this process (collectives = device copies)."""
+        y, z, params = _f64(y), _f64(z), _f64(params)
+        X = _f64(X if np.ndim(X) > 1 else np.asarray(X)[:, None])
+        n, p = X.shape
+        w = None if w is None else _f64(w)
+        g, st, mu = np.empty(len(params)), np.empty(2), C.c_double(0.0)
+        self.check(self.dll.cs_dist_sim_eval(kind, n, p, T, P, Q, _ptr(y), _ptr(X), _ptr(z), _ptr(w), _ptr(params),
+                                             _ptr(g), _ptr(st), C.cast(C.byref(mu), dp)))
+        return g, st, mu.value
+
+    def dist_unique_id(self):
+        buf = C.create_string_buffer(128)
+        self.check(self.dll.cs_dist_unique_id(buf))
+        return buf.raw
+
+
+class DistFit:
+    """One rank of the P x Q distributed evaluation (cs_dist, NCCL)."""
+
+    def __init__(self, lib: "CsLib", kind, y, X, z, w, params, rank, world, P, Q, unique_id):
+        self.lib = lib
+        y, z, params = _f64(y), _f64(z), _f64(params)
+        X = _f64(X if np.ndim(X) > 1 else np.asarray(X)[:, None])
+        n, p = X.shape
+        w = None if w is None else _f64(w)
+        self.nparam = len(params)
+        h = C.c_void_p(None)
+        lib.check(lib.dll.cs_dist_create(kind, n, p, _ptr(y), _ptr(X), _ptr(z), _ptr(w), _ptr(params), rank, world, P, Q,
+                                         unique_id, C.byref(h)))
+        self.h = h
+
+    def eval(self, params=None):
+        g, st, mu, ms = np.empty(self.nparam), np.empty(2), C.c_double(0.0), C.c_float(0.0)
+        pp = None if params is None else _f64(params)
+        self.lib.check(self.lib.dll.cs_dist_eval(self.h, _ptr(pp), _ptr(g), _ptr(st), C.cast(C.byref(mu), dp), C.byref(ms)))
+        return g, st, mu.value, ms.value
+
+    def close(self):
+        if self.h:
+            self.lib.dll.cs_dist_destroy(self.h)
+            self.h = C.c_void_p(None)
 
 
 class Fit:

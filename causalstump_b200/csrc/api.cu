@@ -11,6 +11,10 @@
 #include "dense.cuh"
 #include "kernels.cuh"
 #include "predict.cuh"
+#include "dist.cuh"
+#ifndef CS_EMU
+#include <dlfcn.h>
+#endif
 
 using csdense::DenseEngine;
 using csdense::g_launches;
@@ -208,7 +212,7 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
     ++g_launches;
     CS_LAUNCH(k, f->ncta_grad, csk::ETH, csk::grad_smem_bytes(p), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
               f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)nullptr,
-              (const double*)nullptr, (const double*)nullptr, skip);
+              (const double*)nullptr, (const double*)nullptr, skip, (const int*)nullptr);
   }
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
   {
@@ -966,12 +970,12 @@ static int grad_stats_common(int kind, int n, int p, const double* y, const doub
       auto k3 = csk::grad_trace_kernel<true>;
       CS_LAUNCH(k3, f->ncta_grad, csk::ETH, csk::grad_smem_bytes(p), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
                 f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)dK.d(), (const double*)dM.d(),
-                (const double*)dA.d(), (const int*)nullptr);
+                (const double*)dA.d(), (const int*)nullptr, (const int*)nullptr);
     } else {
       auto k3 = csk::grad_trace_kernel<false>;
       CS_LAUNCH(k3, f->ncta_grad, csk::ETH, csk::grad_smem_bytes(p), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
                 f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)nullptr,
-                (const double*)nullptr, (const double*)nullptr, (const int*)nullptr);
+                (const double*)nullptr, (const double*)nullptr, (const int*)nullptr, (const int*)nullptr);
     }
     auto k40 = csk::rowstats_kernel;
     ++g_launches;
@@ -1067,6 +1071,210 @@ int cs_opt_step(int optim, int nparam, double iter, double lr, double beta1, dou
   if (v) RT(rt::d2h(v, dv.p, b, st));
   RT(rt::d2h(para, dp.p, b, st));
   RT(rt::stream_sync(st));
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------
+// config 5: distributed evaluation over a P x Q process grid
+// ------------------------------------------------------------------------------------
+}  // extern "C" (reopened below)
+
+#ifndef CS_EMU
+// NCCL is resolved at run time (dlopen) so the library has no link-time dependency on it and
+// binds to whichever libnccl.so.2 the process already loaded (e.g. the one bundled with torch).
+struct NcclApi {
+  typedef struct { char internal[128]; } UniqueId;
+  typedef void* Comm_t;
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(Comm_t*, int, UniqueId, int) = nullptr;
+  int (*CommSplit)(Comm_t, int, int, Comm_t*, void*) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, Comm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, Comm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, Comm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(Comm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  void* h = nullptr;
+  bool load() {
+    if (h) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) return false;
+#define SYM(f, name) *(void**)(&f) = dlsym(h, name); if (!f) return false
+    SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommSplit, "ncclCommSplit");
+    SYM(Broadcast, "ncclBroadcast"); SYM(AllGather, "ncclAllGather"); SYM(AllReduce, "ncclAllReduce");
+    SYM(CommDestroy, "ncclCommDestroy"); SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return true;
+  }
+};
+static NcclApi g_nccl;
+enum { NCCL_DOUBLE = 8, NCCL_SUM = 0 };
+
+struct NcclComm : csdist::Comm {
+  NcclApi::Comm_t world = nullptr, row = nullptr, col = nullptr;
+  int err = 0;
+  int chk(int e) { if (e != 0 && err == 0) err = e; return e; }
+  int bcast(std::vector<csdist::DistRank*>& L, int group, int which, int root, const csdist::BufFn& buf, size_t count) override {
+    csdist::DistRank& R = *L[0];
+    const int mine = group == csdist::G_ROW ? R.g.pr : R.g.pc;
+    if (which >= 0 && which != mine) return 0;
+    const int gsize = group == csdist::G_ROW ? R.g.Q : R.g.P;
+    if (gsize == 1) return 0;
+    double* b = buf(R);
+    return chk(g_nccl.Broadcast(b, b, count, NCCL_DOUBLE, root, group == csdist::G_ROW ? row : col, R.st));
+  }
+  int allgather(std::vector<csdist::DistRank*>& L, int group, int which, const csdist::BufFn& send, const csdist::BufFn& recv,
+                size_t count) override {
+    csdist::DistRank& R = *L[0];
+    const int mine = group == csdist::G_ROW ? R.g.pr : R.g.pc;
+    if (which >= 0 && which != mine) return 0;
+    const int gsize = group == csdist::G_ROW ? R.g.Q : R.g.P;
+    if (gsize == 1) return rt::d2d(recv(R), send(R), sizeof(double) * count, R.st);
+    return chk(g_nccl.AllGather(send(R), recv(R), count, NCCL_DOUBLE, group == csdist::G_ROW ? row : col, R.st));
+  }
+  int allreduce_sum(std::vector<csdist::DistRank*>& L, const csdist::BufFn& buf, size_t) override {
+    csdist::DistRank& R = *L[0];
+    double* b = buf(R);
+    return chk(g_nccl.AllReduce(b, b, (size_t)R.red_len, NCCL_DOUBLE, NCCL_SUM, world, R.st));
+  }
+  ~NcclComm() override {
+    if (row) g_nccl.CommDestroy(row);
+    if (col) g_nccl.CommDestroy(col);
+    if (world) g_nccl.CommDestroy(world);
+  }
+};
+#endif
+
+struct cs_dist {
+  std::vector<csdist::DistRank*> ranks;  // 1 (NCCL) or P*Q (in-process)
+  std::unique_ptr<csdist::Comm> comm;
+  csdist::DistEval ev;
+  cudaEvent_t e0{}, e1{};
+  bool ev_ok = false;
+  ~cs_dist() {
+    for (auto* r : ranks) { r->destroy(); delete r; }
+    if (ev_ok) { rt::event_destroy(e0); rt::event_destroy(e1); }
+  }
+};
+
+static int dist_fetch(cs_dist* d, double* grad, double* stats, double* mu_solution) {
+  csdist::DistRank& R = *d->ranks[0];
+  csk::EvalScalars h{};
+  RT(rt::d2h(&h, R.sc, sizeof h, R.st));
+  if (grad) RT(rt::d2h(grad, R.grad, sizeof(double) * R.lay.np(), R.st));
+  int status = 0;
+  RT(rt::d2h(&status, R.status, sizeof(int), R.st));
+  RT(rt::stream_sync(R.st));
+  if (stats) { stats[0] = h.stats[0]; stats[1] = h.stats[1]; }
+  if (mu_solution) *mu_solution = h.mu_sol;
+  if (status != 0x7fffffff && status > 0)
+    return fail(status, "inv_sympd(): matrix is singular or not positive definite (pivot %d)", status);
+  return 0;
+}
+
+extern "C" {
+
+int cs_dist_unique_id(char* id128) {
+#ifdef CS_EMU
+  (void)id128;
+  return fail(CS_ERR_UNSUPPORTED, "NCCL is not available in the emulator build");
+#else
+  if (!id128) return fail(CS_ERR_ARG, "null id");
+  if (!g_nccl.load()) return fail(CS_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded: %s", dlerror());
+  NcclApi::UniqueId id;
+  int e = g_nccl.GetUniqueId(&id);
+  if (e) return fail(CS_ERR_CUDA, "ncclGetUniqueId: %s", g_nccl.GetErrorString(e));
+  std::memcpy(id128, id.internal, 128);
+  return 0;
+#endif
+}
+
+int cs_dist_create(int kind, int n, int p, const double* y, const double* X, const double* z, const double* w,
+                   const double* params, int rank, int world, int P, int Q, const char* id128, cs_dist** out) {
+#ifdef CS_EMU
+  (void)kind; (void)n; (void)p; (void)y; (void)X; (void)z; (void)w; (void)params; (void)rank; (void)world; (void)P; (void)Q; (void)id128; (void)out;
+  return fail(CS_ERR_UNSUPPORTED, "NCCL is not available in the emulator build");
+#else
+  if (!y || !X || !z || !params || !id128 || !out) return fail(CS_ERR_ARG, "cs_dist_create: null argument");
+  if (P * Q != world || rank < 0 || rank >= world) return fail(CS_ERR_ARG, "cs_dist_create: P*Q must equal world");
+  if (p > CS_MAX_P) return fail(CS_ERR_UNSUPPORTED, "p exceeds CS_MAX_P");
+  if (need_device()) return CS_ERR_NODEVICE;
+  if (!g_nccl.load()) return fail(CS_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+  std::unique_ptr<cs_dist> d(new cs_dist());
+  auto* nc = new NcclComm();
+  d->comm.reset(nc);
+  NcclApi::UniqueId id;
+  std::memcpy(id.internal, id128, 128);
+  int e = g_nccl.CommInitRank(&nc->world, world, id, rank);
+  if (e) return fail(CS_ERR_CUDA, "ncclCommInitRank: %s", g_nccl.GetErrorString(e));
+  const int pr = rank / Q, pc = rank % Q;
+  if ((e = g_nccl.CommSplit(nc->world, pr, pc, &nc->row, nullptr))) return fail(CS_ERR_CUDA, "ncclCommSplit(row): %s", g_nccl.GetErrorString(e));
+  if ((e = g_nccl.CommSplit(nc->world, pc, pr, &nc->col, nullptr))) return fail(CS_ERR_CUDA, "ncclCommSplit(col): %s", g_nccl.GetErrorString(e));
+  cudaStream_t st;
+  RT(rt::stream_create(&st));
+  auto* R = new csdist::DistRank();
+  d->ranks.push_back(R);
+  if ((e = csdist::rank_init(*R, n, p, kind, 128, P, Q, pr, pc, y, X, z, w, params, st, true)))
+    return fail(e == 2 ? CS_ERR_NOMEM : CS_ERR_CUDA, "distributed rank init failed: %s", rt::err_str(e));
+  d->ev.L = d->ranks; d->ev.comm = d->comm.get(); d->ev.T = 128; d->ev.N = R->g.N; d->ev.P = P; d->ev.Q = Q; d->ev.n = n;
+  RT(rt::event_create(&d->e0)); RT(rt::event_create(&d->e1)); d->ev_ok = true;
+  *out = d.release();
+  return 0;
+#endif
+}
+
+int cs_dist_eval(cs_dist* d, const double* params, double* grad, double* stats, double* mu_solution, float* ms) {
+  if (!d) return fail(CS_ERR_ARG, "null handle");
+  for (auto* R : d->ranks)
+    if (params) RT(rt::h2d(R->params, params, sizeof(double) * R->lay.np(), R->st));
+  cudaStream_t st = d->ranks[0]->st;
+  if (d->ev_ok) rt::event_record(d->e0, st);
+  int e = d->ev.run();
+  if (e) return fail(CS_ERR_CUDA, "distributed evaluation failed (%d): %s", e, rt::err_str(rt::last_error()));
+  if (d->ev_ok) rt::event_record(d->e1, st);
+  KCHECK();
+  e = dist_fetch(d, grad, stats, mu_solution);
+  if (ms && d->ev_ok) { *ms = 0.f; rt::event_elapsed(ms, d->e0, d->e1); }
+  return e;
+}
+
+void cs_dist_destroy(cs_dist* d) { delete d; }
+
+// All P*Q ranks inside this process (one device / the emulator), collectives as device
+// copies: exercises the identical driver, tables and kernels as the NCCL path.
+int cs_dist_sim_eval(int kind, int n, int p, int T, int P, int Q, const double* y, const double* X, const double* z,
+                     const double* w, const double* params, double* grad, double* stats, double* mu_solution) {
+  if (!y || !X || !z || !params || P < 1 || Q < 1 || (T != 64 && T != 128)) return fail(CS_ERR_ARG, "cs_dist_sim_eval: bad argument");
+  if (need_device()) return CS_ERR_NODEVICE;
+  cs_dist d;
+  d.comm.reset(new csdist::SimComm(P, Q));
+  cudaStream_t st = 0;
+  for (int pr = 0; pr < P; ++pr)
+    for (int pc = 0; pc < Q; ++pc) {
+      auto* R = new csdist::DistRank();
+      d.ranks.push_back(R);
+      if (int e = csdist::rank_init(*R, n, p, kind, T, P, Q, pr, pc, y, X, z, w, params, st, false))
+        return fail(e == 2 ? CS_ERR_NOMEM : CS_ERR_CUDA, "rank init failed: %s", rt::err_str(e));
+    }
+  d.ev.L = d.ranks; d.ev.comm = d.comm.get(); d.ev.T = T; d.ev.N = d.ranks[0]->g.N; d.ev.P = P; d.ev.Q = Q; d.ev.n = n;
+  int e = d.ev.run();
+  if (e) return fail(CS_ERR_CUDA, "simulated distributed evaluation failed (%d)", e);
+  KCHECK();
+  e = dist_fetch(&d, grad, stats, mu_solution);
+  if (e) return e;
+  // every rank must hold the same answer
+  const int NP = d.ranks[0]->lay.np();
+  std::vector<double> g0(NP), gi(NP);
+  RT(rt::d2h(g0.data(), d.ranks[0]->grad, sizeof(double) * NP, st));
+  RT(rt::stream_sync(st));
+  for (size_t r = 1; r < d.ranks.size(); ++r) {
+    RT(rt::d2h(gi.data(), d.ranks[r]->grad, sizeof(double) * NP, st));
+    RT(rt::stream_sync(st));
+    for (int i = 0; i < NP; ++i)
+      if (!(std::fabs(gi[i] - g0[i]) <= 1e-12 * (std::fabs(g0[i]) + 1e-300) + 1e-300))
+        return fail(CS_ERR_CUDA, "rank %d disagrees with rank 0 on gradient entry %d", (int)r, i);
+  }
   return 0;
 }
 

@@ -367,7 +367,7 @@ static int rank_init(DistRank& R, int n, int p, int kind, int T, int P, int Q, i
       for (int J = pc; J <= k; J += Q) {
         for (int I = pr; I < N; I += P) {
           if (I > k) sub_tiles(R.t_acc, cslot(I), T, false, rslot(J), T, true, g.off(I, J), false);
-          else if (I >= J) sub_tiles(R.t_c, rslot(I), T, true, rslot(J), T, true, g.off(I, J), I == J);
+          else if (I >= J) sub_tiles(R.t_c, rslot(I), T, true, rslot(J), T, true, g.off(I, J), false);  // diagonal tiles in full: symv reads them as symmetric
         }
       }
     }

@@ -303,7 +303,11 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
                   const double* __restrict__ Cinv, long long ldc, const double* __restrict__ alpha,
                   const EvalScalars* __restrict__ sc, double* __restrict__ gpart, double* __restrict__ kal_part,
                   long long kal_stride, const double* __restrict__ Kmat_in, const double* __restrict__ Km_in,
-                  const double* __restrict__ Ka_in, const int* __restrict__ skip) {
+                  const double* __restrict__ Ka_in, const int* __restrict__ skip,
+                  const int* __restrict__ tile_tab) {
+  // tile_tab != null (distributed mode): nblk is the number of table entries
+  // (I64, J64, coff_lo, coff_hi); Cinv + coff is the local 64 x 64 tile and K*alpha is
+  // accumulated into the vector kal_part with atomics (kal_stride is ignored).
   if (skip && *skip) return;
   CS_DYN_SMEM(double, sm_);
   const int p = lay.p;
@@ -326,13 +330,22 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
   if (tid < p) { ea[tid] = exp(-params[lay.i_Lm() + tid]); eb[tid] = exp(-params[lay.i_La() + tid]); }
   const double lam_m = params[lay.i_lm()], lam_a = params[lay.i_la()];
   const double coef = sc->coef;
-  const int ntiles = nblk * (nblk + 1) / 2;
+  const int ntiles = tile_tab ? nblk : nblk * (nblk + 1) / 2;
 
   for (int t = (int)blockIdx.x; t < ntiles; t += (int)gridDim.x) {
-    int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((long long)(I + 1) * (I + 2) / 2 <= t) ++I;
-    while ((long long)I * (I + 1) / 2 > t) --I;
-    const int J = t - I * (I + 1) / 2;
+    int I, J;
+    const double* Ct;
+    if (tile_tab) {
+      I = tile_tab[4 * t]; J = tile_tab[4 * t + 1];
+      const long long coff = (long long)(unsigned)tile_tab[4 * t + 2] | ((long long)tile_tab[4 * t + 3] << 32);
+      Ct = Cinv + coff;
+    } else {
+      I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+      while ((long long)(I + 1) * (I + 2) / 2 <= t) ++I;
+      while ((long long)I * (I + 1) / 2 > t) --I;
+      J = t - I * (I + 1) / 2;
+      Ct = Cinv + (long long)J * TB * ldc + (long long)I * TB;
+    }
     const int r0 = I * TB, c0 = J * TB;
     const double wgt = (I == J) ? 1.0 : 2.0;
     __syncthreads();  // previous tile fully consumed
@@ -361,7 +374,7 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
             vka = exp(lam_a - ka[a][b]) * zr[rl] * zc[cl];
             kfull = vkm + vka;
           }
-          T = Cinv[(long long)gc * ldc + gr] - coef * ar[rl] * ac[cl];
+          T = Ct[(long long)cl * ldc + rl] - coef * ar[rl] * ac[cl];
         }
         rs[a] = fma(kfull, ac[cl], rs[a]);
         cs[b] = fma(kfull, ar[rl], cs[b]);
@@ -417,8 +430,13 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
       double sacc = 0.0;
 #pragma unroll
       for (int w8 = 0; w8 < 8; ++w8) sacc += rred[w8 * TB + tid];
-      kal_part[(long long)J * kal_stride + r0 + tid] = sacc;
-      if (I != J) kal_part[(long long)I * kal_stride + c0 + tid] = csum[tid];
+      if (tile_tab) {
+        atomicAdd(kal_part + r0 + tid, sacc);
+        if (I != J) atomicAdd(kal_part + c0 + tid, csum[tid]);
+      } else {
+        kal_part[(long long)J * kal_stride + r0 + tid] = sacc;
+        if (I != J) kal_part[(long long)I * kal_stride + c0 + tid] = csum[tid];
+      }
     }
   }
   __syncthreads();
@@ -556,6 +574,15 @@ __global__ void loop_step_kernel(int optim, Layout lay, double lr, double b1, do
     if (it >= ls->maxiter) done = 1;
     if (done) { ls->iters = it; ls->done = 1; }
     ls->it = it + 1;
+  }
+}
+
+// out[k] = sum over CTAs of gpart[cta][k]  (distributed mode: feeds the all-reduce)
+__global__ void reduce_gpart_kernel(const double* __restrict__ gpart, int ncta, int nacc, double* __restrict__ out) {
+  for (int k = threadIdx.x; k < nacc; k += blockDim.x) {
+    double s = 0.0;
+    for (int c = 0; c < ncta; ++c) s += gpart[(long long)c * nacc + k];
+    out[k] = s;
   }
 }
 

@@ -161,6 +161,24 @@ int cs_treat(cs_fit* f, int n2, const double* X2, double cov_jitter, double* map
 int cs_tp_sample(int n2, const double* cov, double df, int nsampling, unsigned long long seed, double* U,
                  double* ate_U);
 
+/* ---- config 5: one large evaluation over a P x Q process grid (2-D block-cyclic tiles,
+ * NCCL panel broadcasts; no reference equivalent) --------------------- */
+typedef struct cs_dist cs_dist;
+/* rank 0 obtains a 128-byte NCCL unique id and ships it to the other ranks by any means */
+int cs_dist_unique_id(char* id128);
+/* collective: every rank passes the same data (X, y, z, w are replicated: n(p+3) doubles)
+ * and its own rank; world == P*Q, rank = pr*Q + pc. */
+int cs_dist_create(int kind, int n, int p, const double* y, const double* X, const double* z, const double* w,
+                   const double* params, int rank, int world, int P, int Q, const char* id128, cs_dist** out);
+/* collective: one LML + gradient evaluation; every rank receives the same outputs;
+ * *ms (nullable) = device time of this rank's stream for the evaluation. */
+int cs_dist_eval(cs_dist* d, const double* params, double* grad, double* stats, double* mu_solution, float* ms);
+void cs_dist_destroy(cs_dist* d);
+/* the same driver with all P*Q ranks inside the calling process (collectives = device
+ * copies): multi-rank algorithm test on one device.  T = 64 or 128 is the block size. */
+int cs_dist_sim_eval(int kind, int n, int p, int T, int P, int Q, const double* y, const double* X, const double* z,
+                     const double* w, const double* params, double* grad, double* stats, double* mu_solution);
+
 /* ---- measurement helpers (bench.py) -------------------------------------------- */
 /* CUDA events on the handle's stream; slots 0..15 */
 int cs_fit_event_record(cs_fit* f, int slot);

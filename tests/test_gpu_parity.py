@@ -184,3 +184,16 @@ def test_full_size_properties_n8192(gpulib):
     # in-sample prediction = y - exp(sigma) * alpha  =>  finite and close to y in the bulk
     assert np.isfinite(pr["map"]).all() and np.isfinite(pr["var"]).all() and (pr["var"] > 0).all()
     f.close()
+
+
+def test_distributed_driver_simulated_on_one_gpu(gpulib):
+    """Config 5 driver with all ranks of a 2 x 2 grid on this GPU (collectives = device copies);
+    the NCCL run over real ranks is tools/dist_check.py under torchrun."""
+    P = cs.make_problem("GP", 1000, 25, weights=True)
+    g, st, mu = o.eval_lml_grad("GP", P["y"], P["X"], P["z"], P["w"], P["par"])
+    for grid in ((2, 2), (2, 1)):
+        g2, st2, mu2 = gpulib.dist_sim_eval(0, P["y"], P["X"], P["z"], P["w"], o.pack_params(P["par"]), grid[0], grid[1], 128)
+        gref = o.pack_params(g)
+        assert np.max(np.abs(g2 - gref) / np.maximum(np.abs(gref), 1e-6 * np.max(np.abs(gref)))) < cs.TOL_GRAD
+        assert abs(st2[1] - st[1]) < cs.TOL_LML * abs(st[1])
+        assert abs(mu2 - mu) < 1e-8 * abs(mu)
