@@ -3,7 +3,7 @@
 large single fit (default n=32768, p=25).  Launch:
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-      tools/dist_check.py [--n 32768] [--steps 2] [--parity-n 1500]
+      tools/dist_check.py [--size 32768] [--steps 2] [--paritysize 1500]
 
 Rank 0 prints one JSON line.  Grid: N=1 1x1, 2 2x1, 4 2x2, 8 2x4."""
 import argparse
@@ -22,10 +22,10 @@ GRIDS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (2, 4)}
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=32768)
-    ap.add_argument("--p", type=int, default=25)
+    ap.add_argument("--size", type=int, default=32768)
+    ap.add_argument("--dims", type=int, default=25)
     ap.add_argument("--steps", type=int, default=2)
-    ap.add_argument("--parity-n", type=int, default=1500)
+    ap.add_argument("--paritysize", type=int, default=1500)
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -40,7 +40,7 @@ def main():
     P, Q = GRIDS[world]
 
     def make(n):
-        inp = bench.make_inputs(n, args.p, 0)
+        inp = bench.make_inputs(n, args.dims, 0)
         ids = [lib.dist_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         return inp, _lib.DistFit(lib, 0, inp["y"], inp["X"], inp["z"], inp["w"], inp["params"], rank, world, P, Q, ids[0])
@@ -48,15 +48,15 @@ def main():
     out = {"what": "config 5: distributed LML+gradient evaluation, 2-D block-cyclic over a %dx%d grid, NCCL" % (P, Q),
            "n_gpus": world}
     # ---- parity against the oracle (rank 0 computes the oracle) ----
-    if args.parity_n > 0:
-        inp, f = make(args.parity_n)
+    if args.paritysize > 0:
+        inp, f = make(args.paritysize)
         g, st, mu, _ = f.eval()
         f.close()
         if rank == 0:
             from oracle import causalstump_oracle as o
             go, sto, muo = o.eval_lml_grad("GP", inp["y"], inp["X"], inp["z"], inp["w"], inp["par"])
             gref = o.pack_params(go)
-            out["parity"] = {"n": args.parity_n,
+            out["parity"] = {"n": args.paritysize,
                              "grad_rel": float(np.max(np.abs(g - gref) / np.maximum(np.abs(gref), 1e-6 * np.max(np.abs(gref))))),
                              "lml_rel": float(abs(st[1] - sto[1]) / abs(sto[1])), "mu_rel": float(abs(mu - muo) / abs(muo))}
         gs = [None] * world
@@ -64,7 +64,7 @@ def main():
         if rank == 0:
             out["parity"]["ranks_agree"] = all(np.allclose(gs[0][0], x[0], rtol=1e-12, atol=0) for x in gs)
     # ---- timing of the large single fit ----
-    inp, f = make(args.n)
+    inp, f = make(args.size)
     f.eval()  # warm-up
     dist.barrier(); torch.cuda.synchronize(dev)
     ms = []
@@ -78,8 +78,8 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     f.close()
     if rank == 0:
-        n = args.n
-        out.update({"n": n, "p": args.p, "ms_per_eval_device_max": float(t[0]), "ms_per_eval_wall_max": float(t[1]),
+        n = args.size
+        out.update({"n": n, "p": args.dims, "ms_per_eval_device_max": float(t[0]), "ms_per_eval_wall_max": float(t[1]),
                     "evals_per_s": 1e3 / float(t[1]), "tflops_n3": float(n) ** 3 / (float(t[1]) * 1e-3) / 1e12,
                     "lml": float(st[1]), "finite": bool(np.isfinite(g).all() and np.isfinite(st).all())})
         print(json.dumps(out), flush=True)
