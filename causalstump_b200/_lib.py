@@ -60,6 +60,8 @@ _SIGS = {
     "cs_fit_sync": (C.c_int, [C.c_void_p]),
     "cs_fit_fetch": (C.c_int, [C.c_void_p, dp, dp, dp]),
     "cs_fit_run": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_int), dp]),
+    "cs_fit_run_many": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int),
+                                  C.POINTER(dp)]),
     "cs_fit_set_data": (C.c_int, [C.c_void_p, dp, dp, dp, dp]),
     "cs_fit_get_params": (C.c_int, [C.c_void_p, dp]),
     "cs_fit_set_params": (C.c_int, [C.c_void_p, dp]),
@@ -342,6 +344,18 @@ class Fit:
 
     def flush_l2(self):
         self.lib.check(self.lib.dll.cs_flush_l2(self.h))
+
+
+def run_many(fits, maxiter, tol):
+    """cs_fit_run_many: drive several Fit handles concurrently; returns [(iters, trace), ...]."""
+    lib = fits[0].lib
+    n = len(fits)
+    hs = (C.c_void_p * n)(*[f.h for f in fits])
+    iters = (C.c_int * n)()
+    traces = [np.zeros((2, maxiter + 2), order="F") for _ in fits]
+    tp = (dp * n)(*[_ptr(t) for t in traces])
+    lib.check(lib.dll.cs_fit_run_many(hs, n, int(maxiter), float(tol), iters, tp))
+    return [(int(iters[i]), traces[i][:, : int(iters[i]) + 2]) for i in range(n)]
 
 
 _default = None

@@ -152,6 +152,8 @@ struct cs_fit {
   rt::graph_exec_t iter_graph{};   // one captured optimizer iteration
   bool graph_ok = false, graph_tried = false;
   long long launches_per_iter = 0;
+  LoopState* h_ls = nullptr;  // pinned: loop state + status read-back
+  int run_maxiter = 0, run_launched = 0, run_chunk = 1;
   cudaEvent_t ev[16]{};
   bool ev_ok = false;
   std::vector<void*> allocs;
@@ -324,6 +326,7 @@ void cs_fit_destroy(cs_fit* f) {
   if (f->trace) rt::dev_free(f->trace);
   if (f->flush) rt::dev_free(f->flush);
   if (f->pinned) rt::host_free(f->pinned);
+  if (f->h_ls) rt::host_free(f->h_ls);
   if (f->graph_ok) rt::graph_destroy(f->iter_graph);
   f->eng.destroy();
   if (f->ev_ok) for (int i = 0; i < 16; ++i) rt::event_destroy(f->ev[i]);
@@ -355,6 +358,7 @@ int cs_fit_set_data(cs_fit* f, const double* y, const double* X, const double* z
   const size_t need = sizeof(double) * (size_t)n * (p + 3);
   if (f->pinned_bytes < need) {
     if (f->pinned) rt::host_free(f->pinned);
+  if (f->h_ls) rt::host_free(f->h_ls);
   if (f->graph_ok) rt::graph_destroy(f->iter_graph);
     f->pinned = nullptr;
     RT(rt::host_alloc((void**)&f->pinned, need));
@@ -424,9 +428,9 @@ int cs_fit_eval(cs_fit* f, const double* params, double* grad, double* stats, do
   return cs_fit_fetch(f, grad, stats, mu_solution);
 }
 
-int cs_fit_run(cs_fit* f, int maxiter, double tol, int* iters, double* stats_trace) {
-  if (!f) return fail(CS_ERR_ARG, "null handle");
-  if (maxiter < 1) return fail(CS_ERR_ARG, "cs_fit_run: maxiter must be >= 1");
+// ---- the loop of R/main.R:79-88 as begin / enqueue-chunk / poll / finish, so that several
+// ---- fits can be driven concurrently from one host thread (cs_fit_run_many)
+static int fit_run_begin(cs_fit* f, int maxiter, double tol) {
   cudaStream_t st = f->st;
   const int cap = 2 * (maxiter + 2);
   if (f->trace_cap < cap) {
@@ -438,69 +442,127 @@ int cs_fit_run(cs_fit* f, int maxiter, double tol, int* iters, double* stats_tra
     f->graph_tried = false;
   }
   RT(rt::memset0(f->trace, sizeof(double) * cap, st));
-  LoopState h{};
+  if (!f->h_ls) RT(rt::host_alloc((void**)&f->h_ls, sizeof(LoopState) + 16));
+  LoopState& h = *f->h_ls;
+  h = LoopState{};
   h.it = 1; h.done = 0; h.iters = 0; h.maxiter = maxiter; h.tol = tol; h.prev_lml = 0.0;  // stats[,1] = 0 (R/main.R:77)
   RT(rt::h2d(f->ls, &h, sizeof h, st));
-  int chunk = f->cfg.chunk;
-  if (chunk <= 0) {
+  RT(rt::stream_sync(st));
+  f->run_maxiter = maxiter;
+  f->run_launched = 0;
+  f->run_chunk = f->cfg.chunk;
+  if (f->run_chunk <= 0) {
     // keep each poll interval around a few milliseconds of device work
     const double flops = (double)f->np * f->np * f->np;
-    chunk = (int)std::max(1.0, std::min(64.0, 2.0e9 / std::max(flops, 1.0)));
+    f->run_chunk = (int)std::max(1.0, std::min(64.0, 2.0e9 / std::max(flops, 1.0)));
   }
-  auto enqueue_iteration = [&]() {
-    fit_enqueue_eval(f, &f->ls->done, nullptr);
-    auto k = csk::loop_step_kernel;
-    ++g_launches;
-    CS_LAUNCH(k, 1, 64, 0, st, f->cfg.optim, f->lay, f->cfg.lr, f->cfg.beta1, f->cfg.beta2, f->cfg.eps,
-              f->cfg.momentum, f->m, f->v, f->grad, f->params, f->sc, f->ls, f->trace);
-  };
   if (!f->graph_tried && f->cfg.use_graph >= 0) {
     f->graph_tried = true;
     const long long l0 = g_launches;
     if (rt::graph_begin(st) == 0) {
-      enqueue_iteration();
+      fit_enqueue_eval(f, &f->ls->done, nullptr);
+      auto k = csk::loop_step_kernel;
+      ++g_launches;
+      CS_LAUNCH(k, 1, 64, 0, st, f->cfg.optim, f->lay, f->cfg.lr, f->cfg.beta1, f->cfg.beta2, f->cfg.eps,
+                f->cfg.momentum, f->m, f->v, f->grad, f->params, f->sc, f->ls, f->trace);
       f->graph_ok = (rt::graph_end(st, &f->iter_graph) == 0);
       f->launches_per_iter = g_launches - l0;
       g_launches = l0;  // captured, not executed
     }
   }
-  int launched = 0;
-  while (launched < maxiter) {
-    const int todo = std::min(chunk, maxiter - launched);
-    for (int i = 0; i < todo; ++i) {
-      if (f->graph_ok) {
-        if (rt::graph_launch(f->iter_graph, st) != 0) return fail(CS_ERR_CUDA, "graph launch failed: %s", rt::err_str(rt::last_error()));
-        g_launches += f->launches_per_iter;
-      } else {
-        enqueue_iteration();
-      }
+  return 0;
+}
+
+// enqueue the next chunk of iterations and an asynchronous read-back of the loop state
+static int fit_run_enqueue(cs_fit* f) {
+  cudaStream_t st = f->st;
+  const int todo = std::min(f->run_chunk, f->run_maxiter - f->run_launched);
+  for (int i = 0; i < todo; ++i) {
+    if (f->graph_ok) {
+      if (rt::graph_launch(f->iter_graph, st) != 0)
+        return fail(CS_ERR_CUDA, "graph launch failed: %s", rt::err_str(rt::last_error()));
+      g_launches += f->launches_per_iter;
+    } else {
+      fit_enqueue_eval(f, &f->ls->done, nullptr);
+      auto k = csk::loop_step_kernel;
+      ++g_launches;
+      CS_LAUNCH(k, 1, 64, 0, st, f->cfg.optim, f->lay, f->cfg.lr, f->cfg.beta1, f->cfg.beta2, f->cfg.eps,
+                f->cfg.momentum, f->m, f->v, f->grad, f->params, f->sc, f->ls, f->trace);
     }
-    launched += todo;
-    KCHECK();
-    RT(rt::d2h(&h, f->ls, sizeof h, st));
-    RT(rt::stream_sync(st));
-    int stt = 0;
-    RT(rt::d2h(&stt, f->eng.status, sizeof(int), st));
-    RT(rt::stream_sync(st));
-    if (stt != 0x7fffffff && stt > 0)
-      return fail(stt, "inv_sympd(): matrix is singular or not positive definite (pivot %d) at iteration %d", stt,
-                  h.it - 1);
-    if (h.done) break;
   }
-  const int it = h.done ? h.iters : maxiter;
+  f->run_launched += todo;
+  KCHECK();
+  RT(rt::d2h(f->h_ls, f->ls, sizeof(LoopState), st));
+  RT(rt::d2h(reinterpret_cast<char*>(f->h_ls) + sizeof(LoopState), f->eng.status, sizeof(int), st));
+  return 0;
+}
+
+// wait for the chunk; returns 1 when the loop has finished, 0 to continue, <0 / >0 on error
+static int fit_run_poll(cs_fit* f, int* finished) {
+  RT(rt::stream_sync(f->st));
+  int stt = 0;
+  std::memcpy(&stt, reinterpret_cast<char*>(f->h_ls) + sizeof(LoopState), sizeof(int));
+  if (stt != 0x7fffffff && stt > 0)
+    return fail(stt, "inv_sympd(): matrix is singular or not positive definite (pivot %d) at iteration %d", stt,
+                f->h_ls->it - 1);
+  *finished = (f->h_ls->done || f->run_launched >= f->run_maxiter) ? 1 : 0;
+  return 0;
+}
+
+static int fit_run_finish_enqueue(cs_fit* f) {
   // final get_train_stats with the final parameters (R/main.R:88)
   fit_enqueue_eval(f, nullptr, nullptr);
   KCHECK();
+  return 0;
+}
+
+static int fit_run_finish_fetch(cs_fit* f, int* iters, double* stats_trace) {
+  const int it = f->h_ls->done ? f->h_ls->iters : f->run_maxiter;
   double st2[2];
   int e = cs_fit_fetch(f, nullptr, st2, nullptr);
   if (e) return e;
   if (iters) *iters = it;
   if (stats_trace) {
-    RT(rt::d2h(stats_trace, f->trace, sizeof(double) * cap, st));
-    RT(rt::stream_sync(st));
+    const int cap = 2 * (f->run_maxiter + 2);
+    RT(rt::d2h(stats_trace, f->trace, sizeof(double) * cap, f->st));
+    RT(rt::stream_sync(f->st));
     stats_trace[2 * (it + 1) + 0] = st2[0];
     stats_trace[2 * (it + 1) + 1] = st2[1];
   }
+  return 0;
+}
+
+int cs_fit_run(cs_fit* f, int maxiter, double tol, int* iters, double* stats_trace) {
+  if (!f) return fail(CS_ERR_ARG, "null handle");
+  if (maxiter < 1) return fail(CS_ERR_ARG, "cs_fit_run: maxiter must be >= 1");
+  int e = fit_run_begin(f, maxiter, tol);
+  if (e) return e;
+  for (int fin = 0; !fin;) {
+    if ((e = fit_run_enqueue(f))) return e;
+    if ((e = fit_run_poll(f, &fin))) return e;
+  }
+  if ((e = fit_run_finish_enqueue(f))) return e;
+  return fit_run_finish_fetch(f, iters, stats_trace);
+}
+
+int cs_fit_run_many(cs_fit** fits, int nfits, int maxiter, double tol, int* iters, double** stats_traces) {
+  if (!fits || nfits < 1 || maxiter < 1) return fail(CS_ERR_ARG, "cs_fit_run_many: bad argument");
+  for (int i = 0; i < nfits; ++i) if (!fits[i]) return fail(CS_ERR_ARG, "cs_fit_run_many: null handle");
+  int e;
+  for (int i = 0; i < nfits; ++i) if ((e = fit_run_begin(fits[i], maxiter, tol))) return e;
+  std::vector<int> active(nfits, 1);
+  int nactive = nfits;
+  while (nactive > 0) {
+    for (int i = 0; i < nfits; ++i) if (active[i]) { if ((e = fit_run_enqueue(fits[i]))) return e; }
+    for (int i = 0; i < nfits; ++i)
+      if (active[i]) {
+        int fin = 0;
+        if ((e = fit_run_poll(fits[i], &fin))) return e;
+        if (fin) { active[i] = 0; --nactive; if ((e = fit_run_finish_enqueue(fits[i]))) return e; }
+      }
+  }
+  for (int i = 0; i < nfits; ++i)
+    if ((e = fit_run_finish_fetch(fits[i], iters ? iters + i : nullptr, stats_traces ? stats_traces[i] : nullptr))) return e;
   return 0;
 }
 

@@ -306,9 +306,20 @@ struct DenseEngine {
         if (m <= 0) continue;
         double* panel = G + (k + 1) * T + k * T * ld;
         // L21 = A21 * X_kk^T   (NT, in place)
-        grp.push_back(mk(panel, ld, X + k * T * (ld + 1), ld, panel, ld, m, 1, tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
-        add_group(potrf, GK_NT, grp);
-        potrf.back().gtile = tile;  // in place: each CTA owns a full block row of the panel
+        if (rr == 2) {
+          // in place with 64 x 64 CTA tiles: X_kk is lower triangular, so output columns 64..127 need
+          // all input columns but output columns 0..63 only input columns 0..63 -- do the right half
+          // first (reads everything, writes the right half), then the left half with K = 64.
+          double* Xkk = X + k * T * (ld + 1);
+          grp.push_back(mk(panel, ld, Xkk + gt, ld, panel + gt * ld, ld, m * rr, 1, tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
+          add_group(potrf, GK_NT, grp);
+          grp.push_back(mk(panel, ld, Xkk, ld, panel, ld, m * rr, 1, gt, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
+          add_group(potrf, GK_NT, grp);
+        } else {
+          grp.push_back(mk(panel, ld, X + k * T * (ld + 1), ld, panel, ld, m, 1, tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
+          add_group(potrf, GK_NT, grp);
+          potrf.back().gtile = tile;  // in place: each CTA owns a full block row of the panel
+        }
         // inner update: columns k+1 .. p1-1 of the current panel (lower part + rectangle below)
         const int nc = p1 - 1 - k;
         if (nc > 0) {

@@ -130,6 +130,10 @@ int cs_fit_fetch(cs_fit* f, double* grad, double* stats, double* mu_solution);
  * iter > 3), then the final get_train_stats.  stats_trace (nullable) is 2 x (maxiter+2)
  * column-major like `stats` in R/main.R:77; *iters receives the last iteration run. */
 int cs_fit_run(cs_fit* f, int maxiter, double tol, int* iters, double* stats_trace);
+/* The same loop for several independent fits at once (replicates x restarts of config 4):
+ * their iterations are interleaved on separate streams so the small kernels of one fit
+ * fill the SMs another leaves idle.  iters[nfits]; stats_traces[i] nullable. */
+int cs_fit_run_many(cs_fit** fits, int nfits, int maxiter, double tol, int* iters, double** stats_traces);
 
 /* Replace the training data of an existing handle (same n, p): one pinned-staged
  * host->device copy of y, X, z, w (w NULL = ones). */
