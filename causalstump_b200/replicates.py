@@ -48,6 +48,51 @@ def hill_unit(replicate, restart, n=747, p=25, test_frac=0.1, maxiter=3000, tol=
                 e_ate_train=float(np.mean(tau[train]) - t_tr["ate"]), e_ate_test=float(np.mean(tau[test]) - t_te["ate"]))
 
 
+def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1e-1, lr=0.01, prior=False, nu=2000):
+    """The same fits as `hill_unit`, but all `units` = [(replicate, restart), ...] are optimised
+    concurrently on this GPU (cs_fit_run_many: one stream pair per fit), which is how the small
+    n ~ 700 fits fill a B200.  Returns one result dict per unit."""
+    import math as _m
+    from . import _lib, hill, main as M, rcpp_exports as rx
+    lib = rx.lib()
+    prep, fits = [], []
+    for replicate, restart in units:
+        d = hill.hill_surface_b(n=n, p=p, replicate=replicate)
+        rng = np.random.default_rng(565 + 5 * replicate)
+        ntest = int(_m.ceil(n * test_frac))
+        test = np.sort(rng.choice(n, ntest, replace=False))
+        train = np.setdiff1d(np.arange(n), test)
+        nr = M.norm_variables(d["y"][train], d["X"][train])
+        y, X, z = np.ascontiguousarray(nr["y"]), np.asfortranarray(nr["X"]), np.ascontiguousarray(d["z"][train])
+        K = M.KernelClass_TP_SE(p, np.ones(len(y))) if prior else M.KernelClass_GP_SE(p, np.ones(len(y)))
+        draws = hill.restart_draws(replicate, restart, prior)
+        if prior:
+            K.parainit(y, nu, draws)
+        else:
+            K.parainit(y, draws)
+        f = _lib.Fit(lib, K.kind, y, X, z, None, rx.pack(K.parameters), optim=_lib.CS_OPT_NADAM, lr=lr)
+        fits.append(f)
+        prep.append((d, nr["moments"], train, test, replicate, restart))
+    res = _lib.run_many(fits, maxiter, tol)
+    out = []
+    for (d, mom, train, test, replicate, restart), f, (iters, trace) in zip(prep, fits, res):
+        sd = _m.sqrt(mom["varY"])
+        Xall = M.norm_variables(X=d["X"], moments=mom)["X"]
+        pred = f.predict(Xall, d["z"])["map"] * sd + mom["meanY"]
+        t_tr = f.treat(Xall[train])
+        t_te = f.treat(Xall[test])
+        tau = d["tau"]
+        out.append(dict(replicate=replicate, restart=restart, iters=int(iters), lml=float(trace[1, -1]),
+                        pehe_train=float(np.sqrt(np.mean((tau[train] - sd * t_tr["map"]) ** 2))),
+                        pehe_test=float(np.sqrt(np.mean((tau[test] - sd * t_te["map"]) ** 2))),
+                        rmse_train=float(np.sqrt(np.mean((d["y"][train] - pred[train]) ** 2))),
+                        rmse_test=float(np.sqrt(np.mean((d["y"][test] - pred[test]) ** 2))),
+                        e_ate_train=float(np.mean(tau[train]) - sd * t_tr["ate"]),
+                        e_ate_test=float(np.mean(tau[test]) - sd * t_te["ate"])))
+        f.close()
+    return out
+
+
 def select_winners(results):
     """Best restart (highest final LML) per replicate, ordered by replicate."""
     best = {}
