@@ -79,6 +79,7 @@ _SIGS = {
     "cs_fit_event_record": (C.c_int, [C.c_void_p, C.c_int]),
     "cs_fit_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "cs_fit_eval_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "cs_debug_check_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "cs_launch_count": (C.c_longlong, []),
     "cs_flush_l2": (C.c_int, [C.c_void_p]),
 }

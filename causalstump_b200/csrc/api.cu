@@ -593,6 +593,17 @@ int cs_fit_get_matrices(cs_fit* f, double* Kmat, double* Km, double* Ka, double*
   return 0;
 }
 
+// test hook: verifies that the multi-stream Cholesky plan of an n x n engine has no unordered
+// conflicting launches (returns the number of races found; 0 = clean)
+int cs_debug_check_plan(int n, int tile, int gemm_tile, int verbose) {
+  if (need_device()) return CS_ERR_NODEVICE;
+  DenseEngine eng;
+  if (int e = eng.init(n, tile ? tile : csdense::pick_tile(n), gemm_tile)) { eng.destroy(); return fail(CS_ERR_CUDA, "engine init failed (%d)", e); }
+  const int bad = eng.check_plan(eng.potrf, verbose);
+  eng.destroy();
+  return bad;
+}
+
 int cs_fit_event_record(cs_fit* f, int slot) {
   if (!f || slot < 0 || slot >= 16) return fail(CS_ERR_ARG, "bad event slot");
   RT(rt::event_record(f->ev[slot], f->st));

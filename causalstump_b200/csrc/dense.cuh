@@ -242,8 +242,8 @@ struct DenseEngine {
   int panel_blocks = 4;             // outer panel width in blocks
   int n_events = 0;
   std::vector<cudaEvent_t> events;
-  cudaStream_t aux{};
-  bool aux_ok = false;
+  cudaStream_t aux{}, aux2{};       // S1: bulk trailing updates (low priority); S2: panel rest (high)
+  bool aux_ok = false, aux2_ok = false;
 
   static GemmProblem mk(const double* A, long long lda, const double* B, long long ldb, double* C, long long ldc,
                         int mt, int nt, int K, int kmode, int order, int mirror, double alpha, double beta) {
@@ -291,73 +291,104 @@ struct DenseEngine {
     const long long ld = np;
     const long long T = tile;
     std::vector<GemmProblem> grp;
-    // --- two-level blocked right-looking Cholesky with one-panel look-ahead ---
-    // Outer panels of W blocks.  Inside a panel: leaf -> panel multiply -> update of the
-    // panel's remaining columns (k = TILE).  After a panel: trailing update with
-    // k = W*TILE, split into U1 (the next panel's columns, main stream) and U2 (the rest,
-    // auxiliary stream) so the next panel's latency-bound chain overlaps the bulk update.
+    // --- two-level blocked right-looking Cholesky, three streams ---
+    // Outer panels of W blocks.  Inside a panel, step k is split into a *critical* part on the
+    // main stream S0 -- leaf(k), the panel multiply of block row k+1 only, the update of the
+    // next diagonal tile -- and the *rest* (panel rows >= k+2, remaining inner updates) on the
+    // panel stream S2, which runs while S0 is already inside leaf(k+1).  After a panel the
+    // trailing update (k = W*TILE) is split into U1 (next panel's columns, S0) and U2 (the
+    // rest, bulk stream S1).  Dependencies are events; the whole sequence is graph-capturable.
     const int W = panel_blocks;
-    int npanel = 0, last_aux_ev = -1;
+    int npanel = 0, last_aux_ev = -1, nev = 0;
+    auto op = [&](int type, int stream, int ev) { Launch o{}; o.is_leaf = type; o.stream = stream; o.ev = ev; potrf.push_back(o); };
+    // in-place panel multiply L = A * X_kk^T for `nb` block rows starting at block row r0 of column k
+    auto push_panel = [&](int k, int r0, int nb, int stream) {
+      if (nb <= 0) return;
+      double* pan = G + (long long)r0 * T + (long long)k * T * ld;
+      double* Xkk = X + (long long)k * T * (ld + 1);
+      if (rr == 2) {
+        // 64 x 64 CTA tiles: X_kk is lower triangular, so output columns 64..127 need all input
+        // columns but output columns 0..63 only input columns 0..63: right half first, then the
+        // left half with K = 64 (each launch is in-place safe per CTA).
+        grp.push_back(mk(pan, ld, Xkk + gt, ld, pan + gt * ld, ld, nb * rr, 1, tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
+        add_group(potrf, GK_NT, grp); potrf.back().stream = stream;
+        grp.push_back(mk(pan, ld, Xkk, ld, pan, ld, nb * rr, 1, gt, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
+        add_group(potrf, GK_NT, grp); potrf.back().stream = stream;
+      } else {
+        grp.push_back(mk(pan, ld, Xkk, ld, pan, ld, nb, 1, tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
+        add_group(potrf, GK_NT, grp); potrf.back().stream = stream; potrf.back().gtile = tile;
+      }
+    };
     for (int p0 = 0; p0 < N; p0 += W, ++npanel) {
       const int p1 = std::min(p0 + W, N);
+      int ev_rest_prev = -1;
       for (int k = p0; k < p1; ++k) {
-        Launch L{}; L.is_leaf = OP_LEAF; L.blk = k; potrf.push_back(L);
-        const int m = N - k - 1;
+        { Launch L{}; L.is_leaf = OP_LEAF; L.blk = k; potrf.push_back(L); }
+        const int m = N - k - 1;          // block rows below k
         if (m <= 0) continue;
-        double* panel = G + (k + 1) * T + k * T * ld;
-        // L21 = A21 * X_kk^T   (NT, in place)
-        if (rr == 2) {
-          // in place with 64 x 64 CTA tiles: X_kk is lower triangular, so output columns 64..127 need
-          // all input columns but output columns 0..63 only input columns 0..63 -- do the right half
-          // first (reads everything, writes the right half), then the left half with K = 64.
-          double* Xkk = X + k * T * (ld + 1);
-          grp.push_back(mk(panel, ld, Xkk + gt, ld, panel + gt * ld, ld, m * rr, 1, tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
-          add_group(potrf, GK_NT, grp);
-          grp.push_back(mk(panel, ld, Xkk, ld, panel, ld, m * rr, 1, gt, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
-          add_group(potrf, GK_NT, grp);
-        } else {
-          grp.push_back(mk(panel, ld, X + k * T * (ld + 1), ld, panel, ld, m, 1, tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
-          add_group(potrf, GK_NT, grp);
-          potrf.back().gtile = tile;  // in place: each CTA owns a full block row of the panel
-        }
-        // inner update: columns k+1 .. p1-1 of the current panel (lower part + rectangle below)
-        const int nc = p1 - 1 - k;
+        const int ev_leaf = nev++, ev_pp = nev++, ev_rest = nev++;
+        op(OP_RECORD, 0, ev_leaf);
+        // ---- critical part (S0): block row k+1 ----
+        if (ev_rest_prev >= 0) op(OP_WAIT, 0, ev_rest_prev);  // tile (k+1,k) carries the rest-updates of step k-1
+        push_panel(k, k + 1, 1, 0);
+        op(OP_RECORD, 0, ev_pp);
+        const int nc = p1 - 1 - k;        // block columns k+1 .. p1-1 still inside this panel
+        double* row1 = G + (k + 1) * T + k * T * ld;  // L_{k+1,k}
         if (nc > 0) {
-          grp.push_back(mk(panel, ld, panel, ld, G + (k + 1) * T * (ld + 1), ld, nc * rr, nc * rr, tile, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
-          const int mr = N - p1;
-          if (mr > 0)
-            grp.push_back(mk(G + p1 * T + k * T * ld, ld, panel, ld, G + p1 * T + (k + 1) * T * ld, ld, mr * rr, nc * rr, tile,
-                             csg::KM_FULL, csg::ORD_COL, 0, -1.0, 1.0));
+          grp.push_back(mk(row1, ld, row1, ld, G + (k + 1) * T * (ld + 1), ld, rr, rr, tile, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
           add_group(potrf, GK_NT, grp);
         }
+        // ---- rest (S2): block rows >= k+2 ----
+        op(OP_WAIT, 2, ev_leaf);
+        push_panel(k, k + 2, m - 1, 2);
+        if (nc > 0) {
+          op(OP_WAIT, 2, ev_pp);
+          double* row2 = G + (k + 2) * T + k * T * ld;  // L_{k+2..,k}
+          const int mr = N - p1;
+          if (nc >= 2) {
+            // rows k+2..p1-1 x column k+1, and the lower part of rows/cols k+2..p1-1
+            grp.push_back(mk(row2, ld, row1, ld, G + (k + 2) * T + (k + 1) * T * ld, ld, (nc - 1) * rr, rr, tile, csg::KM_FULL,
+                             csg::ORD_COL, 0, -1.0, 1.0));
+            grp.push_back(mk(row2, ld, row2, ld, G + (k + 2) * T * (ld + 1), ld, (nc - 1) * rr, (nc - 1) * rr, tile, csg::KM_FULL,
+                             csg::ORD_LOWER, 0, -1.0, 1.0));
+          }
+          if (mr > 0)
+            grp.push_back(mk(G + p1 * T + k * T * ld, ld, row1, ld, G + p1 * T + (k + 1) * T * ld, ld, mr * rr, nc * rr, tile,
+                             csg::KM_FULL, csg::ORD_COL, 0, -1.0, 1.0));
+          if (!grp.empty()) { add_group(potrf, GK_NT, grp); potrf.back().stream = 2; }
+        }
+        op(OP_RECORD, 2, ev_rest);
+        ev_rest_prev = ev_rest;
       }
+      if (ev_rest_prev >= 0) op(OP_WAIT, 0, ev_rest_prev);  // S0 rejoins S2: the panel is complete
       const int mt = N - p1;  // trailing blocks
       if (mt <= 0) continue;
       const int kw = (p1 - p0) * tile;
       double* pan = G + p1 * T + p0 * T * ld;  // rows >= p1 of the finished panel
       const int n1 = std::min(W, mt);          // next panel's block columns
-      { Launch R{}; R.is_leaf = OP_RECORD; R.stream = 0; R.ev = 2 * npanel; potrf.push_back(R); }
-      if (npanel > 0) { Launch Wt{}; Wt.is_leaf = OP_WAIT; Wt.stream = 0; Wt.ev = 2 * (npanel - 1) + 1; potrf.push_back(Wt); }
-      // U1: columns [p1, p1+n1): lower part + rectangle below (main stream)
+      const int ev_panel = nev++, ev_u2 = nev++;
+      op(OP_RECORD, 0, ev_panel);
+      if (last_aux_ev >= 0) op(OP_WAIT, 0, last_aux_ev);  // U2 of the previous panel also wrote these columns
+      // U1: columns [p1, p1+n1): lower part + rectangle below (S0)
       grp.push_back(mk(pan, ld, pan, ld, G + p1 * T * (ld + 1), ld, n1 * rr, n1 * rr, kw, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
       if (mt > n1)
         grp.push_back(mk(pan + n1 * T, ld, pan, ld, G + (p1 + n1) * T + p1 * T * ld, ld, (mt - n1) * rr, n1 * rr, kw, csg::KM_FULL,
                          csg::ORD_COL, 0, -1.0, 1.0));
       add_group(potrf, GK_NT, grp);
-      // U2: everything to the right of the next panel (auxiliary stream)
+      // U2: everything to the right of the next panel (bulk stream S1)
+      op(OP_WAIT, 1, ev_panel);
       if (mt > n1) {
-        { Launch Wt{}; Wt.is_leaf = OP_WAIT; Wt.stream = 1; Wt.ev = 2 * npanel; potrf.push_back(Wt); }
         grp.push_back(mk(pan + n1 * T, ld, pan + n1 * T, ld, G + (p1 + n1) * T * (ld + 1), ld, (mt - n1) * rr, (mt - n1) * rr, kw,
                          csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
         add_group(potrf, GK_NT, grp);
         potrf.back().stream = 1;
       }
-      { Launch R{}; R.is_leaf = OP_RECORD; R.stream = 1; R.ev = 2 * npanel + 1; potrf.push_back(R); }
-      last_aux_ev = 2 * npanel + 1;
+      op(OP_RECORD, 1, ev_u2);
+      last_aux_ev = ev_u2;
     }
-    // the main stream rejoins the auxiliary stream before anything reads the factor
-    if (last_aux_ev >= 0) { Launch Wt{}; Wt.is_leaf = OP_WAIT; Wt.stream = 0; Wt.ev = last_aux_ev; potrf.push_back(Wt); }
-    n_events = 2 * npanel + 2;
+    // the main stream rejoins the bulk stream before anything reads the factor
+    if (last_aux_ev >= 0) op(OP_WAIT, 0, last_aux_ev);
+    n_events = nev + 1;
     // --- recursive triangular inverse, batched by tree height ---
     std::vector<Node> nodes;
     const int hmax = build_tree(0, N, nodes);
@@ -383,6 +414,8 @@ struct DenseEngine {
 
     if ((e = rt::stream_create_low(&aux))) return e;
     aux_ok = true;
+    if ((e = rt::stream_create(&aux2))) return e;
+    aux2_ok = true;
     events.resize(n_events);
     for (int i = 0; i < n_events; ++i)
       if ((e = rt::event_create_fast(&events[i]))) return e;
@@ -398,12 +431,13 @@ struct DenseEngine {
     for (auto& ev : events) rt::event_destroy(ev);
     events.clear();
     if (aux_ok) { rt::stream_sync(aux); rt::stream_destroy(aux); aux_ok = false; }
+    if (aux2_ok) { rt::stream_sync(aux2); rt::stream_destroy(aux2); aux2_ok = false; }
     G = X = C = logdet_part = nullptr; status = nullptr; d_probs = nullptr;
   }
 
   void run_seq(const std::vector<Launch>& seq, cudaStream_t st, const int* skip = nullptr) {
     for (const Launch& L : seq) {
-      cudaStream_t s = L.stream ? aux : st;
+      cudaStream_t s = L.stream == 1 ? aux : (L.stream == 2 ? aux2 : st);
       if (L.is_leaf == OP_LEAF) {
         launch_leaf(tile, G + (long long)L.blk * tile * ((long long)np + 1), np, X + (long long)L.blk * tile * ((long long)np + 1), np,
                     L.blk * tile, logdet_part + L.blk, status, n, s, skip);
@@ -415,6 +449,83 @@ struct DenseEngine {
         launch_gemm(L.gtile ? L.gtile : gt, L.kind, d_probs + L.first_prob, L.nprob, L.ntiles, s, skip);
       }
     }
+  }
+
+  // ---- plan race detector (host only) ---------------------------------------------------
+  // The Cholesky plan spreads its launches over three streams ordered by events.  This
+  // check rebuilds the happens-before relation of the op list (stream order + record/wait
+  // edges) and verifies that every pair of launches touching overlapping regions of G / X / C
+  // with at least one write is ordered.  Returns the number of unordered conflicting pairs.
+  struct Rect { int buf; long long r0, r1, c0, c1; bool write; };
+  void rect_of(const double* ptr, long long rows, long long cols, bool write, std::vector<Rect>& out) const {
+    const double* bases[3] = {G, X, C};
+    for (int b = 0; b < 3; ++b) {
+      const long long off = ptr - bases[b];
+      if (off >= 0 && off < (long long)np * np) {
+        out.push_back(Rect{b, off % np, off % np + rows, off / np, off / np + cols, write});
+        return;
+      }
+    }
+  }
+  void footprint(const Launch& L, std::vector<Rect>& out) const {
+    out.clear();
+    if (L.is_leaf == OP_LEAF) {
+      const long long o = (long long)L.blk * tile;
+      out.push_back(Rect{0, o, o + tile, o, o + tile, true});
+      out.push_back(Rect{1, o, o + tile, o, o + tile, true});
+      return;
+    }
+    if (L.is_leaf != OP_GEMM) return;
+    const int t = L.gtile ? L.gtile : gt;
+    for (int i = 0; i < L.nprob; ++i) {
+      const GemmProblem& P = probs[L.first_prob + i];
+      const long long M = (long long)P.mt * t, Nn = (long long)P.nt * t, K = P.K;
+      const bool ak = (L.kind == GK_TN), bk = (L.kind != GK_NT);
+      if (ak) rect_of(P.A, K, M, false, out); else rect_of(P.A, M, K, false, out);
+      if (bk) rect_of(P.B, K, Nn, false, out); else rect_of(P.B, Nn, K, false, out);
+      rect_of(P.C, M, Nn, true, out);
+      if (P.mirror) rect_of(P.C, Nn, M, true, out);
+    }
+  }
+  int check_plan(const std::vector<Launch>& seq, int verbose) const {
+    const int n_ops = (int)seq.size();
+    const int words = (n_ops + 63) / 64;
+    std::vector<std::vector<unsigned long long>> anc(n_ops, std::vector<unsigned long long>(words, 0ULL));
+    int last_on_stream[3] = {-1, -1, -1};
+    std::vector<int> last_record(n_events + 1, -1);
+    auto add_pred = [&](int j, int i) {
+      if (i < 0) return;
+      for (int w = 0; w < words; ++w) anc[j][w] |= anc[i][w];
+      anc[j][i / 64] |= 1ULL << (i % 64);
+    };
+    for (int j = 0; j < n_ops; ++j) {
+      const Launch& L = seq[j];
+      add_pred(j, last_on_stream[L.stream]);
+      if (L.is_leaf == OP_WAIT) add_pred(j, last_record[L.ev]);
+      if (L.is_leaf == OP_RECORD) last_record[L.ev] = j;
+      last_on_stream[L.stream] = j;
+    }
+    std::vector<std::vector<Rect>> fp(n_ops);
+    for (int j = 0; j < n_ops; ++j) footprint(seq[j], fp[j]);
+    int bad = 0;
+    for (int j = 0; j < n_ops; ++j)
+      for (int i = 0; i < j; ++i) {
+        if (fp[i].empty() || fp[j].empty()) continue;
+        if (anc[j][i / 64] >> (i % 64) & 1ULL) continue;  // ordered
+        bool conflict = false;
+        for (const Rect& a : fp[i]) {
+          for (const Rect& b : fp[j])
+            if (a.buf == b.buf && (a.write || b.write) && a.r0 < b.r1 && b.r0 < a.r1 && a.c0 < b.c1 && b.c0 < a.c1) { conflict = true; break; }
+          if (conflict) break;
+        }
+        if (conflict) {
+          if (verbose && bad < 10)
+            std::fprintf(stderr, "plan race: op %d (stream %d, type %d, blk %d) vs op %d (stream %d, type %d, blk %d)\n", i,
+                         seq[i].stream, seq[i].is_leaf, seq[i].blk, j, seq[j].stream, seq[j].is_leaf, seq[j].blk);
+          ++bad;
+        }
+      }
+    return bad;
   }
 
   // G (lower) must hold K_n; X and the upper triangle of G must be zero outside diagonal tiles.

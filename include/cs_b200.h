@@ -192,6 +192,8 @@ int cs_fit_event_elapsed_ms(cs_fit* f, int slot_a, int slot_b, float* ms);
 int cs_fit_eval_profile(cs_fit* f, float phase_ms[CS_NPHASE]);
 /* kernels launched by this library since load (claimed launch count for bench.py) */
 long long cs_launch_count(void);
+/* test hook: happens-before check of the multi-stream Cholesky launch plan (0 = no races) */
+int cs_debug_check_plan(int n, int tile, int gemm_tile, int verbose);
 /* write `bytes` of device memory (> L2) to flush the cache between timed iterations */
 int cs_flush_l2(cs_fit* f);
 

@@ -68,3 +68,21 @@ def test_sampler_distribution(emulib, n2):
     ref = np.sqrt(np.diag(cov)) * ss.t.ppf(0.9, 6.0)
     assert np.all(np.abs(U / ref - 1.0) < 0.08)
     assert abs(aU / (np.sqrt(cov.sum()) / n2 * ss.t.ppf(0.9, 6.0)) - 1.0) < 0.08
+
+
+@pytest.mark.parametrize("n,tile,gt", [(8192, 128, 64), (8192, 128, 128), (3000, 128, 64), (1000, 64, 64), (704, 64, 64), (129, 128, 64)])
+def test_multistream_cholesky_plan_has_no_races(emulib, n, tile, gt):
+    """Happens-before check of the three-stream launch plan (stream order + event edges):
+    every pair of launches with overlapping footprints and a write must be ordered."""
+    assert emulib.dll.cs_debug_check_plan(n, tile, gt, 1) == 0
+
+
+def test_concurrent_fits_match_sequential(emulib):
+    Ps = [cs.make_problem("GP", 90, 3, replicate=r) for r in range(3)]
+    fits = [_lib.Fit(emulib, 0, P["y"], P["X"], P["z"], P["w"], o.pack_params(P["par"]), chunk=2) for P in Ps]
+    res = _lib.run_many(fits, 7, 1e-12)
+    for P, f, (it, tr) in zip(Ps, fits, res):
+        ref = cs.oracle_fit(P, "Nadam", 7, 1e-12, 0.01)
+        assert it == ref.iters and cs.rel(tr[1, 1:], ref.stats[1, 1:]) < 1e-10
+        assert cs.rel(f.get_params(), o.pack_params(ref.Kernel.parameters), 1e-9) < 1e-8
+        f.close()

@@ -197,3 +197,24 @@ def test_distributed_driver_simulated_on_one_gpu(gpulib):
         assert np.max(np.abs(g2 - gref) / np.maximum(np.abs(gref), 1e-6 * np.max(np.abs(gref)))) < cs.TOL_GRAD
         assert abs(st2[1] - st[1]) < cs.TOL_LML * abs(st[1])
         assert abs(mu2 - mu) < 1e-8 * abs(mu)
+
+
+def test_concurrent_fits_on_gpu(gpulib):
+    """cs_fit_run_many: several fits interleaved on separate streams give the same results as
+    running them one after another (bitwise: the kernels are deterministic)."""
+    Ps = [cs.make_problem("GP", 300, 25, replicate=r) for r in range(4)]
+    seq = []
+    for P in Ps:
+        f = _lib.Fit(gpulib, 0, P["y"], P["X"], P["z"], P["w"], o.pack_params(P["par"]))
+        it, tr = f.run(20, 1e-12)
+        seq.append((it, tr.copy(), f.get_params()))
+        f.close()
+    fits = [_lib.Fit(gpulib, 0, P["y"], P["X"], P["z"], P["w"], o.pack_params(P["par"])) for P in Ps]
+    res = _lib.run_many(fits, 20, 1e-12)
+    for (it0, tr0, p0), f, (it, tr) in zip(seq, fits, res):
+        assert it == it0 and np.array_equal(tr, tr0) and np.array_equal(f.get_params(), p0)
+        f.close()
+
+
+def test_plan_race_detector_on_gpu_build(gpulib):
+    assert gpulib.dll.cs_debug_check_plan(8192, 128, 64, 1) == 0
