@@ -56,39 +56,64 @@ leaf_kernel(double* __restrict__ Gt, long long ldg, double* __restrict__ Xt, lon
     }
 
   // ---- phase 1: right-looking Cholesky; columns stay unscaled (L[r][j] = S[r][j] / sqrt(d_j)) ----
-  // The step loop is split by the 16-column block bj so every register index and loop bound
-  // is a compile-time constant (no predicated-off work as the trailing matrix shrinks).
+  // Split by the 16-column block bj so every register index / loop bound is a compile-time
+  // constant, and software-pipelined: at step j a thread first updates and publishes column
+  // j+1 (the only data the next step waits for) and defers the bulk of its rank-1 update to
+  // the next step, where it overlaps the latency chain barrier -> pivot -> reciprocal.
+  if (ty == 0) {
 #pragma unroll
-  for (int bj = 0; bj < NA; ++bj) {
-    for (int tj = 0; tj < 16; ++tj) {
-      const int j = 16 * bj + tj;
-      double* buf = colbuf + (j & 1) * TILE;
-      if (ty == tj) {
+    for (int a = 0; a < NA; ++a) colbuf[tx + 16 * a] = reg[a][0];
+  }
+  {
+    double crp[NA], ccp[NA];
 #pragma unroll
-        for (int a = bj; a < NA; ++a) buf[tx + 16 * a] = reg[a][bj];
+    for (int a = 0; a < NA; ++a) { crp[a] = 0.0; ccp[a] = 0.0; }
+#pragma unroll
+    for (int bj = 0; bj < NA; ++bj) {
+      for (int tj = 0; tj < 16; ++tj) {
+        const int j = 16 * bj + tj;
+        const double* buf = colbuf + (j & 1) * TILE;
+        double* nbuf = colbuf + ((j + 1) & 1) * TILE;
+        __syncthreads();
+        double d = buf[j];
+        if (!(d > 0.0)) {
+          const int gidx = pivot_base + j;
+          if (tid == 0 && gidx < n_real) atomicMin(status, gidx + 1);  // LAPACK-style 1-based info
+          d = 1.0;
+        }
+        if (tid == 0) piv[j] = d;
+        const double invd = csd::fast_rcp(d);
+        // deferred bulk of step j-1: columns c > j
+        if (ty > tj) {
+#pragma unroll
+          for (int a = bj; a < NA; ++a) reg[a][bj] -= crp[a] * ccp[bj];
+        }
+#pragma unroll
+        for (int b = bj + 1; b < NA; ++b)
+#pragma unroll
+          for (int a = b; a < NA; ++a) reg[a][b] -= crp[a] * ccp[b];
+        // this step's column
+#pragma unroll
+        for (int a = 0; a < NA; ++a) crp[a] = (a >= bj) ? buf[tx + 16 * a] : 0.0;
+#pragma unroll
+        for (int b = 0; b < NA; ++b) ccp[b] = (b >= bj) ? buf[ty + 16 * b] * invd : 0.0;
+        // early update + publication of column j+1
+        if (tj < 15) {
+          if (ty == tj + 1) {
+#pragma unroll
+            for (int a = bj; a < NA; ++a) { reg[a][bj] -= crp[a] * ccp[bj]; nbuf[tx + 16 * a] = reg[a][bj]; }
+          }
+        } else if (bj + 1 < NA) {
+          if (ty == 0) {
+#pragma unroll
+            constexpr int dummy = 0; (void)dummy;
+            const int b1 = (bj + 1 < NA) ? bj + 1 : bj;  // compile-time after unrolling
+#pragma unroll
+            for (int a = 0; a < NA; ++a)
+              if (a >= b1) { reg[a][b1] -= crp[a] * ccp[b1]; nbuf[tx + 16 * a] = reg[a][b1]; }
+          }
+        }
       }
-      __syncthreads();
-      double d = buf[j];
-      if (!(d > 0.0)) {
-        const int gidx = pivot_base + j;
-        if (tid == 0 && gidx < n_real) atomicMin(status, gidx + 1);  // LAPACK-style 1-based info
-        d = 1.0;
-      }
-      if (tid == 0) piv[j] = d;
-      const double invd = csd::fast_rcp(d);
-      double cr[NA], cc[NA];
-#pragma unroll
-      for (int a = bj; a < NA; ++a) cr[a] = buf[tx + 16 * a];
-#pragma unroll
-      for (int b = bj; b < NA; ++b) cc[b] = buf[ty + 16 * b] * invd;
-      if (ty > tj) {  // columns of block bj to the right of j
-#pragma unroll
-        for (int a = bj; a < NA; ++a) reg[a][bj] -= cr[a] * cc[bj];
-      }
-#pragma unroll
-      for (int b = bj + 1; b < NA; ++b)
-#pragma unroll
-        for (int a = b; a < NA; ++a) reg[a][b] -= cr[a] * cc[b];
     }
   }
   __syncthreads();
@@ -111,47 +136,87 @@ leaf_kernel(double* __restrict__ Gt, long long ldg, double* __restrict__ Xt, lon
   if (tid == 0) *logdet_out = ldsum;  // block_sum ends with a barrier: dinv is visible
 
   // ---- phase 2: in-place inverse X = L^-1, row by row with rank-1 updates of the rows below ----
+  // Same software pipelining: at step i the owners of row i+1 apply step i's update to their
+  // row, finalise and publish it (and column i+1 of L is published); the bulk update of the
+  // rows below is deferred to the next step, off the barrier -> load -> fma -> store chain.
+  // Slot (r,c) of `reg` holds L[r][c] until step c, then the running sum Acc[r][c], then X[r][c].
+  if (tid == 0) { reg[0][0] = dinv[0]; rowbuf[0] = dinv[0]; }
+  if (ty == 0) {
 #pragma unroll
-  for (int bi = 0; bi < NA; ++bi) {
-    for (int ti = 0; ti < 16; ++ti) {
-      const int i = 16 * bi + ti;
-      double* cbuf = colbuf + (i & 1) * TILE;
-      double* rbuf = rowbuf + (i & 1) * TILE;
-      const double xii = dinv[i];
-      if (tx == ti) {  // owners of row i finalise X[i][c], c <= i
+    for (int a = 0; a < NA; ++a) if (a > 0 || tx > 0) colbuf[tx + 16 * a] = reg[a][0];
+  }
+  {
+    double cbp[NA], rbp[NA];
 #pragma unroll
-        for (int b = 0; b <= bi; ++b) {
-          const int c = ty + 16 * b;
-          if (b < bi || ty <= ti) {
-            const double v = (c == i) ? xii : -xii * reg[bi][b];
-            reg[bi][b] = v;
-            rbuf[c] = v;
+    for (int a = 0; a < NA; ++a) { cbp[a] = 0.0; rbp[a] = 0.0; }
+#pragma unroll
+    for (int bi = 0; bi < NA; ++bi) {
+      for (int ti = 0; ti < 16; ++ti) {
+        const int i = 16 * bi + ti;
+        const double* cbuf = colbuf + (i & 1) * TILE;
+        const double* rbuf = rowbuf + (i & 1) * TILE;
+        double* ncbuf = colbuf + ((i + 1) & 1) * TILE;
+        double* nrbuf = rowbuf + ((i + 1) & 1) * TILE;
+        __syncthreads();
+        // deferred bulk of step i-1: rows r > i, columns c <= i-1 (column i-1 starts from 0)
+#pragma unroll
+        for (int b = 0; b < bi; ++b) {
+          const double xv = rbp[b];
+          const bool first = (ti == 0) && (b == bi - 1) && (ty == 15);
+          if (tx > ti) reg[bi][b] = (first ? 0.0 : reg[bi][b]) + cbp[bi] * xv;
+#pragma unroll
+          for (int a = bi + 1; a < NA; ++a) reg[a][b] = (first ? 0.0 : reg[a][b]) + cbp[a] * xv;
+        }
+        if (ti >= 1 && ty <= ti - 1) {
+          const double xv = rbp[bi];
+          const bool first = (ty == ti - 1);
+          if (tx > ti) reg[bi][bi] = (first ? 0.0 : reg[bi][bi]) + cbp[bi] * xv;
+#pragma unroll
+          for (int a = bi + 1; a < NA; ++a) reg[a][bi] = (first ? 0.0 : reg[a][bi]) + cbp[a] * xv;
+        }
+        // this step's column of L (rows > i) and row of X (columns <= i)
+#pragma unroll
+        for (int a = 0; a < NA; ++a) cbp[a] = (a >= bi) ? cbuf[tx + 16 * a] : 0.0;
+#pragma unroll
+        for (int b = 0; b < NA; ++b) rbp[b] = (b <= bi) ? rbuf[ty + 16 * b] : 0.0;
+        if (i + 1 < TILE) {
+          const double x1 = dinv[i + 1];
+          if (ti < 15) {
+            // row i+1 = tx == ti+1 in block bi; column i+1 = ty == ti+1 in block bi
+            if (tx == ti + 1) {
+#pragma unroll
+              for (int b = 0; b <= bi; ++b) {
+                const int c = ty + 16 * b;
+                if (b < bi || ty <= ti) {
+                  const double acc = ((b == bi && ty == ti) ? 0.0 : reg[bi][b]) + cbp[bi] * rbp[b];
+                  const double v = -x1 * acc;
+                  reg[bi][b] = v; nrbuf[c] = v;
+                }
+              }
+              if (ty == ti + 1) { reg[bi][bi] = x1; nrbuf[i + 1] = x1; }
+            }
+            if (ty == ti + 1) {
+#pragma unroll
+              for (int a = bi; a < NA; ++a) if (a > bi || tx > ti + 1) ncbuf[tx + 16 * a] = reg[a][bi];
+            }
+          } else {
+            const int a1 = (bi + 1 < NA) ? bi + 1 : bi;  // compile-time after unrolling
+            if (tx == 0) {
+#pragma unroll
+              for (int b = 0; b <= bi; ++b) {
+                const int c = ty + 16 * b;
+                const double acc = ((b == bi && ty == 15) ? 0.0 : reg[a1][b]) + cbp[a1] * rbp[b];
+                const double v = -x1 * acc;
+                reg[a1][b] = v; nrbuf[c] = v;
+              }
+              if (ty == 0) { reg[a1][a1] = x1; nrbuf[i + 1] = x1; }
+            }
+            if (ty == 0) {
+#pragma unroll
+              for (int a = 0; a < NA; ++a) if (a >= a1 && (a > a1 || tx > 0)) ncbuf[tx + 16 * a] = reg[a][a1];
+            }
           }
         }
-      }
-      if (ty == ti) {  // owners of column i publish L[r][i], r > i
-#pragma unroll
-        for (int a = bi; a < NA; ++a) {
-          const int r = tx + 16 * a;
-          if (a > bi || tx > ti) cbuf[r] = reg[a][bi];
-        }
-      }
-      __syncthreads();
-      // columns c < 16*bi (blocks b < bi): rows r > i
-#pragma unroll
-      for (int b = 0; b < bi; ++b) {
-        const double xv = rbuf[ty + 16 * b];
-        if (tx > ti) reg[bi][b] += cbuf[tx + 16 * bi] * xv;
-#pragma unroll
-        for (int a = bi + 1; a < NA; ++a) reg[a][b] += cbuf[tx + 16 * a] * xv;
-      }
-      // block b == bi: columns c <= i
-      if (ty <= ti) {
-        const double xv = rbuf[ty + 16 * bi];
-        const bool is_i = (ty == ti);
-        if (tx > ti) reg[bi][bi] = (is_i ? 0.0 : reg[bi][bi]) + cbuf[tx + 16 * bi] * xv;
-#pragma unroll
-        for (int a = bi + 1; a < NA; ++a) reg[a][bi] = (is_i ? 0.0 : reg[a][bi]) + cbuf[tx + 16 * a] * xv;
       }
     }
   }
