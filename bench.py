@@ -263,7 +263,7 @@ def run_ours(args, rank, world, local_rank):
         return float(t.item())
 
     inp = make_inputs(N_METRIC, P_METRIC, rank)  # one replicate per rank (weak scaling)
-    fit = _lib.Fit(lib, _lib.CS_GP, inp["y"], inp["X"], inp["z"], inp["w"], inp["params"])
+    fit = _lib.Fit(lib, _lib.CS_GP, inp["y"], inp["X"], inp["z"], inp["w"], inp["params"], inv_pipeline=args.inv_pipeline)
     n, p = N_METRIC, P_METRIC
     K, W = args.steps, max(args.warmup, 0)
 
@@ -403,6 +403,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--fits", type=int, default=16, help="(replicate, restart) fits per GPU for the fits/hour object")
     ap.add_argument("--no-fits", action="store_true")
+    ap.add_argument("--inv-pipeline", type=int, default=1, help="1: inverse pipelined behind the Cholesky (default); 0: recursive inverse after it")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

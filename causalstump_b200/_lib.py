@@ -25,7 +25,7 @@ dp = C.POINTER(C.c_double)
 class cs_fit_config(C.Structure):
     _fields_ = [("kind", C.c_int), ("optim", C.c_int), ("lr", C.c_double), ("beta1", C.c_double),
                 ("beta2", C.c_double), ("eps", C.c_double), ("momentum", C.c_double), ("tile", C.c_int),
-                ("chunk", C.c_int), ("use_graph", C.c_int), ("gemm_tile", C.c_int)]
+                ("chunk", C.c_int), ("use_graph", C.c_int), ("gemm_tile", C.c_int), ("inv_pipeline", C.c_int)]
 
 
 class CsError(RuntimeError):
@@ -237,7 +237,7 @@ class Fit:
     """Device-resident fit handle (cs_fit)."""
 
     def __init__(self, lib: CsLib, kind, y, X, z, w, init_params, optim=CS_OPT_NADAM, lr=0.01, beta1=0.9,
-                 beta2=0.999, eps=1e-8, momentum=0.0, tile=0, chunk=0, use_graph=0, gemm_tile=0):
+                 beta2=0.999, eps=1e-8, momentum=0.0, tile=0, chunk=0, use_graph=0, gemm_tile=0, inv_pipeline=0):
         self.lib = lib
         self.h = C.c_void_p(None)
         y, z, init_params = _f64(y), _f64(z), _f64(init_params)
@@ -245,7 +245,7 @@ class Fit:
         self.n, self.p = X.shape
         self.kind = kind
         w = None if w is None else _f64(w)
-        cfg = cs_fit_config(kind, optim, lr, beta1, beta2, eps, momentum, tile, chunk, use_graph, gemm_tile)
+        cfg = cs_fit_config(kind, optim, lr, beta1, beta2, eps, momentum, tile, chunk, use_graph, gemm_tile, inv_pipeline)
         h = C.c_void_p(None)
         lib.check(lib.dll.cs_fit_create(C.byref(cfg), self.n, self.p, _ptr(y), _ptr(X), _ptr(z), _ptr(w),
                                         _ptr(init_params), C.byref(h)))

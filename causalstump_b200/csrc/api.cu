@@ -191,13 +191,18 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
               f->lay, n, f->eng.G, ld, skip);
   }
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
-  f->eng.set_status_max(st, skip);
-  f->eng.run_seq(f->eng.potrf, st, skip);
-  if (phase_ev) rt::event_record(phase_ev[ph++], st);
-  f->eng.run_seq(f->eng.trtri, st, skip);
-  if (phase_ev) rt::event_record(phase_ev[ph++], st);
-  f->eng.run_seq(f->eng.xtx, st, skip);
-  if (phase_ev) rt::event_record(phase_ev[ph++], st);
+  if (f->eng.inv_pipeline) {
+    f->eng.factor_and_invert(st, skip);  // Cholesky with the inverse pipelined behind it
+    if (phase_ev) { rt::event_record(phase_ev[ph++], st); rt::event_record(phase_ev[ph++], st); rt::event_record(phase_ev[ph++], st); }
+  } else {
+    f->eng.set_status_max(st, skip);
+    f->eng.run_seq(f->eng.potrf, st, skip);
+    if (phase_ev) rt::event_record(phase_ev[ph++], st);
+    f->eng.run_seq(f->eng.trtri, st, skip);
+    if (phase_ev) rt::event_record(phase_ev[ph++], st);
+    f->eng.run_seq(f->eng.xtx, st, skip);
+    if (phase_ev) rt::event_record(phase_ev[ph++], st);
+  }
   {  // alpha, u, s
     auto k = csk::matvec_kernel<3>;
     ++g_launches;
@@ -267,7 +272,7 @@ int cs_fit_create(const cs_fit_config* cfg, int n, int p, const double* y, const
   f->p = p;
   auto bail = [&](int code) { cs_fit_destroy(f); return code; };
   if (rt::stream_create(&f->st)) return bail(fail(CS_ERR_CUDA, "stream create failed"));
-  if (int e = f->eng.init(n, tile, cfg->gemm_tile)) return bail(fail(e == 2 ? CS_ERR_NOMEM : CS_ERR_CUDA, "dense engine init failed: %s", rt::err_str(e)));
+  if (int e = f->eng.init(n, tile, cfg->gemm_tile, cfg->inv_pipeline)) return bail(fail(e == 2 ? CS_ERR_NOMEM : CS_ERR_CUDA, "dense engine init failed: %s", rt::err_str(e)));
   const int np = f->eng.np;
   f->np = np;
   f->nblk = np / csk::TB;
@@ -598,8 +603,8 @@ int cs_fit_get_matrices(cs_fit* f, double* Kmat, double* Km, double* Ka, double*
 int cs_debug_check_plan(int n, int tile, int gemm_tile, int verbose) {
   if (need_device()) return CS_ERR_NODEVICE;
   DenseEngine eng;
-  if (int e = eng.init(n, tile ? tile : csdense::pick_tile(n), gemm_tile)) { eng.destroy(); return fail(CS_ERR_CUDA, "engine init failed (%d)", e); }
-  const int bad = eng.check_plan(eng.potrf, verbose);
+  if (int e = eng.init(n, tile ? tile : csdense::pick_tile(n), gemm_tile, 1)) { eng.destroy(); return fail(CS_ERR_CUDA, "engine init failed (%d)", e); }
+  const int bad = eng.check_plan(eng.potrf, verbose) + eng.check_plan(eng.potrf_inv, verbose);
   eng.destroy();
   return bad;
 }

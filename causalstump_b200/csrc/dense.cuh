@@ -106,7 +106,6 @@ leaf_kernel(double* __restrict__ Gt, long long ldg, double* __restrict__ Xt, lon
         } else if (bj + 1 < NA) {
           if (ty == 0) {
 #pragma unroll
-            constexpr int dummy = 0; (void)dummy;
             const int b1 = (bj + 1 < NA) ? bj + 1 : bj;  // compile-time after unrolling
 #pragma unroll
             for (int a = 0; a < NA; ++a)
@@ -304,11 +303,13 @@ struct DenseEngine {
   GemmProblem* d_probs = nullptr;
   std::vector<GemmProblem> probs;
   std::vector<Launch> potrf, trtri, xtx;
+  std::vector<Launch> potrf_inv;    // Cholesky with the inverse pipelined behind it (inv_pipeline)
+  int inv_pipeline = 0;
   int panel_blocks = 4;             // outer panel width in blocks
   int n_events = 0;
   std::vector<cudaEvent_t> events;
-  cudaStream_t aux{}, aux2{};       // S1: bulk trailing updates (low priority); S2: panel rest (high)
-  bool aux_ok = false, aux2_ok = false;
+  cudaStream_t aux{}, aux2{}, aux3{};  // S1: bulk trailing updates (low); S2: panel rest (high); S3: pipelined inverse (low)
+  bool aux_ok = false, aux2_ok = false, aux3_ok = false;
 
   static GemmProblem mk(const double* A, long long lda, const double* B, long long ldb, double* C, long long ldc,
                         int mt, int nt, int K, int kmode, int order, int mirror, double alpha, double beta) {
@@ -341,7 +342,8 @@ struct DenseEngine {
   }
 
   // returns 0 or a runtime error code
-  int init(int n_, int tile_, int gemm_tile = 64) {
+  int init(int n_, int tile_, int gemm_tile = 64, int inv_pipe = 0) {
+    inv_pipeline = inv_pipe;
     n = n_; tile = tile_; N = (n + tile - 1) / tile; np = N * tile;
     gt = (gemm_tile == 128 && tile == 128) ? 128 : 64;
     rr = tile / gt;
@@ -364,8 +366,10 @@ struct DenseEngine {
     // trailing update (k = W*TILE) is split into U1 (next panel's columns, S0) and U2 (the
     // rest, bulk stream S1).  Dependencies are events; the whole sequence is graph-capturable.
     const int W = panel_blocks;
-    int npanel = 0, last_aux_ev = -1, nev = 0;
-    auto op = [&](int type, int stream, int ev) { Launch o{}; o.is_leaf = type; o.stream = stream; o.ev = ev; potrf.push_back(o); };
+    int nev = 0;
+    auto build_chol = [&](std::vector<Launch>& seq, bool with_inverse) {
+    auto op = [&](int type, int stream, int ev) { Launch o{}; o.is_leaf = type; o.stream = stream; o.ev = ev; seq.push_back(o); };
+    int npanel = 0, last_aux_ev = -1, last_inv_ev = -1;
     // in-place panel multiply L = A * X_kk^T for `nb` block rows starting at block row r0 of column k
     auto push_panel = [&](int k, int r0, int nb, int stream) {
       if (nb <= 0) return;
@@ -376,19 +380,19 @@ struct DenseEngine {
         // columns but output columns 0..63 only input columns 0..63: right half first, then the
         // left half with K = 64 (each launch is in-place safe per CTA).
         grp.push_back(mk(pan, ld, Xkk + gt, ld, pan + gt * ld, ld, nb * rr, 1, tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
-        add_group(potrf, GK_NT, grp); potrf.back().stream = stream;
+        add_group(seq, GK_NT, grp); seq.back().stream = stream;
         grp.push_back(mk(pan, ld, Xkk, ld, pan, ld, nb * rr, 1, gt, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
-        add_group(potrf, GK_NT, grp); potrf.back().stream = stream;
+        add_group(seq, GK_NT, grp); seq.back().stream = stream;
       } else {
         grp.push_back(mk(pan, ld, Xkk, ld, pan, ld, nb, 1, tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
-        add_group(potrf, GK_NT, grp); potrf.back().stream = stream; potrf.back().gtile = tile;
+        add_group(seq, GK_NT, grp); seq.back().stream = stream; seq.back().gtile = tile;
       }
     };
     for (int p0 = 0; p0 < N; p0 += W, ++npanel) {
       const int p1 = std::min(p0 + W, N);
       int ev_rest_prev = -1;
       for (int k = p0; k < p1; ++k) {
-        { Launch L{}; L.is_leaf = OP_LEAF; L.blk = k; potrf.push_back(L); }
+        { Launch L{}; L.is_leaf = OP_LEAF; L.blk = k; seq.push_back(L); }
         const int m = N - k - 1;          // block rows below k
         if (m <= 0) continue;
         const int ev_leaf = nev++, ev_pp = nev++, ev_rest = nev++;
@@ -401,7 +405,7 @@ struct DenseEngine {
         double* row1 = G + (k + 1) * T + k * T * ld;  // L_{k+1,k}
         if (nc > 0) {
           grp.push_back(mk(row1, ld, row1, ld, G + (k + 1) * T * (ld + 1), ld, rr, rr, tile, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
-          add_group(potrf, GK_NT, grp);
+          add_group(seq, GK_NT, grp);
         }
         // ---- rest (S2): block rows >= k+2 ----
         op(OP_WAIT, 2, ev_leaf);
@@ -420,12 +424,58 @@ struct DenseEngine {
           if (mr > 0)
             grp.push_back(mk(G + p1 * T + k * T * ld, ld, row1, ld, G + p1 * T + (k + 1) * T * ld, ld, mr * rr, nc * rr, tile,
                              csg::KM_FULL, csg::ORD_COL, 0, -1.0, 1.0));
-          if (!grp.empty()) { add_group(potrf, GK_NT, grp); potrf.back().stream = 2; }
+          if (!grp.empty()) { add_group(seq, GK_NT, grp); seq.back().stream = 2; }
         }
         op(OP_RECORD, 2, ev_rest);
         ev_rest_prev = ev_rest;
       }
       if (ev_rest_prev >= 0) op(OP_WAIT, 0, ev_rest_prev);  // S0 rejoins S2: the panel is complete
+      if (with_inverse) {
+        // ---- pipelined inverse (stream S3): as soon as panel P of L is final, rows P of X = L^-1
+        // are finalised and their contribution to the rows below (Acc) and to K^-1 = X^T X is
+        // accumulated with K = W*TILE -- bulk work that fills the SMs the Cholesky chain leaves idle.
+        const int ev_done = nev++;
+        op(OP_RECORD, 0, ev_done);
+        op(OP_WAIT, 3, ev_done);
+        const int pw = p1 - p0;
+        for (int k = p0; k < p1; ++k) {
+          double* Xkk = X + (long long)k * T * (ld + 1);
+          double* rowk = X + (long long)k * T;  // block row k of X, column 0
+          if (k > 0) {  // X_kJ = -X_kk Acc_kJ, J < k  (in place: one CTA per whole tile)
+            grp.push_back(mk(Xkk, ld, rowk, ld, rowk, ld, 1, k, tile, csg::KM_FULL, csg::ORD_COL, 0, -1.0, 0.0));
+            add_group(seq, GK_NN, grp); seq.back().stream = 3; seq.back().gtile = tile;
+          }
+          const int nr = p1 - 1 - k;
+          if (nr > 0) {  // Acc_iJ += L_ik X_kJ for the rows i in (k, p1) of this panel, J <= k
+            grp.push_back(mk(G + (k + 1) * T + k * T * ld, ld, rowk, ld, X + (k + 1) * T, ld, nr * rr, (k + 1) * rr, tile,
+                             csg::KM_FULL, csg::ORD_COL, 0, 1.0, 1.0));
+            add_group(seq, GK_NN, grp); seq.back().stream = 3;
+          }
+        }
+        const int mb = N - p1;
+        if (mb > 0) {  // Acc_IJ += sum_{k in P} L_Ik X_kJ for I >= p1  (K = pw*TILE)
+          double* Lp = G + p1 * T + p0 * T * ld;
+          if (p0 > 0)
+            grp.push_back(mk(Lp, ld, X + p0 * T, ld, X + p1 * T, ld, mb * rr, p0 * rr, pw * tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 1.0));
+          grp.push_back(mk(Lp, ld, X + p0 * T * (ld + 1), ld, X + p1 * T + p0 * T * ld, ld, mb * rr, pw * rr, pw * tile, csg::KM_GE_J,
+                           csg::ORD_COL, 0, 1.0, 1.0));
+          add_group(seq, GK_NN, grp); seq.back().stream = 3;
+        }
+        {  // C_IJ += sum_{k in P} X_kI^T X_kJ for J <= I <= k  (mirrored store keeps C symmetric)
+          double* Xp = X + p0 * T;              // rows of the panel, column 0
+          double* Xd = X + p0 * T * (ld + 1);   // rows and columns of the panel
+          if (p0 > 0) {
+            grp.push_back(mk(Xp, ld, Xp, ld, C, ld, p0 * rr, p0 * rr, pw * tile, csg::KM_FULL, csg::ORD_LOWER, 1, 1.0, 1.0));
+            GemmProblem q = mk(Xd, ld, Xp, ld, C + p0 * T, ld, pw * rr, p0 * rr, pw * tile, csg::KM_GE_I, csg::ORD_COL, 2, 1.0, 1.0);
+            q.Cm = C + p0 * T * ld;  // transposed block: rows 0.., columns of the panel
+            grp.push_back(q);
+          }
+          grp.push_back(mk(Xd, ld, Xd, ld, C + p0 * T * (ld + 1), ld, pw * rr, pw * rr, pw * tile, csg::KM_GE_I, csg::ORD_LOWER, 1, 1.0, 1.0));
+          add_group(seq, GK_TN, grp); seq.back().stream = 3;
+        }
+        last_inv_ev = nev++;
+        op(OP_RECORD, 3, last_inv_ev);
+      }
       const int mt = N - p1;  // trailing blocks
       if (mt <= 0) continue;
       const int kw = (p1 - p0) * tile;
@@ -439,20 +489,24 @@ struct DenseEngine {
       if (mt > n1)
         grp.push_back(mk(pan + n1 * T, ld, pan, ld, G + (p1 + n1) * T + p1 * T * ld, ld, (mt - n1) * rr, n1 * rr, kw, csg::KM_FULL,
                          csg::ORD_COL, 0, -1.0, 1.0));
-      add_group(potrf, GK_NT, grp);
+      add_group(seq, GK_NT, grp);
       // U2: everything to the right of the next panel (bulk stream S1)
       op(OP_WAIT, 1, ev_panel);
       if (mt > n1) {
         grp.push_back(mk(pan + n1 * T, ld, pan + n1 * T, ld, G + (p1 + n1) * T * (ld + 1), ld, (mt - n1) * rr, (mt - n1) * rr, kw,
                          csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
-        add_group(potrf, GK_NT, grp);
-        potrf.back().stream = 1;
+        add_group(seq, GK_NT, grp);
+        seq.back().stream = 1;
       }
       op(OP_RECORD, 1, ev_u2);
       last_aux_ev = ev_u2;
     }
-    // the main stream rejoins the bulk stream before anything reads the factor
+    // the main stream rejoins the bulk (and inverse) streams before anything reads the results
     if (last_aux_ev >= 0) op(OP_WAIT, 0, last_aux_ev);
+    if (last_inv_ev >= 0) op(OP_WAIT, 0, last_inv_ev);
+    };
+    build_chol(potrf, false);
+    if (inv_pipeline) build_chol(potrf_inv, true);
     n_events = nev + 1;
     // --- recursive triangular inverse, batched by tree height ---
     std::vector<Node> nodes;
@@ -481,6 +535,8 @@ struct DenseEngine {
     aux_ok = true;
     if ((e = rt::stream_create(&aux2))) return e;
     aux2_ok = true;
+    if ((e = rt::stream_create_low(&aux3))) return e;
+    aux3_ok = true;
     events.resize(n_events);
     for (int i = 0; i < n_events; ++i)
       if ((e = rt::event_create_fast(&events[i]))) return e;
@@ -497,12 +553,13 @@ struct DenseEngine {
     events.clear();
     if (aux_ok) { rt::stream_sync(aux); rt::stream_destroy(aux); aux_ok = false; }
     if (aux2_ok) { rt::stream_sync(aux2); rt::stream_destroy(aux2); aux2_ok = false; }
+    if (aux3_ok) { rt::stream_sync(aux3); rt::stream_destroy(aux3); aux3_ok = false; }
     G = X = C = logdet_part = nullptr; status = nullptr; d_probs = nullptr;
   }
 
   void run_seq(const std::vector<Launch>& seq, cudaStream_t st, const int* skip = nullptr) {
     for (const Launch& L : seq) {
-      cudaStream_t s = L.stream == 1 ? aux : (L.stream == 2 ? aux2 : st);
+      cudaStream_t s = L.stream == 1 ? aux : (L.stream == 2 ? aux2 : (L.stream == 3 ? aux3 : st));
       if (L.is_leaf == OP_LEAF) {
         launch_leaf(tile, G + (long long)L.blk * tile * ((long long)np + 1), np, X + (long long)L.blk * tile * ((long long)np + 1), np,
                     L.blk * tile, logdet_part + L.blk, status, n, s, skip);
@@ -549,14 +606,14 @@ struct DenseEngine {
       if (ak) rect_of(P.A, K, M, false, out); else rect_of(P.A, M, K, false, out);
       if (bk) rect_of(P.B, K, Nn, false, out); else rect_of(P.B, Nn, K, false, out);
       rect_of(P.C, M, Nn, true, out);
-      if (P.mirror) rect_of(P.C, Nn, M, true, out);
+      if (P.mirror) rect_of(P.Cm ? P.Cm : P.C, Nn, M, true, out);
     }
   }
   int check_plan(const std::vector<Launch>& seq, int verbose) const {
     const int n_ops = (int)seq.size();
     const int words = (n_ops + 63) / 64;
     std::vector<std::vector<unsigned long long>> anc(n_ops, std::vector<unsigned long long>(words, 0ULL));
-    int last_on_stream[3] = {-1, -1, -1};
+    int last_on_stream[4] = {-1, -1, -1, -1};
     std::vector<int> last_record(n_events + 1, -1);
     auto add_pred = [&](int j, int i) {
       if (i < 0) return;
@@ -596,6 +653,20 @@ struct DenseEngine {
   // G (lower) must hold K_n; X and the upper triangle of G must be zero outside diagonal tiles.
   void factor(cudaStream_t st, const int* skip = nullptr) { set_status_max(st, skip); run_seq(potrf, st, skip); }
   void invert(cudaStream_t st, const int* skip = nullptr) { run_seq(trtri, st, skip); run_seq(xtx, st, skip); }
+  // K_n (in G) -> L, L^-1, K_n^-1.  With inv_pipeline the inverse trails the factorization on its
+  // own stream; X and C are accumulated into and must start from zero.
+  void factor_and_invert(cudaStream_t st, const int* skip = nullptr) {
+    if (inv_pipeline) {
+      const size_t mb = sizeof(double) * (size_t)np * np;
+      rt::memset0(X, mb, st);
+      rt::memset0(C, mb, st);
+      set_status_max(st, skip);
+      run_seq(potrf_inv, st, skip);
+    } else {
+      factor(st, skip);
+      invert(st, skip);
+    }
+  }
 
   void set_status_max(cudaStream_t st, const int* skip);
 };

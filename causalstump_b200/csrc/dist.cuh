@@ -110,13 +110,12 @@ gram_dist_kernel(const double* __restrict__ X, long long ldx, const double* __re
 }
 
 // symmetric mat-vec on the local lower tiles: out[k][rows I] += T v_k[J];  (I != J) out[k][rows J] += T^T v_k[I]
-// one CTA per (tile, 64-row strip); three vectors; fp64 atomics (distributed mode only).
+// one CTA per tile; three vectors; fp64 atomics (distributed mode only).
 static __global__ void __launch_bounds__(256)
 symv_dist_kernel(const double* __restrict__ C, long long ldc, const int* __restrict__ tiles, int T, int P, int Q,
                  const double* __restrict__ v0, const double* __restrict__ shift0, const double* __restrict__ v1,
                  const double* __restrict__ v2, double* __restrict__ out, long long out_stride) {
   __shared__ double sv[3][128];
-  __shared__ double colacc[3][128];
   const int e = (int)blockIdx.x;
   const int I = tiles[2 * e], J = tiles[2 * e + 1];
   const double* Ct = C + (long long)(I / P) * T + (long long)(J / Q) * T * ldc;
@@ -125,7 +124,6 @@ symv_dist_kernel(const double* __restrict__ C, long long ldc, const int* __restr
   // rows of I:  sum_c Ct[r,c] v[J*T + c]
   for (int c = tid; c < T; c += 256) {
     sv[0][c] = v0[J * T + c] - sh; sv[1][c] = v1[J * T + c]; sv[2][c] = v2[J * T + c];
-    colacc[0][c] = 0.0; colacc[1][c] = 0.0; colacc[2][c] = 0.0;
   }
   __syncthreads();
   if (tid < T) {
@@ -155,7 +153,6 @@ symv_dist_kernel(const double* __restrict__ C, long long ldc, const int* __restr
       atomicAdd(out + 2 * out_stride + J * T + tid, a2);
     }
   }
-  (void)colacc;
 }
 
 // sigma-trace partial over the diagonal tiles this rank owns: sum_r (C_rr - coef a_r^2) e^sigma / w_r

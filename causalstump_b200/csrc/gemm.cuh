@@ -26,13 +26,14 @@ struct GemmProblem {
   int K;            // k extent in elements (multiple of GEMM_BK)
   int kmode;        // KMode, in units of TILE
   int order;        // TileOrder; ORD_LOWER enumerates only I >= J (mt == nt)
-  int mirror;       // also store C(j,i) = C(i,j)
+  int mirror;       // 1: also store C(j,i) = C(i,j) for I != J (square, diagonal origin); 2: always (rectangular)
   int tile_base;    // first linear tile id of this problem inside the launch
   int ntiles;
   double alpha, beta;  // C = beta*C + alpha*acc   (beta in {0,1})
   // Table mode (distributed block-cyclic sweeps): tile t uses element offsets
   // table[3t] into A, table[3t+1] into B, table[3t+2] into C and the full k-range.
   const long long* table;
+  double* Cm;       // base of the transposed block for mirror == 2 (nullptr: same as C)
 };
 
 constexpr int GEMM_BK = 16;
@@ -212,8 +213,8 @@ gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restr
       double* p1 = p0 + P.ldc;
       const double v0 = alpha * acc[a][b][0], v1 = alpha * acc[a][b][1];
       *p0 = v0; *p1 = v1;
-      if (P.mirror && I != J) {
-        double* q = P.C + cc + r * P.ldc;  // (cc, r) and (cc+1, r) are adjacent
+      if (P.mirror == 2 || (P.mirror == 1 && I != J)) {
+        double* q = (P.Cm ? P.Cm : P.C) + cc + r * P.ldc;  // (cc, r) and (cc+1, r) are adjacent
         q[0] = v0; q[1] = v1;
       }
     }

@@ -293,7 +293,7 @@ scalars_kernel(const double* __restrict__ mv_part, int nsplit, long long stride_
 // and K*alpha row partials go to kal_part[slot][row] (each slot/row written exactly once).
 // ---------------------------------------------------------------------------------
 inline int grad_smem_bytes(int p) {
-  return ((2 * p + 2) * ETH + 2 * p * TB + 2 * PMAX + 6 * TB + 8 * TB + 32) * (int)sizeof(double);
+  return ((2 * p + 2) * ETH + 2 * p * TB + 2 * PMAX + 5 * TB + 8 * TB + 32) * (int)sizeof(double);
 }
 
 template <bool FROM_MEM>
@@ -321,8 +321,7 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
   double* zc = zr + TB;
   double* ar = zc + TB;                 // alpha rows
   double* ac = ar + TB;                 // alpha cols
-  double* rsum = ac + TB;               // [TB] row sums final
-  double* csum = rsum + TB;             // [TB] col sums final
+  double* csum = ac + TB;               // [TB] column sums of the current tile
   double* rred = csum + TB;             // [8][TB]
   double* red = rred + 8 * TB;          // [32]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, wid = tid >> 5;
@@ -444,7 +443,6 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
     const double v = csd::block_sum(acc[k * ETH + tid], red);
     if (tid == 0) gpart[(long long)blockIdx.x * nacc + k] = v;
   }
-  (void)rsum;
 }
 
 // ---------------------------------------------------------------------------------

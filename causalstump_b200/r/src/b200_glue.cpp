@@ -133,7 +133,7 @@ typedef XPtr<cs_fit, PreserveStorage, fit_finalizer> FitPtr;
 // [[Rcpp::export]]
 SEXP b200_fit_create(int kind, int optim, double lr, double beta1, double beta2, double momentum, NumericVector y,
                      NumericMatrix X, NumericVector z, NumericVector w, List parameters) {
-  cs_fit_config cfg = {kind, optim, lr, beta1, beta2, 1e-8, momentum, 0, 0, 0, 0};
+  cs_fit_config cfg = {kind, optim, lr, beta1, beta2, 1e-8, momentum, 0, 0, 0, 0, 0};
   NumericVector pv = pack(parameters);
   cs_fit* f = NULL;
   cs_check(cs_fit_create(&cfg, X.nrow(), X.ncol(), y.begin(), X.begin(), z.begin(), w.begin(), pv.begin(), &f));

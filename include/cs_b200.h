@@ -57,6 +57,8 @@ typedef struct cs_fit_config {
   int chunk;       /* optimizer iterations enqueued between host polls (0 = auto)   */
   int use_graph;   /* 0 = replay one captured iteration as a CUDA graph; -1 = eager  */
   int gemm_tile;   /* 0 / 64 = 64x64 CTA tiles (default); 128 = 128x128 CTA tiles    */
+  int inv_pipeline;/* 1 = inverse pipelined behind the Cholesky on its own stream;   */
+                   /* 0 = recursive triangular inverse + X^T X after the Cholesky    */
 } cs_fit_config;
 
 /* ---- library / device ---------------------------------------------------------- */

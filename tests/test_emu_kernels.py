@@ -86,3 +86,16 @@ def test_concurrent_fits_match_sequential(emulib):
         assert it == ref.iters and cs.rel(tr[1, 1:], ref.stats[1, 1:]) < 1e-10
         assert cs.rel(f.get_params(), o.pack_params(ref.Kernel.parameters), 1e-9) < 1e-8
         f.close()
+
+
+@pytest.mark.parametrize("n,p,tile", [(150, 3, 64), (330, 4, 64), (300, 3, 128), (520, 2, 128)])
+def test_pipelined_inverse(emulib, n, p, tile):
+    P = cs.make_problem("GP", n, p, weights=True)
+    g, st, mu = o.eval_lml_grad("GP", P["y"], P["X"], P["z"], P["w"], P["par"])
+    f = _lib.Fit(emulib, 0, P["y"], P["X"], P["z"], P["w"], o.pack_params(P["par"]), tile=tile, inv_pipeline=1)
+    g2, st2, mu2 = f.eval()
+    g3, st3, _ = f.eval()
+    f.close()
+    assert np.array_equal(g2, g3)
+    assert cs.rel(g2, o.pack_params(g), 1e-9) < cs.TOL_GRAD and abs(st2[1] - st[1]) < cs.TOL_LML * abs(st[1])
+    assert abs(st2[0] - st[0]) < 1e-8 * abs(st[0]) and abs(mu2 - mu) < 1e-9 * abs(mu)

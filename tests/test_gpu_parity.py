@@ -218,3 +218,27 @@ def test_concurrent_fits_on_gpu(gpulib):
 
 def test_plan_race_detector_on_gpu_build(gpulib):
     assert gpulib.dll.cs_debug_check_plan(8192, 128, 64, 1) == 0
+
+
+@pytest.mark.parametrize("n,p,tile", [(747, 25, 0), (2000, 25, 128), (1100, 5, 64)])
+def test_pipelined_inverse_matches_recursive(gpulib, n, p, tile):
+    """cfg.inv_pipeline: the inverse trails the Cholesky on its own stream; same results as the
+    recursive inverse (to rounding) and the same parity against the oracle."""
+    P = cs.make_problem("GP", n, p, weights=True)
+    outs = []
+    for mode in (0, 1):
+        f = _lib.Fit(gpulib, 0, P["y"], P["X"], P["z"], P["w"], o.pack_params(P["par"]), tile=tile, inv_pipeline=mode)
+        g, st, mu = f.eval()
+        g2, st2, _ = f.eval()
+        assert np.array_equal(g, g2) and np.array_equal(st, st2)  # deterministic, re-entrant
+        outs.append((g, st, mu, f.get_matrices(want=("invK",))["invK"]))
+        f.close()
+    (g0, s0, m0, i0), (g1, s1, m1, i1) = outs
+    assert np.max(np.abs(g1 - g0) / np.maximum(np.abs(g0), 1e-6 * np.max(np.abs(g0)))) < 1e-9
+    assert abs(s1[1] - s0[1]) < 1e-11 * abs(s0[1]) and abs(m1 - m0) < 1e-10 * abs(m0)
+    assert cs.relm(i1, i0) < 1e-10
+    if n <= 1200:
+        go, sto, muo = o.eval_lml_grad("GP", P["y"], P["X"], P["z"], P["w"], P["par"])
+        gref = o.pack_params(go)
+        assert np.max(np.abs(g1 - gref) / np.maximum(np.abs(gref), 1e-6 * np.max(np.abs(gref)))) < cs.TOL_GRAD
+        assert abs(s1[1] - sto[1]) < cs.TOL_LML * abs(sto[1])
