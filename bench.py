@@ -31,6 +31,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N_METRIC, P_METRIC = 8192, 25
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
+# `ncu --set full` capture (per launch; None until a capture of the current kernel exists)
+XTX_TRAFFIC_BYTES = None
+XTX_TRAFFIC_SOURCE = None
 METRIC = "fp64 LML+gradient evals/sec at n=8192,p=25"
 UNIT = "evals/s"
 
@@ -263,7 +267,7 @@ def run_ours(args, rank, world, local_rank):
         return float(t.item())
 
     inp = make_inputs(N_METRIC, P_METRIC, rank)  # one replicate per rank (weak scaling)
-    fit = _lib.Fit(lib, _lib.CS_GP, inp["y"], inp["X"], inp["z"], inp["w"], inp["params"], inv_pipeline=args.inv_pipeline)
+    fit = _lib.Fit(lib, _lib.CS_GP, inp["y"], inp["X"], inp["z"], inp["w"], inp["params"], inv_pipeline=args.inv_pipeline, partition=args.partition)
     n, p = N_METRIC, P_METRIC
     K, W = args.steps, max(args.warmup, 0)
 
@@ -308,10 +312,22 @@ def run_ours(args, rank, world, local_rank):
     e2e = {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
 
     # ---- per-phase device times and the roofline of the dominant kernel ----
+    # `phases` comes from the plan that was timed above.  With the pipelined plan the three dense
+    # phases overlap on four streams (their total is reported under "potrf"), so the per-launch
+    # duration of the dominant kernel is measured on a second handle that runs the same kernels
+    # back to back on one stream (inv_pipeline=0): K^-1 = X^T X there is ONE launch.
     phases = None
     for _ in range(3):
         ph = fit.eval_profile()
         phases = ph if phases is None else {k: min(phases[k], ph[k]) for k in ph}
+    seq_phases = phases
+    if args.inv_pipeline:
+        fit_seq = _lib.Fit(lib, _lib.CS_GP, inp["y"], inp["X"], inp["z"], inp["w"], inp["params"], inv_pipeline=0)
+        seq_phases = None
+        for _ in range(4):
+            ph = fit_seq.eval_profile()
+            seq_phases = ph if seq_phases is None else {k: min(seq_phases[k], ph[k]) for k in ph}
+        fit_seq.close()
     line_extra = {}
     if rank == 0:
         peaks = {}
@@ -322,22 +338,27 @@ def run_ours(args, rank, world, local_rank):
         fp64_peak = measure_fp64_peak(torch, dev)
         npad = n
         f_xtx = npad ** 3 / 3.0
-        xtx_tflops = f_xtx / (phases["xtx"] * 1e-3) / 1e12
+        xtx_tflops = f_xtx / (seq_phases["xtx"] * 1e-3) / 1e12
         dense_ms = phases["potrf"] + phases["trtri"] + phases["xtx"]
         dense_tflops = float(npad) ** 3 / (dense_ms * 1e-3) / 1e12
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         line_extra["roofline"] = {
-            "kernel": "csg::gemm_kernel<128,2,4,true,true> (K^-1 = X^T X, one launch, DMMA.8x8x4)",
+            "kernel": "csg::gemm_kernel<128,2,4,true,true> (K^-1 = X^T X as one launch, DMMA.8x8x4), timed alone on its stream",
             "bound": "tensor", "achieved": xtx_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": xtx_tflops / fp64_peak, "traffic": None,
+            "frac": xtx_tflops / fp64_peak, "traffic": XTX_TRAFFIC_BYTES,
+            "traffic_source": XTX_TRAFFIC_SOURCE,
             "peak_source": "cuBLAS DGEMM 8192^3 fp64 burst measured live in this run (MEASURED_PEAKS.json has no fp64 entry)",
-            "flops_per_launch": f_xtx, "ms_per_launch": phases["xtx"],
+            "flops_per_launch": f_xtx, "ms_per_launch": seq_phases["xtx"],
         }
         line_extra["roofline_dense_path"] = {
-            "what": "Cholesky + triangular inverse + X^T X (n^3 algorithmic flops, %d launches)" % 0,
+            "what": "Cholesky + triangular inverse + X^T X of the plan timed in `value` (n^3 algorithmic flops, every launch "
+                    "an instance of csg::gemm_kernel or the leaf kernel; %s)" %
+                    ("inverse pipelined behind the Cholesky on 4 streams" if args.inv_pipeline else "phases back to back"),
             "bound": "tensor", "achieved": dense_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": dense_tflops / fp64_peak, "ms": dense_ms,
         }
+        if args.inv_pipeline:
+            line_extra["phases_ms_sequential_plan"] = seq_phases
         b_gram = 8.0 * n * n / 2 + 8.0 * n * (p + 2)   # lower triangle written once
         b_grad = 8.0 * n * n / 2 + 8.0 * n * (p + 3)   # lower triangle of K^-1 read once
         line_extra["roofline_elementwise"] = {
@@ -404,6 +425,7 @@ def main():
     ap.add_argument("--fits", type=int, default=16, help="(replicate, restart) fits per GPU for the fits/hour object")
     ap.add_argument("--no-fits", action="store_true")
     ap.add_argument("--inv-pipeline", type=int, default=1, help="1: inverse pipelined behind the Cholesky (default); 0: recursive inverse after it")
+    ap.add_argument("--partition", type=int, default=0, help="SM partition for the Cholesky chain: 0 auto, 1 on, -1 off")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -25,7 +25,8 @@ dp = C.POINTER(C.c_double)
 class cs_fit_config(C.Structure):
     _fields_ = [("kind", C.c_int), ("optim", C.c_int), ("lr", C.c_double), ("beta1", C.c_double),
                 ("beta2", C.c_double), ("eps", C.c_double), ("momentum", C.c_double), ("tile", C.c_int),
-                ("chunk", C.c_int), ("use_graph", C.c_int), ("gemm_tile", C.c_int), ("inv_pipeline", C.c_int)]
+                ("chunk", C.c_int), ("use_graph", C.c_int), ("gemm_tile", C.c_int), ("inv_pipeline", C.c_int),
+                ("partition", C.c_int)]
 
 
 class CsError(RuntimeError):
@@ -80,6 +81,7 @@ _SIGS = {
     "cs_fit_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "cs_fit_eval_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "cs_debug_check_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cs_debug_timeline": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     "cs_launch_count": (C.c_longlong, []),
     "cs_flush_l2": (C.c_int, [C.c_void_p]),
 }
@@ -237,7 +239,7 @@ class Fit:
     """Device-resident fit handle (cs_fit)."""
 
     def __init__(self, lib: CsLib, kind, y, X, z, w, init_params, optim=CS_OPT_NADAM, lr=0.01, beta1=0.9,
-                 beta2=0.999, eps=1e-8, momentum=0.0, tile=0, chunk=0, use_graph=0, gemm_tile=0, inv_pipeline=0):
+                 beta2=0.999, eps=1e-8, momentum=0.0, tile=0, chunk=0, use_graph=0, gemm_tile=0, inv_pipeline=0, partition=0):
         self.lib = lib
         self.h = C.c_void_p(None)
         y, z, init_params = _f64(y), _f64(z), _f64(init_params)
@@ -245,7 +247,7 @@ class Fit:
         self.n, self.p = X.shape
         self.kind = kind
         w = None if w is None else _f64(w)
-        cfg = cs_fit_config(kind, optim, lr, beta1, beta2, eps, momentum, tile, chunk, use_graph, gemm_tile, inv_pipeline)
+        cfg = cs_fit_config(kind, optim, lr, beta1, beta2, eps, momentum, tile, chunk, use_graph, gemm_tile, inv_pipeline, partition)
         h = C.c_void_p(None)
         lib.check(lib.dll.cs_fit_create(C.byref(cfg), self.n, self.p, _ptr(y), _ptr(X), _ptr(z), _ptr(w),
                                         _ptr(init_params), C.byref(h)))
@@ -342,6 +344,13 @@ class Fit:
         arr = (C.c_float * CS_NPHASE)()
         self.lib.check(self.lib.dll.cs_fit_eval_profile(self.h, arr))
         return dict(zip(PHASES, [float(x) for x in arr]))
+
+    def timeline(self, cap=4096):
+        """Per-launch timeline of the dense plan: rows (stream, type, tiles, K|block, t0_ms, t1_ms)."""
+        buf = np.zeros((cap, 6), dtype=np.float32)
+        n = C.c_int(0)
+        self.lib.check(self.lib.dll.cs_debug_timeline(self.h, cap, C.byref(n), buf.ctypes.data_as(C.POINTER(C.c_float))))
+        return buf[: n.value].copy()
 
     def flush_l2(self):
         self.lib.check(self.lib.dll.cs_flush_l2(self.h))

@@ -196,7 +196,7 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
     if (phase_ev) { rt::event_record(phase_ev[ph++], st); rt::event_record(phase_ev[ph++], st); rt::event_record(phase_ev[ph++], st); }
   } else {
     f->eng.set_status_max(st, skip);
-    f->eng.run_seq(f->eng.potrf, st, skip);
+    f->eng.run_seq(f->eng.potrf, st, skip, true);
     if (phase_ev) rt::event_record(phase_ev[ph++], st);
     f->eng.run_seq(f->eng.trtri, st, skip);
     if (phase_ev) rt::event_record(phase_ev[ph++], st);
@@ -272,7 +272,7 @@ int cs_fit_create(const cs_fit_config* cfg, int n, int p, const double* y, const
   f->p = p;
   auto bail = [&](int code) { cs_fit_destroy(f); return code; };
   if (rt::stream_create(&f->st)) return bail(fail(CS_ERR_CUDA, "stream create failed"));
-  if (int e = f->eng.init(n, tile, cfg->gemm_tile, cfg->inv_pipeline)) return bail(fail(e == 2 ? CS_ERR_NOMEM : CS_ERR_CUDA, "dense engine init failed: %s", rt::err_str(e)));
+  if (int e = f->eng.init(n, tile, cfg->gemm_tile, cfg->inv_pipeline, cfg->partition)) return bail(fail(e == 2 ? CS_ERR_NOMEM : CS_ERR_CUDA, "dense engine init failed: %s", rt::err_str(e)));
   const int np = f->eng.np;
   f->np = np;
   f->nblk = np / csk::TB;
@@ -629,6 +629,57 @@ int cs_fit_eval_profile(cs_fit* f, float phase_ms[CS_NPHASE]) {
   RT(rt::stream_sync(f->st));
   for (int i = 0; i < CS_NPHASE; ++i) RT(rt::event_elapsed(&phase_ms[i], f->ev[i], f->ev[i + 1]));
   return read_status(f);
+}
+
+// Timeline of the dense plan of one evaluation: every leaf / GEMM launch is bracketed by timing
+// events on its own stream.  rows[6*i..] = (stream, type (0 gemm, 1 leaf), tiles, K of the first
+// problem, t_begin_ms, t_end_ms) relative to the start of the factorization.
+int cs_debug_timeline(cs_fit* f, int cap, int* n_out, float* rows) {
+  if (!f || !n_out || !rows) return fail(CS_ERR_ARG, "null argument");
+  cudaStream_t st = f->st;
+  std::vector<cudaEvent_t> evs;
+  {  // Gram first so the factorization sees a valid matrix
+    auto k = csk::gram_train_kernel;
+    ++g_launches;
+    CS_LAUNCH(k, csg::lower_tiles(f->nblk), csk::ETH, csk::gram_smem_bytes(f->p), st, f->X, (long long)f->np, f->z, f->w,
+              f->params, f->lay, f->n, f->eng.G, (long long)f->np, (const int*)nullptr);
+  }
+  RT(rt::stream_sync(st));
+  cudaEvent_t base;
+  RT(rt::event_create(&base));
+  RT(rt::event_record(base, st));
+  f->eng.tl = &evs;
+  f->eng.factor_and_invert(st, nullptr);
+  f->eng.tl = nullptr;
+  KCHECK();
+  RT(rt::stream_sync(st));
+  const std::vector<csdense::Launch>& seq = f->eng.inv_pipeline ? f->eng.potrf_inv : f->eng.potrf;
+  int n = 0;
+  size_t e = 0;
+  auto emit = [&](const std::vector<csdense::Launch>& sq) {
+    for (const csdense::Launch& L : sq) {
+      if (L.is_leaf != csdense::OP_LEAF && L.is_leaf != csdense::OP_GEMM) continue;
+      if (e + 1 >= evs.size()) break;
+      float t0 = 0.f, t1 = 0.f;
+      rt::event_elapsed(&t0, base, evs[e]);
+      rt::event_elapsed(&t1, base, evs[e + 1]);
+      e += 2;
+      if (n < cap) {
+        float* r = rows + 6 * (size_t)n;
+        r[0] = (float)L.stream; r[1] = (float)L.is_leaf;
+        r[2] = (float)(L.is_leaf == csdense::OP_LEAF ? 1 : L.ntiles);
+        r[3] = (float)(L.is_leaf == csdense::OP_LEAF ? L.blk : f->eng.probs[L.first_prob].K);
+        r[4] = t0; r[5] = t1;
+        ++n;
+      }
+    }
+  };
+  emit(seq);
+  if (!f->eng.inv_pipeline) { emit(f->eng.trtri); emit(f->eng.xtx); }
+  for (cudaEvent_t ev : evs) rt::event_destroy(ev);
+  rt::event_destroy(base);
+  *n_out = n;
+  return 0;
 }
 
 int cs_flush_l2(cs_fit* f) {

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "libcausalstump_b200.so")
 SOURCES = ["api.cu"]
-DEPS = ["api.cu", "cs_rt.h", "cs_dev.cuh", "gemm.cuh", "dense.cuh", "kernels.cuh", "predict.cuh",
+DEPS = ["api.cu", "cs_rt.h", "cs_dev.cuh", "gemm.cuh", "dense.cuh", "kernels.cuh", "predict.cuh", "dist.cuh",
         os.path.join("..", "..", "include", "cs_b200.h")]
 
 

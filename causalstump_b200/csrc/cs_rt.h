@@ -45,6 +45,8 @@ inline int set_device(int) { return 0; }
 inline int sm_count() { return 4; }
 inline int host_alloc(void** p, size_t b) { *p = std::malloc(b ? b : 1); return *p ? 0 : 2; }
 inline int host_free(void* p) { std::free(p); return 0; }
+inline int partition_streams(int, cudaStream_t*, cudaStream_t**, const int*, int, int*, int*) { return 1; }
+inline int stream_create_level(cudaStream_t* s, int) { *s = 0; return 0; }
 typedef int graph_exec_t;
 inline int graph_begin(cudaStream_t) { return 1; }  // no graphs on the emulator: eager launches
 inline int graph_end(cudaStream_t, graph_exec_t*) { return 1; }
@@ -52,6 +54,7 @@ inline int graph_launch(graph_exec_t, cudaStream_t) { return 1; }
 inline int graph_destroy(graph_exec_t) { return 0; }
 }  // namespace rt
 #else
+#include <cuda.h>
 #include <cuda_runtime.h>
 #define CS_DYN_SMEM(T, name) \
   extern __shared__ __align__(16) unsigned char cs_dyn_smem_raw[]; \
@@ -77,6 +80,16 @@ inline int stream_create_low(cudaStream_t* s) {
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
   return (int)cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, lo);
 }
+// level 0 = highest priority, larger = lower (clamped to the device's range)
+inline int prio_of_level(int level) {
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi is numerically smallest
+  int p = hi + level;
+  return p > lo ? lo : p;
+}
+inline int stream_create_level(cudaStream_t* s, int level) {
+  return (int)cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, prio_of_level(level));
+}
 inline int event_create_fast(cudaEvent_t* e) { return (int)cudaEventCreateWithFlags(e, cudaEventDisableTiming); }
 inline int stream_destroy(cudaStream_t s) { return (int)cudaStreamDestroy(s); }
 inline int stream_sync(cudaStream_t s) { return (int)cudaStreamSynchronize(s); }
@@ -98,6 +111,74 @@ inline int sm_count() {
 }
 inline int host_alloc(void** p, size_t b) { return (int)cudaMallocHost(p, b ? b : 1); }
 inline int host_free(void* p) { return (int)cudaFreeHost(p); }
+
+// SM partition (CUDA green contexts, driver API resolved through cudaGetDriverEntryPoint so the
+// library still links only cudart).  The blocked Cholesky has a latency-bound chain of one-CTA
+// kernels (diagonal-block factorizations) that must never queue behind the bulk GEMM CTAs of the
+// trailing update / pipelined inverse: stream priorities are not enough, because a register-heavy
+// CTA only starts once enough co-resident bulk CTAs of ONE SM have drained.  So the chain gets a
+// small partition A (8 SMs, the hardware minimum on sm_90+) of its own and the bulk streams run on
+// partition B (the remaining SMs).  One pair of green contexts per device, created lazily, shared
+// by every handle; returns non-zero when the driver cannot partition (callers fall back to plain
+// priority streams).
+struct PartitionCtx { int state = 0; CUgreenCtx a = nullptr, b = nullptr; int sm_a = 0, sm_b = 0; };
+inline PartitionCtx& partition_ctx(int dev) { static PartitionCtx tab[64]; return tab[dev & 63]; }
+template <class F> inline bool drv_sym(const char* name, F* fn) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+    cudaGetLastError();
+    return false;
+  }
+  *fn = reinterpret_cast<F>(p);
+  return true;
+}
+inline int partition_streams(int sm_crit, cudaStream_t* crit_hi, cudaStream_t** bulk, const int* level, int nbulk,
+                             int* sm_a, int* sm_b) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+  PartitionCtx& P = partition_ctx(dev);
+  CUresult (*f_devget)(CUdevice*, int) = nullptr;
+  CUresult (*f_getres)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+  CUresult (*f_split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int) = nullptr;
+  CUresult (*f_desc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+  CUresult (*f_gcreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+  CUresult (*f_gstream)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+  if (!drv_sym("cuGreenCtxStreamCreate", &f_gstream)) return 1;
+  if (P.state == 0) {
+    P.state = -1;
+    if (!drv_sym("cuDeviceGet", &f_devget) || !drv_sym("cuDeviceGetDevResource", &f_getres) ||
+        !drv_sym("cuDevSmResourceSplitByCount", &f_split) || !drv_sym("cuDevResourceGenerateDesc", &f_desc) ||
+        !drv_sym("cuGreenCtxCreate", &f_gcreate))
+      return 1;
+    cudaFree(0);  // make sure the primary context exists
+    CUdevice cd;
+    CUdevResource all{}, ga{}, gb{};
+    unsigned int nb = 1;
+    CUdevResourceDesc da = nullptr, db = nullptr;
+    if (f_devget(&cd, dev) != CUDA_SUCCESS) return 1;
+    if (f_getres(cd, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return 1;
+    if (f_split(&ga, &nb, &all, &gb, 0, (unsigned int)sm_crit) != CUDA_SUCCESS || nb != 1) return 1;
+    if (ga.sm.smCount == 0 || gb.sm.smCount == 0) return 1;
+    if (f_desc(&da, &ga, 1) != CUDA_SUCCESS || f_desc(&db, &gb, 1) != CUDA_SUCCESS) return 1;
+    if (f_gcreate(&P.a, da, cd, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return 1;
+    if (f_gcreate(&P.b, db, cd, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return 1;
+    P.sm_a = (int)ga.sm.smCount; P.sm_b = (int)gb.sm.smCount;
+    P.state = 1;
+  }
+  if (P.state != 1) return 1;
+  CUstream s0 = nullptr;
+  if (f_gstream(&s0, P.a, CU_STREAM_NON_BLOCKING, prio_of_level(0)) != CUDA_SUCCESS) return 1;
+  *crit_hi = (cudaStream_t)s0;
+  for (int i = 0; i < nbulk; ++i) {
+    CUstream sb = nullptr;
+    if (f_gstream(&sb, P.b, CU_STREAM_NON_BLOCKING, prio_of_level(level[i])) != CUDA_SUCCESS) return 1;
+    *bulk[i] = (cudaStream_t)sb;
+  }
+  if (sm_a) *sm_a = P.sm_a;
+  if (sm_b) *sm_b = P.sm_b;
+  return 0;
+}
 // CUDA graphs: one optimizer iteration (all its launches, both streams) is captured once
 // and replayed, removing per-launch CPU cost from latency-bound small-n fits.
 typedef cudaGraphExec_t graph_exec_t;

@@ -308,8 +308,14 @@ struct DenseEngine {
   int panel_blocks = 4;             // outer panel width in blocks
   int n_events = 0;
   std::vector<cudaEvent_t> events;
-  cudaStream_t aux{}, aux2{}, aux3{};  // S1: bulk trailing updates (low); S2: panel rest (high); S3: pipelined inverse (low)
-  bool aux_ok = false, aux2_ok = false, aux3_ok = false;
+  cudaStream_t aux{}, aux2{}, aux3{}, aux4{}, aux5{};  // S4: K^-1 accumulation (lowest); S5: Acc rows below the next panel; S1: bulk trailing updates (low); S2: panel rest (high); S3: pipelined inverse (low)
+  bool aux_ok = false, aux2_ok = false, aux3_ok = false, aux4_ok = false, aux5_ok = false;
+  // SM partition (rt::partition_streams): the critical chain of the Cholesky (leaf + one-tile GEMMs, plan
+  // stream 0) runs on `crit`, a stream of the small partition A; S1..S3 live on partition B.
+  cudaStream_t crit{};
+  bool crit_ok = false;
+  int sm_crit = 0, sm_bulk = 0;
+  cudaEvent_t ev_in{}, ev_out{};
 
   static GemmProblem mk(const double* A, long long lda, const double* B, long long ldb, double* C, long long ldc,
                         int mt, int nt, int K, int kmode, int order, int mirror, double alpha, double beta) {
@@ -342,7 +348,7 @@ struct DenseEngine {
   }
 
   // returns 0 or a runtime error code
-  int init(int n_, int tile_, int gemm_tile = 64, int inv_pipe = 0) {
+  int init(int n_, int tile_, int gemm_tile = 64, int inv_pipe = 0, int partition = 0) {
     inv_pipeline = inv_pipe;
     n = n_; tile = tile_; N = (n + tile - 1) / tile; np = N * tile;
     gt = (gemm_tile == 128 && tile == 128) ? 128 : 64;
@@ -369,7 +375,7 @@ struct DenseEngine {
     int nev = 0;
     auto build_chol = [&](std::vector<Launch>& seq, bool with_inverse) {
     auto op = [&](int type, int stream, int ev) { Launch o{}; o.is_leaf = type; o.stream = stream; o.ev = ev; seq.push_back(o); };
-    int npanel = 0, last_aux_ev = -1, last_inv_ev = -1;
+    int npanel = 0, last_aux_ev = -1, last_inv_ev = -1, last_inv3_ev = -1, last_rest_ev = -1;
     // in-place panel multiply L = A * X_kk^T for `nb` block rows starting at block row r0 of column k
     auto push_panel = [&](int k, int r0, int nb, int stream) {
       if (nb <= 0) return;
@@ -452,15 +458,11 @@ struct DenseEngine {
             add_group(seq, GK_NN, grp); seq.back().stream = 3;
           }
         }
-        const int mb = N - p1;
-        if (mb > 0) {  // Acc_IJ += sum_{k in P} L_Ik X_kJ for I >= p1  (K = pw*TILE)
-          double* Lp = G + p1 * T + p0 * T * ld;
-          if (p0 > 0)
-            grp.push_back(mk(Lp, ld, X + p0 * T, ld, X + p1 * T, ld, mb * rr, p0 * rr, pw * tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 1.0));
-          grp.push_back(mk(Lp, ld, X + p0 * T * (ld + 1), ld, X + p1 * T + p0 * T * ld, ld, mb * rr, pw * rr, pw * tile, csg::KM_GE_J,
-                           csg::ORD_COL, 0, 1.0, 1.0));
-          add_group(seq, GK_NN, grp); seq.back().stream = 3;
-        }
+        // rows P of X are final here: their contribution to K^-1 goes to the accumulation stream S4 (lowest
+        // priority, nobody waits for it before the end) so that it overlaps the row chain of the next panel
+        const int ev_rows = nev++;
+        op(OP_RECORD, 3, ev_rows);
+        op(OP_WAIT, 4, ev_rows);
         {  // C_IJ += sum_{k in P} X_kI^T X_kJ for J <= I <= k  (mirrored store keeps C symmetric)
           double* Xp = X + p0 * T;              // rows of the panel, column 0
           double* Xd = X + p0 * T * (ld + 1);   // rows and columns of the panel
@@ -471,25 +473,55 @@ struct DenseEngine {
             grp.push_back(q);
           }
           grp.push_back(mk(Xd, ld, Xd, ld, C + p0 * T * (ld + 1), ld, pw * rr, pw * rr, pw * tile, csg::KM_GE_I, csg::ORD_LOWER, 1, 1.0, 1.0));
-          add_group(seq, GK_TN, grp); seq.back().stream = 3;
+          add_group(seq, GK_TN, grp); seq.back().stream = 4;
         }
         last_inv_ev = nev++;
-        op(OP_RECORD, 3, last_inv_ev);
+        op(OP_RECORD, 4, last_inv_ev);
+        // Acc_IJ += sum_{k in P} L_Ik X_kJ for I >= p1 (K = pw*TILE) feeds the later row chains.  Look-ahead:
+        // the rows of the NEXT panel are updated on the chain stream S3 right away (AccNext), the rows
+        // below them on the bulk stream S5 (AccRest); both accumulate into the same tiles of the panel
+        // after next, so AccNext(P) is ordered after AccRest(P-1).
+        const int mb = N - p1;
+        if (mb > 0) {
+          const int nn = std::min(W, mb);  // block rows of the next panel
+          auto push_acc = [&](int r0, int nb_rows, int stream) {
+            double* Lp = G + (long long)r0 * T + p0 * T * ld;
+            if (p0 > 0)
+              grp.push_back(mk(Lp, ld, X + p0 * T, ld, X + (long long)r0 * T, ld, nb_rows * rr, p0 * rr, pw * tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 1.0));
+            grp.push_back(mk(Lp, ld, X + p0 * T * (ld + 1), ld, X + (long long)r0 * T + p0 * T * ld, ld, nb_rows * rr, pw * rr, pw * tile,
+                             csg::KM_GE_J, csg::ORD_COL, 0, 1.0, 1.0));
+            add_group(seq, GK_NN, grp); seq.back().stream = stream;
+          };
+          if (last_rest_ev >= 0) op(OP_WAIT, 3, last_rest_ev);
+          push_acc(p1, nn, 3);
+          last_inv3_ev = nev++;
+          op(OP_RECORD, 3, last_inv3_ev);
+          if (mb > nn) {
+            op(OP_WAIT, 5, ev_rows);
+            push_acc(p1 + nn, mb - nn, 5);
+            last_rest_ev = nev++;
+            op(OP_RECORD, 5, last_rest_ev);
+          }
+        }
       }
       const int mt = N - p1;  // trailing blocks
       if (mt <= 0) continue;
       const int kw = (p1 - p0) * tile;
       double* pan = G + p1 * T + p0 * T * ld;  // rows >= p1 of the finished panel
       const int n1 = std::min(W, mt);          // next panel's block columns
-      const int ev_panel = nev++, ev_u2 = nev++;
+      const int ev_panel = nev++, ev_u2 = nev++, ev_u1 = nev++;
       op(OP_RECORD, 0, ev_panel);
-      if (last_aux_ev >= 0) op(OP_WAIT, 0, last_aux_ev);  // U2 of the previous panel also wrote these columns
-      // U1: columns [p1, p1+n1): lower part + rectangle below (S0)
+      // U1: columns [p1, p1+n1): lower part + rectangle below, on the panel stream S2 (every SM of the
+      // bulk partition, high priority); the critical stream only waits for it
+      op(OP_WAIT, 2, ev_panel);
+      if (last_aux_ev >= 0) op(OP_WAIT, 2, last_aux_ev);  // U2 of the previous panel also wrote these columns
       grp.push_back(mk(pan, ld, pan, ld, G + p1 * T * (ld + 1), ld, n1 * rr, n1 * rr, kw, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
       if (mt > n1)
         grp.push_back(mk(pan + n1 * T, ld, pan, ld, G + (p1 + n1) * T + p1 * T * ld, ld, (mt - n1) * rr, n1 * rr, kw, csg::KM_FULL,
                          csg::ORD_COL, 0, -1.0, 1.0));
-      add_group(seq, GK_NT, grp);
+      add_group(seq, GK_NT, grp); seq.back().stream = 2;
+      op(OP_RECORD, 2, ev_u1);
+      op(OP_WAIT, 0, ev_u1);
       // U2: everything to the right of the next panel (bulk stream S1)
       op(OP_WAIT, 1, ev_panel);
       if (mt > n1) {
@@ -504,6 +536,8 @@ struct DenseEngine {
     // the main stream rejoins the bulk (and inverse) streams before anything reads the results
     if (last_aux_ev >= 0) op(OP_WAIT, 0, last_aux_ev);
     if (last_inv_ev >= 0) op(OP_WAIT, 0, last_inv_ev);
+    if (last_inv3_ev >= 0) op(OP_WAIT, 0, last_inv3_ev);
+    if (last_rest_ev >= 0) op(OP_WAIT, 0, last_rest_ev);
     };
     build_chol(potrf, false);
     if (inv_pipeline) build_chol(potrf_inv, true);
@@ -531,12 +565,30 @@ struct DenseEngine {
     grp.push_back(mk(X, ld, X, ld, C, ld, N * rr, N * rr, np, csg::KM_GE_I, csg::ORD_LOWER, 1, 1.0, 0.0));
     add_group(xtx, GK_TN, grp);
 
-    if ((e = rt::stream_create_low(&aux))) return e;
-    aux_ok = true;
-    if ((e = rt::stream_create(&aux2))) return e;
-    aux2_ok = true;
-    if ((e = rt::stream_create_low(&aux3))) return e;
-    aux3_ok = true;
+    // partition: 0 = auto (large problems only: the chain of a small fit is launch-bound, not slot-bound,
+    // and many small fits share the device), 1 = on, -1 = off
+    const bool want_part = partition > 0 || (partition == 0 && np >= 4096 && std::getenv("CS_NO_PARTITION") == nullptr);
+    // priorities: S2 (panel work the Cholesky chain waits for) highest, then S3 (row chain of the inverse),
+    // S1 (trailing update), S5 (Acc of the rows below the next panel), S4 (K^-1 accumulation) lowest
+    cudaStream_t* bulk[5] = {&aux, &aux2, &aux3, &aux4, &aux5};
+    int level[5] = {2, 0, 1, 5, 3};  // 0 = highest
+    if (const char* ev = std::getenv("CS_PRIO")) std::sscanf(ev, "%d,%d,%d,%d,%d", &level[0], &level[1], &level[2], &level[3], &level[4]);
+    if (want_part && rt::partition_streams(8, &crit, bulk, level, 5, &sm_crit, &sm_bulk) == 0) {
+      crit_ok = aux_ok = aux2_ok = aux3_ok = aux4_ok = aux5_ok = true;
+      if ((e = rt::event_create_fast(&ev_in))) return e;
+      if ((e = rt::event_create_fast(&ev_out))) return e;
+    } else {
+      if ((e = rt::stream_create_level(&aux, level[0]))) return e;
+      aux_ok = true;
+      if ((e = rt::stream_create_level(&aux2, level[1]))) return e;
+      aux2_ok = true;
+      if ((e = rt::stream_create_level(&aux3, level[2]))) return e;
+      aux3_ok = true;
+      if ((e = rt::stream_create_level(&aux4, level[3]))) return e;
+      aux4_ok = true;
+      if ((e = rt::stream_create_level(&aux5, level[4]))) return e;
+      aux5_ok = true;
+    }
     events.resize(n_events);
     for (int i = 0; i < n_events; ++i)
       if ((e = rt::event_create_fast(&events[i]))) return e;
@@ -554,12 +606,30 @@ struct DenseEngine {
     if (aux_ok) { rt::stream_sync(aux); rt::stream_destroy(aux); aux_ok = false; }
     if (aux2_ok) { rt::stream_sync(aux2); rt::stream_destroy(aux2); aux2_ok = false; }
     if (aux3_ok) { rt::stream_sync(aux3); rt::stream_destroy(aux3); aux3_ok = false; }
+    if (aux4_ok) { rt::stream_sync(aux4); rt::stream_destroy(aux4); aux4_ok = false; }
+    if (aux5_ok) { rt::stream_sync(aux5); rt::stream_destroy(aux5); aux5_ok = false; }
+    if (crit_ok) { rt::stream_sync(crit); rt::stream_destroy(crit); rt::event_destroy(ev_in); rt::event_destroy(ev_out); crit_ok = false; }
     G = X = C = logdet_part = nullptr; status = nullptr; d_probs = nullptr;
   }
 
-  void run_seq(const std::vector<Launch>& seq, cudaStream_t st, const int* skip = nullptr) {
+  // timeline capture (cs_debug_timeline): when set, every kernel launch of run_seq is bracketed
+  // by a pair of timing events on its own stream
+  std::vector<cudaEvent_t>* tl = nullptr;
+
+  // use_crit: plan stream 0 is the critical chain of the Cholesky and runs on the partition-A stream
+  // (entered and left through events on `st`); plans whose stream 0 carries bulk work pass false
+  void run_seq(const std::vector<Launch>& seq, cudaStream_t st, const int* skip = nullptr, bool use_crit = false) {
+    const bool part = use_crit && crit_ok;
+    cudaStream_t s0 = st;
+    if (part) {
+      rt::event_record(ev_in, st);
+      rt::stream_wait_event(crit, ev_in);
+      s0 = crit;
+    }
     for (const Launch& L : seq) {
-      cudaStream_t s = L.stream == 1 ? aux : (L.stream == 2 ? aux2 : (L.stream == 3 ? aux3 : st));
+      cudaStream_t s = L.stream == 1 ? aux : (L.stream == 2 ? aux2 : (L.stream == 3 ? aux3 : (L.stream == 4 ? aux4 : (L.stream == 5 ? aux5 : s0))));
+      const bool timed = tl && (L.is_leaf == OP_LEAF || L.is_leaf == OP_GEMM);
+      if (timed) { cudaEvent_t e0; rt::event_create(&e0); rt::event_record(e0, s); tl->push_back(e0); }
       if (L.is_leaf == OP_LEAF) {
         launch_leaf(tile, G + (long long)L.blk * tile * ((long long)np + 1), np, X + (long long)L.blk * tile * ((long long)np + 1), np,
                     L.blk * tile, logdet_part + L.blk, status, n, s, skip);
@@ -570,6 +640,11 @@ struct DenseEngine {
       } else {
         launch_gemm(L.gtile ? L.gtile : gt, L.kind, d_probs + L.first_prob, L.nprob, L.ntiles, s, skip);
       }
+      if (timed) { cudaEvent_t e1; rt::event_create(&e1); rt::event_record(e1, s); tl->push_back(e1); }
+    }
+    if (part) {
+      rt::event_record(ev_out, crit);
+      rt::stream_wait_event(st, ev_out);
     }
   }
 
@@ -613,7 +688,7 @@ struct DenseEngine {
     const int n_ops = (int)seq.size();
     const int words = (n_ops + 63) / 64;
     std::vector<std::vector<unsigned long long>> anc(n_ops, std::vector<unsigned long long>(words, 0ULL));
-    int last_on_stream[4] = {-1, -1, -1, -1};
+    int last_on_stream[6] = {-1, -1, -1, -1, -1, -1};
     std::vector<int> last_record(n_events + 1, -1);
     auto add_pred = [&](int j, int i) {
       if (i < 0) return;
@@ -651,7 +726,7 @@ struct DenseEngine {
   }
 
   // G (lower) must hold K_n; X and the upper triangle of G must be zero outside diagonal tiles.
-  void factor(cudaStream_t st, const int* skip = nullptr) { set_status_max(st, skip); run_seq(potrf, st, skip); }
+  void factor(cudaStream_t st, const int* skip = nullptr) { set_status_max(st, skip); run_seq(potrf, st, skip, true); }
   void invert(cudaStream_t st, const int* skip = nullptr) { run_seq(trtri, st, skip); run_seq(xtx, st, skip); }
   // K_n (in G) -> L, L^-1, K_n^-1.  With inv_pipeline the inverse trails the factorization on its
   // own stream; X and C are accumulated into and must start from zero.
@@ -661,7 +736,7 @@ struct DenseEngine {
       rt::memset0(X, mb, st);
       rt::memset0(C, mb, st);
       set_status_max(st, skip);
-      run_seq(potrf_inv, st, skip);
+      run_seq(potrf_inv, st, skip, true);
     } else {
       factor(st, skip);
       invert(st, skip);

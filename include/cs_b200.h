@@ -59,6 +59,8 @@ typedef struct cs_fit_config {
   int gemm_tile;   /* 0 / 64 = 64x64 CTA tiles (default); 128 = 128x128 CTA tiles    */
   int inv_pipeline;/* 1 = inverse pipelined behind the Cholesky on its own stream;   */
                    /* 0 = recursive triangular inverse + X^T X after the Cholesky    */
+  int partition;   /* SM partition for the Cholesky's critical chain (CUDA green contexts):   */
+                   /* 0 = auto (padded n >= 4096), 1 = on, -1 = off                            */
 } cs_fit_config;
 
 /* ---- library / device ---------------------------------------------------------- */
@@ -196,6 +198,9 @@ int cs_fit_eval_profile(cs_fit* f, float phase_ms[CS_NPHASE]);
 long long cs_launch_count(void);
 /* test hook: happens-before check of the multi-stream Cholesky launch plan (0 = no races) */
 int cs_debug_check_plan(int n, int tile, int gemm_tile, int verbose);
+/* debug: per-launch timeline of the dense plan (rows of 6 floats: stream, type, tiles, K | block,
+ * t_begin_ms, t_end_ms); used by tools/timeline.py to find idle gaps on the critical path */
+int cs_debug_timeline(cs_fit* f, int cap, int* n_out, float* rows);
 /* write `bytes` of device memory (> L2) to flush the cache between timed iterations */
 int cs_flush_l2(cs_fit* f);
 

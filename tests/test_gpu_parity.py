@@ -87,6 +87,69 @@ def test_golden_fixtures(gpulib):
         f.close()
 
 
+def test_golden_ref(gpulib):
+    """CUDA path vs vectors produced by the reference's own C++ (oracle/_ref; tests/golden/make_golden_ref.py)."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_ref_v1.npz"))
+    for nm in sorted({k.split("/")[0] for k in G.files}):
+        kind, n, p, iters, optim = (int(v) for v in G[nm + "/meta"][:5])
+        lr, mom = float(G[nm + "/meta"][5]), float(G[nm + "/meta"][6])
+        f = _lib.Fit(gpulib, kind, G[nm + "/y"], G[nm + "/X"], G[nm + "/z"], G[nm + "/w"], G[nm + "/init_params"],
+                     optim=optim, lr=lr, momentum=mom)
+        g, st, mu = f.eval()
+        gref = G[nm + "/grad"]
+        assert np.max(np.abs(g - gref) / np.maximum(np.abs(gref), 1e-6 * np.max(np.abs(gref)))) < cs.TOL_GRAD, nm
+        assert abs(st[1] - G[nm + "/stats"][1]) < cs.TOL_LML * abs(G[nm + "/stats"][1]), nm
+        assert abs(st[0] - G[nm + "/stats"][0]) < 1e-7 * abs(G[nm + "/stats"][0]), nm
+        assert abs(mu - float(G[nm + "/mu_sol"])) < 1e-9 * abs(float(G[nm + "/mu_sol"])), nm
+        m = f.get_matrices(want=("Kmat", "Km", "Ka", "invK"))
+        assert cs.relm(m["Kmat"][0], G[nm + "/K_row0"]) < 1e-13 and cs.relm(m["Km"][0], G[nm + "/Km_row0"]) < 1e-13
+        assert cs.relm(m["Ka"][0], G[nm + "/Ka_row0"]) < 1e-13
+        assert cs.relm(np.diag(m["invK"]), G[nm + "/invK_diag"]) < 1e-9 and cs.relm(m["invK"][0], G[nm + "/invK_row0"]) < 1e-9
+        it, trace = f.run(iters, 0.0)
+        assert it == iters
+        assert cs.rel(f.get_params(), G[nm + "/fit_params"], 1e-9) < 1e-7, nm
+        assert cs.rel(trace[1, 1:], G[nm + "/fit_trace"][1, 1:]) < 1e-8, nm
+        assert cs.rel(trace[0, 1:], G[nm + "/fit_trace"][0, 1:]) < 1e-6, nm
+        pr = f.predict(G[nm + "/X2"], G[nm + "/z2"])
+        tr = f.treat(G[nm + "/X2"], cov_jitter=1e-6 if kind == 1 else 0.0)
+        assert cs.relm(pr["map"], G[nm + "/pred_map"]) < cs.TOL_MAP and cs.relm(pr["var"], G[nm + "/pred_var"]) < 1e-7, nm
+        assert cs.relm(tr["map"], G[nm + "/treat_map"]) < cs.TOL_MAP and cs.relm(tr["var"], G[nm + "/treat_var"]) < 1e-7, nm
+        assert abs(tr["ate"] - float(G[nm + "/treat_ate"])) < 1e-8 * max(abs(float(G[nm + "/treat_ate"])), 1e-3), nm
+        assert abs(tr["ate_var"] - float(G[nm + "/treat_ate_var"])) < 1e-7 * abs(float(G[nm + "/treat_ate_var"])), nm
+        f.close()
+
+
+def test_stateless_mirrors_vs_compiled_reference(gpulib):
+    """The stateless C-ABI mirrors against oracle/_ref (the reference's C++ compiled with the header shim),
+    which travels to the GPU box as a prebuilt .so; skipped when it is absent."""
+    from oracle import ref_binding as rb
+    if not rb.available():
+        pytest.skip("oracle/_ref/libcausalstump_ref.so not present")
+    ref = rb.RefLib()
+    for kind, n, p in ((0, 300, 25), (1, 257, 7)):
+        P = cs.make_problem("GP" if kind == 0 else "TP", n, p, weights=True)
+        par, y, X, z, w = P["par"], P["y"], P["X"], P["z"], P["w"]
+        flat = o.pack_params(par)
+        la = par["lambdaa"] if kind == 0 else par["lambda0"]
+        K, Km, Ka = ref.kernmat(kind, X[:101], X, z[:101], z, par["Lm"], par["La"], par["lambdam"], la)
+        out = gpulib.kernmat(X[:101], X, z[:101], z, par["Lm"], par["La"], par["lambdam"], la)
+        assert cs.relm(out["K"], K) < 1e-13 and cs.relm(out["Km"], Km) < 1e-13 and cs.relm(out["Ka"], Ka) < 1e-13
+        g, st, mu, mats = ref.eval_lml_grad(kind, y, X, z, w, flat)
+        inv2 = gpulib.invkernel(w, mats["K"], par["sigma"])
+        assert cs.relm(inv2, mats["invK"]) < 1e-9
+        assert abs(gpulib.mu_solution(y, mats["invK"]) - mu) < 1e-10 * abs(mu)
+        for kw in ({}, dict(invK=mats["invK"], Kmat=mats["K"], Km=mats["Km"], Ka=mats["Ka"])):
+            g2, st2 = gpulib.grad(kind, y, X, z, w, flat, **kw)
+            assert np.max(np.abs(g2 - g) / np.maximum(np.abs(g), 1e-6 * np.max(np.abs(g)))) < cs.TOL_GRAD
+            assert abs(st2[1] - st[1]) < cs.TOL_LML * abs(st[1]) and abs(st2[0] - st[0]) < 1e-7 * abs(st[0])
+        m0, v0 = np.zeros_like(flat), np.zeros_like(flat)
+        for optim in (0, 1, 2):
+            mr, vr, pr_ = ref.opt_step(optim, kind, p, 3.0, 0.01, 0.9 if optim < 2 else 0.5, 0.999, 1e-8, m0 + 0.01, v0 + 0.02, g, flat)
+            m2, v2, p2 = gpulib.opt_step(optim, 3.0, 0.01, 0.9 if optim < 2 else 0.5, 0.999, 1e-8, m0 + 0.01, v0 + 0.02, g, flat)
+            # the C-ABI step leaves mu to the caller's closed form (quirk Q1): compare all entries but the last
+            assert np.allclose(p2[:-1], pr_[:-1], rtol=1e-13, atol=0) and np.allclose(m2[:-1], mr[:-1], rtol=1e-13, atol=1e-300)
+
+
 def test_stateless_mirrors(gpulib):
     P = cs.make_problem("GP", 500, 25, weights=True)
     par, y, X, z, w = P["par"], P["y"], P["X"], P["z"], P["w"]
