@@ -45,7 +45,11 @@ inline int set_device(int) { return 0; }
 inline int sm_count() { return 4; }
 inline int host_alloc(void** p, size_t b) { *p = std::malloc(b ? b : 1); return *p ? 0 : 2; }
 inline int host_free(void* p) { std::free(p); return 0; }
-inline int partition_streams(int, cudaStream_t*, cudaStream_t**, const int*, int, int*, int*) { return 1; }
+inline int partition_streams(int, cudaStream_t*, cudaStream_t*, cudaStream_t**, const int*, int, int*, int*) { return 1; }
+inline int copy2d(double* dst, const double* src, long long ld, long long rows, long long cols, cudaStream_t) {
+  for (long long c = 0; c < cols; ++c) std::memmove(dst + c * ld, src + c * ld, sizeof(double) * rows);
+  return 0;
+}
 inline int stream_create_level(cudaStream_t* s, int) { *s = 0; return 0; }
 typedef int graph_exec_t;
 inline int graph_begin(cudaStream_t) { return 1; }  // no graphs on the emulator: eager launches
@@ -133,7 +137,11 @@ template <class F> inline bool drv_sym(const char* name, F* fn) {
   *fn = reinterpret_cast<F>(p);
   return true;
 }
-inline int partition_streams(int sm_crit, cudaStream_t* crit_hi, cudaStream_t** bulk, const int* level, int nbulk,
+inline int copy2d(double* dst, const double* src, long long ld, long long rows, long long cols, cudaStream_t s) {
+  return (int)cudaMemcpy2DAsync(dst, sizeof(double) * ld, src, sizeof(double) * ld, sizeof(double) * rows, (size_t)cols,
+                                cudaMemcpyDeviceToDevice, s);
+}
+inline int partition_streams(int sm_crit, cudaStream_t* crit_hi, cudaStream_t* crit_hi2, cudaStream_t** bulk, const int* level, int nbulk,
                              int* sm_a, int* sm_b) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 1;
@@ -170,6 +178,9 @@ inline int partition_streams(int sm_crit, cudaStream_t* crit_hi, cudaStream_t** 
   CUstream s0 = nullptr;
   if (f_gstream(&s0, P.a, CU_STREAM_NON_BLOCKING, prio_of_level(0)) != CUDA_SUCCESS) return 1;
   *crit_hi = (cudaStream_t)s0;
+  CUstream s0b = nullptr;
+  if (f_gstream(&s0b, P.a, CU_STREAM_NON_BLOCKING, prio_of_level(0)) != CUDA_SUCCESS) return 1;
+  *crit_hi2 = (cudaStream_t)s0b;
   for (int i = 0; i < nbulk; ++i) {
     CUstream sb = nullptr;
     if (f_gstream(&sb, P.b, CU_STREAM_NON_BLOCKING, prio_of_level(level[i])) != CUDA_SUCCESS) return 1;

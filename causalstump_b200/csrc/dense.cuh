@@ -235,7 +235,7 @@ enum GemmKind { GK_NT = 0, GK_NN = 1, GK_TN = 2 };
 
 static long long g_launches = 0;  // kernels launched by this library (claimed count for bench.py)
 
-enum OpType { OP_GEMM = 0, OP_LEAF = 1, OP_RECORD = 2, OP_WAIT = 3 };
+enum OpType { OP_GEMM = 0, OP_LEAF = 1, OP_RECORD = 2, OP_WAIT = 3, OP_COPY = 4 };
 
 struct Launch {
   int is_leaf;     // OpType (1: leaf_kernel(blk), 0: gemm group, 2/3: event record / wait)
@@ -247,6 +247,8 @@ struct Launch {
   int stream;      // 0: main (critical path, high priority)   1: auxiliary (bulk updates)
   int ev;          // event index for OP_RECORD / OP_WAIT
   int gtile;       // CTA tile of this launch (0 = engine default gt)
+  // OP_COPY: 2-D device copy of `rows` x `cols` doubles (leading dimension np on both sides)
+  double* cp_dst; const double* cp_src; long long cp_rows, cp_cols;
 };
 
 inline int pick_tile(int n) { return n <= 1536 ? 64 : 128; }
@@ -299,17 +301,19 @@ struct DenseEngine {
   int gt = 0, rr = 1;                   // gt: CTA tile of the GEMM kernel, rr = tile / gt
   double *G = nullptr, *X = nullptr, *C = nullptr;  // device, np x np each
   double* logdet_part = nullptr;                     // device, N
+  double* Pbuf = nullptr;                            // device, np x (panel_blocks*tile): out-of-place panel multiply
   int* status = nullptr;                             // device, 1 (0 = OK, else 1-based failing pivot)
   GemmProblem* d_probs = nullptr;
   std::vector<GemmProblem> probs;
   std::vector<Launch> potrf, trtri, xtx;
   std::vector<Launch> potrf_inv;    // Cholesky with the inverse pipelined behind it (inv_pipeline)
   int inv_pipeline = 0;
+  int plan_version = 2;
   int panel_blocks = 4;             // outer panel width in blocks
   int n_events = 0;
   std::vector<cudaEvent_t> events;
-  cudaStream_t aux{}, aux2{}, aux3{}, aux4{}, aux5{};  // S4: K^-1 accumulation (lowest); S5: Acc rows below the next panel; S1: bulk trailing updates (low); S2: panel rest (high); S3: pipelined inverse (low)
-  bool aux_ok = false, aux2_ok = false, aux3_ok = false, aux4_ok = false, aux5_ok = false;
+  cudaStream_t aux{}, aux2{}, aux3{}, aux4{}, aux5{}, aux6{};  // S6: second chain stream (X_PP), partition A;  // S4: K^-1 accumulation (lowest); S5: Acc rows below the next panel; S1: bulk trailing updates (low); S2: panel rest (high); S3: pipelined inverse (low)
+  bool aux_ok = false, aux2_ok = false, aux3_ok = false, aux4_ok = false, aux5_ok = false, aux6_ok = false;
   // SM partition (rt::partition_streams): the critical chain of the Cholesky (leaf + one-tile GEMMs, plan
   // stream 0) runs on `crit`, a stream of the small partition A; S1..S3 live on partition B.
   cudaStream_t crit{};
@@ -350,6 +354,7 @@ struct DenseEngine {
   // returns 0 or a runtime error code
   int init(int n_, int tile_, int gemm_tile = 64, int inv_pipe = 0, int partition = 0) {
     inv_pipeline = inv_pipe;
+    if (const char* pb = std::getenv("CS_PANEL")) { const int v = std::atoi(pb); if (v >= 1 && v <= 16) panel_blocks = v; }
     n = n_; tile = tile_; N = (n + tile - 1) / tile; np = N * tile;
     gt = (gemm_tile == 128 && tile == 128) ? 128 : 64;
     rr = tile / gt;
@@ -359,6 +364,7 @@ struct DenseEngine {
     if ((e = rt::dev_malloc((void**)&X, bytes))) return e;
     if ((e = rt::dev_malloc((void**)&C, bytes))) return e;
     if ((e = rt::dev_malloc((void**)&logdet_part, sizeof(double) * N))) return e;
+    if ((e = rt::dev_malloc((void**)&Pbuf, sizeof(double) * (size_t)np * panel_blocks * tile))) return e;
     if ((e = rt::dev_malloc((void**)&status, sizeof(int)))) return e;
     configure_kernels();
     const long long ld = np;
@@ -539,8 +545,183 @@ struct DenseEngine {
     if (last_inv3_ev >= 0) op(OP_WAIT, 0, last_inv3_ev);
     if (last_rest_ev >= 0) op(OP_WAIT, 0, last_rest_ev);
     };
-    build_chol(potrf, false);
-    if (inv_pipeline) build_chol(potrf_inv, true);
+
+    // ---- plan v2: the diagonal block of a panel (W x W tiles) is factored AND inverted by the chain
+    // alone (streams S0 / S6 on the small partition), everything below it is ONE multiply with the
+    // explicit inverse, L_IP = A_IP X_PP^T (out of place through Pbuf), so the chain never waits for
+    // bulk-partition work inside a panel.  Look-ahead: the rows of the next panel are multiplied and
+    // the next diagonal block is updated first (Ltop / U1top), the rest follows.
+    auto build_chol2 = [&](std::vector<Launch>& seq, bool with_inverse) {
+    auto op = [&](int type, int stream, int ev) { Launch o{}; o.is_leaf = type; o.stream = stream; o.ev = ev; seq.push_back(o); };
+    auto copy_op = [&](int stream, double* dst, const double* src, long long rows, long long cols) {
+      Launch o{}; o.is_leaf = OP_COPY; o.stream = stream; o.cp_dst = dst; o.cp_src = src; o.cp_rows = rows; o.cp_cols = cols; seq.push_back(o);
+    };
+    int last_aux_ev = -1, last_inv_ev = -1, last_inv3_ev = -1, last_rest_ev = -1, ev_u1top_prev = -1, last_s6_ev = -1, last_u2b_ev = -1;
+    auto push_panel = [&](int k, int r0, int nb, int stream) {  // in-place L = A X_kk^T for nb block rows of column k
+      if (nb <= 0) return;
+      double* pan = G + (long long)r0 * T + (long long)k * T * ld;
+      double* Xkk = X + (long long)k * T * (ld + 1);
+      if (rr == 2) {
+        grp.push_back(mk(pan, ld, Xkk + gt, ld, pan + gt * ld, ld, nb * rr, 1, tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
+        add_group(seq, GK_NT, grp); seq.back().stream = stream;
+        grp.push_back(mk(pan, ld, Xkk, ld, pan, ld, nb * rr, 1, gt, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
+        add_group(seq, GK_NT, grp); seq.back().stream = stream;
+      } else {
+        grp.push_back(mk(pan, ld, Xkk, ld, pan, ld, nb, 1, tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
+        add_group(seq, GK_NT, grp); seq.back().stream = stream; seq.back().gtile = tile;
+      }
+    };
+    for (int p0 = 0; p0 < N; p0 += W) {
+      const int p1 = std::min(p0 + W, N);
+      const int pw = p1 - p0;
+      double* Xpp = X + (long long)p0 * T * (ld + 1);   // diagonal block of X = inverse of the diagonal block of L
+      // ---- D(P) on the chain (S0): factor the diagonal block; S6 builds the off-diagonal tiles of X_PP
+      if (ev_u1top_prev >= 0) op(OP_WAIT, 0, ev_u1top_prev);
+      if (last_s6_ev >= 0) op(OP_WAIT, 0, last_s6_ev);   // keeps the happens-before relation of S6 simple
+      for (int k = p0; k < p1; ++k) {
+        { Launch L{}; L.is_leaf = OP_LEAF; L.blk = k; seq.push_back(L); }
+        const int ev_leaf = nev++;
+        op(OP_RECORD, 0, ev_leaf);
+        const int nb = p1 - 1 - k;
+        if (nb > 0) {
+          push_panel(k, k + 1, nb, 0);
+          double* col = G + (long long)(k + 1) * T + (long long)k * T * ld;  // L_{k+1..p1-1, k}
+          grp.push_back(mk(col, ld, col, ld, G + (long long)(k + 1) * T * (ld + 1), ld, nb * rr, nb * rr, tile, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
+          add_group(seq, GK_NT, grp);
+        }
+        if (k > p0) {
+          // row k of X_PP: T = L_{k,p0:k} X_{p0:k,p0:k} (X lower: k-range >= j), then X_{k,p0:k} = -X_kk T in place
+          const int q = k - p0;
+          double* rowk = X + (long long)k * T + (long long)p0 * T * ld;
+          op(OP_WAIT, 6, ev_leaf);
+          grp.push_back(mk(G + (long long)k * T + (long long)p0 * T * ld, ld, Xpp, ld, rowk, ld, rr, q * rr, q * tile, csg::KM_GE_J, csg::ORD_COL, 0, 1.0, 0.0));
+          add_group(seq, GK_NN, grp); seq.back().stream = 6;
+          grp.push_back(mk(X + (long long)k * T * (ld + 1), ld, rowk, ld, rowk, ld, 1, q, tile, csg::KM_FULL, csg::ORD_COL, 0, -1.0, 0.0));
+          add_group(seq, GK_NN, grp); seq.back().stream = 6; seq.back().gtile = tile;
+        }
+      }
+      const int ev_diag = nev++, ev_xpp = nev++;
+      op(OP_RECORD, 0, ev_diag);
+      op(OP_WAIT, 6, ev_diag);
+      op(OP_RECORD, 6, ev_xpp);
+      last_s6_ev = ev_xpp;
+      const int mt = N - p1;  // block rows below the panel
+      const int n1 = std::min(W, mt);
+      int ev_lpanel = -1;
+      if (mt > 0) {
+        // ---- S2: L_IP = A_IP X_PP^T for the rows below (k <= j), next panel's rows first
+        const long long kw = (long long)pw * tile;
+        double* pan = G + (long long)p1 * T + (long long)p0 * T * ld;
+        op(OP_WAIT, 2, ev_xpp);
+        auto lmul = [&](int r0, int nb_rows) {
+          double* src = G + (long long)r0 * T + (long long)p0 * T * ld;
+          double* dst = Pbuf + (long long)r0 * T;
+          grp.push_back(mk(src, ld, Xpp, ld, dst, ld, nb_rows * rr, pw * rr, (int)kw, csg::KM_LE_J, csg::ORD_COL, 0, 1.0, 0.0));
+          add_group(seq, GK_NT, grp); seq.back().stream = 2;
+          copy_op(2, src, dst, (long long)nb_rows * tile, kw);
+        };
+        lmul(p1, n1);
+        // U1top: next diagonal block (lower tiles), K = panel width
+        if (last_aux_ev >= 0) op(OP_WAIT, 2, last_aux_ev);  // U2 of the previous panel also wrote these columns
+        grp.push_back(mk(pan, ld, pan, ld, G + (long long)p1 * T * (ld + 1), ld, n1 * rr, n1 * rr, (int)kw, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
+        add_group(seq, GK_NT, grp); seq.back().stream = 2;
+        ev_u1top_prev = nev++;
+        op(OP_RECORD, 2, ev_u1top_prev);
+        if (mt > n1) {
+          lmul(p1 + n1, mt - n1);
+          // U1rest: rectangle below the next diagonal block (next panel's columns)
+          grp.push_back(mk(pan + (long long)n1 * T, ld, pan, ld, G + (long long)(p1 + n1) * T + (long long)p1 * T * ld, ld, (mt - n1) * rr, n1 * rr, (int)kw,
+                           csg::KM_FULL, csg::ORD_COL, 0, -1.0, 1.0));
+          add_group(seq, GK_NT, grp); seq.back().stream = 2;
+        }
+        ev_lpanel = nev++;
+        op(OP_RECORD, 2, ev_lpanel);
+        // ---- S1: U2, everything to the right of the next panel.  Look-ahead of depth two: the columns of
+        // the panel after next (U2a) come first and are the only part U1 of the next panel waits for.
+        if (mt > n1) {
+          op(OP_WAIT, 1, ev_lpanel);
+          const int m2 = mt - n1;                 // block rows / columns right of the next panel
+          const int n2 = std::min(W, m2);         // columns of the panel after next
+          double* pan2 = pan + (long long)n1 * T; // L rows >= p1 + n1
+          double* D2 = G + (long long)(p1 + n1) * T * (ld + 1);
+          grp.push_back(mk(pan2, ld, pan2, ld, D2, ld, n2 * rr, n2 * rr, (int)kw, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
+          if (m2 > n2)
+            grp.push_back(mk(pan2 + (long long)n2 * T, ld, pan2, ld, D2 + (long long)n2 * T, ld, (m2 - n2) * rr, n2 * rr, (int)kw, csg::KM_FULL, csg::ORD_COL, 0, -1.0, 1.0));
+          add_group(seq, GK_NT, grp); seq.back().stream = 1;
+          last_aux_ev = nev++;
+          op(OP_RECORD, 1, last_aux_ev);
+          if (m2 > n2) {
+            double* pan3 = pan2 + (long long)n2 * T;
+            grp.push_back(mk(pan3, ld, pan3, ld, D2 + (long long)n2 * T * (ld + 1), ld, (m2 - n2) * rr, (m2 - n2) * rr, (int)kw, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
+            add_group(seq, GK_NT, grp); seq.back().stream = 1;
+            last_u2b_ev = nev++;
+            op(OP_RECORD, 1, last_u2b_ev);
+          }
+        }
+      }
+      if (with_inverse) {
+        // ---- S3: rows P of X left of the diagonal block, X_iJ = -sum_{l<=i} X_il Acc_lJ, bottom row first (in place)
+        op(OP_WAIT, 3, ev_xpp);
+        if (p0 > 0) {
+          for (int i = p1 - 1; i >= p0; --i) {
+            grp.push_back(mk(X + (long long)i * T + (long long)p0 * T * ld, ld, X + (long long)p0 * T, ld, X + (long long)i * T, ld, 1, p0, (i - p0 + 1) * tile,
+                             csg::KM_FULL, csg::ORD_COL, 0, -1.0, 0.0));
+            add_group(seq, GK_NN, grp); seq.back().stream = 3; seq.back().gtile = tile;
+          }
+        }
+        const int ev_rows = nev++;
+        op(OP_RECORD, 3, ev_rows);
+        op(OP_WAIT, 4, ev_rows);
+        {  // S4: C_IJ += sum_{k in P} X_kI^T X_kJ  (mirrored store keeps C symmetric)
+          double* Xp = X + (long long)p0 * T;
+          if (p0 > 0) {
+            grp.push_back(mk(Xp, ld, Xp, ld, C, ld, p0 * rr, p0 * rr, pw * tile, csg::KM_FULL, csg::ORD_LOWER, 1, 1.0, 1.0));
+            GemmProblem q = mk(Xpp, ld, Xp, ld, C + (long long)p0 * T, ld, pw * rr, p0 * rr, pw * tile, csg::KM_GE_I, csg::ORD_COL, 2, 1.0, 1.0);
+            q.Cm = C + (long long)p0 * T * ld;
+            grp.push_back(q);
+          }
+          grp.push_back(mk(Xpp, ld, Xpp, ld, C + (long long)p0 * T * (ld + 1), ld, pw * rr, pw * rr, pw * tile, csg::KM_GE_I, csg::ORD_LOWER, 1, 1.0, 1.0));
+          add_group(seq, GK_TN, grp); seq.back().stream = 4;
+        }
+        last_inv_ev = nev++;
+        op(OP_RECORD, 4, last_inv_ev);
+        if (mt > 0) {
+          // Acc_IJ += sum_{k in P} L_Ik X_kJ for I >= p1: next panel's rows on S3 (AccNext), the rest on S5
+          auto push_acc = [&](int r0, int nb_rows, int stream) {
+            double* Lp = G + (long long)r0 * T + (long long)p0 * T * ld;
+            if (p0 > 0)
+              grp.push_back(mk(Lp, ld, X + (long long)p0 * T, ld, X + (long long)r0 * T, ld, nb_rows * rr, p0 * rr, pw * tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 1.0));
+            grp.push_back(mk(Lp, ld, Xpp, ld, X + (long long)r0 * T + (long long)p0 * T * ld, ld, nb_rows * rr, pw * rr, pw * tile, csg::KM_GE_J, csg::ORD_COL, 0, 1.0, 1.0));
+            add_group(seq, GK_NN, grp); seq.back().stream = stream;
+          };
+          op(OP_WAIT, 3, ev_lpanel);
+          if (last_rest_ev >= 0) op(OP_WAIT, 3, last_rest_ev);
+          push_acc(p1, n1, 3);
+          last_inv3_ev = nev++;
+          op(OP_RECORD, 3, last_inv3_ev);
+          if (mt > n1) {
+            op(OP_WAIT, 5, ev_rows);
+            op(OP_WAIT, 5, ev_lpanel);
+            push_acc(p1 + n1, mt - n1, 5);
+            last_rest_ev = nev++;
+            op(OP_RECORD, 5, last_rest_ev);
+          }
+        }
+      }
+    }
+    // the chain stream rejoins every other stream before anything reads the results
+    for (int ev : {last_aux_ev, last_u2b_ev, last_inv_ev, last_inv3_ev, last_rest_ev, last_s6_ev, ev_u1top_prev})
+      if (ev >= 0) op(OP_WAIT, 0, ev);
+    };
+    plan_version = 2;
+    if (const char* pv = std::getenv("CS_PLAN")) plan_version = std::atoi(pv);
+    if (plan_version == 1) {
+      build_chol(potrf, false);
+      if (inv_pipeline) build_chol(potrf_inv, true);
+    } else {
+      build_chol2(potrf, false);
+      if (inv_pipeline) build_chol2(potrf_inv, true);
+    }
     n_events = nev + 1;
     // --- recursive triangular inverse, batched by tree height ---
     std::vector<Node> nodes;
@@ -573,8 +754,8 @@ struct DenseEngine {
     cudaStream_t* bulk[5] = {&aux, &aux2, &aux3, &aux4, &aux5};
     int level[5] = {2, 0, 1, 5, 3};  // 0 = highest
     if (const char* ev = std::getenv("CS_PRIO")) std::sscanf(ev, "%d,%d,%d,%d,%d", &level[0], &level[1], &level[2], &level[3], &level[4]);
-    if (want_part && rt::partition_streams(8, &crit, bulk, level, 5, &sm_crit, &sm_bulk) == 0) {
-      crit_ok = aux_ok = aux2_ok = aux3_ok = aux4_ok = aux5_ok = true;
+    if (want_part && rt::partition_streams(8, &crit, &aux6, bulk, level, 5, &sm_crit, &sm_bulk) == 0) {
+      crit_ok = aux_ok = aux2_ok = aux3_ok = aux4_ok = aux5_ok = aux6_ok = true;
       if ((e = rt::event_create_fast(&ev_in))) return e;
       if ((e = rt::event_create_fast(&ev_out))) return e;
     } else {
@@ -588,6 +769,8 @@ struct DenseEngine {
       aux4_ok = true;
       if ((e = rt::stream_create_level(&aux5, level[4]))) return e;
       aux5_ok = true;
+      if ((e = rt::stream_create_level(&aux6, 0))) return e;
+      aux6_ok = true;
     }
     events.resize(n_events);
     for (int i = 0; i < n_events; ++i)
@@ -599,7 +782,7 @@ struct DenseEngine {
   }
 
   void destroy() {
-    rt::dev_free(G); rt::dev_free(X); rt::dev_free(C); rt::dev_free(logdet_part); rt::dev_free(status);
+    rt::dev_free(G); rt::dev_free(X); rt::dev_free(C); rt::dev_free(logdet_part); rt::dev_free(status); rt::dev_free(Pbuf); Pbuf = nullptr;
     rt::dev_free(d_probs);
     for (auto& ev : events) rt::event_destroy(ev);
     events.clear();
@@ -608,6 +791,7 @@ struct DenseEngine {
     if (aux3_ok) { rt::stream_sync(aux3); rt::stream_destroy(aux3); aux3_ok = false; }
     if (aux4_ok) { rt::stream_sync(aux4); rt::stream_destroy(aux4); aux4_ok = false; }
     if (aux5_ok) { rt::stream_sync(aux5); rt::stream_destroy(aux5); aux5_ok = false; }
+    if (aux6_ok) { rt::stream_sync(aux6); rt::stream_destroy(aux6); aux6_ok = false; }
     if (crit_ok) { rt::stream_sync(crit); rt::stream_destroy(crit); rt::event_destroy(ev_in); rt::event_destroy(ev_out); crit_ok = false; }
     G = X = C = logdet_part = nullptr; status = nullptr; d_probs = nullptr;
   }
@@ -627,12 +811,14 @@ struct DenseEngine {
       s0 = crit;
     }
     for (const Launch& L : seq) {
-      cudaStream_t s = L.stream == 1 ? aux : (L.stream == 2 ? aux2 : (L.stream == 3 ? aux3 : (L.stream == 4 ? aux4 : (L.stream == 5 ? aux5 : s0))));
-      const bool timed = tl && (L.is_leaf == OP_LEAF || L.is_leaf == OP_GEMM);
+      cudaStream_t s = L.stream == 1 ? aux : (L.stream == 2 ? aux2 : (L.stream == 3 ? aux3 : (L.stream == 4 ? aux4 : (L.stream == 5 ? aux5 : (L.stream == 6 ? aux6 : s0)))));
+      const bool timed = tl && (L.is_leaf == OP_LEAF || L.is_leaf == OP_GEMM || L.is_leaf == OP_COPY);
       if (timed) { cudaEvent_t e0; rt::event_create(&e0); rt::event_record(e0, s); tl->push_back(e0); }
       if (L.is_leaf == OP_LEAF) {
         launch_leaf(tile, G + (long long)L.blk * tile * ((long long)np + 1), np, X + (long long)L.blk * tile * ((long long)np + 1), np,
                     L.blk * tile, logdet_part + L.blk, status, n, s, skip);
+      } else if (L.is_leaf == OP_COPY) {
+        rt::copy2d(L.cp_dst, L.cp_src, np, L.cp_rows, L.cp_cols, s);
       } else if (L.is_leaf == OP_RECORD) {
         rt::event_record(events[L.ev], s);
       } else if (L.is_leaf == OP_WAIT) {
@@ -655,10 +841,10 @@ struct DenseEngine {
   // with at least one write is ordered.  Returns the number of unordered conflicting pairs.
   struct Rect { int buf; long long r0, r1, c0, c1; bool write; };
   void rect_of(const double* ptr, long long rows, long long cols, bool write, std::vector<Rect>& out) const {
-    const double* bases[3] = {G, X, C};
-    for (int b = 0; b < 3; ++b) {
+    const double* bases[4] = {G, X, C, Pbuf};
+    for (int b = 0; b < 4; ++b) {
       const long long off = ptr - bases[b];
-      if (off >= 0 && off < (long long)np * np) {
+      if (off >= 0 && off < (b == 3 ? (long long)np * panel_blocks * tile : (long long)np * np)) {
         out.push_back(Rect{b, off % np, off % np + rows, off / np, off / np + cols, write});
         return;
       }
@@ -670,6 +856,11 @@ struct DenseEngine {
       const long long o = (long long)L.blk * tile;
       out.push_back(Rect{0, o, o + tile, o, o + tile, true});
       out.push_back(Rect{1, o, o + tile, o, o + tile, true});
+      return;
+    }
+    if (L.is_leaf == OP_COPY) {
+      rect_of(L.cp_src, L.cp_rows, L.cp_cols, false, out);
+      rect_of(L.cp_dst, L.cp_rows, L.cp_cols, true, out);
       return;
     }
     if (L.is_leaf != OP_GEMM) return;
@@ -688,7 +879,7 @@ struct DenseEngine {
     const int n_ops = (int)seq.size();
     const int words = (n_ops + 63) / 64;
     std::vector<std::vector<unsigned long long>> anc(n_ops, std::vector<unsigned long long>(words, 0ULL));
-    int last_on_stream[6] = {-1, -1, -1, -1, -1, -1};
+    int last_on_stream[7] = {-1, -1, -1, -1, -1, -1, -1};
     std::vector<int> last_record(n_events + 1, -1);
     auto add_pred = [&](int j, int i) {
       if (i < 0) return;

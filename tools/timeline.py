@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--inv-pipeline", type=int, default=1)
     ap.add_argument("--partition", type=int, default=0)
     ap.add_argument("--out", default="")
+    ap.add_argument("--window", default="", help="t0,t1 in ms: list every launch that starts inside")
     a = ap.parse_args()
     import bench
     from causalstump_b200 import _lib
@@ -34,7 +35,7 @@ def main():
         np.savetxt(a.out, tl, fmt="%.4f", delimiter=",", header="stream,type,tiles,K_or_blk,t0_ms,t1_ms")
     end = tl[:, 5].max()
     print("launches %d, span %.3f ms" % (len(tl), end))
-    for s in range(6):
+    for s in range(7):
         m = tl[:, 0] == s
         if not m.any():
             continue
@@ -53,6 +54,11 @@ def main():
     outer = [per[i] for i in range(len(per)) if (i + 1) % W == 0]
     print("  inside a panel: mean %.1f us;  across a panel boundary (incl. U1): mean %.1f us" %
           (1e3 * np.mean(inner), 1e3 * np.mean(outer)))
+    if a.window:
+        lo, hi = [float(x) for x in a.window.split(",")]
+        for r in tl[(tl[:, 4] >= lo) & (tl[:, 4] < hi)]:
+            print("S%d %-4s tiles %5d K/blk %5d  t0 %.4f t1 %.4f dur %7.1f us" %
+                  (r[0], {0: "gemm", 1: "leaf", 4: "copy"}.get(int(r[1]), "?"), r[2], r[3], r[4], r[5], 1e3 * (r[5] - r[4])))
     s0 = tl[m0]
     print("S0 launches by duration (top 12):")
     d0 = s0[:, 5] - s0[:, 4]
