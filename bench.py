@@ -224,7 +224,7 @@ def measure_fp64_peak(torch, dev):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def measure_fits(lib, rank, world, nfit):
+def measure_fits(lib, rank, world, nfit, batch=32):
     """Metric ii: one 'fit' = CausalStump() on a 672 x 25 training split to the reference's
     stopping rule (maxiter=3000, tol=1e-1, lr=.01, Nadam; test/sec5-3_Hill2011.R:344-345)
     + predict on 747 + treatment on 672 and 75.  The nfit fits of this rank (replicates x
@@ -232,9 +232,9 @@ def measure_fits(lib, rank, world, nfit):
     Returns (seconds, fits, iterations, mean PEHE of the restart winners)."""
     from causalstump_b200 import replicates as rp
     units = [(rank * ((nfit + 3) // 4) + k // 4, k % 4) for k in range(nfit)]
-    rp.hill_units_concurrent(units[:1])  # warm-up: library load, graph capture, allocator
+    rp.hill_units_concurrent(units[:2], batch=batch)  # warm-up: library load, graph capture, allocator
     t0 = time.perf_counter()
-    res = rp.hill_units_concurrent(units)
+    res = rp.hill_units_concurrent(units, batch=batch)
     secs = time.perf_counter() - t0
     win = rp.select_winners(res)
     return secs, nfit, [r["iters"] for r in res], float(np.mean([w["pehe_test"] for w in win]))
@@ -383,7 +383,7 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_fits:
         nfit = args.fits
         barrier()
-        secs, nf, iters, pehe = measure_fits(lib, rank, world, nfit)
+        secs, nf, iters, pehe = measure_fits(lib, rank, world, nfit, args.fit_batch)
         secs = max_over_ranks(secs)
         if dist is not None:
             all_it = [None] * world
@@ -392,8 +392,9 @@ def run_ours(args, rank, world, local_rank):
         fits_obj = {"value": world * nf / secs * 3600.0, "unit": "fits/hour", "fits": world * nf,
                     "iterations_mean": float(np.mean(iters)), "pehe_test_winners_rank0": pehe,
                     "what": "GP fit on a 672x25 Hill surface-B split to the reference stopping rule (maxiter 3000, tol 1e-1, "
-                            "lr .01, Nadam) + predict(747) + treatment(672, 75); %d (replicate, restart) fits per GPU run "
-                            "concurrently (cs_fit_run_many); includes host data generation and handle creation" % nf}
+                            "lr .01, Nadam) + predict(747) + treatment(672, 75); %d (replicate, restart) fits per GPU in batched handles of %d "
+                            "members (cs_fit_create_batch, every launch serves a whole batch), handles driven concurrently "
+                            "(cs_fit_run_many); includes host data generation and handle creation" % (nf, args.fit_batch)}
 
     if rank == 0:
         line = {
@@ -422,7 +423,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--fits", type=int, default=16, help="(replicate, restart) fits per GPU for the fits/hour object")
+    ap.add_argument("--fits", type=int, default=128, help="(replicate, restart) fits per GPU for the fits/hour object")
+    ap.add_argument("--fit-batch", type=int, default=32, help="members per batched handle (cs_fit_create_batch); 1 = one handle per fit")
     ap.add_argument("--no-fits", action="store_true")
     ap.add_argument("--inv-pipeline", type=int, default=1, help="1: inverse pipelined behind the Cholesky (default); 0: recursive inverse after it")
     ap.add_argument("--partition", type=int, default=0, help="SM partition for the Cholesky chain: 0 auto, 1 on, -1 off")

@@ -54,6 +54,10 @@ _SIGS = {
                               dp, dp]),
     "cs_fit_create": (C.c_int, [C.POINTER(cs_fit_config), C.c_int, C.c_int, dp, dp, dp, dp, dp,
                                 C.POINTER(C.c_void_p)]),
+    "cs_fit_create_batch": (C.c_int, [C.POINTER(cs_fit_config), C.c_int, C.c_int, C.c_int, C.POINTER(dp), C.POINTER(dp),
+                                      C.POINTER(dp), C.POINTER(dp), C.POINTER(dp), C.POINTER(C.c_void_p)]),
+    "cs_fit_batch_size": (C.c_int, [C.c_void_p]),
+    "cs_fit_select": (C.c_int, [C.c_void_p, C.c_int]),
     "cs_fit_destroy": (None, [C.c_void_p]),
     "cs_fit_nparam": (C.c_int, [C.c_void_p]),
     "cs_fit_eval": (C.c_int, [C.c_void_p, dp, dp, dp, dp]),
@@ -356,16 +360,63 @@ class Fit:
         self.lib.check(self.lib.dll.cs_flush_l2(self.h))
 
 
+class FitBatch(Fit):
+    """Batched handle (cs_fit_create_batch): B independent fits of the same (n, p, kind) advance with every
+    launch.  `members` is a list of (y, X, z, w, init_params).  eval_async / run act on all members;
+    predict / treat / get_params / fetch / get_matrices act on the member chosen with select(b)."""
+
+    def __init__(self, lib: CsLib, kind, members, optim=CS_OPT_NADAM, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8,
+                 momentum=0.0, tile=0, chunk=0, use_graph=0, gemm_tile=0):
+        self.lib = lib
+        self.h = C.c_void_p(None)
+        B = len(members)
+        assert B >= 1
+        ys, Xs, zs, ws, ps = [], [], [], [], []
+        for (y, X, z, w, ip) in members:
+            ys.append(_f64(y)); zs.append(_f64(z)); ps.append(_f64(ip))
+            Xs.append(_f64(X if np.ndim(X) > 1 else np.asarray(X)[:, None]))
+            ws.append(None if w is None else _f64(w))
+        self.n, self.p = Xs[0].shape
+        assert all(X.shape == (self.n, self.p) for X in Xs) and all(len(y) == self.n for y in ys)
+        self.kind, self.B = kind, B
+        arr = lambda lst: (dp * B)(*[_ptr(a) for a in lst])
+        cfg = cs_fit_config(kind, optim, lr, beta1, beta2, eps, momentum, tile, chunk, use_graph, gemm_tile, 0, 0)
+        h = C.c_void_p(None)
+        lib.check(lib.dll.cs_fit_create_batch(C.byref(cfg), B, self.n, self.p, arr(ys), arr(Xs), arr(zs), arr(ws), arr(ps),
+                                              C.byref(h)))
+        self.h = h
+        self.nparam = lib.dll.cs_fit_nparam(self.h)
+
+    def select(self, member):
+        self.lib.check(self.lib.dll.cs_fit_select(self.h, int(member)))
+        return self
+
+    def run(self, maxiter, tol):
+        """-> [(iters, trace[2, iters+2]), ...] per member"""
+        its = (C.c_int * self.B)()
+        traces = np.zeros((self.B, maxiter + 2, 2))
+        self.lib.check(self.lib.dll.cs_fit_run(self.h, int(maxiter), float(tol), its, _ptr(traces)))
+        return [(int(its[b]), traces[b, : int(its[b]) + 2].T.copy()) for b in range(self.B)]
+
+
 def run_many(fits, maxiter, tol):
-    """cs_fit_run_many: drive several Fit handles concurrently; returns [(iters, trace), ...]."""
+    """cs_fit_run_many: drive several handles (Fit or FitBatch) concurrently; returns [(iters, trace), ...]
+    with one entry per fit, batched handles expanded member by member in order."""
     lib = fits[0].lib
     n = len(fits)
+    sizes = [getattr(f, "B", 1) for f in fits]
+    total = sum(sizes)
     hs = (C.c_void_p * n)(*[f.h for f in fits])
-    iters = (C.c_int * n)()
-    traces = [np.zeros((2, maxiter + 2), order="F") for _ in fits]
+    iters = (C.c_int * total)()
+    traces = [np.zeros((b, maxiter + 2, 2)) for b in sizes]
     tp = (dp * n)(*[_ptr(t) for t in traces])
     lib.check(lib.dll.cs_fit_run_many(hs, n, int(maxiter), float(tol), iters, tp))
-    return [(int(iters[i]), traces[i][:, : int(iters[i]) + 2]) for i in range(n)]
+    out, k = [], 0
+    for t, b in zip(traces, sizes):
+        for m in range(b):
+            it = int(iters[k]); k += 1
+            out.append((it, t[m, : it + 2].T.copy()))
+    return out
 
 
 _default = None

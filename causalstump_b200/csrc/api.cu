@@ -125,6 +125,8 @@ static int upload_vector(double* dst, int npad, const double* src, int n, double
 // ------------------------------------------------------------------------------------
 // the fit handle
 // ------------------------------------------------------------------------------------
+struct HostLoop { LoopState ls; int status; int pad; };
+
 struct cs_fit {
   cs_fit_config cfg{};
   Layout lay{};
@@ -152,18 +154,50 @@ struct cs_fit {
   rt::graph_exec_t iter_graph{};   // one captured optimizer iteration
   bool graph_ok = false, graph_tried = false;
   long long launches_per_iter = 0;
-  LoopState* h_ls = nullptr;  // pinned: loop state + status read-back
+  HostLoop* h_ls = nullptr;  // pinned: loop state + status read-back, one per member
+  double* trace_unused = nullptr;
   int run_maxiter = 0, run_launched = 0, run_chunk = 1;
   cudaEvent_t ev[16]{};
   bool ev_ok = false;
-  std::vector<void*> allocs;
+  // Batched handle (cs_fit_create_batch): nbatch independent fits of the same (n, p, kind) share every
+  // launch (blockIdx.z = member).  Each per-fit device buffer lives at the same offset of a per-member slab,
+  // `bstride` bytes apart (0 for a single fit).  The pointer fields above always address member `cur`
+  // (cs_fit_select rebases them); batched launches are enqueued with member 0 selected.
+  int nbatch = 1, cur = 0;
+  long long bstride = 0, slab_bytes = 0;
+  char* slab = nullptr;
+  std::vector<std::pair<void**, size_t>> slab_req;
+  bool trace_in_slab = false;
 
-  int dalloc(void** ptr, size_t bytes) {
-    int e = rt::dev_malloc(ptr, bytes);
-    if (e == 0) allocs.push_back(*ptr);
-    return e;
+  void want(void** field, size_t bytes) { slab_req.emplace_back(field, bytes); }
+  int commit_slab() {
+    size_t off = 0;
+    std::vector<size_t> offs;
+    for (auto& r : slab_req) { offs.push_back(off); off += (r.second + 255) / 256 * 256; }
+    slab_bytes = (long long)off;
+    int e = rt::dev_malloc((void**)&slab, (size_t)slab_bytes * nbatch);
+    if (e) return e;
+    for (size_t i = 0; i < slab_req.size(); ++i) *slab_req[i].first = slab + offs[i];
+    bstride = nbatch > 1 ? slab_bytes : 0;
+    cur = 0;
+    return 0;
+  }
+  void select(int member) {
+    if (member == cur) return;
+    const long long delta = (long long)(member - cur) * slab_bytes;
+    for (auto& r : slab_req) *r.first = static_cast<char*>(*r.first) + delta;
+    cur = member;
   }
 };
+
+// batched launches address member 0; the caller's selection is restored afterwards
+struct BaseMember {
+  cs_fit* f; int keep;
+  explicit BaseMember(cs_fit* f_) : f(f_), keep(f_->cur) { f->select(0); }
+  ~BaseMember() { f->select(keep); }
+};
+
+static constexpr int TRACE_CAP_ITERS = 6000;  // per-member trace capacity inside the slab (reference default maxiter = 5000)
 
 static int split_plan(int row_blocks, int cols, int* nsplit, int* cols_per_split) {
   int target = 4 * rt::sm_count();
@@ -182,12 +216,13 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
   const int n = f->n, np = f->np, p = f->p;
   cudaStream_t st = f->st;
   const long long ld = np;
+  const unsigned B = (unsigned)f->nbatch;
   int ph = 0;
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
   {  // K1
     auto k = csk::gram_train_kernel;
     ++g_launches;
-    CS_LAUNCH(k, csg::lower_tiles(f->nblk), csk::ETH, csk::gram_smem_bytes(p), st, f->X, ld, f->z, f->w, f->params,
+    CS_LAUNCH(k, dim3(csg::lower_tiles(f->nblk), 1, B), csk::ETH, csk::gram_smem_bytes(p), st, f->X, ld, f->z, f->w, f->params,
               f->lay, n, f->eng.G, ld, skip);
   }
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
@@ -206,18 +241,18 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
   {  // alpha, u, s
     auto k = csk::matvec_kernel<3>;
     ++g_launches;
-    CS_LAUNCH(k, dim3(f->nblk, f->nsplit), csk::ETH, 0, st, f->eng.C, ld, f->cols_per_split, np, f->y, f->y, f->ones,
-              f->params + f->lay.i_mu(), f->mv_part, ld, 3 * ld, skip);
+    CS_LAUNCH(k, dim3(f->nblk, f->nsplit, B), csk::ETH, 0, st, f->eng.C, ld, f->cols_per_split, np, f->y, f->y, f->ones,
+              f->params + f->lay.i_mu(), f->mv_part, ld, 3 * ld, skip, f->bstride);
     auto k2 = csk::scalars_kernel;
     ++g_launches;
-    CS_LAUNCH(k2, 1, csk::ETH, 0, st, f->mv_part, f->nsplit, ld, 3 * ld, n, np, f->y, f->params, f->lay,
+    CS_LAUNCH(k2, dim3(1, 1, B), csk::ETH, 0, st, f->mv_part, f->nsplit, ld, 3 * ld, n, np, f->y, f->params, f->lay,
               f->eng.logdet_part, f->eng.N, f->alpha, f->u, f->s, f->sc, skip);
   }
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
   {  // K3 / K4
     auto k = csk::grad_trace_kernel<false>;
     ++g_launches;
-    CS_LAUNCH(k, f->ncta_grad, csk::ETH, csk::grad_smem_bytes(p), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
+    CS_LAUNCH(k, dim3(f->ncta_grad, 1, B), csk::ETH, csk::grad_smem_bytes(p), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
               f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)nullptr,
               (const double*)nullptr, (const double*)nullptr, skip, (const int*)nullptr);
   }
@@ -225,15 +260,22 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
   {
     auto k0 = csk::rowstats_kernel;
     ++g_launches;
-    CS_LAUNCH(k0, f->nrs, csk::ETH, 0, st, f->kal_part, ld, f->nblk, f->eng.C, ld, f->alpha, f->y, f->w, f->params,
+    CS_LAUNCH(k0, dim3(f->nrs, 1, B), csk::ETH, 0, st, f->kal_part, ld, f->nblk, f->eng.C, ld, f->alpha, f->y, f->w, f->params,
               f->lay, n, f->sc, f->rs_part, skip);
     auto k = csk::finalize_kernel;
     ++g_launches;
-    CS_LAUNCH(k, 1, csk::ETH, 0, st, f->gpart, f->ncta_grad, f->rs_part, f->nrs, f->params, f->lay, n, f->sc, f->grad,
+    CS_LAUNCH(k, dim3(1, 1, B), csk::ETH, 0, st, f->gpart, f->ncta_grad, f->rs_part, f->nrs, f->params, f->lay, n, f->sc, f->grad,
               skip);
   }
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
   return 0;
+}
+
+static void fit_enqueue_loop_step(cs_fit* f) {
+  auto k = csk::loop_step_kernel;
+  ++g_launches;
+  CS_LAUNCH(k, dim3(1, 1, (unsigned)f->nbatch), 64, 0, f->st, f->cfg.optim, f->lay, f->cfg.lr, f->cfg.beta1, f->cfg.beta2, f->cfg.eps,
+            f->cfg.momentum, f->m, f->v, f->grad, f->params, f->sc, f->ls, f->trace);
 }
 
 extern "C" {
@@ -252,9 +294,13 @@ int cs_set_device(int device) {
 }
 long long cs_launch_count(void) { return g_launches; }
 
-int cs_fit_create(const cs_fit_config* cfg, int n, int p, const double* y, const double* X, const double* z,
-                  const double* w, const double* init_params, cs_fit** out) {
-  if (!cfg || !y || !X || !z || !init_params || !out) return fail(CS_ERR_ARG, "cs_fit_create: null argument");
+static int fit_create_impl(const cs_fit_config* cfg, int nbatch, int n, int p, const double* const* ys,
+                           const double* const* Xs, const double* const* zs, const double* const* ws,
+                           const double* const* inits, cs_fit** out) {
+  if (!cfg || !ys || !Xs || !zs || !inits || !out) return fail(CS_ERR_ARG, "cs_fit_create: null argument");
+  if (nbatch < 1) return fail(CS_ERR_ARG, "cs_fit_create_batch: nbatch must be positive");
+  for (int b = 0; b < nbatch; ++b)
+    if (!ys[b] || !Xs[b] || !zs[b] || !inits[b]) return fail(CS_ERR_ARG, "cs_fit_create: null argument (member %d)", b);
   if (n < 1 || p < 1) return fail(CS_ERR_ARG, "cs_fit_create: n and p must be positive");
   if (p > CS_MAX_P) return fail(CS_ERR_UNSUPPORTED, "cs_fit_create: p=%d exceeds CS_MAX_P=%d", p, CS_MAX_P);
   if (cfg->kind != CS_GP && cfg->kind != CS_TP) return fail(CS_ERR_ARG, "cs_fit_create: bad kind");
@@ -266,51 +312,65 @@ int cs_fit_create(const cs_fit_config* cfg, int n, int p, const double* y, const
   *out = nullptr;
   f->cfg = *cfg;
   f->cfg.tile = tile;
+  if (nbatch > 1) f->cfg.inv_pipeline = 0;  // the pipelined inverse re-zeroes X and C per member and evaluation
   f->lay.kind = cfg->kind;
   f->lay.p = p;
   f->n = n;
   f->p = p;
+  f->nbatch = nbatch;
   auto bail = [&](int code) { cs_fit_destroy(f); return code; };
   if (rt::stream_create(&f->st)) return bail(fail(CS_ERR_CUDA, "stream create failed"));
-  if (int e = f->eng.init(n, tile, cfg->gemm_tile, cfg->inv_pipeline, cfg->partition)) return bail(fail(e == 2 ? CS_ERR_NOMEM : CS_ERR_CUDA, "dense engine init failed: %s", rt::err_str(e)));
-  const int np = f->eng.np;
+  const int np = DenseEngine::padded(n, tile);
   f->np = np;
   f->nblk = np / csk::TB;
   const int NP = f->lay.np();
   const size_t vb = sizeof(double) * np;
-#define DA(ptr, bytes) if (f->dalloc((void**)&(ptr), (bytes))) return bail(fail(CS_ERR_NOMEM, "device allocation failed"))
-  DA(f->X, vb * p); DA(f->y, vb); DA(f->z, vb); DA(f->w, vb); DA(f->ones, vb);
-  DA(f->params, sizeof(double) * NP); DA(f->grad, sizeof(double) * NP);
-  DA(f->m, sizeof(double) * NP); DA(f->v, sizeof(double) * NP);
-  DA(f->alpha, vb); DA(f->u, vb); DA(f->s, vb);
-  split_plan(f->nblk, np, &f->nsplit, &f->cols_per_split);
-  DA(f->mv_part, vb * 3 * f->nsplit);
-  f->ncta_grad = std::min(csg::lower_tiles(f->nblk), rt::sm_count());
-  DA(f->gpart, sizeof(double) * (2 * p + 2) * f->ncta_grad);
-  DA(f->kal_part, vb * f->nblk);
-  f->nrs = (np + csk::ETH - 1) / csk::ETH;
-  DA(f->rs_part, sizeof(double) * 2 * f->nrs);
-  DA(f->sc, sizeof(EvalScalars)); DA(f->ls, sizeof(LoopState));
-#undef DA
-  cudaStream_t st = f->st;
   const size_t mb = sizeof(double) * (size_t)np * np;
-  if (rt::memset0(f->eng.G, mb, st) || rt::memset0(f->eng.X, mb, st) || rt::memset0(f->eng.C, mb, st))
-    return bail(fail(CS_ERR_CUDA, "memset failed"));
-  if (upload_matrix(f->X, np, np, p, X, n, p, st)) return bail(fail(CS_ERR_CUDA, "upload X failed"));
-  if (upload_vector(f->y, np, y, n, 0.0, st) || upload_vector(f->z, np, z, n, 0.0, st))
-    return bail(fail(CS_ERR_CUDA, "upload y/z failed"));
-  {
+  // ---- one slab per member: dense engine buffers first, then the vectors ----
+  DenseEngine& E = f->eng;
+  f->want((void**)&E.G, mb); f->want((void**)&E.X, mb); f->want((void**)&E.C, mb);
+  f->want((void**)&E.logdet_part, sizeof(double) * (np / tile));
+  f->want((void**)&E.Pbuf, DenseEngine::pbuf_bytes(np, tile));
+  f->want((void**)&E.status, sizeof(int));
+  f->want((void**)&f->X, vb * p); f->want((void**)&f->y, vb); f->want((void**)&f->z, vb); f->want((void**)&f->w, vb);
+  f->want((void**)&f->ones, vb);
+  f->want((void**)&f->params, sizeof(double) * NP); f->want((void**)&f->grad, sizeof(double) * NP);
+  f->want((void**)&f->m, sizeof(double) * NP); f->want((void**)&f->v, sizeof(double) * NP);
+  f->want((void**)&f->alpha, vb); f->want((void**)&f->u, vb); f->want((void**)&f->s, vb);
+  split_plan(f->nblk, np, &f->nsplit, &f->cols_per_split);
+  f->want((void**)&f->mv_part, vb * 3 * f->nsplit);
+  // persistent gradient CTAs: one per SM for a single fit, shared between the members of a batch
+  f->ncta_grad = std::min(csg::lower_tiles(f->nblk), std::max(4, (nbatch > 1 ? 2 : 1) * rt::sm_count() / nbatch));
+  f->want((void**)&f->gpart, sizeof(double) * (2 * p + 2) * f->ncta_grad);
+  f->want((void**)&f->kal_part, vb * f->nblk);
+  f->nrs = (np + csk::ETH - 1) / csk::ETH;
+  f->want((void**)&f->rs_part, sizeof(double) * 2 * f->nrs);
+  f->want((void**)&f->sc, sizeof(EvalScalars)); f->want((void**)&f->ls, sizeof(LoopState));
+  f->trace_cap = 2 * (TRACE_CAP_ITERS + 2);
+  f->want((void**)&f->trace, sizeof(double) * f->trace_cap);
+  f->trace_in_slab = true;
+  if (f->commit_slab()) return bail(fail(CS_ERR_NOMEM, "device allocation failed (%lld bytes x %d members)", f->slab_bytes, nbatch));
+  f->lay.bstride = f->bstride;
+  E.external_buffers = true;
+  E.nbatch = nbatch;
+  E.bstride = f->bstride;
+  if (int e = E.init(n, tile, cfg->gemm_tile, f->cfg.inv_pipeline, cfg->partition)) return bail(fail(e == 2 ? CS_ERR_NOMEM : CS_ERR_CUDA, "dense engine init failed: %s", rt::err_str(e)));
+  cudaStream_t st = f->st;
+  if (rt::memset0(f->slab, (size_t)f->slab_bytes * nbatch, st)) return bail(fail(CS_ERR_CUDA, "memset failed"));
+  for (int b = 0; b < nbatch; ++b) {
+    f->select(b);
+    if (upload_matrix(f->X, np, np, p, Xs[b], n, p, st)) return bail(fail(CS_ERR_CUDA, "upload X failed"));
+    if (upload_vector(f->y, np, ys[b], n, 0.0, st) || upload_vector(f->z, np, zs[b], n, 0.0, st))
+      return bail(fail(CS_ERR_CUDA, "upload y/z failed"));
     auto k = fill_kernel;
     ++g_launches;
     CS_LAUNCH(k, (np + 255) / 256, 256, 0, st, f->ones, (long long)np, 1.0);
+    const double* w = ws ? ws[b] : nullptr;
     if (w) { if (upload_vector(f->w, np, w, n, 1.0, st)) return bail(fail(CS_ERR_CUDA, "upload w failed")); }
     else { ++g_launches; CS_LAUNCH(k, (np + 255) / 256, 256, 0, st, f->w, (long long)np, 1.0); }
+    if (rt::h2d(f->params, inits[b], sizeof(double) * NP, st)) return bail(fail(CS_ERR_CUDA, "upload params failed"));
   }
-  if (rt::h2d(f->params, init_params, sizeof(double) * NP, st)) return bail(fail(CS_ERR_CUDA, "upload params failed"));
-  if (rt::memset0(f->m, sizeof(double) * NP, st) || rt::memset0(f->v, sizeof(double) * NP, st) ||
-      rt::memset0(f->grad, sizeof(double) * NP, st) || rt::memset0(f->sc, sizeof(EvalScalars), st) ||
-      rt::memset0(f->ls, sizeof(LoopState), st))
-    return bail(fail(CS_ERR_CUDA, "memset failed"));
+  f->select(0);
   { auto k = csk::gram_train_kernel; CS_SET_SMEM(k, csk::gram_smem_bytes(csk::PMAX)); }
   { auto k = csk::gram_cross_kernel; CS_SET_SMEM(k, csk::gram_smem_bytes(csk::PMAX)); }
   { auto k = csk::grad_trace_kernel<false>; CS_SET_SMEM(k, csk::grad_smem_bytes(csk::PMAX)); }
@@ -324,11 +384,30 @@ int cs_fit_create(const cs_fit_config* cfg, int n, int p, const double* y, const
   return 0;
 }
 
+int cs_fit_create(const cs_fit_config* cfg, int n, int p, const double* y, const double* X, const double* z,
+                  const double* w, const double* init_params, cs_fit** out) {
+  const double* ws[1] = {w};
+  return fit_create_impl(cfg, 1, n, p, &y, &X, &z, ws, &init_params, out);
+}
+
+int cs_fit_create_batch(const cs_fit_config* cfg, int nbatch, int n, int p, const double* const* y, const double* const* X,
+                        const double* const* z, const double* const* w, const double* const* init_params, cs_fit** out) {
+  return fit_create_impl(cfg, nbatch, n, p, y, X, z, w, init_params, out);
+}
+
+int cs_fit_batch_size(const cs_fit* f) { return f ? f->nbatch : CS_ERR_ARG; }
+
+int cs_fit_select(cs_fit* f, int member) {
+  if (!f || member < 0 || member >= f->nbatch) return fail(CS_ERR_ARG, "cs_fit_select: member out of range");
+  f->select(member);
+  return 0;
+}
+
 void cs_fit_destroy(cs_fit* f) {
   if (!f) return;
   rt::stream_sync(f->st);
-  for (void* p : f->allocs) rt::dev_free(p);
-  if (f->trace) rt::dev_free(f->trace);
+  if (f->trace && !f->trace_in_slab) rt::dev_free(f->trace);
+  if (f->slab) rt::dev_free(f->slab);
   if (f->flush) rt::dev_free(f->flush);
   if (f->pinned) rt::host_free(f->pinned);
   if (f->h_ls) rt::host_free(f->h_ls);
@@ -363,8 +442,6 @@ int cs_fit_set_data(cs_fit* f, const double* y, const double* X, const double* z
   const size_t need = sizeof(double) * (size_t)n * (p + 3);
   if (f->pinned_bytes < need) {
     if (f->pinned) rt::host_free(f->pinned);
-  if (f->h_ls) rt::host_free(f->h_ls);
-  if (f->graph_ok) rt::graph_destroy(f->iter_graph);
     f->pinned = nullptr;
     RT(rt::host_alloc((void**)&f->pinned, need));
     f->pinned_bytes = need;
@@ -392,6 +469,7 @@ int cs_fit_reset_optimizer(cs_fit* f) {
 
 int cs_fit_eval_async(cs_fit* f) {
   if (!f) return fail(CS_ERR_ARG, "null handle");
+  BaseMember base(f);
   fit_enqueue_eval(f, nullptr, nullptr);
   KCHECK();
   return 0;
@@ -414,6 +492,7 @@ static int read_status(cs_fit* f) {
   return 0;
 }
 
+// outputs of the SELECTED member (cs_fit_select; member 0 for a single fit)
 int cs_fit_fetch(cs_fit* f, double* grad, double* stats, double* mu_solution) {
   if (!f) return fail(CS_ERR_ARG, "null handle");
   EvalScalars h{};
@@ -434,31 +513,40 @@ int cs_fit_eval(cs_fit* f, const double* params, double* grad, double* stats, do
 }
 
 // ---- the loop of R/main.R:79-88 as begin / enqueue-chunk / poll / finish, so that several
-// ---- fits can be driven concurrently from one host thread (cs_fit_run_many)
+// ---- handles can be driven concurrently from one host thread (cs_fit_run_many); a batched handle
+// ---- advances all of its members with every launch
+
 static int fit_run_begin(cs_fit* f, int maxiter, double tol) {
+  BaseMember base(f);
   cudaStream_t st = f->st;
+  const int B = f->nbatch;
   const int cap = 2 * (maxiter + 2);
   if (f->trace_cap < cap) {
-    if (f->trace) rt::dev_free(f->trace);
+    if (B > 1) return fail(CS_ERR_UNSUPPORTED, "cs_fit_run: maxiter %d exceeds the batched trace capacity %d", maxiter, TRACE_CAP_ITERS);
+    if (f->trace && !f->trace_in_slab) rt::dev_free(f->trace);
     f->trace = nullptr;
+    f->trace_in_slab = false;  // single fit: a private buffer (bstride == 0, no slab addressing involved)
+    for (auto& r : f->slab_req) if (r.first == (void**)&f->trace) r.first = (void**)&f->trace_unused;
     RT(rt::dev_malloc((void**)&f->trace, sizeof(double) * cap));
     f->trace_cap = cap;
     if (f->graph_ok) { rt::graph_destroy(f->iter_graph); f->graph_ok = false; }  // graph holds the old pointer
     f->graph_tried = false;
   }
-  RT(rt::memset0(f->trace, sizeof(double) * cap, st));
-  if (!f->h_ls) RT(rt::host_alloc((void**)&f->h_ls, sizeof(LoopState) + 16));
-  LoopState& h = *f->h_ls;
-  h = LoopState{};
-  h.it = 1; h.done = 0; h.iters = 0; h.maxiter = maxiter; h.tol = tol; h.prev_lml = 0.0;  // stats[,1] = 0 (R/main.R:77)
-  RT(rt::h2d(f->ls, &h, sizeof h, st));
+  if (!f->h_ls) RT(rt::host_alloc((void**)&f->h_ls, sizeof(HostLoop) * B));
+  for (int b = 0; b < B; ++b) {
+    RT(rt::memset0(reinterpret_cast<char*>(f->trace) + b * f->bstride, sizeof(double) * cap, st));
+    HostLoop& h = f->h_ls[b];
+    h = HostLoop{};
+    h.ls.it = 1; h.ls.done = 0; h.ls.iters = 0; h.ls.maxiter = maxiter; h.ls.tol = tol; h.ls.prev_lml = 0.0;  // stats[,1] = 0 (R/main.R:77)
+    RT(rt::h2d(reinterpret_cast<char*>(f->ls) + b * f->bstride, &h.ls, sizeof(LoopState), st));
+  }
   RT(rt::stream_sync(st));
   f->run_maxiter = maxiter;
   f->run_launched = 0;
   f->run_chunk = f->cfg.chunk;
   if (f->run_chunk <= 0) {
     // keep each poll interval around a few milliseconds of device work
-    const double flops = (double)f->np * f->np * f->np;
+    const double flops = (double)f->np * f->np * f->np * B;
     f->run_chunk = (int)std::max(1.0, std::min(64.0, 2.0e9 / std::max(flops, 1.0)));
   }
   if (!f->graph_tried && f->cfg.use_graph >= 0) {
@@ -466,10 +554,7 @@ static int fit_run_begin(cs_fit* f, int maxiter, double tol) {
     const long long l0 = g_launches;
     if (rt::graph_begin(st) == 0) {
       fit_enqueue_eval(f, &f->ls->done, nullptr);
-      auto k = csk::loop_step_kernel;
-      ++g_launches;
-      CS_LAUNCH(k, 1, 64, 0, st, f->cfg.optim, f->lay, f->cfg.lr, f->cfg.beta1, f->cfg.beta2, f->cfg.eps,
-                f->cfg.momentum, f->m, f->v, f->grad, f->params, f->sc, f->ls, f->trace);
+      fit_enqueue_loop_step(f);
       f->graph_ok = (rt::graph_end(st, &f->iter_graph) == 0);
       f->launches_per_iter = g_launches - l0;
       g_launches = l0;  // captured, not executed
@@ -480,6 +565,7 @@ static int fit_run_begin(cs_fit* f, int maxiter, double tol) {
 
 // enqueue the next chunk of iterations and an asynchronous read-back of the loop state
 static int fit_run_enqueue(cs_fit* f) {
+  BaseMember base(f);
   cudaStream_t st = f->st;
   const int todo = std::min(f->run_chunk, f->run_maxiter - f->run_launched);
   for (int i = 0; i < todo; ++i) {
@@ -489,52 +575,62 @@ static int fit_run_enqueue(cs_fit* f) {
       g_launches += f->launches_per_iter;
     } else {
       fit_enqueue_eval(f, &f->ls->done, nullptr);
-      auto k = csk::loop_step_kernel;
-      ++g_launches;
-      CS_LAUNCH(k, 1, 64, 0, st, f->cfg.optim, f->lay, f->cfg.lr, f->cfg.beta1, f->cfg.beta2, f->cfg.eps,
-                f->cfg.momentum, f->m, f->v, f->grad, f->params, f->sc, f->ls, f->trace);
+      fit_enqueue_loop_step(f);
     }
   }
   f->run_launched += todo;
   KCHECK();
-  RT(rt::d2h(f->h_ls, f->ls, sizeof(LoopState), st));
-  RT(rt::d2h(reinterpret_cast<char*>(f->h_ls) + sizeof(LoopState), f->eng.status, sizeof(int), st));
+  for (int b = 0; b < f->nbatch; ++b) {
+    RT(rt::d2h(&f->h_ls[b].ls, reinterpret_cast<char*>(f->ls) + b * f->bstride, sizeof(LoopState), st));
+    RT(rt::d2h(&f->h_ls[b].status, reinterpret_cast<char*>(f->eng.status) + b * f->bstride, sizeof(int), st));
+  }
   return 0;
 }
 
-// wait for the chunk; returns 1 when the loop has finished, 0 to continue, <0 / >0 on error
+// wait for the chunk; *finished = 1 when every member has stopped; <0 / >0 on error
 static int fit_run_poll(cs_fit* f, int* finished) {
   RT(rt::stream_sync(f->st));
-  int stt = 0;
-  std::memcpy(&stt, reinterpret_cast<char*>(f->h_ls) + sizeof(LoopState), sizeof(int));
-  if (stt != 0x7fffffff && stt > 0)
-    return fail(stt, "inv_sympd(): matrix is singular or not positive definite (pivot %d) at iteration %d", stt,
-                f->h_ls->it - 1);
-  *finished = (f->h_ls->done || f->run_launched >= f->run_maxiter) ? 1 : 0;
+  int all_done = 1;
+  for (int b = 0; b < f->nbatch; ++b) {
+    const int stt = f->h_ls[b].status;
+    if (stt != 0x7fffffff && stt > 0)
+      return fail(stt, "inv_sympd(): matrix is singular or not positive definite (pivot %d) at iteration %d (member %d)", stt,
+                  f->h_ls[b].ls.it - 1, b);
+    if (!f->h_ls[b].ls.done) all_done = 0;
+  }
+  *finished = (all_done || f->run_launched >= f->run_maxiter) ? 1 : 0;
   return 0;
 }
 
 static int fit_run_finish_enqueue(cs_fit* f) {
   // final get_train_stats with the final parameters (R/main.R:88)
+  BaseMember base(f);
   fit_enqueue_eval(f, nullptr, nullptr);
   KCHECK();
   return 0;
 }
 
+// iters[nbatch]; stats_trace = nbatch consecutive 2 x (maxiter+2) column-major blocks
 static int fit_run_finish_fetch(cs_fit* f, int* iters, double* stats_trace) {
-  const int it = f->h_ls->done ? f->h_ls->iters : f->run_maxiter;
-  double st2[2];
-  int e = cs_fit_fetch(f, nullptr, st2, nullptr);
-  if (e) return e;
-  if (iters) *iters = it;
-  if (stats_trace) {
-    const int cap = 2 * (f->run_maxiter + 2);
-    RT(rt::d2h(stats_trace, f->trace, sizeof(double) * cap, f->st));
-    RT(rt::stream_sync(f->st));
-    stats_trace[2 * (it + 1) + 0] = st2[0];
-    stats_trace[2 * (it + 1) + 1] = st2[1];
+  const int keep = f->cur;
+  const int cap = 2 * (f->run_maxiter + 2);
+  int rc = 0;
+  for (int b = 0; b < f->nbatch && rc == 0; ++b) {
+    f->select(b);
+    const int it = f->h_ls[b].ls.done ? f->h_ls[b].ls.iters : f->run_maxiter;
+    double st2[2];
+    rc = cs_fit_fetch(f, nullptr, st2, nullptr);
+    if (rc) break;
+    if (iters) iters[b] = it;
+    if (stats_trace) {
+      double* tr = stats_trace + (size_t)b * cap;
+      if ((rc = rt::d2h(tr, f->trace, sizeof(double) * cap, f->st)) || (rc = rt::stream_sync(f->st))) { rc = fail(CS_ERR_CUDA, "trace download failed"); break; }
+      tr[2 * (it + 1) + 0] = st2[0];
+      tr[2 * (it + 1) + 1] = st2[1];
+    }
   }
-  return 0;
+  f->select(keep);
+  return rc;
 }
 
 int cs_fit_run(cs_fit* f, int maxiter, double tol, int* iters, double* stats_trace) {
@@ -550,6 +646,7 @@ int cs_fit_run(cs_fit* f, int maxiter, double tol, int* iters, double* stats_tra
   return fit_run_finish_fetch(f, iters, stats_trace);
 }
 
+// handles may be batched: iters then holds sum(batch sizes) entries in handle order, stats_traces[i] nbatch_i blocks
 int cs_fit_run_many(cs_fit** fits, int nfits, int maxiter, double tol, int* iters, double** stats_traces) {
   if (!fits || nfits < 1 || maxiter < 1) return fail(CS_ERR_ARG, "cs_fit_run_many: bad argument");
   for (int i = 0; i < nfits; ++i) if (!fits[i]) return fail(CS_ERR_ARG, "cs_fit_run_many: null handle");
@@ -566,8 +663,11 @@ int cs_fit_run_many(cs_fit** fits, int nfits, int maxiter, double tol, int* iter
         if (fin) { active[i] = 0; --nactive; if ((e = fit_run_finish_enqueue(fits[i]))) return e; }
       }
   }
-  for (int i = 0; i < nfits; ++i)
-    if ((e = fit_run_finish_fetch(fits[i], iters ? iters + i : nullptr, stats_traces ? stats_traces[i] : nullptr))) return e;
+  int off = 0;
+  for (int i = 0; i < nfits; ++i) {
+    if ((e = fit_run_finish_fetch(fits[i], iters ? iters + off : nullptr, stats_traces ? stats_traces[i] : nullptr))) return e;
+    off += fits[i]->nbatch;
+  }
   return 0;
 }
 
@@ -624,7 +724,7 @@ int cs_fit_event_elapsed_ms(cs_fit* f, int a, int b, float* ms) {
 
 int cs_fit_eval_profile(cs_fit* f, float phase_ms[CS_NPHASE]) {
   if (!f || !phase_ms) return fail(CS_ERR_ARG, "null argument");
-  fit_enqueue_eval(f, nullptr, f->ev);
+  { BaseMember base(f); fit_enqueue_eval(f, nullptr, f->ev); }
   KCHECK();
   RT(rt::stream_sync(f->st));
   for (int i = 0; i < CS_NPHASE; ++i) RT(rt::event_elapsed(&phase_ms[i], f->ev[i], f->ev[i + 1]));
@@ -736,7 +836,7 @@ static int cross_common(cs_fit* f, CrossWork& W, int n2, const double* X2, const
     ++g_launches;
     const double* nul = nullptr;
     CS_LAUNCH(k, dim3(rb2, W.nsplit), csk::ETH, 0, st, W.Kc.d(), (long long)n2p, W.cps, np, f->alpha, nul, nul, nul,
-              W.part.d(), (long long)n2p, (long long)n2p, (const int*)nullptr);
+              W.part.d(), (long long)n2p, (long long)n2p, (const int*)nullptr, 0LL);
     auto k2 = csp::reduce_parts_kernel;
     ++g_launches;
     CS_LAUNCH(k2, (n2p + 255) / 256, 256, 0, st, W.part.d(), W.nsplit, (long long)n2p, n2p,
@@ -832,7 +932,7 @@ int cs_treat(cs_fit* f, int n2, const double* X2, double cov_jitter, double* map
     ++g_launches;
     const double* nul = nullptr;
     CS_LAUNCH(k2, dim3(f->nblk, ns), csk::ETH, 0, st, f->eng.C, (long long)np, cps, np, c.d(), nul, nul, nul, part.d(),
-              (long long)np, (long long)np, (const int*)nullptr);
+              (long long)np, (long long)np, (const int*)nullptr, 0LL);
     auto k3 = csp::reduce_parts_kernel;
     ++g_launches;
     CS_LAUNCH(k3, (np + 255) / 256, 256, 0, st, part.d(), ns, (long long)np, np, nul, t.d());
@@ -1035,7 +1135,7 @@ int cs_mu_solution(int n, const double* y, const double* invK, double* mu) {
     auto k2 = csk::matvec_kernel<2>; ++g_launches;
     const double* nul = nullptr;
     CS_LAUNCH(k2, dim3(nb, ns), csk::ETH, 0, st, dA.d(), (long long)np, cps, np, dy.d(), d1.d(), nul, nul, part.d(),
-              (long long)np, (long long)(2 * np), (const int*)nullptr);
+              (long long)np, (long long)(2 * np), (const int*)nullptr, 0LL);
     auto k3 = csk::mu_solution_kernel; ++g_launches;
     CS_LAUNCH(k3, 1, csk::ETH, 0, st, part.d(), ns, (long long)np, (long long)(2 * np), n, out.d());
   }
@@ -1089,7 +1189,7 @@ static int grad_stats_common(int kind, int n, int p, const double* y, const doub
     auto k = csk::matvec_kernel<3>;
     ++g_launches;
     CS_LAUNCH(k, dim3(f->nblk, f->nsplit), csk::ETH, 0, st, f->eng.C, ld, f->cols_per_split, np, f->y, f->y, f->ones,
-              f->params + f->lay.i_mu(), f->mv_part, ld, 3 * ld, (const int*)nullptr);
+              f->params + f->lay.i_mu(), f->mv_part, ld, 3 * ld, (const int*)nullptr, 0LL);
     auto k2 = csk::scalars_kernel;
     ++g_launches;
     CS_LAUNCH(k2, 1, csk::ETH, 0, st, f->mv_part, f->nsplit, ld, 3 * ld, n, np, f->y, f->params, f->lay,
@@ -1157,14 +1257,14 @@ int cs_stats(int kind, int n, const double* y, const double* Kmat, const double*
   auto rp = csp::reduce_parts_kernel;
   ++g_launches;  // alpha = invK (y - mu); padded rows of C are zero, padded alpha is discarded below
   CS_LAUNCH(mv, dim3(nb, ns), csk::ETH, 0, st, eng.C, ld, cps, np, dy.d(), nul, nul, (const double*)dmu.d(), part.d(), ld,
-            ld, (const int*)nullptr);
+            ld, (const int*)nullptr, 0LL);
   ++g_launches;
   CS_LAUNCH(rp, (np + 255) / 256, 256, 0, st, part.d(), ns, ld, n, nul, alpha.d());
   if (np > n) { auto kf = fill_kernel; ++g_launches; CS_LAUNCH(kf, (np - n + 255) / 256, 256, 0, st, alpha.d() + n, (long long)(np - n), 0.0); }
   RT(upload_matrix(eng.C, np, np, np, Kmat, n, n, st));  // reuse C for Kmat (stream-ordered after the mat-vec)
   ++g_launches;
   CS_LAUNCH(mv, dim3(nb, ns), csk::ETH, 0, st, eng.C, ld, cps, np, alpha.d(), nul, nul, nul, part.d(), ld, ld,
-            (const int*)nullptr);
+            (const int*)nullptr, 0LL);
   ++g_launches;
   CS_LAUNCH(rp, (np + 255) / 256, 256, 0, st, part.d(), ns, ld, n, nul, kal.d());
   auto ks = csk::stats_only_kernel;

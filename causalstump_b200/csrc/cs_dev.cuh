@@ -1,6 +1,8 @@
 // Device primitives for sm_100a: FP64 tensor-core MMA (DMMA.8x8x4), cp.async staging,
 // warp reductions.  Under CS_EMU (tests only) each primitive has a behavioural model.
 #pragma once
+#include <type_traits>
+
 #include "cs_rt.h"
 
 namespace csd {
@@ -50,6 +52,15 @@ __device__ __forceinline__ void cp_async_wait() {
 #ifndef CS_EMU
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 #endif
+}
+
+// Batched launches (cs_fit_create_batch): every per-fit device buffer sits at the same offset of a
+// per-fit slab, so one launch serves B fits with blockIdx.z selecting the slab (bstride bytes apart).
+template <class T>
+__device__ __forceinline__ T* bshift(T* p, long long bstride) {
+  if (bstride == 0 || p == nullptr) return p;
+  return reinterpret_cast<T*>(reinterpret_cast<char*>(const_cast<typename std::remove_const<T>::type*>(p)) +
+                              (long long)blockIdx.z * bstride);
 }
 
 // reciprocal without the slow-path subroutine call of IEEE division

@@ -34,9 +34,12 @@ template <int TILE>
 __global__ void __launch_bounds__(LEAF_THREADS)
 leaf_kernel(double* __restrict__ Gt, long long ldg, double* __restrict__ Xt, long long ldx, int pivot_base,
             double* __restrict__ logdet_out, int* __restrict__ status, int n_real,
-            const int* __restrict__ skip) {
+            const int* __restrict__ skip, long long bstride) {
   // Gt / Xt point at the diagonal tile; pivot_base is its first global row (for LAPACK `info`)
+  skip = csd::bshift(skip, bstride);
   if (skip && *skip) return;
+  Gt = csd::bshift(Gt, bstride); Xt = csd::bshift(Xt, bstride); logdet_out = csd::bshift(logdet_out, bstride);
+  status = csd::bshift(status, bstride);
   constexpr int NA = TILE / 16;
   CS_DYN_SMEM(double, sm);
   double* colbuf = sm;              // [2][TILE]
@@ -254,9 +257,10 @@ struct Launch {
 inline int pick_tile(int n) { return n <= 1536 ? 64 : 128; }
 
 template <int TILE>
-inline void launch_gemm_t(int kind, const GemmProblem* dprobs, int nprob, int ntiles, cudaStream_t st,
-                          const int* skip) {
-  if (ntiles <= 0) return;
+inline void launch_gemm_t(int kind, const GemmProblem* dprobs, int nprob, int ntiles_, cudaStream_t st,
+                          const int* skip, int nbatch) {
+  if (ntiles_ <= 0) return;
+  const dim3 ntiles(ntiles_, 1, nbatch);
   if (TILE == 128) {
     if (kind == GK_NT) { auto k = csg::gemm_kernel<128, 2, 4, false, false>; CS_LAUNCH(k, ntiles, 256, (csg::gemm_smem_bytes<128, false, false>()), st, dprobs, nprob, skip); }
     else if (kind == GK_NN) { auto k = csg::gemm_kernel<128, 2, 4, false, true>; CS_LAUNCH(k, ntiles, 256, (csg::gemm_smem_bytes<128, false, true>()), st, dprobs, nprob, skip); }
@@ -271,10 +275,10 @@ inline void launch_gemm_t(int kind, const GemmProblem* dprobs, int nprob, int nt
 }
 
 inline void launch_gemm(int tile, int kind, const GemmProblem* dprobs, int nprob, int ntiles, cudaStream_t st,
-                        const int* skip = nullptr) {
+                        const int* skip = nullptr, int nbatch = 1) {
   ++g_launches;
-  if (tile == 128) launch_gemm_t<128>(kind, dprobs, nprob, ntiles, st, skip);
-  else launch_gemm_t<64>(kind, dprobs, nprob, ntiles, st, skip);
+  if (tile == 128) launch_gemm_t<128>(kind, dprobs, nprob, ntiles, st, skip, nbatch);
+  else launch_gemm_t<64>(kind, dprobs, nprob, ntiles, st, skip, nbatch);
 }
 
 // opt-in to > 48 KB dynamic shared memory (per device; cheap, called at every engine init)
@@ -290,10 +294,12 @@ inline void configure_kernels() {
 }
 
 inline void launch_leaf(int tile, double* Gt, long long ldg, double* Xt, long long ldx, int pivot_base,
-                        double* logdet_out, int* status, int n_real, cudaStream_t s, const int* skip) {
+                        double* logdet_out, int* status, int n_real, cudaStream_t s, const int* skip, int nbatch = 1,
+                        long long bstride = 0) {
   ++g_launches;
-  if (tile == 128) { auto k = leaf_kernel<128>; CS_LAUNCH(k, 1, LEAF_THREADS, leaf_smem_bytes<128>(), s, Gt, ldg, Xt, ldx, pivot_base, logdet_out, status, n_real, skip); }
-  else { auto k = leaf_kernel<64>; CS_LAUNCH(k, 1, LEAF_THREADS, leaf_smem_bytes<64>(), s, Gt, ldg, Xt, ldx, pivot_base, logdet_out, status, n_real, skip); }
+  const dim3 grid(1, 1, nbatch);
+  if (tile == 128) { auto k = leaf_kernel<128>; CS_LAUNCH(k, grid, LEAF_THREADS, leaf_smem_bytes<128>(), s, Gt, ldg, Xt, ldx, pivot_base, logdet_out, status, n_real, skip, bstride); }
+  else { auto k = leaf_kernel<64>; CS_LAUNCH(k, grid, LEAF_THREADS, leaf_smem_bytes<64>(), s, Gt, ldg, Xt, ldx, pivot_base, logdet_out, status, n_real, skip, bstride); }
 }
 
 struct DenseEngine {
@@ -309,6 +315,10 @@ struct DenseEngine {
   std::vector<Launch> potrf_inv;    // Cholesky with the inverse pipelined behind it (inv_pipeline)
   int inv_pipeline = 0;
   int plan_version = 2;
+  // batched engine (cs_fit_create_batch): nbatch fits share the plan; their buffers are bstride bytes apart
+  int nbatch = 1;
+  long long bstride = 0;
+  bool external_buffers = false;  // G, X, C, logdet_part, status, Pbuf belong to the caller's slab
   int panel_blocks = 4;             // outer panel width in blocks
   int n_events = 0;
   std::vector<cudaEvent_t> events;
@@ -336,7 +346,7 @@ struct DenseEngine {
     Launch L{};
     L.is_leaf = OP_GEMM; L.kind = kind; L.first_prob = (int)probs.size(); L.nprob = (int)group.size();
     int base = 0;
-    for (auto& p : group) { p.tile_base = base; base += p.ntiles; probs.push_back(p); }
+    for (auto& p : group) { p.tile_base = base; p.bstride = bstride; base += p.ntiles; probs.push_back(p); }
     L.ntiles = base;
     if (L.ntiles > 0) seq.push_back(L);
     group.clear();
@@ -351,21 +361,31 @@ struct DenseEngine {
     return h;
   }
 
+  static int padded(int n_, int tile_) { return (n_ + tile_ - 1) / tile_ * tile_; }
+  static int panel_width() {
+    int w = 4;
+    if (const char* pb = std::getenv("CS_PANEL")) { const int v = std::atoi(pb); if (v >= 1 && v <= 16) w = v; }
+    return w;
+  }
+  static size_t pbuf_bytes(int np_, int tile_) { return sizeof(double) * (size_t)np_ * panel_width() * tile_; }
+
   // returns 0 or a runtime error code
   int init(int n_, int tile_, int gemm_tile = 64, int inv_pipe = 0, int partition = 0) {
     inv_pipeline = inv_pipe;
-    if (const char* pb = std::getenv("CS_PANEL")) { const int v = std::atoi(pb); if (v >= 1 && v <= 16) panel_blocks = v; }
+    panel_blocks = panel_width();
     n = n_; tile = tile_; N = (n + tile - 1) / tile; np = N * tile;
     gt = (gemm_tile == 128 && tile == 128) ? 128 : 64;
     rr = tile / gt;
     const size_t bytes = (size_t)np * np * sizeof(double);
     int e;
-    if ((e = rt::dev_malloc((void**)&G, bytes))) return e;
-    if ((e = rt::dev_malloc((void**)&X, bytes))) return e;
-    if ((e = rt::dev_malloc((void**)&C, bytes))) return e;
-    if ((e = rt::dev_malloc((void**)&logdet_part, sizeof(double) * N))) return e;
-    if ((e = rt::dev_malloc((void**)&Pbuf, sizeof(double) * (size_t)np * panel_blocks * tile))) return e;
-    if ((e = rt::dev_malloc((void**)&status, sizeof(int)))) return e;
+    if (!external_buffers) {
+      if ((e = rt::dev_malloc((void**)&G, bytes))) return e;
+      if ((e = rt::dev_malloc((void**)&X, bytes))) return e;
+      if ((e = rt::dev_malloc((void**)&C, bytes))) return e;
+      if ((e = rt::dev_malloc((void**)&logdet_part, sizeof(double) * N))) return e;
+      if ((e = rt::dev_malloc((void**)&Pbuf, pbuf_bytes(np, tile)))) return e;
+      if ((e = rt::dev_malloc((void**)&status, sizeof(int)))) return e;
+    }
     configure_kernels();
     const long long ld = np;
     const long long T = tile;
@@ -782,7 +802,10 @@ struct DenseEngine {
   }
 
   void destroy() {
-    rt::dev_free(G); rt::dev_free(X); rt::dev_free(C); rt::dev_free(logdet_part); rt::dev_free(status); rt::dev_free(Pbuf); Pbuf = nullptr;
+    if (!external_buffers) {
+      rt::dev_free(G); rt::dev_free(X); rt::dev_free(C); rt::dev_free(logdet_part); rt::dev_free(status); rt::dev_free(Pbuf);
+    }
+    Pbuf = nullptr;
     rt::dev_free(d_probs);
     for (auto& ev : events) rt::event_destroy(ev);
     events.clear();
@@ -816,15 +839,17 @@ struct DenseEngine {
       if (timed) { cudaEvent_t e0; rt::event_create(&e0); rt::event_record(e0, s); tl->push_back(e0); }
       if (L.is_leaf == OP_LEAF) {
         launch_leaf(tile, G + (long long)L.blk * tile * ((long long)np + 1), np, X + (long long)L.blk * tile * ((long long)np + 1), np,
-                    L.blk * tile, logdet_part + L.blk, status, n, s, skip);
+                    L.blk * tile, logdet_part + L.blk, status, n, s, skip, nbatch, bstride);
       } else if (L.is_leaf == OP_COPY) {
-        rt::copy2d(L.cp_dst, L.cp_src, np, L.cp_rows, L.cp_cols, s);
+        for (int b = 0; b < nbatch; ++b)
+          rt::copy2d(reinterpret_cast<double*>(reinterpret_cast<char*>(L.cp_dst) + b * bstride),
+                     reinterpret_cast<const double*>(reinterpret_cast<const char*>(L.cp_src) + b * bstride), np, L.cp_rows, L.cp_cols, s);
       } else if (L.is_leaf == OP_RECORD) {
         rt::event_record(events[L.ev], s);
       } else if (L.is_leaf == OP_WAIT) {
         rt::stream_wait_event(s, events[L.ev]);
       } else {
-        launch_gemm(L.gtile ? L.gtile : gt, L.kind, d_probs + L.first_prob, L.nprob, L.ntiles, s, skip);
+        launch_gemm(L.gtile ? L.gtile : gt, L.kind, d_probs + L.first_prob, L.nprob, L.ntiles, s, skip, nbatch);
       }
       if (timed) { cudaEvent_t e1; rt::event_create(&e1); rt::event_record(e1, s); tl->push_back(e1); }
     }
@@ -924,8 +949,10 @@ struct DenseEngine {
   void factor_and_invert(cudaStream_t st, const int* skip = nullptr) {
     if (inv_pipeline) {
       const size_t mb = sizeof(double) * (size_t)np * np;
-      rt::memset0(X, mb, st);
-      rt::memset0(C, mb, st);
+      for (int b = 0; b < nbatch; ++b) {
+        rt::memset0(reinterpret_cast<char*>(X) + b * bstride, mb, st);
+        rt::memset0(reinterpret_cast<char*>(C) + b * bstride, mb, st);
+      }
       set_status_max(st, skip);
       run_seq(potrf_inv, st, skip, true);
     } else {
@@ -937,14 +964,16 @@ struct DenseEngine {
   void set_status_max(cudaStream_t st, const int* skip);
 };
 
-static __global__ void set_int_kernel(int* p, int v, const int* skip) {
+static __global__ void set_int_kernel(int* p, int v, const int* skip, long long bstride) {
+  skip = csd::bshift(skip, bstride);
   if (skip && *skip) return;
+  p = csd::bshift(p, bstride);
   if (threadIdx.x == 0 && blockIdx.x == 0) *p = v;
 }
 inline void DenseEngine::set_status_max(cudaStream_t st, const int* skip) {
   auto k = set_int_kernel;
   ++g_launches;
-  CS_LAUNCH(k, 1, 32, 0, st, status, 0x7fffffff, skip);
+  CS_LAUNCH(k, dim3(1, 1, nbatch), 32, 0, st, status, 0x7fffffff, skip, bstride);
 }
 
 }  // namespace csdense

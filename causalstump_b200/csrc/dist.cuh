@@ -433,7 +433,7 @@ struct DistEval {
       rt::memset0(R.Xl, lm, R.st); rt::memset0(R.C, lm, R.st);
       rt::memset0(R.red, sizeof(double) * R.red_len, R.st);
       auto k0 = csdense::set_int_kernel; ++g_launches;
-      CS_LAUNCH(k0, 1, 32, 0, R.st, R.status, 0x7fffffff, (const int*)nullptr);
+      CS_LAUNCH(k0, 1, 32, 0, R.st, R.status, 0x7fffffff, (const int*)nullptr, 0LL);
       const int ntl = (int)R.lower_tiles.size() / 2, sub = T / csk::TB;
       if (ntl > 0) {
         auto k = gram_dist_kernel; ++g_launches;

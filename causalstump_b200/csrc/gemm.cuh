@@ -34,6 +34,7 @@ struct GemmProblem {
   // table[3t] into A, table[3t+1] into B, table[3t+2] into C and the full k-range.
   const long long* table;
   double* Cm;       // base of the transposed block for mirror == 2 (nullptr: same as C)
+  long long bstride; // batched launch: byte offset between consecutive fits (blockIdx.z), 0 = single problem set
 };
 
 constexpr int GEMM_BK = 16;
@@ -107,6 +108,7 @@ __device__ __forceinline__ void load_operand(double* __restrict__ s, const doubl
 template <int TILE, int WM, int WN, bool AK, bool BK_, int KC = GEMM_BK, int NS = GEMM_STAGES>
 __global__ void __launch_bounds__(WM * WN * 32)
 gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restrict__ skip) {
+  skip = csd::bshift(skip, probs[0].bstride);
   if (skip && *skip) return;
   using Cfg = GemmCfg<TILE, WM, WN>;
   using SA = OperandSmem<TILE, AK, KC>;
@@ -122,6 +124,8 @@ gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restr
   const int bt = (int)blockIdx.x;
   while (pi + 1 < nprob && bt >= probs[pi + 1].tile_base) ++pi;
   GemmProblem P = probs[pi];
+  P.A = csd::bshift(P.A, P.bstride); P.B = csd::bshift(P.B, P.bstride); P.C = csd::bshift(P.C, P.bstride);
+  P.Cm = csd::bshift(P.Cm, P.bstride);
   int I = 0, J = 0;
   int kbeg = 0, kend = P.K;
   if (P.table) {

@@ -8,6 +8,8 @@
 #pragma once
 #include "cs_dev.cuh"
 
+#define CS_BS(ptr) ptr = csd::bshift(ptr, lay.bstride)
+
 namespace csk {
 
 constexpr int TB = 64;        // tile edge of the element-wise kernels
@@ -22,6 +24,7 @@ enum Optim { OPT_ADAM = 0, OPT_NADAM = 1, OPT_NESTEROV = 2 };
 //   TP: sigma, lambdam, nu, lambda0, Lm[p], La[p], mu      (R/kernel_TP_SE_class.R:14-21)
 struct Layout {
   int kind, p;
+  long long bstride = 0;  // batched launches: byte distance between the slabs of consecutive fits (0 = single fit)
   __host__ __device__ int base() const { return kind == KIND_TP ? 4 : 3; }
   __host__ __device__ int i_sigma() const { return 0; }
   __host__ __device__ int i_lm() const { return 1; }
@@ -100,7 +103,9 @@ __global__ void __launch_bounds__(ETH)
 gram_train_kernel(const double* __restrict__ X, long long ldx, const double* __restrict__ z,
                   const double* __restrict__ w, const double* __restrict__ params, Layout lay, int n,
                   double* __restrict__ G, long long ldg, const int* __restrict__ skip) {
+  CS_BS(skip);
   if (skip && *skip) return;
+  CS_BS(X); CS_BS(z); CS_BS(w); CS_BS(params); CS_BS(G);
   CS_DYN_SMEM(double, sm_);
   const int p = lay.p;
   double* xr = sm_;
@@ -202,8 +207,11 @@ __global__ void __launch_bounds__(ETH)
 matvec_kernel(const double* __restrict__ A, long long ld, int cols_per_split, int cols,
               const double* __restrict__ v0, const double* __restrict__ v1, const double* __restrict__ v2,
               const double* __restrict__ shift0, double* __restrict__ out_part, long long out_stride_k,
-              long long out_stride_split, const int* __restrict__ skip) {
+              long long out_stride_split, const int* __restrict__ skip, long long bstride) {
+  skip = csd::bshift(skip, bstride);
   if (skip && *skip) return;
+  A = csd::bshift(A, bstride); v0 = csd::bshift(v0, bstride); v1 = csd::bshift(v1, bstride); v2 = csd::bshift(v2, bstride);
+  shift0 = csd::bshift(shift0, bstride); out_part = csd::bshift(out_part, bstride);
   __shared__ double red[3][4][TB];
   const double sh = shift0 ? *shift0 : 0.0;  // v0 is used as (v0 - *shift0): ybar = y - mu
   const int tid = threadIdx.x, rl = tid & 63, cl = tid >> 6;
@@ -242,7 +250,9 @@ scalars_kernel(const double* __restrict__ mv_part, int nsplit, long long stride_
                const double* __restrict__ logdet_part, int nblk, double* __restrict__ alpha,
                double* __restrict__ u, double* __restrict__ s, EvalScalars* __restrict__ sc,
                const int* __restrict__ skip) {
+  CS_BS(skip);
   if (skip && *skip) return;
+  CS_BS(mv_part); CS_BS(y); CS_BS(params); CS_BS(logdet_part); CS_BS(alpha); CS_BS(u); CS_BS(s); CS_BS(sc);
   __shared__ double red[32];
   const int tid = threadIdx.x;
   const double mu = params[lay.i_mu()];
@@ -308,7 +318,9 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
   // tile_tab != null (distributed mode): nblk is the number of table entries
   // (I64, J64, coff_lo, coff_hi); Cinv + coff is the local 64 x 64 tile and K*alpha is
   // accumulated into the vector kal_part with atomics (kal_stride is ignored).
+  CS_BS(skip);
   if (skip && *skip) return;
+  CS_BS(X); CS_BS(z); CS_BS(params); CS_BS(Cinv); CS_BS(alpha); CS_BS(sc); CS_BS(gpart); CS_BS(kal_part);
   CS_DYN_SMEM(double, sm_);
   const int p = lay.p;
   const int nacc = 2 * p + 2;
@@ -456,7 +468,9 @@ rowstats_kernel(const double* __restrict__ kal_part, long long kal_stride, int n
                 const double* __restrict__ y, const double* __restrict__ w, const double* __restrict__ params,
                 Layout lay, int n, const EvalScalars* __restrict__ sc, double* __restrict__ rs_part,
                 const int* __restrict__ skip) {
+  CS_BS(skip);
   if (skip && *skip) return;
+  CS_BS(kal_part); CS_BS(Cinv); CS_BS(alpha); CS_BS(y); CS_BS(w); CS_BS(params); CS_BS(sc); CS_BS(rs_part);
   __shared__ double red[32];
   const int r = (int)blockIdx.x * ETH + (int)threadIdx.x;
   const double coef = sc->coef;
@@ -484,7 +498,9 @@ __global__ void __launch_bounds__(ETH)
 finalize_kernel(const double* __restrict__ gpart, int ncta, const double* __restrict__ rs_part, int nrs,
                 const double* __restrict__ params, Layout lay, int n, EvalScalars* __restrict__ sc,
                 double* __restrict__ grad, const int* __restrict__ skip) {
+  CS_BS(skip);
   if (skip && *skip) return;
+  CS_BS(gpart); CS_BS(rs_part); CS_BS(params); CS_BS(sc); CS_BS(grad);
   __shared__ double red[32];
   __shared__ double gsum[2 * PMAX + 2];
   const int tid = threadIdx.x;
@@ -555,7 +571,9 @@ __global__ void opt_step_kernel(int optim, int nparam, double iter, double lr, d
 __global__ void loop_step_kernel(int optim, Layout lay, double lr, double b1, double b2, double eps, double momentum,
                                  double* m, double* v, const double* grad, double* para, EvalScalars* sc,
                                  LoopState* ls, double* trace) {
+  CS_BS(ls);
   if (ls->done) return;
+  CS_BS(m); CS_BS(v); CS_BS(grad); CS_BS(para); CS_BS(sc); CS_BS(trace);
   const int it = ls->it;
   const int nparam = lay.np();
   for (int i = threadIdx.x; i < nparam; i += blockDim.x)

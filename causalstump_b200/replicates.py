@@ -48,14 +48,17 @@ def hill_unit(replicate, restart, n=747, p=25, test_frac=0.1, maxiter=3000, tol=
                 e_ate_train=float(np.mean(tau[train]) - t_tr["ate"]), e_ate_test=float(np.mean(tau[test]) - t_te["ate"]))
 
 
-def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1e-1, lr=0.01, prior=False, nu=2000):
+def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1e-1, lr=0.01, prior=False, nu=2000,
+                          batch=32):
     """The same fits as `hill_unit`, but all `units` = [(replicate, restart), ...] are optimised
-    concurrently on this GPU (cs_fit_run_many: one stream pair per fit), which is how the small
-    n ~ 700 fits fill a B200.  Returns one result dict per unit."""
+    together on this GPU, which is how the small n ~ 700 fits fill a B200: groups of `batch` fits share
+    one batched handle (cs_fit_create_batch: every launch serves the whole group) and the groups are
+    driven concurrently (cs_fit_run_many).  batch <= 1: one handle and stream set per fit.
+    Returns one result dict per unit."""
     import math as _m
     from . import _lib, hill, main as M, rcpp_exports as rx
     lib = rx.lib()
-    prep, fits = [], []
+    prep, fits, members = [], [], []
     for replicate, restart in units:
         d = hill.hill_surface_b(n=n, p=p, replicate=replicate)
         rng = np.random.default_rng(565 + 5 * replicate)
@@ -70,12 +73,25 @@ def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1
             K.parainit(y, nu, draws)
         else:
             K.parainit(y, draws)
-        f = _lib.Fit(lib, K.kind, y, X, z, None, rx.pack(K.parameters), optim=_lib.CS_OPT_NADAM, lr=lr)
-        fits.append(f)
+        if batch > 1:
+            members.append((y, X, z, None, rx.pack(K.parameters)))
+        else:
+            fits.append(_lib.Fit(lib, K.kind, y, X, z, None, rx.pack(K.parameters), optim=_lib.CS_OPT_NADAM, lr=lr))
+        kind = K.kind
         prep.append((d, nr["moments"], train, test, replicate, restart))
-    res = _lib.run_many(fits, maxiter, tol)
+    if batch > 1:
+        handles = [_lib.FitBatch(lib, kind, members[i:i + batch], optim=_lib.CS_OPT_NADAM, lr=lr)
+                   for i in range(0, len(members), batch)]
+        res = _lib.run_many(handles, maxiter, tol)
+        views = [(h, b) for h in handles for b in range(h.B)]
+    else:
+        handles = fits
+        res = _lib.run_many(fits, maxiter, tol)
+        views = [(f, None) for f in fits]
     out = []
-    for (d, mom, train, test, replicate, restart), f, (iters, trace) in zip(prep, fits, res):
+    for (d, mom, train, test, replicate, restart), (f, member), (iters, trace) in zip(prep, views, res):
+        if member is not None:
+            f.select(member)
         sd = _m.sqrt(mom["varY"])
         Xall = M.norm_variables(X=d["X"], moments=mom)["X"]
         pred = f.predict(Xall, d["z"])["map"] * sd + mom["meanY"]
@@ -89,7 +105,8 @@ def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1
                         rmse_test=float(np.sqrt(np.mean((d["y"][test] - pred[test]) ** 2))),
                         e_ate_train=float(np.mean(tau[train]) - sd * t_tr["ate"]),
                         e_ate_test=float(np.mean(tau[test]) - sd * t_te["ate"])))
-        f.close()
+    for h in handles:
+        h.close()
     return out
 
 

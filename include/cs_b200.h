@@ -119,6 +119,19 @@ int cs_fit_create(const cs_fit_config* cfg, int n, int p, const double* y, const
 void cs_fit_destroy(cs_fit* f);
 int cs_fit_nparam(const cs_fit* f);
 
+/* Batched handle: nbatch independent fits of the same (n, p, kind, optimizer) -- the replicates x
+ * restarts of config 4 (test/sec5-3_Hill2011.R:611-616 runs them as forked R workers).  Every launch
+ * of the evaluation / optimisation loop serves all members (one CTA slice per member), which removes
+ * the launch-rate bound of n ~ 700 fits.  y, X, z, w, init_params are arrays of nbatch host pointers
+ * (w, or any w[i], may be NULL = ones).  cs_fit_eval_async / cs_fit_run act on all members;
+ * host transfers (set/get params, set_data, fetch, get_matrices, predict, treat) act on the member
+ * chosen with cs_fit_select (initially 0).  cs_fit_run then fills iters[nbatch] and nbatch
+ * consecutive 2 x (maxiter+2) trace blocks; maxiter <= 6000 for nbatch > 1. */
+int cs_fit_create_batch(const cs_fit_config* cfg, int nbatch, int n, int p, const double* const* y, const double* const* X,
+                        const double* const* z, const double* const* w, const double* const* init_params, cs_fit** out);
+int cs_fit_batch_size(const cs_fit* f);
+int cs_fit_select(cs_fit* f, int member);
+
 /* One "LML + gradient evaluation" (SURVEY.md 8d): Gram -> Cholesky -> inverse -> fused
  * trace gradients -> LML/stats -> closed-form mu.  params NULL = current parameters.
  * No parameter update.  Outputs nullable. */

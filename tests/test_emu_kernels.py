@@ -99,3 +99,33 @@ def test_pipelined_inverse(emulib, n, p, tile):
     assert np.array_equal(g2, g3)
     assert cs.rel(g2, o.pack_params(g), 1e-9) < cs.TOL_GRAD and abs(st2[1] - st[1]) < cs.TOL_LML * abs(st[1])
     assert abs(st2[0] - st[0]) < 1e-8 * abs(st[0]) and abs(mu2 - mu) < 1e-9 * abs(mu)
+
+
+@pytest.mark.parametrize("kind,n,p,B", [("GP", 90, 3, 3), ("TP", 70, 2, 2), ("GP", 150, 4, 4)])
+def test_batched_handle_matches_individual_fits(emulib, kind, n, p, B):
+    """cs_fit_create_batch: every launch serves all members (blockIdx.z); members differ in data, start
+    and stopping iteration.  Each member must equal the oracle fit of its own problem."""
+    Ps = [cs.make_problem(kind, n, p, replicate=r, draws=(0.4 + 0.1 * r, 0.6 - 0.05 * r)) for r in range(B)]
+    members = [(P["y"], P["X"], P["z"], P["w"] if r % 2 else None, o.pack_params(P["par"])) for r, P in enumerate(Ps)]
+    fb = _lib.FitBatch(emulib, cs.kcode(kind), members, chunk=3)
+    assert emulib.dll.cs_fit_batch_size(fb.h) == B
+    fb.eval_async(); fb.sync()
+    for b, P in enumerate(Ps):
+        g, st, mu = o.eval_lml_grad(kind, P["y"], P["X"], P["z"], P["w"], P["par"])
+        g2, st2, mu2 = fb.select(b).fetch()
+        assert cs.rel(g2, o.pack_params(g), 1e-9) < cs.TOL_GRAD and abs(st2[1] - st[1]) < cs.TOL_LML * abs(st[1])
+        assert abs(mu2 - mu) < 1e-9 * abs(mu)
+    tol = 0.5  # loose: members stop at different iterations
+    res = fb.select(0).run(14, tol)
+    its = []
+    for b, (P, (it, tr)) in enumerate(zip(Ps, res)):
+        ref = cs.oracle_fit(P, "Nadam", 14, tol, 0.01)
+        its.append(it)
+        assert it == ref.iters, (b, it, ref.iters)
+        assert cs.rel(tr[1, 1:], ref.stats[1, 1:]) < 1e-9
+        assert cs.rel(fb.select(b).get_params(), o.pack_params(ref.Kernel.parameters), 1e-9) < 1e-8
+        X2 = P["X"][:11] * 0.9
+        t2 = fb.treat(X2, cov_jitter=1e-6 if kind == "TP" else 0.0)
+        tr_o = ref.Kernel.predict_treat(P["y"], P["X"], P["z"], X2)
+        assert cs.relm(t2["map"], tr_o["map"]) < cs.TOL_MAP
+    fb.close()

@@ -119,6 +119,38 @@ def test_golden_ref(gpulib):
         f.close()
 
 
+def test_batched_handle(gpulib):
+    """cs_fit_create_batch at the size of config 4 (672 x 25 training splits): all members advance with every
+    launch; each must equal its own single-handle fit (to rounding: the per-fit CTA count of the trace-gradient
+    reduction differs between a batch and a single handle) and the oracle to tolerance."""
+    B, n, p = 6, 672, 25
+    Ps = [cs.make_problem("GP", n, p, replicate=r, draws=(0.3 + 0.1 * r, 0.9 - 0.1 * r)) for r in range(B)]
+    members = [(P["y"], P["X"], P["z"], None, o.pack_params(P["par"])) for P in Ps]
+    fb = _lib.FitBatch(gpulib, 0, members)
+    fb.eval_async(); fb.sync()
+    for b in (0, B - 1):
+        P = Ps[b]
+        g, st, mu = o.eval_lml_grad("GP", P["y"], P["X"], P["z"], P["w"], P["par"])
+        g2, st2, mu2 = fb.select(b).fetch()
+        gref = o.pack_params(g)
+        assert np.max(np.abs(g2 - gref) / np.maximum(np.abs(gref), 1e-6 * np.max(np.abs(gref)))) < cs.TOL_GRAD
+        assert abs(st2[1] - st[1]) < cs.TOL_LML * abs(st[1]) and abs(mu2 - mu) < 1e-9 * abs(mu)
+    res = fb.select(0).run(40, 2.0)
+    its = [it for it, _ in res]
+    for b, P in enumerate(Ps):
+        f1 = _lib.Fit(gpulib, 0, P["y"], P["X"], P["z"], None, o.pack_params(P["par"]))
+        it1, tr1 = f1.run(40, 2.0)
+        assert its[b] == it1 and cs.rel(res[b][1][1, 1:], tr1[1, 1:]) < 1e-11
+        assert cs.rel(fb.select(b).get_params(), f1.get_params(), 1e-9) < 1e-9
+        X2 = P["X"][:75] * 0.97
+        assert cs.relm(fb.treat(X2)["map"], f1.treat(X2)["map"]) < 1e-9
+        assert cs.relm(fb.predict(X2, P["z"][:75])["map"], f1.predict(X2, P["z"][:75])["map"]) < 1e-9
+        f1.close()
+    ref = cs.oracle_fit(Ps[1], "Nadam", 40, 2.0, 0.01)
+    assert its[1] == ref.iters and cs.rel(res[1][1][1, 1:], ref.stats[1, 1:]) < 1e-8
+    fb.close()
+
+
 def test_stateless_mirrors_vs_compiled_reference(gpulib):
     """The stateless C-ABI mirrors against oracle/_ref (the reference's C++ compiled with the header shim),
     which travels to the GPU box as a prebuilt .so; skipped when it is absent."""
