@@ -33,8 +33,9 @@ if ROOT not in sys.path:
 N_METRIC, P_METRIC = 8192, 25
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
 # `ncu --set full` capture (per launch; None until a capture of the current kernel exists)
-XTX_TRAFFIC_BYTES = None
-XTX_TRAFFIC_SOURCE = None
+XTX_TRAFFIC_BYTES = 4.111889e9 + 486.338048e6
+XTX_TRAFFIC_SOURCE = ("profiles/r01_s2_ncu_xtx.txt: ncu --set full of this kernel in `bench.py --inv-pipeline 0` "
+                      "(dram__bytes_read.sum 4.112 GB + dram__bytes_write.sum 486.3 MB per launch)")
 METRIC = "fp64 LML+gradient evals/sec at n=8192,p=25"
 UNIT = "evals/s"
 
@@ -343,7 +344,8 @@ def run_ours(args, rank, world, local_rank):
         dense_tflops = float(npad) ** 3 / (dense_ms * 1e-3) / 1e12
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         line_extra["roofline"] = {
-            "kernel": "csg::gemm_kernel<128,2,4,true,true> (K^-1 = X^T X as one launch, DMMA.8x8x4), timed alone on its stream",
+            "kernel": "csg::gemm_kernel<64,2,2,true,true,16,2> (K^-1 = X^T X as one launch of 8256 CTA tiles, DMMA.8x8x4), "
+                      "timed alone on its stream (sequential plan, second handle)",
             "bound": "tensor", "achieved": xtx_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": xtx_tflops / fp64_peak, "traffic": XTX_TRAFFIC_BYTES,
             "traffic_source": XTX_TRAFFIC_SOURCE,

@@ -331,6 +331,7 @@ static int fit_create_impl(const cs_fit_config* cfg, int nbatch, int n, int p, c
   f->want((void**)&E.G, mb); f->want((void**)&E.X, mb); f->want((void**)&E.C, mb);
   f->want((void**)&E.logdet_part, sizeof(double) * (np / tile));
   f->want((void**)&E.Pbuf, DenseEngine::pbuf_bytes(np, tile));
+  f->want((void**)&E.Rbuf, DenseEngine::pbuf_bytes(np, tile));
   f->want((void**)&E.status, sizeof(int));
   f->want((void**)&f->X, vb * p); f->want((void**)&f->y, vb); f->want((void**)&f->z, vb); f->want((void**)&f->w, vb);
   f->want((void**)&f->ones, vb);

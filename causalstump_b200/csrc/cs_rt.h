@@ -46,8 +46,8 @@ inline int sm_count() { return 4; }
 inline int host_alloc(void** p, size_t b) { *p = std::malloc(b ? b : 1); return *p ? 0 : 2; }
 inline int host_free(void* p) { std::free(p); return 0; }
 inline int partition_streams(int, cudaStream_t*, cudaStream_t*, cudaStream_t**, const int*, int, int*, int*) { return 1; }
-inline int copy2d(double* dst, const double* src, long long ld, long long rows, long long cols, cudaStream_t) {
-  for (long long c = 0; c < cols; ++c) std::memmove(dst + c * ld, src + c * ld, sizeof(double) * rows);
+inline int copy2d(double* dst, long long ldd, const double* src, long long lds, long long rows, long long cols, cudaStream_t) {
+  for (long long c = 0; c < cols; ++c) std::memmove(dst + c * ldd, src + c * lds, sizeof(double) * rows);
   return 0;
 }
 inline int stream_create_level(cudaStream_t* s, int) { *s = 0; return 0; }
@@ -137,8 +137,8 @@ template <class F> inline bool drv_sym(const char* name, F* fn) {
   *fn = reinterpret_cast<F>(p);
   return true;
 }
-inline int copy2d(double* dst, const double* src, long long ld, long long rows, long long cols, cudaStream_t s) {
-  return (int)cudaMemcpy2DAsync(dst, sizeof(double) * ld, src, sizeof(double) * ld, sizeof(double) * rows, (size_t)cols,
+inline int copy2d(double* dst, long long ldd, const double* src, long long lds, long long rows, long long cols, cudaStream_t s) {
+  return (int)cudaMemcpy2DAsync(dst, sizeof(double) * ldd, src, sizeof(double) * lds, sizeof(double) * rows, (size_t)cols,
                                 cudaMemcpyDeviceToDevice, s);
 }
 inline int partition_streams(int sm_crit, cudaStream_t* crit_hi, cudaStream_t* crit_hi2, cudaStream_t** bulk, const int* level, int nbulk,

@@ -251,7 +251,7 @@ struct Launch {
   int ev;          // event index for OP_RECORD / OP_WAIT
   int gtile;       // CTA tile of this launch (0 = engine default gt)
   // OP_COPY: 2-D device copy of `rows` x `cols` doubles (leading dimension np on both sides)
-  double* cp_dst; const double* cp_src; long long cp_rows, cp_cols;
+  double* cp_dst; const double* cp_src; long long cp_rows, cp_cols, cp_ldd, cp_lds;
 };
 
 inline int pick_tile(int n) { return n <= 1536 ? 64 : 128; }
@@ -308,6 +308,7 @@ struct DenseEngine {
   double *G = nullptr, *X = nullptr, *C = nullptr;  // device, np x np each
   double* logdet_part = nullptr;                     // device, N
   double* Pbuf = nullptr;                            // device, np x (panel_blocks*tile): out-of-place panel multiply
+  double* Rbuf = nullptr;                            // device, (panel_blocks*tile) x np: out-of-place row panel of L^-1
   int* status = nullptr;                             // device, 1 (0 = OK, else 1-based failing pivot)
   GemmProblem* d_probs = nullptr;
   std::vector<GemmProblem> probs;
@@ -384,6 +385,7 @@ struct DenseEngine {
       if ((e = rt::dev_malloc((void**)&C, bytes))) return e;
       if ((e = rt::dev_malloc((void**)&logdet_part, sizeof(double) * N))) return e;
       if ((e = rt::dev_malloc((void**)&Pbuf, pbuf_bytes(np, tile)))) return e;
+      if ((e = rt::dev_malloc((void**)&Rbuf, pbuf_bytes(np, tile)))) return e;
       if ((e = rt::dev_malloc((void**)&status, sizeof(int)))) return e;
     }
     configure_kernels();
@@ -573,8 +575,9 @@ struct DenseEngine {
     // the next diagonal block is updated first (Ltop / U1top), the rest follows.
     auto build_chol2 = [&](std::vector<Launch>& seq, bool with_inverse) {
     auto op = [&](int type, int stream, int ev) { Launch o{}; o.is_leaf = type; o.stream = stream; o.ev = ev; seq.push_back(o); };
-    auto copy_op = [&](int stream, double* dst, const double* src, long long rows, long long cols) {
-      Launch o{}; o.is_leaf = OP_COPY; o.stream = stream; o.cp_dst = dst; o.cp_src = src; o.cp_rows = rows; o.cp_cols = cols; seq.push_back(o);
+    auto copy_op = [&](int stream, double* dst, long long ldd, const double* src, long long lds, long long rows, long long cols) {
+      Launch o{}; o.is_leaf = OP_COPY; o.stream = stream; o.cp_dst = dst; o.cp_src = src; o.cp_rows = rows; o.cp_cols = cols;
+      o.cp_ldd = ldd; o.cp_lds = lds; seq.push_back(o);
     };
     int last_aux_ev = -1, last_inv_ev = -1, last_inv3_ev = -1, last_rest_ev = -1, ev_u1top_prev = -1, last_s6_ev = -1, last_u2b_ev = -1;
     auto push_panel = [&](int k, int r0, int nb, int stream) {  // in-place L = A X_kk^T for nb block rows of column k
@@ -638,7 +641,7 @@ struct DenseEngine {
           double* dst = Pbuf + (long long)r0 * T;
           grp.push_back(mk(src, ld, Xpp, ld, dst, ld, nb_rows * rr, pw * rr, (int)kw, csg::KM_LE_J, csg::ORD_COL, 0, 1.0, 0.0));
           add_group(seq, GK_NT, grp); seq.back().stream = 2;
-          copy_op(2, src, dst, (long long)nb_rows * tile, kw);
+          copy_op(2, src, ld, dst, ld, (long long)nb_rows * tile, kw);
         };
         lmul(p1, n1);
         // U1top: next diagonal block (lower tiles), K = panel width
@@ -683,11 +686,11 @@ struct DenseEngine {
         // ---- S3: rows P of X left of the diagonal block, X_iJ = -sum_{l<=i} X_il Acc_lJ, bottom row first (in place)
         op(OP_WAIT, 3, ev_xpp);
         if (p0 > 0) {
-          for (int i = p1 - 1; i >= p0; --i) {
-            grp.push_back(mk(X + (long long)i * T + (long long)p0 * T * ld, ld, X + (long long)p0 * T, ld, X + (long long)i * T, ld, 1, p0, (i - p0 + 1) * tile,
-                             csg::KM_FULL, csg::ORD_COL, 0, -1.0, 0.0));
-            add_group(seq, GK_NN, grp); seq.back().stream = 3; seq.back().gtile = tile;
-          }
+          // one launch for the whole row panel, out of place through Rbuf (k <= i: X_PP is lower triangular)
+          const long long ldr = (long long)panel_blocks * tile;
+          grp.push_back(mk(Xpp, ld, X + (long long)p0 * T, ld, Rbuf, ldr, pw * rr, p0 * rr, pw * tile, csg::KM_LE_I, csg::ORD_COL, 0, -1.0, 0.0));
+          add_group(seq, GK_NN, grp); seq.back().stream = 3;
+          copy_op(3, X + (long long)p0 * T, ld, Rbuf, ldr, (long long)pw * tile, (long long)p0 * tile);
         }
         const int ev_rows = nev++;
         op(OP_RECORD, 3, ev_rows);
@@ -804,8 +807,9 @@ struct DenseEngine {
   void destroy() {
     if (!external_buffers) {
       rt::dev_free(G); rt::dev_free(X); rt::dev_free(C); rt::dev_free(logdet_part); rt::dev_free(status); rt::dev_free(Pbuf);
+      rt::dev_free(Rbuf);
     }
-    Pbuf = nullptr;
+    Pbuf = nullptr; Rbuf = nullptr;
     rt::dev_free(d_probs);
     for (auto& ev : events) rt::event_destroy(ev);
     events.clear();
@@ -842,8 +846,9 @@ struct DenseEngine {
                     L.blk * tile, logdet_part + L.blk, status, n, s, skip, nbatch, bstride);
       } else if (L.is_leaf == OP_COPY) {
         for (int b = 0; b < nbatch; ++b)
-          rt::copy2d(reinterpret_cast<double*>(reinterpret_cast<char*>(L.cp_dst) + b * bstride),
-                     reinterpret_cast<const double*>(reinterpret_cast<const char*>(L.cp_src) + b * bstride), np, L.cp_rows, L.cp_cols, s);
+          rt::copy2d(reinterpret_cast<double*>(reinterpret_cast<char*>(L.cp_dst) + b * bstride), L.cp_ldd,
+                     reinterpret_cast<const double*>(reinterpret_cast<const char*>(L.cp_src) + b * bstride), L.cp_lds, L.cp_rows,
+                     L.cp_cols, s);
       } else if (L.is_leaf == OP_RECORD) {
         rt::event_record(events[L.ev], s);
       } else if (L.is_leaf == OP_WAIT) {
@@ -866,11 +871,15 @@ struct DenseEngine {
   // with at least one write is ordered.  Returns the number of unordered conflicting pairs.
   struct Rect { int buf; long long r0, r1, c0, c1; bool write; };
   void rect_of(const double* ptr, long long rows, long long cols, bool write, std::vector<Rect>& out) const {
-    const double* bases[4] = {G, X, C, Pbuf};
-    for (int b = 0; b < 4; ++b) {
+    const long long pb = (long long)np * panel_blocks * tile;
+    const double* bases[5] = {G, X, C, Pbuf, Rbuf};
+    const long long sizes[5] = {(long long)np * np, (long long)np * np, (long long)np * np, pb, pb};
+    const long long lds[5] = {np, np, np, np, (long long)panel_blocks * tile};
+    for (int b = 0; b < 5; ++b) {
+      if (!bases[b]) continue;
       const long long off = ptr - bases[b];
-      if (off >= 0 && off < (b == 3 ? (long long)np * panel_blocks * tile : (long long)np * np)) {
-        out.push_back(Rect{b, off % np, off % np + rows, off / np, off / np + cols, write});
+      if (off >= 0 && off < sizes[b]) {
+        out.push_back(Rect{b, off % lds[b], off % lds[b] + rows, off / lds[b], off / lds[b] + cols, write});
         return;
       }
     }

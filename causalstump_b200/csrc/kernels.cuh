@@ -364,6 +364,16 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
     load_x_tile(xc, X, ldx, c0, p, tid);
     if (tid < TB) { zr[tid] = z[r0 + tid]; zc[tid] = z[c0 + tid]; ar[tid] = alpha[r0 + tid]; ac[tid] = alpha[c0 + tid]; }
     __syncthreads();
+    // the K^-1 entries of this tile are requested first so that their HBM latency hides behind the
+    // distance / exponent arithmetic
+    double tv[4][4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int rl = tx + 16 * a, cl = ty + 16 * b;
+        tv[a][b] = (r0 + rl < n && c0 + cl < n) ? Ct[(long long)cl * ldc + rl] : 0.0;
+      }
     double km[4][4], ka[4][4];
     if (!FROM_MEM) sqdist_4x4(xr, xc, ea, eb, p, tx, ty, km, ka);
     double rs[4] = {0.0, 0.0, 0.0, 0.0}, cs[4] = {0.0, 0.0, 0.0, 0.0};
@@ -385,7 +395,7 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
             vka = exp(lam_a - ka[a][b]) * zr[rl] * zc[cl];
             kfull = vkm + vka;
           }
-          T = Ct[(long long)cl * ldc + rl] - coef * ar[rl] * ac[cl];
+          T = tv[a][b] - coef * ar[rl] * ac[cl];
         }
         rs[a] = fma(kfull, ac[cl], rs[a]);
         cs[b] = fma(kfull, ar[rl], cs[b]);
@@ -403,18 +413,19 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
       for (int a = 0; a < 4; ++a) xa[a] = xr[i * TB + tx + 16 * a];
 #pragma unroll
       for (int b = 0; b < 4; ++b) xb[b] = xc[i * TB + ty + 16 * b];
-      double gm = 0.0, ga = 0.0;
+      // four independent partial sums per kernel: no 16-long dependent FMA chain
+      double gm[4] = {0.0, 0.0, 0.0, 0.0}, ga[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const double d = xa[a] - xb[b];
           const double d2 = d * d;
-          gm = fma(km[a][b], d2, gm);
-          ga = fma(ka[a][b], d2, ga);
+          gm[b] = fma(km[a][b], d2, gm[b]);
+          ga[b] = fma(ka[a][b], d2, ga[b]);
         }
-      acc[(2 + i) * ETH + tid] += wgt * gm;
-      acc[(2 + p + i) * ETH + tid] += wgt * ga;
+      acc[(2 + i) * ETH + tid] += wgt * ((gm[0] + gm[1]) + (gm[2] + gm[3]));
+      acc[(2 + p + i) * ETH + tid] += wgt * ((ga[0] + ga[1]) + (ga[2] + ga[3]));
     }
     // K*alpha partials: rows (reduce over ty) and columns (reduce over tx)
 #pragma unroll

@@ -49,7 +49,7 @@ def hill_unit(replicate, restart, n=747, p=25, test_frac=0.1, maxiter=3000, tol=
 
 
 def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1e-1, lr=0.01, prior=False, nu=2000,
-                          batch=32):
+                          batch=32, tile=0):
     """The same fits as `hill_unit`, but all `units` = [(replicate, restart), ...] are optimised
     together on this GPU, which is how the small n ~ 700 fits fill a B200: groups of `batch` fits share
     one batched handle (cs_fit_create_batch: every launch serves the whole group) and the groups are
@@ -80,7 +80,7 @@ def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1
         kind = K.kind
         prep.append((d, nr["moments"], train, test, replicate, restart))
     if batch > 1:
-        handles = [_lib.FitBatch(lib, kind, members[i:i + batch], optim=_lib.CS_OPT_NADAM, lr=lr)
+        handles = [_lib.FitBatch(lib, kind, members[i:i + batch], optim=_lib.CS_OPT_NADAM, lr=lr, tile=tile)
                    for i in range(0, len(members), batch)]
         res = _lib.run_many(handles, maxiter, tol)
         views = [(h, b) for h in handles for b in range(h.B)]
