@@ -219,11 +219,27 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
   const unsigned B = (unsigned)f->nbatch;
   int ph = 0;
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
-  {  // K1
+  {  // K1.  With the v2 plan the build is split: the tiles of the first diagonal block (rows < W*TILE) on the
+     // handle's stream, the rest on the panel stream S2, which every other consumer of G is ordered behind
+     // (DenseEngine::build_chol2) -- so the first diagonal block is factored while the rest is still built.
     auto k = csk::gram_train_kernel;
+    const int total = csg::lower_tiles(f->nblk);
+    int first = total;
+    static const bool no_split = std::getenv("CS_NO_GRAM_SPLIT") != nullptr;
+    if (f->eng.plan_version == 2 && f->eng.aux2_ok && !no_split) {
+      const int bw = std::min(f->nblk, f->eng.panel_blocks * f->eng.tile / csk::TB);
+      first = csg::lower_tiles(bw);
+    }
     ++g_launches;
-    CS_LAUNCH(k, dim3(csg::lower_tiles(f->nblk), 1, B), csk::ETH, csk::gram_smem_bytes(p), st, f->X, ld, f->z, f->w, f->params,
-              f->lay, n, f->eng.G, ld, skip);
+    CS_LAUNCH(k, dim3(first, 1, B), csk::ETH, csk::gram_smem_bytes(p), st, f->X, ld, f->z, f->w, f->params,
+              f->lay, n, f->eng.G, ld, skip, 0);
+    if (first < total) {
+      rt::event_record(f->eng.ev_gram, st);   // orders S2 behind everything already on the handle's stream
+      rt::stream_wait_event(f->eng.aux2, f->eng.ev_gram);
+      ++g_launches;
+      CS_LAUNCH(k, dim3(total - first, 1, B), csk::ETH, csk::gram_smem_bytes(p), f->eng.aux2, f->X, ld, f->z, f->w, f->params,
+                f->lay, n, f->eng.G, ld, skip, first);
+    }
   }
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
   if (f->eng.inv_pipeline) {
@@ -743,7 +759,7 @@ int cs_debug_timeline(cs_fit* f, int cap, int* n_out, float* rows) {
     auto k = csk::gram_train_kernel;
     ++g_launches;
     CS_LAUNCH(k, csg::lower_tiles(f->nblk), csk::ETH, csk::gram_smem_bytes(f->p), st, f->X, (long long)f->np, f->z, f->w,
-              f->params, f->lay, f->n, f->eng.G, (long long)f->np, (const int*)nullptr);
+              f->params, f->lay, f->n, f->eng.G, (long long)f->np, (const int*)nullptr, 0);
   }
   RT(rt::stream_sync(st));
   cudaEvent_t base;

@@ -331,6 +331,8 @@ struct DenseEngine {
   bool crit_ok = false;
   int sm_crit = 0, sm_bulk = 0;
   cudaEvent_t ev_in{}, ev_out{};
+  cudaEvent_t ev_gram{};  // split Gram build (api.cu): S2 starts behind the handle's stream
+  bool ev_gram_ok = false;
 
   static GemmProblem mk(const double* A, long long lda, const double* B, long long ldb, double* C, long long ldc,
                         int mt, int nt, int K, int kmode, int order, int mirror, double alpha, double beta) {
@@ -699,11 +701,12 @@ struct DenseEngine {
           double* Xp = X + (long long)p0 * T;
           if (p0 > 0) {
             grp.push_back(mk(Xp, ld, Xp, ld, C, ld, p0 * rr, p0 * rr, pw * tile, csg::KM_FULL, csg::ORD_LOWER, 1, 1.0, 1.0));
-            GemmProblem q = mk(Xpp, ld, Xp, ld, C + (long long)p0 * T, ld, pw * rr, p0 * rr, pw * tile, csg::KM_GE_I, csg::ORD_COL, 2, 1.0, 1.0);
+            // rows P of K^-1 are touched for the first time here: beta = 0 (no memset of C per evaluation)
+            GemmProblem q = mk(Xpp, ld, Xp, ld, C + (long long)p0 * T, ld, pw * rr, p0 * rr, pw * tile, csg::KM_GE_I, csg::ORD_COL, 2, 1.0, 0.0);
             q.Cm = C + (long long)p0 * T * ld;
             grp.push_back(q);
           }
-          grp.push_back(mk(Xpp, ld, Xpp, ld, C + (long long)p0 * T * (ld + 1), ld, pw * rr, pw * rr, pw * tile, csg::KM_GE_I, csg::ORD_LOWER, 1, 1.0, 1.0));
+          grp.push_back(mk(Xpp, ld, Xpp, ld, C + (long long)p0 * T * (ld + 1), ld, pw * rr, pw * rr, pw * tile, csg::KM_GE_I, csg::ORD_LOWER, 1, 1.0, 0.0));
           add_group(seq, GK_TN, grp); seq.back().stream = 4;
         }
         last_inv_ev = nev++;
@@ -714,7 +717,8 @@ struct DenseEngine {
             double* Lp = G + (long long)r0 * T + (long long)p0 * T * ld;
             if (p0 > 0)
               grp.push_back(mk(Lp, ld, X + (long long)p0 * T, ld, X + (long long)r0 * T, ld, nb_rows * rr, p0 * rr, pw * tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 1.0));
-            grp.push_back(mk(Lp, ld, Xpp, ld, X + (long long)r0 * T + (long long)p0 * T * ld, ld, nb_rows * rr, pw * rr, pw * tile, csg::KM_GE_J, csg::ORD_COL, 0, 1.0, 1.0));
+            // columns P of Acc are touched for the first time by panel P: beta = 0 (no memset of X per evaluation)
+            grp.push_back(mk(Lp, ld, Xpp, ld, X + (long long)r0 * T + (long long)p0 * T * ld, ld, nb_rows * rr, pw * rr, pw * tile, csg::KM_GE_J, csg::ORD_COL, 0, 1.0, 0.0));
             add_group(seq, GK_NN, grp); seq.back().stream = stream;
           };
           op(OP_WAIT, 3, ev_lpanel);
@@ -795,6 +799,8 @@ struct DenseEngine {
       if ((e = rt::stream_create_level(&aux6, 0))) return e;
       aux6_ok = true;
     }
+    if ((e = rt::event_create_fast(&ev_gram))) return e;
+    ev_gram_ok = true;
     events.resize(n_events);
     for (int i = 0; i < n_events; ++i)
       if ((e = rt::event_create_fast(&events[i]))) return e;
@@ -813,6 +819,7 @@ struct DenseEngine {
     rt::dev_free(d_probs);
     for (auto& ev : events) rt::event_destroy(ev);
     events.clear();
+    if (ev_gram_ok) { rt::event_destroy(ev_gram); ev_gram_ok = false; }
     if (aux_ok) { rt::stream_sync(aux); rt::stream_destroy(aux); aux_ok = false; }
     if (aux2_ok) { rt::stream_sync(aux2); rt::stream_destroy(aux2); aux2_ok = false; }
     if (aux3_ok) { rt::stream_sync(aux3); rt::stream_destroy(aux3); aux3_ok = false; }
@@ -957,8 +964,10 @@ struct DenseEngine {
   // own stream; X and C are accumulated into and must start from zero.
   void factor_and_invert(cudaStream_t st, const int* skip = nullptr) {
     if (inv_pipeline) {
+      // plan v2 initialises every tile of X and C with its first contribution (beta = 0); the upper off-diagonal
+      // tiles of X are zeroed once at creation and never written
       const size_t mb = sizeof(double) * (size_t)np * np;
-      for (int b = 0; b < nbatch; ++b) {
+      for (int b = 0; b < (plan_version == 2 ? 0 : nbatch); ++b) {
         rt::memset0(reinterpret_cast<char*>(X) + b * bstride, mb, st);
         rt::memset0(reinterpret_cast<char*>(C) + b * bstride, mb, st);
       }

@@ -102,7 +102,9 @@ inline int gram_smem_bytes(int p) { return (2 * p * TB + 2 * PMAX + 3 * TB) * (i
 __global__ void __launch_bounds__(ETH)
 gram_train_kernel(const double* __restrict__ X, long long ldx, const double* __restrict__ z,
                   const double* __restrict__ w, const double* __restrict__ params, Layout lay, int n,
-                  double* __restrict__ G, long long ldg, const int* __restrict__ skip) {
+                  double* __restrict__ G, long long ldg, const int* __restrict__ skip, int tile0) {
+  // tile0: first lower-triangular tile of this launch (the Gram build is split so that the first diagonal
+  // block of the Cholesky can start while the rest of the matrix is still being built)
   CS_BS(skip);
   if (skip && *skip) return;
   CS_BS(X); CS_BS(z); CS_BS(w); CS_BS(params); CS_BS(G);
@@ -117,7 +119,7 @@ gram_train_kernel(const double* __restrict__ X, long long ldx, const double* __r
   double* wr = zc + TB;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   // lower-triangular tile enumeration
-  const int t = (int)blockIdx.x;
+  const int t = (int)blockIdx.x + tile0;
   int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
   while ((long long)(I + 1) * (I + 2) / 2 <= t) ++I;
   while ((long long)I * (I + 1) / 2 > t) --I;
