@@ -79,10 +79,41 @@ static __global__ void add_noise_diag_kernel(double* A, long long ld, int n, con
   if (i < n) A[(long long)i * ld + i] += esig / w[i];
 }
 
+// Scratch arena for the predict / treatment calls: chunks are kept for the life of the handle and handed
+// out again on the next call, so a replicate loop of 3 calls per fit does not pay cudaMalloc / cudaFree
+// (which also synchronises the device) every time.  Active only inside an ArenaScope.
+struct Arena {
+  struct Chunk { char* base; size_t cap, off; };
+  std::vector<Chunk> chunks;
+  void reset() { for (auto& c : chunks) c.off = 0; }
+  void* take(size_t bytes) {
+    bytes = (bytes + 255) / 256 * 256;
+    if (bytes == 0) bytes = 256;
+    for (auto& c : chunks)
+      if (c.cap - c.off >= bytes) { void* q = c.base + c.off; c.off += bytes; return q; }
+    Chunk c{nullptr, std::max(bytes, (size_t)8 << 20), 0};
+    if (rt::dev_malloc((void**)&c.base, c.cap)) return nullptr;
+    c.off = bytes;
+    chunks.push_back(c);
+    return c.base;
+  }
+  void release() { for (auto& c : chunks) rt::dev_free(c.base); chunks.clear(); }
+};
+static thread_local Arena* g_arena = nullptr;
+struct ArenaScope {
+  Arena* prev;
+  explicit ArenaScope(Arena* a) : prev(g_arena) { g_arena = a; if (a) a->reset(); }
+  ~ArenaScope() { g_arena = prev; }
+};
+
 struct DevBuf {
   void* p = nullptr;
-  ~DevBuf() { if (p) rt::dev_free(p); }
-  int alloc(size_t bytes) { return rt::dev_malloc(&p, bytes); }
+  bool owned = true;
+  ~DevBuf() { if (p && owned) rt::dev_free(p); }
+  int alloc(size_t bytes) {
+    if (g_arena) { owned = false; p = g_arena->take(bytes); return p ? 0 : 2; }
+    return rt::dev_malloc(&p, bytes);
+  }
   double* d() const { return static_cast<double*>(p); }
 };
 
@@ -168,6 +199,7 @@ struct cs_fit {
   char* slab = nullptr;
   std::vector<std::pair<void**, size_t>> slab_req;
   bool trace_in_slab = false;
+  Arena arena;  // scratch of cs_predict / cs_treat
 
   void want(void** field, size_t bytes) { slab_req.emplace_back(field, bytes); }
   int commit_slab() {
@@ -425,6 +457,7 @@ void cs_fit_destroy(cs_fit* f) {
   rt::stream_sync(f->st);
   if (f->trace && !f->trace_in_slab) rt::dev_free(f->trace);
   if (f->slab) rt::dev_free(f->slab);
+  f->arena.release();
   if (f->flush) rt::dev_free(f->flush);
   if (f->pinned) rt::host_free(f->pinned);
   if (f->h_ls) rt::host_free(f->h_ls);
@@ -910,6 +943,7 @@ static int cross_common(cs_fit* f, CrossWork& W, int n2, const double* X2, const
 
 int cs_predict(cs_fit* f, int n2, const double* X2, const double* z2, double* map, double* var_diag, double* cov) {
   if (!f || !X2 || !z2 || n2 < 1) return fail(CS_ERR_ARG, "cs_predict: bad argument");
+  ArenaScope scope(&f->arena);
   CrossWork W;
   int e = cross_common(f, W, n2, X2, z2, false, map, var_diag, 1.0, 0.0, cov);
   if (e) return e;
@@ -920,6 +954,7 @@ int cs_predict(cs_fit* f, int n2, const double* X2, const double* z2, double* ma
 int cs_treat(cs_fit* f, int n2, const double* X2, double cov_jitter, double* map, double* var_diag, double* ate,
              double* ate_var, double* cov) {
   if (!f || !X2 || n2 < 1) return fail(CS_ERR_ARG, "cs_treat: bad argument");
+  ArenaScope scope(&f->arena);
   CrossWork W;
   std::vector<double> hmap(n2);
   int e = cross_common(f, W, n2, X2, nullptr, true, hmap.data(), var_diag, 0.0, cov_jitter, cov);

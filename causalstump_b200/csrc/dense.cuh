@@ -775,7 +775,10 @@ struct DenseEngine {
 
     // partition: 0 = auto (large problems only: the chain of a small fit is launch-bound, not slot-bound,
     // and many small fits share the device), 1 = on, -1 = off
-    const bool want_part = partition > 0 || (partition == 0 && np >= 4096 && std::getenv("CS_NO_PARTITION") == nullptr);
+    // Nsight Compute cannot attach to kernels launched into green-context streams ("Failed to prepare kernel for
+    // profiling", the application dies): under its injection environment the auto mode keeps plain priority streams
+    const bool under_ncu = std::getenv("NV_NSIGHT_INJECTION_PORT_BASE") != nullptr;
+    const bool want_part = partition > 0 || (partition == 0 && np >= 4096 && !under_ncu && std::getenv("CS_NO_PARTITION") == nullptr);
     // priorities: S2 (panel work the Cholesky chain waits for) highest, then S3 (row chain of the inverse),
     // S1 (trailing update), S5 (Acc of the rows below the next panel), S4 (K^-1 accumulation) lowest
     cudaStream_t* bulk[5] = {&aux, &aux2, &aux3, &aux4, &aux5};

@@ -56,9 +56,11 @@ def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1
     driven concurrently (cs_fit_run_many).  batch <= 1: one handle and stream set per fit.
     Returns one result dict per unit."""
     import math as _m
+    import time as _t
     from . import _lib, hill, main as M, rcpp_exports as rx
     lib = rx.lib()
     prep, fits, members = [], [], []
+    t_start = _t.perf_counter()
     for replicate, restart in units:
         d = hill.hill_surface_b(n=n, p=p, replicate=replicate)
         rng = np.random.default_rng(565 + 5 * replicate)
@@ -79,15 +81,19 @@ def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1
             fits.append(_lib.Fit(lib, K.kind, y, X, z, None, rx.pack(K.parameters), optim=_lib.CS_OPT_NADAM, lr=lr))
         kind = K.kind
         prep.append((d, nr["moments"], train, test, replicate, restart))
+    t_prep = _t.perf_counter()
     if batch > 1:
         handles = [_lib.FitBatch(lib, kind, members[i:i + batch], optim=_lib.CS_OPT_NADAM, lr=lr, tile=tile)
                    for i in range(0, len(members), batch)]
+        t_create = _t.perf_counter()
         res = _lib.run_many(handles, maxiter, tol)
         views = [(h, b) for h in handles for b in range(h.B)]
     else:
         handles = fits
+        t_create = _t.perf_counter()
         res = _lib.run_many(fits, maxiter, tol)
         views = [(f, None) for f in fits]
+    t_run = _t.perf_counter()
     out = []
     for (d, mom, train, test, replicate, restart), (f, member), (iters, trace) in zip(prep, views, res):
         if member is not None:
@@ -107,7 +113,11 @@ def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1
                         e_ate_test=float(np.mean(tau[test]) - sd * t_te["ate"])))
     for h in handles:
         h.close()
+    LAST_TIMING.update(prep=t_prep - t_start, create=t_create - t_prep, run=t_run - t_create, post=_t.perf_counter() - t_run)
     return out
+
+
+LAST_TIMING = {}  # seconds spent by the last hill_units_concurrent call: host data prep / handle creation / device loop / predict+treat
 
 
 def select_winners(results):

@@ -30,7 +30,8 @@ def main():
         s = time.perf_counter() - t0
         it = [r["iters"] for r in res]
         print(json.dumps({"fits": nf, "batch": batch, "tile": tile, "seconds": s, "fits_per_hour": nf / s * 3600, "iters_mean": float(np.mean(it)),
-                          "iters_total": int(np.sum(it)), "us_per_fit_iter": 1e6 * s / np.sum(it), "launches": lib.launch_count() - l0}), flush=True)
+                          "iters_total": int(np.sum(it)), "us_per_fit_iter": 1e6 * s / np.sum(it), "launches": lib.launch_count() - l0,
+                          "phases_s": {k: round(v, 3) for k, v in rp.LAST_TIMING.items()}}), flush=True)
 
 
 if __name__ == "__main__":
