@@ -30,11 +30,20 @@ def hill_covariates(n, rng, p=25):
     return X
 
 
-def hill_surface_b(n=747, p=25, replicate=0, seed=None):
-    """Returns dict(y, X, z, tau, y1, y0) -- raw (un-normalised) data."""
+def hill_surface_b(n=747, p=25, replicate=0, seed=None, X=None, z=None):
+    """Returns dict(y, X, z, tau, y1, y0) -- raw (un-normalised) data.  With X (and z) given -- e.g. the real
+    IHDP covariates and treatment indicator read by causalstump_b200.rdata from the reference's workspace
+    files -- only the response surface is drawn, as test/sec5-3_Hill2011.R:49-66 does."""
     rng = np.random.default_rng(565 + 5 * replicate if seed is None else seed)
-    X = hill_covariates(n, rng, p)
-    z = (rng.random(n) < 0.186).astype(np.float64)
+    if X is None:
+        X = hill_covariates(n, rng, p)
+    else:
+        X = np.array(X, dtype=np.float64)
+        n, p = X.shape
+    if z is None:
+        z = (rng.random(n) < 0.186).astype(np.float64)
+    else:
+        z = np.asarray(z, dtype=np.float64)
     if z.sum() == 0:
         z[0] = 1.0
     beta = rng.choice(np.array([0.0, 0.1, 0.2, 0.3, 0.4]), size=p + 1, replace=True, p=[.6, .1, .1, .1, .1])

@@ -49,11 +49,13 @@ def hill_unit(replicate, restart, n=747, p=25, test_frac=0.1, maxiter=3000, tol=
 
 
 def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1e-1, lr=0.01, prior=False, nu=2000,
-                          batch=32, tile=0):
+                          batch=32, tile=0, covariates=None):
     """The same fits as `hill_unit`, but all `units` = [(replicate, restart), ...] are optimised
     together on this GPU, which is how the small n ~ 700 fits fill a B200: groups of `batch` fits share
     one batched handle (cs_fit_create_batch: every launch serves the whole group) and the groups are
     driven concurrently (cs_fit_run_many).  batch <= 1: one handle and stream set per fit.
+    covariates=(X, z): draw the response surface on given covariates / treatment indicator (the real IHDP
+    data of the reference's workspace files, causalstump_b200.rdata) instead of synthetic ones.
     Returns one result dict per unit."""
     import math as _m
     import time as _t
@@ -61,8 +63,13 @@ def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1
     lib = rx.lib()
     prep, fits, members = [], [], []
     t_start = _t.perf_counter()
+    if covariates is not None:
+        n, p = np.asarray(covariates[0]).shape
     for replicate, restart in units:
-        d = hill.hill_surface_b(n=n, p=p, replicate=replicate)
+        if covariates is None:
+            d = hill.hill_surface_b(n=n, p=p, replicate=replicate)
+        else:
+            d = hill.hill_surface_b(replicate=replicate, X=covariates[0], z=covariates[1])
         rng = np.random.default_rng(565 + 5 * replicate)
         ntest = int(_m.ceil(n * test_frac))
         test = np.sort(rng.choice(n, ntest, replace=False))

@@ -151,6 +151,35 @@ def test_batched_handle(gpulib):
     fb.close()
 
 
+def test_real_ihdp_covariates(gpulib):
+    """The reference's own data: IHDP covariates and treatment indicator decoded from its workspace file by
+    causalstump_b200/rdata.py (tests/golden/ihdp_covariates.npz), response surface B drawn on top.  Evaluation
+    parity against the oracle at n = 747, p = 25, then a 12-replicate mini simulation through the batched driver
+    whose aggregates must sit inside the band of the GP arm stored in the reference's `results` matrix."""
+    from causalstump_b200 import replicates as rp
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ihdp_covariates.npz"))
+    X, z = G["X"], G["Trt"]
+    d = hill.hill_surface_b(replicate=3, X=X, z=z)
+    nr = o.norm_variables(d["y"], d["X"])
+    K = o.KernelClass_GP_SE(25, np.ones(747))
+    K.parainit(nr["y"], 0.5, 0.7)
+    g, st, mu = o.eval_lml_grad("GP", nr["y"], nr["X"], d["z"], np.ones(747), K.parameters)
+    f = _lib.Fit(gpulib, 0, nr["y"], np.asfortranarray(nr["X"]), d["z"], None, o.pack_params(K.parameters))
+    g2, st2, mu2 = f.eval()
+    f.close()
+    gref = o.pack_params(g)
+    assert np.max(np.abs(g2 - gref) / np.maximum(np.abs(gref), 1e-6 * np.max(np.abs(gref)))) < cs.TOL_GRAD
+    assert abs(st2[1] - st[1]) < cs.TOL_LML * abs(st[1]) and abs(mu2 - mu) < 1e-9 * abs(mu)
+    res = rp.hill_units_concurrent([(r, 0) for r in range(12)], covariates=(X, z), batch=12)
+    ref = dict(zip(G["metrics"], G["gp_results"]))
+    pehe = np.mean([r["pehe_train"] for r in res])
+    rmse = np.mean([r["rmse_train"] for r in res])
+    lo, hi = np.nanpercentile(ref["PEHE.all.train"], [2, 98])
+    assert 0.5 * lo < pehe < max(hi, 3.0), (pehe, lo, hi)          # reference: mean 1.40, heavy right tail
+    assert 0.6 < rmse < 1.3, rmse                                   # reference: 0.88 (noise sd 1)
+    assert all(3 < r["iters"] <= 3000 for r in res)
+
+
 def test_stateless_mirrors_vs_compiled_reference(gpulib):
     """The stateless C-ABI mirrors against oracle/_ref (the reference's C++ compiled with the header shim),
     which travels to the GPU box as a prebuilt .so; skipped when it is absent."""
