@@ -48,6 +48,43 @@ def hill_unit(replicate, restart, n=747, p=25, test_frac=0.1, maxiter=3000, tol=
                 e_ate_train=float(np.mean(tau[train]) - t_tr["ate"]), e_ate_test=float(np.mean(tau[test]) - t_te["ate"]))
 
 
+METRICS = ("PEHE.all.train", "PEHE.tt.train", "RMSE.all.train", "RMSE.tt.train", "E.ate.train", "E.att.train", "SE.ate.train",
+           "SE.att.train", "coverage.ite.train", "coverage.ate.train", "range.ate.train", "PEHE.all.test", "PEHE.tt.test",
+           "RMSE.all.test", "RMSE.tt.test", "E.ate.test", "E.att.test", "SE.ate.test", "SE.att.test", "coverage.ite.test",
+           "coverage.ate.test", "range.ate.test")
+
+
+def update_results(testindex, y_hat_all, tau_hat_all, tau_ci_all, ate_ci_train, ate_ci_test, y, z, y1, y0):
+    """The metric block of the simulation scripts, /root/reference/test/sec5-3_Hill2011.R:104-152, as a dict over
+    METRICS (row order of `result.item`, :163-164).  Reproduced as written, including the `[z.train=1]` subscripts
+    of the PEHE.tt rows (:122,:124): `x[z.train=1]` passes a named argument, not a comparison, so R selects the
+    FIRST element -- PEHE.tt.* is |error of unit 1|, while E.att / RMSE.tt use the intended `==` masks."""
+    n = len(y)
+    te = np.zeros(n, dtype=bool)
+    te[np.asarray(testindex)] = True
+    tr = ~te
+    tau = np.asarray(y1) - np.asarray(y0)
+    out = {}
+    for name, m in (("train", tr), ("test", te)):
+        err = (tau - tau_hat_all)[m]
+        zz, yy, yh = np.asarray(z)[m], np.asarray(y)[m], np.asarray(y_hat_all)[m]
+        t1 = zz == 1
+        out["PEHE.all." + name] = float(np.sqrt(np.mean(err ** 2)))
+        out["PEHE.tt." + name] = float(np.sqrt(np.mean(err[:1] ** 2)))  # quirk, see above
+        e_ate = float(np.mean(tau[m]) - np.mean(tau_hat_all[m]))
+        e_att = float(np.mean(tau[m][t1]) - np.mean(tau_hat_all[m][t1])) if t1.any() else float("nan")
+        out["E.ate." + name], out["E.att." + name] = e_ate, e_att
+        out["SE.ate." + name], out["SE.att." + name] = e_ate ** 2, e_att ** 2
+        out["RMSE.all." + name] = float(np.sqrt(np.mean((yy - yh) ** 2)))
+        out["RMSE.tt." + name] = float(np.sqrt(np.mean(((yy - yh)[t1]) ** 2))) if t1.any() else float("nan")
+        ci = np.asarray(tau_ci_all)[m]
+        out["coverage.ite." + name] = float(np.mean((ci[:, 0] < tau[m]) & (ci[:, 1] > tau[m])))
+        ac = ate_ci_train if name == "train" else ate_ci_test
+        out["coverage.ate." + name] = float((ac[0] < np.mean(tau[m])) and (ac[1] > np.mean(tau[m])))
+        out["range.ate." + name] = float(ac[1] - ac[0])
+    return out
+
+
 def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1e-1, lr=0.01, prior=False, nu=2000,
                           batch=32, tile=0, covariates=None):
     """The same fits as `hill_unit`, but all `units` = [(replicate, restart), ...] are optimised
@@ -111,7 +148,18 @@ def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1
         t_tr = f.treat(Xall[train])
         t_te = f.treat(Xall[test])
         tau = d["tau"]
-        out.append(dict(replicate=replicate, restart=restart, iters=int(iters), lml=float(trace[1, -1]),
+        # the 22 metrics of update.results; intervals as treatment.R:28-31 builds them for the GP class
+        # (varY * (+-1.96 * variance) + map, quirk Q8; ATE interval from sqrt(ate_var))
+        vy = mom["varY"]
+        tau_hat, tau_ci = np.empty(n), np.empty((n, 2))
+        for idx, t in ((train, t_tr), (test, t_te)):
+            tau_hat[idx] = sd * t["map"]
+            tau_ci[idx, 0] = vy * (-1.96 * t["var"]) + sd * t["map"]
+            tau_ci[idx, 1] = vy * (1.96 * t["var"]) + sd * t["map"]
+        ate_ci = [(vy * (-1.96 * _m.sqrt(max(t["ate_var"], 0.0))) + sd * t["ate"], vy * (1.96 * _m.sqrt(max(t["ate_var"], 0.0))) + sd * t["ate"])
+                  for t in (t_tr, t_te)]
+        metrics = update_results(test, pred, tau_hat, tau_ci, ate_ci[0], ate_ci[1], d["y"], d["z"], d["y1"], d["y0"])
+        out.append(dict(replicate=replicate, restart=restart, iters=int(iters), lml=float(trace[1, -1]), metrics=metrics,
                         pehe_train=float(np.sqrt(np.mean((tau[train] - sd * t_tr["map"]) ** 2))),
                         pehe_test=float(np.sqrt(np.mean((tau[test] - sd * t_te["map"]) ** 2))),
                         rmse_train=float(np.sqrt(np.mean((d["y"][train] - pred[train]) ** 2))),

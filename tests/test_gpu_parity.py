@@ -178,6 +178,14 @@ def test_real_ihdp_covariates(gpulib):
     assert 0.5 * lo < pehe < max(hi, 3.0), (pehe, lo, hi)          # reference: mean 1.40, heavy right tail
     assert 0.6 < rmse < 1.3, rmse                                   # reference: 0.88 (noise sd 1)
     assert all(3 < r["iters"] <= 3000 for r in res)
+    # the full metric block (update.results) against the stored GP arm: same quirky interval construction
+    M = {k: np.mean([r["metrics"][k] for r in res]) for k in rp.METRICS}
+    R = {k: np.nanmean(v) for k, v in ref.items()}
+    assert abs(M["PEHE.all.train"] - pehe) < 1e-12 and M["coverage.ate.train"] == 1.0 == R["coverage.ate.train"]
+    assert 0.4 < M["coverage.ite.train"] < 0.95 and abs(R["coverage.ite.train"] - 0.67) < 0.01
+    assert 0.5 * R["range.ate.train"] < M["range.ate.train"] < 2.0 * R["range.ate.train"], (M["range.ate.train"], R["range.ate.train"])
+    assert 0.4 * R["range.ate.test"] < M["range.ate.test"] < 2.5 * R["range.ate.test"], (M["range.ate.test"], R["range.ate.test"])
+    assert abs(M["E.ate.train"]) < 0.6 and 0.7 < M["RMSE.all.test"] < 2.5
 
 
 def test_stateless_mirrors_vs_compiled_reference(gpulib):

@@ -101,3 +101,27 @@ def test_reads_every_reference_workspace_file():
         assert ws["update.results"].kind == "closure"
     ws = rdata.read_rdata(files[0])
     assert np.array_equal(rdata.as_matrix(ws["X"])[0], G["X"]) and list(rdata.as_matrix(ws["X"])[1]) == list(G["names"])
+
+
+def test_update_results_mirrors_the_reference_metric_block():
+    """replicates.update_results = test/sec5-3_Hill2011.R:104-152, including the `[z.train=1]` quirk."""
+    from causalstump_b200 import replicates as rp
+    rng = np.random.default_rng(0)
+    n = 60
+    y1, y0 = rng.normal(size=n) + 4.0, rng.normal(size=n)
+    z = (rng.random(n) < 0.3).astype(float)
+    y = np.where(z == 1, y1, y0)
+    tau = y1 - y0
+    th = tau + np.linspace(-0.5, 0.5, n)
+    ci = np.column_stack([th - 0.3, th + 0.3])
+    test = np.array([3, 7, 11, 50])
+    m = rp.update_results(test, y + 0.2, th, ci, (3.0, 5.5), (3.9, 4.0), y, z, y1, y0)
+    assert tuple(m) != () and set(m) == set(rp.METRICS)
+    tr = np.setdiff1d(np.arange(n), test)
+    assert abs(m["PEHE.all.train"] - np.sqrt(np.mean((tau - th)[tr] ** 2))) < 1e-15
+    assert abs(m["PEHE.tt.train"] - abs((tau - th)[tr][0])) < 1e-15          # first element, not the treated
+    assert abs(m["PEHE.tt.test"] - abs((tau - th)[test][0])) < 1e-15
+    assert abs(m["RMSE.all.test"] - 0.2) < 1e-12 and abs(m["SE.ate.train"] - m["E.ate.train"] ** 2) < 1e-18
+    assert abs(m["coverage.ite.train"] - np.mean(np.abs((tau - th)[tr]) < 0.3)) < 1e-15
+    assert m["range.ate.train"] == 2.5 and m["coverage.ate.train"] in (0.0, 1.0)
+    assert abs(m["E.att.test"] - (np.mean(tau[test][z[test] == 1]) - np.mean(th[test][z[test] == 1]))) < 1e-15 or np.isnan(m["E.att.test"])
