@@ -259,7 +259,7 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
     int first = total;
     static const bool no_split = std::getenv("CS_NO_GRAM_SPLIT") != nullptr;
     if (f->eng.plan_version == 2 && f->eng.aux2_ok && !no_split) {
-      const int bw = std::min(f->nblk, f->eng.panel_blocks * f->eng.tile / csk::TB);
+      const int bw = std::min(f->nblk, (f->eng.bounds.size() > 1 ? f->eng.bounds[1] : f->eng.panel_blocks) * f->eng.tile / csk::TB);
       first = csg::lower_tiles(bw);
     }
     ++g_launches;

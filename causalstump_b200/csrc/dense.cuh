@@ -320,7 +320,8 @@ struct DenseEngine {
   int nbatch = 1;
   long long bstride = 0;
   bool external_buffers = false;  // G, X, C, logdet_part, status, Pbuf belong to the caller's slab
-  int panel_blocks = 4;             // outer panel width in blocks
+  int panel_blocks = 4;             // outer panel width in blocks (maximum)
+  std::vector<int> bounds;          // plan v2: panel boundaries in blocks (graded: narrow first and last panels)
   int n_events = 0;
   std::vector<cudaEvent_t> events;
   cudaStream_t aux{}, aux2{}, aux3{}, aux4{}, aux5{}, aux6{};  // S6: second chain stream (X_PP), partition A;  // S4: K^-1 accumulation (lowest); S5: Acc rows below the next panel; S1: bulk trailing updates (low); S2: panel rest (high); S3: pipelined inverse (low)
@@ -596,9 +597,11 @@ struct DenseEngine {
         add_group(seq, GK_NT, grp); seq.back().stream = stream; seq.back().gtile = tile;
       }
     };
-    for (int p0 = 0; p0 < N; p0 += W) {
-      const int p1 = std::min(p0 + W, N);
+    for (size_t pi = 0; pi + 1 < bounds.size(); ++pi) {
+      const int p0 = bounds[pi], p1 = bounds[pi + 1];
       const int pw = p1 - p0;
+      const int w_next = pi + 2 < bounds.size() ? bounds[pi + 2] - bounds[pi + 1] : 0;   // width of the next panel
+      const int w_next2 = pi + 3 < bounds.size() ? bounds[pi + 3] - bounds[pi + 2] : 0;  // and of the one after
       double* Xpp = X + (long long)p0 * T * (ld + 1);   // diagonal block of X = inverse of the diagonal block of L
       // ---- D(P) on the chain (S0): factor the diagonal block; S6 builds the off-diagonal tiles of X_PP
       if (ev_u1top_prev >= 0) op(OP_WAIT, 0, ev_u1top_prev);
@@ -631,7 +634,7 @@ struct DenseEngine {
       op(OP_RECORD, 6, ev_xpp);
       last_s6_ev = ev_xpp;
       const int mt = N - p1;  // block rows below the panel
-      const int n1 = std::min(W, mt);
+      const int n1 = w_next;
       int ev_lpanel = -1;
       if (mt > 0) {
         // ---- S2: L_IP = A_IP X_PP^T for the rows below (k <= j), next panel's rows first
@@ -666,7 +669,7 @@ struct DenseEngine {
         if (mt > n1) {
           op(OP_WAIT, 1, ev_lpanel);
           const int m2 = mt - n1;                 // block rows / columns right of the next panel
-          const int n2 = std::min(W, m2);         // columns of the panel after next
+          const int n2 = w_next2;                 // columns of the panel after next
           double* pan2 = pan + (long long)n1 * T; // L rows >= p1 + n1
           double* D2 = G + (long long)(p1 + n1) * T * (ld + 1);
           grp.push_back(mk(pan2, ld, pan2, ld, D2, ld, n2 * rr, n2 * rr, (int)kw, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
@@ -742,6 +745,30 @@ struct DenseEngine {
     };
     plan_version = 2;
     if (const char* pv = std::getenv("CS_PLAN")) plan_version = std::atoi(pv);
+    {
+      // Panel widths: uniform W by default.  CS_GRADED=1 selects a narrow first panel (the bulk streams start after
+      // two leaves instead of four) and narrow last panels (a shorter tail); measured on the B200 at n = 8192 it is
+      // 1 % SLOWER (19.35 vs 19.13 ms): the run is bound by the throughput of the K = 512 bulk launches, not by
+      // the head or the tail, and narrower panels lower it.  Kept as an option (2 = also for small N, tests).
+      bounds.assign(1, 0);
+      bool graded = false;
+      if (const char* gv = std::getenv("CS_GRADED")) {
+        const int g = std::atoi(gv);
+        graded = W == 4 && (g == 2 ? N >= 9 : (g == 1 && N >= 6 * W));
+      }
+      if (graded) {
+        const int tail[4] = {2, 2, 1, 1};
+        int pos = 2;
+        bounds.push_back(pos);
+        const int rem = (N - 2 - 6) % W;
+        if (rem > 0) { pos += rem; bounds.push_back(pos); }
+        while (pos < N - 6) { pos += W; bounds.push_back(pos); }
+        for (int t : tail) { pos += t; bounds.push_back(pos); }
+      } else {
+        for (int pos = W; pos < N; pos += W) bounds.push_back(pos);
+        bounds.push_back(N);
+      }
+    }
     if (plan_version == 1) {
       build_chol(potrf, false);
       if (inv_pipeline) build_chol(potrf_inv, true);

@@ -129,3 +129,19 @@ def test_batched_handle_matches_individual_fits(emulib, kind, n, p, B):
         tr_o = ref.Kernel.predict_treat(P["y"], P["X"], P["z"], X2)
         assert cs.relm(t2["map"], tr_o["map"]) < cs.TOL_MAP
     fb.close()
+
+
+@pytest.mark.parametrize("n,tile,pipe", [(600, 64, 1), (700, 64, 0), (1200, 128, 1)])
+def test_graded_panel_widths(emulib, monkeypatch, n, tile, pipe):
+    """Plan v2 with a narrow first panel and narrow last panels (the n = 8192 layout), forced at small N."""
+    monkeypatch.setenv("CS_GRADED", "2")
+    assert emulib.dll.cs_debug_check_plan(n, tile, 64, 1) == 0
+    P = cs.make_problem("GP", n, 3)
+    g, st, mu = o.eval_lml_grad("GP", P["y"], P["X"], P["z"], P["w"], P["par"])
+    f = _lib.Fit(emulib, 0, P["y"], P["X"], P["z"], P["w"], o.pack_params(P["par"]), tile=tile, inv_pipeline=pipe)
+    g2, st2, mu2 = f.eval()
+    g3, st3, _ = f.eval()
+    f.close()
+    assert np.array_equal(g2, g3)
+    assert cs.rel(g2, o.pack_params(g), 1e-9) < cs.TOL_GRAD and abs(st2[1] - st[1]) < cs.TOL_LML * abs(st[1])
+    assert abs(mu2 - mu) < 1e-9 * abs(mu)
