@@ -425,7 +425,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--fits", type=int, default=128, help="(replicate, restart) fits per GPU for the fits/hour object")
+    ap.add_argument("--fits", type=int, default=256, help="(replicate, restart) fits per GPU for the fits/hour object")
     ap.add_argument("--fit-batch", type=int, default=32, help="members per batched handle (cs_fit_create_batch); 1 = one handle per fit")
     ap.add_argument("--no-fits", action="store_true")
     ap.add_argument("--inv-pipeline", type=int, default=1, help="1: inverse pipelined behind the Cholesky (default); 0: recursive inverse after it")

@@ -100,6 +100,16 @@ struct Arena {
   void release() { for (auto& c : chunks) rt::dev_free(c.base); chunks.clear(); }
 };
 static thread_local Arena* g_arena = nullptr;
+// one arena per host thread and device, shared by every handle: replicate loops create and destroy handles,
+// the scratch survives them (predict / treatment calls are synchronous, so it is idle between calls)
+static Arena* thread_arena() {
+  static thread_local Arena pool[16];
+  int dev = 0;
+#ifndef CS_EMU
+  cudaGetDevice(&dev);
+#endif
+  return &pool[dev & 15];
+}
 struct ArenaScope {
   Arena* prev;
   explicit ArenaScope(Arena* a) : prev(g_arena) { g_arena = a; if (a) a->reset(); }
@@ -199,7 +209,6 @@ struct cs_fit {
   char* slab = nullptr;
   std::vector<std::pair<void**, size_t>> slab_req;
   bool trace_in_slab = false;
-  Arena arena;  // scratch of cs_predict / cs_treat
 
   void want(void** field, size_t bytes) { slab_req.emplace_back(field, bytes); }
   int commit_slab() {
@@ -457,7 +466,6 @@ void cs_fit_destroy(cs_fit* f) {
   rt::stream_sync(f->st);
   if (f->trace && !f->trace_in_slab) rt::dev_free(f->trace);
   if (f->slab) rt::dev_free(f->slab);
-  f->arena.release();
   if (f->flush) rt::dev_free(f->flush);
   if (f->pinned) rt::host_free(f->pinned);
   if (f->h_ls) rt::host_free(f->h_ls);
@@ -943,7 +951,7 @@ static int cross_common(cs_fit* f, CrossWork& W, int n2, const double* X2, const
 
 int cs_predict(cs_fit* f, int n2, const double* X2, const double* z2, double* map, double* var_diag, double* cov) {
   if (!f || !X2 || !z2 || n2 < 1) return fail(CS_ERR_ARG, "cs_predict: bad argument");
-  ArenaScope scope(&f->arena);
+  ArenaScope scope(thread_arena());
   CrossWork W;
   int e = cross_common(f, W, n2, X2, z2, false, map, var_diag, 1.0, 0.0, cov);
   if (e) return e;
@@ -954,7 +962,7 @@ int cs_predict(cs_fit* f, int n2, const double* X2, const double* z2, double* ma
 int cs_treat(cs_fit* f, int n2, const double* X2, double cov_jitter, double* map, double* var_diag, double* ate,
              double* ate_var, double* cov) {
   if (!f || !X2 || n2 < 1) return fail(CS_ERR_ARG, "cs_treat: bad argument");
-  ArenaScope scope(&f->arena);
+  ArenaScope scope(thread_arena());
   CrossWork W;
   std::vector<double> hmap(n2);
   int e = cross_common(f, W, n2, X2, nullptr, true, hmap.data(), var_diag, 0.0, cov_jitter, cov);

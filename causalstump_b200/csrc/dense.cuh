@@ -882,10 +882,7 @@ struct DenseEngine {
         launch_leaf(tile, G + (long long)L.blk * tile * ((long long)np + 1), np, X + (long long)L.blk * tile * ((long long)np + 1), np,
                     L.blk * tile, logdet_part + L.blk, status, n, s, skip, nbatch, bstride);
       } else if (L.is_leaf == OP_COPY) {
-        for (int b = 0; b < nbatch; ++b)
-          rt::copy2d(reinterpret_cast<double*>(reinterpret_cast<char*>(L.cp_dst) + b * bstride), L.cp_ldd,
-                     reinterpret_cast<const double*>(reinterpret_cast<const char*>(L.cp_src) + b * bstride), L.cp_lds, L.cp_rows,
-                     L.cp_cols, s);
+        launch_copy(L, s, skip);
       } else if (L.is_leaf == OP_RECORD) {
         rt::event_record(events[L.ev], s);
       } else if (L.is_leaf == OP_WAIT) {
@@ -1010,7 +1007,26 @@ struct DenseEngine {
   }
 
   void set_status_max(cudaStream_t st, const int* skip);
+  void launch_copy(const Launch& L, cudaStream_t s, const int* skip);
 };
+
+// 2-D copy of a rows x cols block of doubles, one launch for every member of a batched handle (blockIdx.z)
+static __global__ void __launch_bounds__(256)
+copy2d_kernel(double* __restrict__ dst, long long ldd, const double* __restrict__ src, long long lds, long long rows,
+              long long cols, const int* __restrict__ skip, long long bstride) {
+  skip = csd::bshift(skip, bstride);
+  if (skip && *skip) return;
+  dst = csd::bshift(dst, bstride); src = csd::bshift(src, bstride);
+  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (r >= rows) return;
+  for (long long c = blockIdx.y; c < cols; c += gridDim.y) {
+    const double* s = src + c * lds + r;
+    double* d = dst + c * ldd + r;
+    const double v0 = s[0], v1 = (r + 1 < rows) ? s[1] : 0.0;
+    d[0] = v0;
+    if (r + 1 < rows) d[1] = v1;
+  }
+}
 
 static __global__ void set_int_kernel(int* p, int v, const int* skip, long long bstride) {
   skip = csd::bshift(skip, bstride);
@@ -1018,6 +1034,16 @@ static __global__ void set_int_kernel(int* p, int v, const int* skip, long long 
   p = csd::bshift(p, bstride);
   if (threadIdx.x == 0 && blockIdx.x == 0) *p = v;
 }
+inline void DenseEngine::launch_copy(const Launch& L, cudaStream_t s, const int* skip) {
+  // rows, leading dimensions and offsets are even (multiples of the tile) and the buffers 256-byte aligned:
+  // 16-byte accesses are aligned
+  auto k = copy2d_kernel;
+  ++g_launches;
+  const unsigned gx = (unsigned)((L.cp_rows / 2 + 255) / 256);
+  const unsigned gy = (unsigned)std::min<long long>(L.cp_cols, 4096);
+  CS_LAUNCH(k, dim3(gx, gy, nbatch), 256, 0, s, L.cp_dst, L.cp_ldd, L.cp_src, L.cp_lds, L.cp_rows, L.cp_cols, skip, bstride);
+}
+
 inline void DenseEngine::set_status_max(cudaStream_t st, const int* skip) {
   auto k = set_int_kernel;
   ++g_launches;
