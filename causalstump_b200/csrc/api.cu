@@ -302,7 +302,7 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
               f->params + f->lay.i_mu(), f->mv_part, ld, 3 * ld, skip, f->bstride);
     auto k2 = csk::scalars_kernel;
     ++g_launches;
-    CS_LAUNCH(k2, dim3(1, 1, B), csk::ETH, 0, st, f->mv_part, f->nsplit, ld, 3 * ld, n, np, f->y, f->params, f->lay,
+    CS_LAUNCH(k2, dim3(1, 1, B), csk::SCALARS_THREADS, 0, st, f->mv_part, f->nsplit, ld, 3 * ld, n, np, f->y, f->params, f->lay,
               f->eng.logdet_part, f->eng.N, f->alpha, f->u, f->s, f->sc, skip);
   }
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
@@ -1252,7 +1252,7 @@ static int grad_stats_common(int kind, int n, int p, const double* y, const doub
               f->params + f->lay.i_mu(), f->mv_part, ld, 3 * ld, (const int*)nullptr, 0LL);
     auto k2 = csk::scalars_kernel;
     ++g_launches;
-    CS_LAUNCH(k2, 1, csk::ETH, 0, st, f->mv_part, f->nsplit, ld, 3 * ld, n, np, f->y, f->params, f->lay,
+    CS_LAUNCH(k2, 1, csk::SCALARS_THREADS, 0, st, f->mv_part, f->nsplit, ld, 3 * ld, n, np, f->y, f->params, f->lay,
               f->eng.logdet_part, f->eng.N, f->alpha, f->u, f->s, f->sc, (const int*)nullptr);
     ++g_launches;
     if (from_mem) {

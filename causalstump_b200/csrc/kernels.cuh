@@ -246,7 +246,8 @@ matvec_kernel(const double* __restrict__ A, long long ld, int cols_per_split, in
 // splits), then the scalars M, sums, TP coefficient, log det and the closed-form mu.
 // One CTA.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ETH)
+constexpr int SCALARS_THREADS = 1024;  // one CTA; the loop is latency-bound (strided partials), so use every warp slot
+__global__ void __launch_bounds__(SCALARS_THREADS)
 scalars_kernel(const double* __restrict__ mv_part, int nsplit, long long stride_k, long long stride_split, int n,
                int npad, const double* __restrict__ y, const double* __restrict__ params, Layout lay,
                const double* __restrict__ logdet_part, int nblk, double* __restrict__ alpha,
@@ -259,7 +260,7 @@ scalars_kernel(const double* __restrict__ mv_part, int nsplit, long long stride_
   const int tid = threadIdx.x;
   const double mu = params[lay.i_mu()];
   double M = 0.0, sa = 0.0, su = 0.0, ss = 0.0;
-  for (int r = tid; r < npad; r += ETH) {
+  for (int r = tid; r < npad; r += (int)blockDim.x) {
     double a = 0.0, uu = 0.0, s1 = 0.0;
     if (r < n) {
       for (int k = 0; k < nsplit; ++k) {
@@ -278,7 +279,7 @@ scalars_kernel(const double* __restrict__ mv_part, int nsplit, long long stride_
   su = csd::block_sum(su, red);
   ss = csd::block_sum(ss, red);
   double ld = 0.0;
-  for (int b = tid; b < nblk; b += ETH) ld += logdet_part[b];
+  for (int b = tid; b < nblk; b += (int)blockDim.x) ld += logdet_part[b];
   ld = csd::block_sum(ld, red);
   if (tid == 0) {
     sc->M = M; sc->sum_alpha = sa; sc->sum_u = su; sc->sum_s = ss;
