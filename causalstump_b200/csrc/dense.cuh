@@ -807,9 +807,9 @@ struct DenseEngine {
     const bool under_ncu = std::getenv("NV_NSIGHT_INJECTION_PORT_BASE") != nullptr;
     const bool want_part = partition > 0 || (partition == 0 && np >= 4096 && !under_ncu && std::getenv("CS_NO_PARTITION") == nullptr);
     // priorities: S2 (panel work the Cholesky chain waits for) highest, then S3 (row chain of the inverse),
-    // S1 (trailing update), S5 (Acc of the rows below the next panel), S4 (K^-1 accumulation) lowest
+    // S1 (trailing update), then S5 (Acc of the rows below the next panel) and S4 (K^-1 accumulation) lowest
     cudaStream_t* bulk[5] = {&aux, &aux2, &aux3, &aux4, &aux5};
-    int level[5] = {2, 0, 1, 5, 3};  // 0 = highest
+    int level[5] = {2, 0, 1, 5, 5};  // 0 = highest (swept on the B200: tools/gpu_sweep.sh)
     if (const char* ev = std::getenv("CS_PRIO")) std::sscanf(ev, "%d,%d,%d,%d,%d", &level[0], &level[1], &level[2], &level[3], &level[4]);
     if (want_part && rt::partition_streams(8, &crit, &aux6, bulk, level, 5, &sm_crit, &sm_bulk) == 0) {
       crit_ok = aux_ok = aux2_ok = aux3_ok = aux4_ok = aux5_ok = aux6_ok = true;
