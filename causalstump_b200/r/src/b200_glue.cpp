@@ -133,7 +133,7 @@ typedef XPtr<cs_fit, PreserveStorage, fit_finalizer> FitPtr;
 // [[Rcpp::export]]
 SEXP b200_fit_create(int kind, int optim, double lr, double beta1, double beta2, double momentum, NumericVector y,
                      NumericMatrix X, NumericVector z, NumericVector w, List parameters) {
-  cs_fit_config cfg = {kind, optim, lr, beta1, beta2, 1e-8, momentum, 0, 0, 0, 0, 0};
+  cs_fit_config cfg = {kind, optim, lr, beta1, beta2, 1e-8, momentum, 0, 0, 0, 0, 0, 0};
   NumericVector pv = pack(parameters);
   cs_fit* f = NULL;
   cs_check(cs_fit_create(&cfg, X.nrow(), X.ncol(), y.begin(), X.begin(), z.begin(), w.begin(), pv.begin(), &f));
@@ -148,6 +148,49 @@ List b200_fit_run(SEXP handle, int maxiter, double tol, List parameters) {
   NumericVector pv(cs_fit_nparam(f.get()));
   cs_check(cs_fit_get_params(f.get(), pv.begin()));
   return List::create(Named("iter") = iters, Named("stats") = stats, Named("parameters") = unpack(pv, parameters));
+}
+// Batched handle: the replicates x restarts of test/sec5-3_Hill2011.R:611-616 behind one device handle
+// (cs_fit_create_batch); ys / Xs / zs / ws / inits are lists of equally shaped members, ws may be NULL.
+// [[Rcpp::export]]
+SEXP b200_fit_create_batch(int kind, int optim, double lr, double beta1, double beta2, double momentum, List ys, List Xs,
+                           List zs, Nullable<List> ws, List inits) {
+  const int B = ys.size();
+  cs_fit_config cfg = {kind, optim, lr, beta1, beta2, 1e-8, momentum, 0, 0, 0, 0, 0, 0};
+  std::vector<NumericVector> yv(B), zv(B), wv(B), pv(B);
+  std::vector<NumericMatrix> Xv(B);
+  std::vector<const double*> yp(B), Xp(B), zp(B), wp(B, (const double*)NULL), pp(B);
+  List wl = ws.isNotNull() ? List(ws) : List();
+  for (int b = 0; b < B; ++b) {
+    yv[b] = as<NumericVector>(ys[b]); Xv[b] = as<NumericMatrix>(Xs[b]); zv[b] = as<NumericVector>(zs[b]);
+    pv[b] = pack(as<List>(inits[b]));
+    yp[b] = yv[b].begin(); Xp[b] = Xv[b].begin(); zp[b] = zv[b].begin(); pp[b] = pv[b].begin();
+    if (ws.isNotNull()) { wv[b] = as<NumericVector>(wl[b]); wp[b] = wv[b].begin(); }
+  }
+  cs_fit* f = NULL;
+  cs_check(cs_fit_create_batch(&cfg, B, Xv[0].nrow(), Xv[0].ncol(), yp.data(), Xp.data(), zp.data(), wp.data(), pp.data(), &f));
+  return FitPtr(f, true);
+}
+// [[Rcpp::export]]
+List b200_fit_run_batch(SEXP handle, int maxiter, double tol) {
+  FitPtr f(handle);
+  const int B = cs_fit_batch_size(f.get());
+  IntegerVector iters(B);
+  NumericVector stats(2 * (maxiter + 2) * B);
+  cs_check(cs_fit_run(f.get(), maxiter, tol, iters.begin(), stats.begin()));
+  stats.attr("dim") = IntegerVector::create(2, maxiter + 2, B);   // stats[, , b] = the `stats` matrix of R/main.R:77
+  return List::create(Named("iter") = iters, Named("stats") = stats);
+}
+// [[Rcpp::export]]
+void b200_fit_select(SEXP handle, int member) {   // 0-based; predict / treat / get_params then act on this member
+  FitPtr f(handle);
+  cs_check(cs_fit_select(f.get(), member));
+}
+// [[Rcpp::export]]
+List b200_fit_get_params(SEXP handle, List parameters) {
+  FitPtr f(handle);
+  NumericVector pv(cs_fit_nparam(f.get()));
+  cs_check(cs_fit_get_params(f.get(), pv.begin()));
+  return unpack(pv, parameters);
 }
 // [[Rcpp::export]]
 List b200_predict(SEXP handle, NumericMatrix X2, NumericVector z2, bool want_cov) {
