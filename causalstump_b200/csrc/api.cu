@@ -259,6 +259,9 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
   const long long ld = np;
   const unsigned B = (unsigned)f->nbatch;
   int ph = 0;
+  // inside the optimisation loop (skip = the member's `done` flag) the status word is not reset per iteration: a
+  // non positive definite matrix at ANY iteration of a chunk must reach the host (the reference throws there)
+  f->eng.reset_status = (skip == nullptr);
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
   {  // K1.  With the v2 plan the build is split: the tiles of the first diagonal block (rows < W*TILE) on the
      // handle's stream, the rest on the panel stream S2, which every other consumer of G is ordered behind
@@ -597,6 +600,8 @@ static int fit_run_begin(cs_fit* f, int maxiter, double tol) {
     h = HostLoop{};
     h.ls.it = 1; h.ls.done = 0; h.ls.iters = 0; h.ls.maxiter = maxiter; h.ls.tol = tol; h.ls.prev_lml = 0.0;  // stats[,1] = 0 (R/main.R:77)
     RT(rt::h2d(reinterpret_cast<char*>(f->ls) + b * f->bstride, &h.ls, sizeof(LoopState), st));
+    static const int status_ok = 0x7fffffff;
+    RT(rt::h2d(reinterpret_cast<char*>(f->eng.status) + b * f->bstride, &status_ok, sizeof(int), st));
   }
   RT(rt::stream_sync(st));
   f->run_maxiter = maxiter;
@@ -807,6 +812,7 @@ int cs_debug_timeline(cs_fit* f, int cap, int* n_out, float* rows) {
   RT(rt::event_create(&base));
   RT(rt::event_record(base, st));
   f->eng.tl = &evs;
+  f->eng.reset_status = true;
   f->eng.factor_and_invert(st, nullptr);
   f->eng.tl = nullptr;
   KCHECK();

@@ -320,6 +320,7 @@ struct DenseEngine {
   int nbatch = 1;
   long long bstride = 0;
   bool external_buffers = false;  // G, X, C, logdet_part, status, Pbuf belong to the caller's slab
+  bool reset_status = true;       // false while the optimisation loop runs: a non-PD pivot of ANY iteration must survive
   int panel_blocks = 4;             // outer panel width in blocks (maximum)
   std::vector<int> bounds;          // plan v2: panel boundaries in blocks (graded: narrow first and last panels)
   int n_events = 0;
@@ -1045,6 +1046,7 @@ inline void DenseEngine::launch_copy(const Launch& L, cudaStream_t s, const int*
 }
 
 inline void DenseEngine::set_status_max(cudaStream_t st, const int* skip) {
+  if (!reset_status) return;  // inside cs_fit_run the failing pivot is sticky (reset once per run)
   auto k = set_int_kernel;
   ++g_launches;
   CS_LAUNCH(k, dim3(1, 1, nbatch), 32, 0, st, status, 0x7fffffff, skip, bstride);

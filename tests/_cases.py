@@ -113,3 +113,45 @@ def check_fit(lib, kind, n, p, optim="Nadam", maxiter=10, tol=1e-12, lr=0.01, mo
     finally:
         f.close()
     return pehe_c
+
+
+class _raises:
+    """minimal pytest.raises (this module is also imported by __graft_entry__.smoke without pytest)"""
+
+    def __init__(self, exc):
+        self.exc, self.value = exc, None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, et, ev, tb):
+        assert et is not None and issubclass(et, self.exc), ("expected", self.exc, "got", et)
+        self.value = ev
+        return True
+
+
+def check_limits(emulib):
+    """p = CS_MAX_P works, p > CS_MAX_P is refused; a non positive definite member of a batch is reported with its
+    pivot (what makes arma::inv_sympd throw at src/kernel_GP_SE_cpp.cpp:56) instead of producing numbers."""
+    P = make_problem("GP", 70, 40)
+    g, st, mu = o.eval_lml_grad("GP", P["y"], P["X"], P["z"], P["w"], P["par"])
+    f = _lib.Fit(emulib, 0, P["y"], P["X"], P["z"], P["w"], o.pack_params(P["par"]))
+    g2, st2, _ = f.eval()
+    f.close()
+    assert rel(g2, o.pack_params(g), 1e-9) < TOL_GRAD and abs(st2[1] - st[1]) < TOL_LML * abs(st[1])
+    with _raises(_lib.CsError) as ei:
+        _lib.Fit(emulib, 0, np.zeros(10), np.zeros((10, 41)), np.zeros(10), None, np.zeros(86))
+    assert ei.value.code == -5
+    # member 1: two identical rows and (numerically) no noise -> singular Gram matrix
+    good = make_problem("GP", 40, 2)
+    bad = make_problem("GP", 40, 2, replicate=1)
+    Xb = bad["X"].copy(); Xb[7] = Xb[3]
+    zb = bad["z"].copy(); zb[7] = zb[3]
+    pb = o.pack_params(bad["par"]); pb[0] = -80.0
+    fb = _lib.FitBatch(emulib, 0, [(good["y"], good["X"], good["z"], None, o.pack_params(good["par"])), (bad["y"], Xb, zb, None, pb)])
+    with _raises(_lib.NotPositiveDefinite) as ei:
+        fb.run(5, 1e-12)
+    assert 1 <= ei.value.code <= 40 and "member 1" in str(ei.value)
+    fb.close()
+    with _raises(o.NotPositiveDefinite):
+        o.eval_lml_grad("GP", bad["y"], Xb, zb, np.ones(40), o.unpack_params(pb, "GP", 2))

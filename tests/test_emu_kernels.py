@@ -145,3 +145,7 @@ def test_graded_panel_widths(emulib, monkeypatch, n, tile, pipe):
     assert np.array_equal(g2, g3)
     assert cs.rel(g2, o.pack_params(g), 1e-9) < cs.TOL_GRAD and abs(st2[1] - st[1]) < cs.TOL_LML * abs(st[1])
     assert abs(mu2 - mu) < 1e-9 * abs(mu)
+
+
+def test_limits_and_failure_reporting(emulib):
+    cs.check_limits(emulib)

@@ -119,6 +119,10 @@ def test_golden_ref(gpulib):
         f.close()
 
 
+def test_limits_and_failure_reporting(gpulib):
+    cs.check_limits(gpulib)
+
+
 def test_batched_handle(gpulib):
     """cs_fit_create_batch at the size of config 4 (672 x 25 training splits): all members advance with every
     launch; each must equal its own single-handle fit (to rounding: the per-fit CTA count of the trace-gradient
