@@ -60,6 +60,8 @@ inline int graph_destroy(graph_exec_t) { return 0; }
 #else
 #include <cuda.h>
 #include <cuda_runtime.h>
+
+#include <mutex>
 #define CS_DYN_SMEM(T, name) \
   extern __shared__ __align__(16) unsigned char cs_dyn_smem_raw[]; \
   T* name = reinterpret_cast<T*>(cs_dyn_smem_raw)
@@ -145,6 +147,8 @@ inline int partition_streams(int sm_crit, cudaStream_t* crit_hi, cudaStream_t* c
                              int* sm_a, int* sm_b) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+  static std::mutex mu;  // handles may be created from several host threads
+  std::lock_guard<std::mutex> lock(mu);
   PartitionCtx& P = partition_ctx(dev);
   CUresult (*f_devget)(CUdevice*, int) = nullptr;
   CUresult (*f_getres)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;

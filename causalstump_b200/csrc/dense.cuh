@@ -10,6 +10,7 @@
 // The padded tail (rows/cols n..np-1) is an identity block, so every tile is full and
 // log det is unchanged.
 #pragma once
+#include <atomic>
 #include <vector>
 
 #include "gemm.cuh"
@@ -236,7 +237,7 @@ leaf_kernel(double* __restrict__ Gt, long long ldg, double* __restrict__ Xt, lon
 // ---------------------------------------------------------------------------------
 enum GemmKind { GK_NT = 0, GK_NN = 1, GK_TN = 2 };
 
-static long long g_launches = 0;  // kernels launched by this library (claimed count for bench.py)
+static std::atomic<long long> g_launches{0};  // kernels launched by this library (claimed count for bench.py)
 
 enum OpType { OP_GEMM = 0, OP_LEAF = 1, OP_RECORD = 2, OP_WAIT = 3, OP_COPY = 4 };
 
