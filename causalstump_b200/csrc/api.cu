@@ -521,10 +521,13 @@ int cs_fit_set_data(cs_fit* f, const double* y, const double* X, const double* z
   return 0;
 }
 
-int cs_fit_reset_optimizer(cs_fit* f) {
+int cs_fit_reset_optimizer(cs_fit* f) {  // every member of a batched handle (cs_fit_run advances all of them)
   if (!f) return fail(CS_ERR_ARG, "null handle");
-  RT(rt::memset0(f->m, sizeof(double) * f->lay.np(), f->st));
-  RT(rt::memset0(f->v, sizeof(double) * f->lay.np(), f->st));
+  BaseMember base(f);
+  for (int b = 0; b < f->nbatch; ++b) {
+    RT(rt::memset0(reinterpret_cast<char*>(f->m) + b * f->bstride, sizeof(double) * f->lay.np(), f->st));
+    RT(rt::memset0(reinterpret_cast<char*>(f->v) + b * f->bstride, sizeof(double) * f->lay.np(), f->st));
+  }
   return 0;
 }
 
