@@ -322,6 +322,35 @@ def test_full_size_properties_n8192(gpulib):
     f.close()
 
 
+@pytest.mark.parametrize("n", [8192, 4000])
+def test_bench_plan_at_full_size(gpulib, n):
+    """The plan `bench.py` times (inverse pipelined behind the Cholesky on seven streams, chain on its own SM
+    partition) against the sequential plan on plain streams, at the metric's size and at a ragged size that
+    still enables the partition (padded n = 4096): same gradient / LML / mu / K^-1 to rounding, re-entrant,
+    and K_n K^-1 = I on sampled columns."""
+    P = cs.make_problem("GP", n, 25, weights=True)
+    p0 = o.pack_params(P["par"])
+    outs = []
+    for pipe, part in ((1, 0), (0, -1)):
+        f = _lib.Fit(gpulib, 0, P["y"], P["X"], P["z"], P["w"], p0, inv_pipeline=pipe, partition=part)
+        g, st, mu = f.eval()
+        g2, st2, _ = f.eval()
+        assert np.array_equal(g, g2) and np.array_equal(st, st2)
+        outs.append((g, st, mu, f.get_matrices(want=("invK",))["invK"] if pipe else None, f))
+    (g1, s1, m1, inv1, f1), (g0, s0, m0, _, f0) = outs
+    assert np.max(np.abs(g1 - g0) / np.maximum(np.abs(g0), 1e-6 * np.max(np.abs(g0)))) < 1e-9
+    assert abs(s1[1] - s0[1]) < 1e-11 * abs(s0[1]) and abs(m1 - m0) < 1e-10 * abs(m0) and abs(s1[0] - s0[0]) < 1e-8 * abs(s0[0])
+    assert np.array_equal(inv1, inv1.T)
+    cols = np.array([0, 1, 63, 64, 127, 128, 511, 512, n // 2, n - 129, n - 2, n - 1])
+    par = P["par"]
+    Kc = o.kernmat_GP_SE_cpp(P["X"], P["X"][cols], P["z"], P["z"][cols], par)["Kmat"]          # n x 12 columns of K
+    Kc[cols, np.arange(len(cols))] += np.exp(par["sigma"]) / P["w"][cols]
+    E = inv1 @ Kc                                                                              # = I[:, cols]
+    E[cols, np.arange(len(cols))] -= 1.0
+    assert np.max(np.abs(E)) < 1e-8, np.max(np.abs(E))
+    f1.close(); f0.close()
+
+
 def test_distributed_driver_simulated_on_one_gpu(gpulib):
     """Config 5 driver with all ranks of a 2 x 2 grid on this GPU (collectives = device copies);
     the NCCL run over real ranks is tools/dist_check.py under torchrun."""
