@@ -205,6 +205,7 @@ struct Comm {
 // one rank's state
 // ---------------------------------------------------------------------------------
 struct StepTab { std::vector<long long> off; std::vector<int> start; long long* d = nullptr; };
+constexpr int NPK = 6;  // problems per step
 
 struct DistRank {
   Geom g;
@@ -218,6 +219,13 @@ struct DistRank {
   double *G = nullptr, *Xl = nullptr, *C = nullptr;
   // panels (tile-contiguous, T x T each)
   double *colsend = nullptr, *COL = nullptr, *rowsend = nullptr, *ROW = nullptr, *xkk = nullptr;
+  // look-ahead: the bulk of step k's update runs on the side stream st2 while the main stream already does the
+  // leaf / panel / communication of step k+1, so the gathered panels are double-buffered by step parity
+  double *COLb[2] = {nullptr, nullptr}, *ROWb[2] = {nullptr, nullptr};
+  cudaStream_t st2{};
+  bool own_st2 = false;
+  cudaEvent_t ev_share{}, ev_side{};
+  bool ev_ok = false;
   // reductions
   double *mv = nullptr, *alpha = nullptr, *u = nullptr, *s = nullptr, *logdet_part = nullptr, *gpart = nullptr,
          *kal = nullptr, *tsig = nullptr, *rs_part = nullptr, *red = nullptr;
@@ -230,7 +238,8 @@ struct DistRank {
   int *d_lower = nullptr, *d_diag = nullptr;
   int* d_k3 = nullptr; int n_k3 = 0;  // (I64, J64, coff_lo, coff_hi) per 64 x 64 lower sub-tile
   StepTab t_potrf, t_acc, t_c, t_fin;
-  GemmProblem* d_probs = nullptr;   // [4 * N]: potrf, acc, c, fin per step
+  std::vector<int> na_potrf, na_acc;  // entries of step k's table that the NEXT step depends on (they come first)
+  GemmProblem* d_probs = nullptr;   // [NPK * N] per step: potrf (next column), fin, acc (next row), c, potrf rest, acc rest
   std::vector<GemmProblem> probs;
   GemmProblem* d_panel = nullptr;   // [N] panel multiply problems
   std::vector<void*> allocs;
@@ -239,6 +248,8 @@ struct DistRank {
   int dalloc(void** p, size_t bytes) { int e = rt::dev_malloc(p, bytes); if (!e) allocs.push_back(*p); return e; }
   void destroy() {
     rt::stream_sync(st);
+    if (own_st2) { rt::stream_sync(st2); rt::stream_destroy(st2); own_st2 = false; }
+    if (ev_ok) { rt::event_destroy(ev_share); rt::event_destroy(ev_side); ev_ok = false; }
     for (void* p : allocs) rt::dev_free(p);
     allocs.clear();
     if (own_stream) rt::stream_destroy(st);
@@ -270,8 +281,17 @@ static int rank_init(DistRank& R, int n, int p, int kind, int T, int P, int Q, i
   DA(R.X, vb * p); DA(R.y, vb); DA(R.z, vb); DA(R.w, vb); DA(R.ones, vb); DA(R.params, sizeof(double) * NP);
   DA(R.grad, sizeof(double) * NP);
   DA(R.G, lm); DA(R.Xl, lm); DA(R.C, lm);
-  DA(R.colsend, sizeof(double) * T2 * g.mt); DA(R.COL, sizeof(double) * T2 * g.mt * P);
-  DA(R.rowsend, sizeof(double) * T2 * g.nt); DA(R.ROW, sizeof(double) * T2 * g.nt * Q);
+  DA(R.colsend, sizeof(double) * T2 * g.mt); DA(R.COLb[0], sizeof(double) * T2 * g.mt * P); DA(R.COLb[1], sizeof(double) * T2 * g.mt * P);
+  DA(R.rowsend, sizeof(double) * T2 * g.nt); DA(R.ROWb[0], sizeof(double) * T2 * g.nt * Q); DA(R.ROWb[1], sizeof(double) * T2 * g.nt * Q);
+  R.COL = R.COLb[0]; R.ROW = R.ROWb[0];
+  if (own_stream) {
+    if ((e = rt::stream_create_low(&R.st2))) return e;
+    R.own_st2 = true;
+  } else {
+    R.st2 = st;  // in-process grid (tests): one stream for everything, same op order
+  }
+  if ((e = rt::event_create_fast(&R.ev_share)) || (e = rt::event_create_fast(&R.ev_side))) return e;
+  R.ev_ok = true;
   DA(R.xkk, sizeof(double) * T2);
   R.ncta_grad = rt::sm_count();
   const int nacc = 2 * p + 2;
@@ -343,11 +363,16 @@ static int rank_init(DistRank& R, int n, int p, int kind, int T, int P, int Q, i
     {
       const int li0 = k / P, cnt = g.mt - li0;
       auto slot = [&](int I) { return ((long long)(I % P) * cnt + (I / P - li0)) * (long long)T2; };
+      // lower_tiles is ordered by J: the tiles of block column k+1 (what step k+1 needs) come first
+      const size_t before = R.t_potrf.off.size();
+      size_t after_next = before;
       for (size_t q = 0; q < R.lower_tiles.size(); q += 2) {
         const int I = R.lower_tiles[q], J = R.lower_tiles[q + 1];
         if (J <= k) continue;
         sub_tiles(R.t_potrf, slot(I), T, false, slot(J), T, false, g.off(I, J), I == J);
+        if (J == k + 1) after_next = R.t_potrf.off.size();
       }
+      R.na_potrf.push_back((int)((after_next - before) / 3));
     }
     // ---- finalize row k: X_kJ = -X_kk * Acc_kJ for owned (k,J), J < k  (one CTA per 128-tile, in place)
     R.t_fin.start.push_back((int)R.t_fin.off.size() / 3);
@@ -361,10 +386,15 @@ static int rank_init(DistRank& R, int n, int p, int kind, int T, int P, int Q, i
       auto cslot = [&](int I) { return ((long long)(I % P) * cnt + (I / P - li0)) * (long long)T2; };
       const int cntr = k / Q + 1;
       auto rslot = [&](int J) { return ((long long)(J % Q) * cntr + J / Q) * (long long)T2; };
+      // Acc: the tiles of block row k+1 (finalised by step k+1) first, then the rows below
+      const size_t before = R.t_acc.off.size();
+      if ((k + 1) < N && (k + 1) % P == pr)
+        for (int J = pc; J <= k; J += Q) sub_tiles(R.t_acc, cslot(k + 1), T, false, rslot(J), T, true, g.off(k + 1, J), false);
+      R.na_acc.push_back((int)((R.t_acc.off.size() - before) / 3));
       for (int J = pc; J <= k; J += Q) {
         for (int I = pr; I < N; I += P) {
-          if (I > k) sub_tiles(R.t_acc, cslot(I), T, false, rslot(J), T, true, g.off(I, J), false);
-          else if (I >= J) sub_tiles(R.t_c, rslot(I), T, true, rslot(J), T, true, g.off(I, J), false);  // diagonal tiles in full: symv reads them as symmetric
+          if (I > k + 1) sub_tiles(R.t_acc, cslot(I), T, false, rslot(J), T, true, g.off(I, J), false);
+          else if (I <= k && I >= J) sub_tiles(R.t_c, rslot(I), T, true, rslot(J), T, true, g.off(I, J), false);  // diagonal tiles in full: symv reads them as symmetric
         }
       }
     }
@@ -375,22 +405,28 @@ static int rank_init(DistRank& R, int n, int p, int kind, int T, int P, int Q, i
   R.t_c.start.push_back((int)R.t_c.off.size() / 3);
   if ((e = upload_tab(R, R.t_potrf)) || (e = upload_tab(R, R.t_fin)) || (e = upload_tab(R, R.t_acc)) || (e = upload_tab(R, R.t_c))) return e;
 
-  // per-step problems: [4k+0] potrf update, [4k+1] finalize row, [4k+2] Acc, [4k+3] C
-  R.probs.assign(4 * (size_t)N, GemmProblem{});
+  // per-step problems: [0] potrf update of block column k+1, [1] finalize row, [2] Acc of block row k+1, [3] C,
+  // [4] rest of the potrf update, [5] rest of Acc.  Panels are read from the buffer of the step's parity.
+  R.probs.assign(NPK * (size_t)N, GemmProblem{});
   std::vector<GemmProblem> panel(N, GemmProblem{});
   for (int k = 0; k < N; ++k) {
-    auto mkp = [&](const double* A, long long lda, const double* B, long long ldb, double* Cc, StepTab& tab, double alpha,
-                   double beta) {
+    auto mkp = [&](const double* A, long long lda, const double* B, long long ldb, double* Cc, StepTab& tab, int first, int count,
+                   double alpha, double beta) {
       GemmProblem p_{};
       p_.A = A; p_.B = B; p_.C = Cc; p_.lda = lda; p_.ldb = ldb; p_.ldc = g.ldl; p_.K = T; p_.alpha = alpha; p_.beta = beta;
-      p_.ntiles = tab.start[k + 1] - tab.start[k]; p_.tile_base = 0; p_.table = tab.d + 3LL * tab.start[k];
+      p_.ntiles = count; p_.tile_base = 0; p_.table = tab.d + 3LL * (tab.start[k] + first);
       p_.mt = p_.ntiles; p_.nt = 1;
       return p_;
     };
-    R.probs[4 * k + 0] = mkp(R.COL, T, R.COL, T, R.G, R.t_potrf, -1.0, 1.0);
-    R.probs[4 * k + 1] = mkp(R.xkk, T, R.Xl, g.ldl, R.Xl, R.t_fin, -1.0, 0.0);
-    R.probs[4 * k + 2] = mkp(R.COL, T, R.ROW, T, R.Xl, R.t_acc, 1.0, 1.0);
-    R.probs[4 * k + 3] = mkp(R.ROW, T, R.ROW, T, R.C, R.t_c, 1.0, 1.0);
+    double* COLk = R.COLb[k & 1];
+    double* ROWk = R.ROWb[k & 1];
+    const int n_potrf = R.t_potrf.start[k + 1] - R.t_potrf.start[k], n_acc = R.t_acc.start[k + 1] - R.t_acc.start[k];
+    R.probs[NPK * k + 0] = mkp(COLk, T, COLk, T, R.G, R.t_potrf, 0, R.na_potrf[k], -1.0, 1.0);
+    R.probs[NPK * k + 4] = mkp(COLk, T, COLk, T, R.G, R.t_potrf, R.na_potrf[k], n_potrf - R.na_potrf[k], -1.0, 1.0);
+    R.probs[NPK * k + 1] = mkp(R.xkk, T, R.Xl, g.ldl, R.Xl, R.t_fin, 0, R.t_fin.start[k + 1] - R.t_fin.start[k], -1.0, 0.0);
+    R.probs[NPK * k + 2] = mkp(COLk, T, ROWk, T, R.Xl, R.t_acc, 0, R.na_acc[k], 1.0, 1.0);
+    R.probs[NPK * k + 5] = mkp(COLk, T, ROWk, T, R.Xl, R.t_acc, R.na_acc[k], n_acc - R.na_acc[k], 1.0, 1.0);
+    R.probs[NPK * k + 3] = mkp(ROWk, T, ROWk, T, R.C, R.t_c, 0, R.t_c.start[k + 1] - R.t_c.start[k], 1.0, 1.0);
     // panel multiply L_Ik = A_Ik X_kk^T for the local rows below k (process column k mod Q only)
     if (k % Q == pc) {
       int first = -1, cntp = 0;
@@ -405,7 +441,7 @@ static int rank_init(DistRank& R, int n, int p, int kind, int T, int P, int Q, i
   if ((e = rt::h2d(R.d_probs, R.probs.data(), sizeof(GemmProblem) * R.probs.size(), st))) return e;
   if ((e = R.dalloc((void**)&R.d_panel, sizeof(GemmProblem) * N))) return e;
   if ((e = rt::h2d(R.d_panel, panel.data(), sizeof(GemmProblem) * N, st))) return e;
-  R.probs.insert(R.probs.end(), panel.begin(), panel.end());  // keep host copies alive: [4N .. 5N) = panel
+  R.probs.insert(R.probs.end(), panel.begin(), panel.end());  // keep host copies alive: [NPK*N .. (NPK+1)*N) = panel
   if ((e = rt::stream_sync(st))) return e;
   csdense::configure_kernels();
   { auto kf = gram_dist_kernel; CS_SET_SMEM(kf, csk::gram_smem_bytes(csk::PMAX)); }
@@ -441,7 +477,14 @@ struct DistEval {
                   R.lay, g.n, (const int*)R.d_lower, T, P, Q, R.G, g.ldl);
       }
     });
-    // ---- sweep 1: Cholesky ----
+    // ---- sweep 1: Cholesky, with look-ahead.  The update of step k is split: block column k+1 on the main
+    // stream (the next leaf / panel multiply wait for nothing else), the rest on the side stream st2 where it
+    // overlaps the leaf, the panel multiply and the communication of step k+1.
+    bool side_pending = false;
+    auto join_side = [&]() {  // main stream waits for the side stream's last update
+      if (!side_pending) return;
+      each([&](DistRank& R) { rt::stream_wait_event(R.st, R.ev_side); });
+    };
     for (int k = 0; k < N; ++k) {
       const int prk = k % P, pck = k % Q;
       each([&](DistRank& R) {
@@ -456,18 +499,26 @@ struct DistEval {
       const int li0 = k / P;
       each([&](DistRank& R) {
         if (R.g.pc != pck) return;
-        const GemmProblem& pp = R.probs[4 * (size_t)N + k];
+        const GemmProblem& pp = R.probs[NPK * (size_t)N + k];
         if (pp.ntiles > 0) csdense::launch_gemm(T, csdense::GK_NT, R.d_panel + k, 1, pp.ntiles, R.st);
         // publish the local part of column panel k (tiles li >= li0)
         pack(R, R.G + (long long)li0 * T + (long long)R.g.lj(k) * T * R.g.ldl, R.g.ldl, T, R.colsend, R.g.mt - li0);
       });
       if ((e = share_col_panel(k))) return e;
+      join_side();  // the rest of step k-1 also updated block column k+1 (and has finished reading the other panel buffer)
       each([&](DistRank& R) {
-        const GemmProblem& pp = R.probs[4 * (size_t)k + 0];
-        if (pp.ntiles > 0) csdense::launch_gemm(R.gt, csdense::GK_NT, R.d_probs + 4 * k + 0, 1, pp.ntiles, R.st);
+        rt::event_record(R.ev_share, R.st);
+        const GemmProblem& pa = R.probs[NPK * (size_t)k + 0];
+        if (pa.ntiles > 0) csdense::launch_gemm(R.gt, csdense::GK_NT, R.d_probs + NPK * k + 0, 1, pa.ntiles, R.st);
+        rt::stream_wait_event(R.st2, R.ev_share);
+        const GemmProblem& pb = R.probs[NPK * (size_t)k + 4];
+        if (pb.ntiles > 0) csdense::launch_gemm(R.gt, csdense::GK_NT, R.d_probs + NPK * k + 4, 1, pb.ntiles, R.st2);
+        rt::event_record(R.ev_side, R.st2);
       });
+      side_pending = true;
     }
-    // ---- sweep 2: triangular inverse + K^-1 = X^T X, fused ----
+    join_side();
+    // ---- sweep 2: triangular inverse + K^-1 = X^T X, fused; same look-ahead (block row k+1 of Acc first) ----
     for (int k = 0; k < N; ++k) {
       const int prk = k % P, pck = k % Q;
       each([&](DistRank& R) {
@@ -475,15 +526,17 @@ struct DistEval {
       });
       if ((e = comm->bcast(L, G_ROW, prk, pck, [](DistRank& R) { return R.xkk; }, T2))) return e;
       const int cntr = k / Q + 1;
+      const int par = k & 1;
       each([&](DistRank& R) {
         if (R.g.pr != prk) return;
-        const GemmProblem& pf = R.probs[4 * (size_t)k + 1];
-        if (pf.ntiles > 0) csdense::launch_gemm(T, csdense::GK_NN, R.d_probs + 4 * k + 1, 1, pf.ntiles, R.st);
+        const GemmProblem& pf = R.probs[NPK * (size_t)k + 1];
+        if (pf.ntiles > 0) csdense::launch_gemm(T, csdense::GK_NN, R.d_probs + NPK * k + 1, 1, pf.ntiles, R.st);
         // publish the local part of row panel k of X (local column tiles 0 .. cntr-1)
         pack(R, R.Xl + (long long)R.g.li(k) * T, R.g.ldl, (long long)T * R.g.ldl, R.rowsend, cntr);
       });
-      if ((e = comm->allgather(L, G_ROW, prk, [](DistRank& R) { return R.rowsend; }, [](DistRank& R) { return R.ROW; }, cntr * T2))) return e;
-      if ((e = comm->bcast(L, G_COL, -1, prk, [](DistRank& R) { return R.ROW; }, (size_t)Q * cntr * T2))) return e;
+      // the side stream of step k-2 has finished with this parity's buffers: the main stream joined it at step k-1
+      if ((e = comm->allgather(L, G_ROW, prk, [](DistRank& R) { return R.rowsend; }, [par](DistRank& R) { return R.ROWb[par]; }, cntr * T2))) return e;
+      if ((e = comm->bcast(L, G_COL, -1, prk, [par](DistRank& R) { return R.ROWb[par]; }, (size_t)Q * cntr * T2))) return e;
       if (k < N - 1) {
         const int li0 = k / P;
         each([&](DistRank& R) {
@@ -492,13 +545,21 @@ struct DistEval {
         });
         if ((e = share_col_panel(k))) return e;
       }
+      join_side();
       each([&](DistRank& R) {
-        const GemmProblem& pa = R.probs[4 * (size_t)k + 2];
-        if (pa.ntiles > 0) csdense::launch_gemm(R.gt, csdense::GK_NN, R.d_probs + 4 * k + 2, 1, pa.ntiles, R.st);
-        const GemmProblem& pcx = R.probs[4 * (size_t)k + 3];
-        if (pcx.ntiles > 0) csdense::launch_gemm(R.gt, csdense::GK_TN, R.d_probs + 4 * k + 3, 1, pcx.ntiles, R.st);
+        rt::event_record(R.ev_share, R.st);
+        const GemmProblem& pa = R.probs[NPK * (size_t)k + 2];
+        if (pa.ntiles > 0) csdense::launch_gemm(R.gt, csdense::GK_NN, R.d_probs + NPK * k + 2, 1, pa.ntiles, R.st);
+        rt::stream_wait_event(R.st2, R.ev_share);
+        const GemmProblem& pb = R.probs[NPK * (size_t)k + 5];
+        if (pb.ntiles > 0) csdense::launch_gemm(R.gt, csdense::GK_NN, R.d_probs + NPK * k + 5, 1, pb.ntiles, R.st2);
+        const GemmProblem& pcx = R.probs[NPK * (size_t)k + 3];
+        if (pcx.ntiles > 0) csdense::launch_gemm(R.gt, csdense::GK_TN, R.d_probs + NPK * k + 3, 1, pcx.ntiles, R.st2);
+        rt::event_record(R.ev_side, R.st2);
       });
+      side_pending = true;
     }
+    join_side();
     // ---- reductions: alpha/u/s, scalars, trace gradients, stats ----
     each([&](DistRank& R) {
       const Geom& g = R.g;
@@ -558,8 +619,9 @@ struct DistEval {
     const int pck = k % Q, li0 = k / P;
     int e;
     const size_t cnt = (size_t)(L[0]->g.mt - li0) * T2;
-    if ((e = comm->allgather(L, G_COL, pck, [](DistRank& R) { return R.colsend; }, [](DistRank& R) { return R.COL; }, cnt))) return e;
-    if ((e = comm->bcast(L, G_ROW, -1, pck, [](DistRank& R) { return R.COL; }, (size_t)P * cnt))) return e;
+    const int par = k & 1;  // the updates of step k read COLb[k & 1]
+    if ((e = comm->allgather(L, G_COL, pck, [](DistRank& R) { return R.colsend; }, [par](DistRank& R) { return R.COLb[par]; }, cnt))) return e;
+    if ((e = comm->bcast(L, G_ROW, -1, pck, [par](DistRank& R) { return R.COLb[par]; }, (size_t)P * cnt))) return e;
     return 0;
   }
 };
