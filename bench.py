@@ -33,9 +33,9 @@ if ROOT not in sys.path:
 N_METRIC, P_METRIC = 8192, 25
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
 # `ncu --set full` capture (per launch; None until a capture of the current kernel exists)
-XTX_TRAFFIC_BYTES = 4.111889e9 + 486.338048e6
+XTX_TRAFFIC_BYTES = 4.107949e9 + 485.392896e6
 XTX_TRAFFIC_SOURCE = ("profiles/r01_s2_ncu_xtx.txt: ncu --set full of this kernel in `bench.py --inv-pipeline 0` "
-                      "(dram__bytes_read.sum 4.112 GB + dram__bytes_write.sum 486.3 MB per launch)")
+                      "(dram__bytes_read.sum 4.108 GB + dram__bytes_write.sum 485.4 MB per launch)")
 METRIC = "fp64 LML+gradient evals/sec at n=8192,p=25"
 UNIT = "evals/s"
 
