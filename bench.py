@@ -163,6 +163,21 @@ def cpu_eval_seconds(inp, budget_s):
     return total, desc
 
 
+def host_env():
+    """OMP / BLAS thread settings and the BLAS build, for the cpu_baseline record."""
+    info = {"OMP_NUM_THREADS": os.environ.get("OMP_NUM_THREADS"), "OPENBLAS_NUM_THREADS": os.environ.get("OPENBLAS_NUM_THREADS"),
+            "nproc": os.cpu_count()}
+    try:
+        from threadpoolctl import threadpool_info
+        for i in threadpool_info():
+            if i.get("user_api") == "blas":
+                info["blas"] = "%s %s (%s, %d threads)" % (i.get("internal_api"), i.get("version"), i.get("architecture"), i.get("num_threads", 0))
+                break
+    except Exception:
+        pass
+    return info
+
+
 def host_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -194,7 +209,7 @@ def run_reference(args, rank, world):
         "data": "synthetic", "impl": "reference",
         "config": {"workload": "Hill-(2011)-shaped synthetic n=8192 p=25, GP (prior=FALSE), one LML+gradient evaluation per step",
                    "n": N_METRIC, "p": P_METRIC},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": desc, "host": host_env()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -377,7 +392,7 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu:
             secs, desc = cpu_eval_seconds(inp, 25.0)
             line_extra["cpu_baseline"] = {"value": 1.0 / secs, "unit": UNIT, "cores": host_threads(), "kind": "port",
-                                          "sample": desc}
+                                          "sample": desc, "host": host_env()}
     fit.close()
 
     # ---- metric ii: replicate fits/hour (extra object) ----
