@@ -194,6 +194,11 @@ def run_reference(args, rank, world):
         return 0
     total_steps = args.steps + args.warmup
     budget = max(6.0, min(30.0, 150.0 / max(total_steps, 1)))
+    try:  # torchrun exports OMP_NUM_THREADS=1 to every rank: give the reference arm all host threads back
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1, user_api="blas")
+    except Exception:
+        pass
     inp = make_inputs(N_METRIC, P_METRIC, 0)
     secs = []
     desc = ""
