@@ -195,6 +195,8 @@ def run_reference(args, rank, world):
     total_steps = args.steps + args.warmup
     budget = max(6.0, min(30.0, 150.0 / max(total_steps, 1)))
     try:  # torchrun exports OMP_NUM_THREADS=1 to every rank: give the reference arm all host threads back
+        import scipy.linalg  # noqa: F401  (load SciPy's OpenBLAS before limits are applied)
+        from oracle import causalstump_oracle  # noqa: F401
         from threadpoolctl import threadpool_limits
         threadpool_limits(limits=os.cpu_count() or 1, user_api="blas")
     except Exception:
