@@ -199,6 +199,15 @@ struct Comm {
   virtual int bcast(std::vector<DistRank*>& L, int group, int which, int root, const BufFn& buf, size_t count) = 0;
   virtual int allgather(std::vector<DistRank*>& L, int group, int which, const BufFn& send, const BufFn& recv, size_t count) = 0;
   virtual int allreduce_sum(std::vector<DistRank*>& L, const BufFn& buf, size_t count) = 0;
+  // Panel sharing: the ranks of one process column (group == G_COL, index `which`) or process row (G_ROW) each hold
+  // `count` doubles in send(); afterwards EVERY rank of the grid holds all pieces in recv(), piece r at r * count.
+  // Default: all-gather inside the owning group, then broadcast across the other dimension (two dependent
+  // collectives); back-ends may fuse it into one.
+  virtual int share_panel(std::vector<DistRank*>& L, int group, int which, const BufFn& send, const BufFn& recv, size_t count,
+                          int pieces) {
+    if (int e = allgather(L, group, which, send, recv, count)) return e;
+    return bcast(L, group == G_COL ? G_ROW : G_COL, -1, which, recv, (size_t)pieces * count);
+  }
 };
 
 // ---------------------------------------------------------------------------------
@@ -535,8 +544,7 @@ struct DistEval {
         pack(R, R.Xl + (long long)R.g.li(k) * T, R.g.ldl, (long long)T * R.g.ldl, R.rowsend, cntr);
       });
       // the side stream of step k-2 has finished with this parity's buffers: the main stream joined it at step k-1
-      if ((e = comm->allgather(L, G_ROW, prk, [](DistRank& R) { return R.rowsend; }, [par](DistRank& R) { return R.ROWb[par]; }, cntr * T2))) return e;
-      if ((e = comm->bcast(L, G_COL, -1, prk, [par](DistRank& R) { return R.ROWb[par]; }, (size_t)Q * cntr * T2))) return e;
+      if ((e = comm->share_panel(L, G_ROW, prk, [](DistRank& R) { return R.rowsend; }, [par](DistRank& R) { return R.ROWb[par]; }, cntr * T2, Q))) return e;
       if (k < N - 1) {
         const int li0 = k / P;
         each([&](DistRank& R) {
@@ -620,8 +628,7 @@ struct DistEval {
     int e;
     const size_t cnt = (size_t)(L[0]->g.mt - li0) * T2;
     const int par = k & 1;  // the updates of step k read COLb[k & 1]
-    if ((e = comm->allgather(L, G_COL, pck, [](DistRank& R) { return R.colsend; }, [par](DistRank& R) { return R.COLb[par]; }, cnt))) return e;
-    if ((e = comm->bcast(L, G_ROW, -1, pck, [par](DistRank& R) { return R.COLb[par]; }, (size_t)P * cnt))) return e;
+    if ((e = comm->share_panel(L, G_COL, pck, [](DistRank& R) { return R.colsend; }, [par](DistRank& R) { return R.COLb[par]; }, cnt, P))) return e;
     return 0;
   }
 };
