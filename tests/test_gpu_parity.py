@@ -351,6 +351,21 @@ def test_bench_plan_at_full_size(gpulib, n):
     f1.close(); f0.close()
 
 
+def test_optimisation_loop_with_sm_partition_and_graph(gpulib):
+    """cs_fit_run at a size that enables the SM partition: the captured CUDA graph spans the green-context streams;
+    same trajectory as eager launches on plain priority streams."""
+    P = cs.make_problem("GP", 4200, 10)
+    p0 = o.pack_params(P["par"])
+    outs = []
+    for kw in (dict(partition=0, use_graph=0, inv_pipeline=1), dict(partition=-1, use_graph=-1, inv_pipeline=0)):
+        f = _lib.Fit(gpulib, 0, P["y"], P["X"], P["z"], P["w"], p0, **kw)
+        it, tr = f.run(4, 0.0)
+        outs.append((it, tr.copy(), f.get_params()))
+        f.close()
+    (i1, t1, q1), (i0, t0, q0) = outs
+    assert i1 == i0 == 4 and cs.rel(t1[1, 1:], t0[1, 1:]) < 1e-10 and cs.rel(q1, q0, 1e-9) < 1e-9
+
+
 def test_distributed_driver_simulated_on_one_gpu(gpulib):
     """Config 5 driver with all ranks of a 2 x 2 grid on this GPU (collectives = device copies);
     the NCCL run over real ranks is tools/dist_check.py under torchrun."""
