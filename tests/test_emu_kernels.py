@@ -149,3 +149,19 @@ def test_graded_panel_widths(emulib, monkeypatch, n, tile, pipe):
 
 def test_limits_and_failure_reporting(emulib):
     cs.check_limits(emulib)
+
+
+@pytest.mark.parametrize("pipe", [0, 1])
+def test_first_generation_plan_still_works(emulib, monkeypatch, pipe):
+    """CS_PLAN=1 keeps the per-step plan (panel multiply + update per 128 columns, memset-initialised inverse) as an
+    A/B reference for the v2 plan; it must stay race-free and numerically equivalent."""
+    monkeypatch.setenv("CS_PLAN", "1")
+    assert emulib.dll.cs_debug_check_plan(3000, 128, 64, 1) == 0
+    P = cs.make_problem("GP", 330, 4, weights=True)
+    g, st, mu = o.eval_lml_grad("GP", P["y"], P["X"], P["z"], P["w"], P["par"])
+    f = _lib.Fit(emulib, 0, P["y"], P["X"], P["z"], P["w"], o.pack_params(P["par"]), tile=64, inv_pipeline=pipe)
+    g2, st2, mu2 = f.eval()
+    g3, _, _ = f.eval()
+    f.close()
+    assert np.array_equal(g2, g3)
+    assert cs.rel(g2, o.pack_params(g), 1e-9) < cs.TOL_GRAD and abs(st2[1] - st[1]) < cs.TOL_LML * abs(st[1])
