@@ -454,6 +454,24 @@ def run_ours(args, rank, world, local_rank):
                             "members (cs_fit_create_batch, every launch serves a whole batch), handles driven concurrently "
                             "(cs_fit_run_many); includes host data generation and handle creation" % (nf, args.fit_batch)}
 
+    if rank == 0 and fits_obj and world == 1 and not args.no_cpu:
+        # the same fit on the host: one reference-faithful optimizer iteration of the oracle port (para_update, which
+        # builds Gram + inverse twice for the GP class, R/kernel_GP_SE_class.R:48,58) at the replicate size, timed
+        # over 3 iterations and scaled by the mean iteration count measured above
+        from oracle import causalstump_oracle as o
+        sinp = make_inputs(672, P_METRIC, 1)
+        Kc = o.KernelClass_GP_SE(P_METRIC, np.ones(672))
+        Kc.parameters = o.unpack_params(sinp["params"], "GP", P_METRIC)
+        opt = o.optNadam(0.01, 0.9, 0.999)
+        opt.initOpt(Kc)
+        Kc.para_update(1, sinp["y"], sinp["X"], sinp["z"], opt)
+        t0 = time.perf_counter()
+        for it in range(2, 5):
+            Kc.para_update(it, sinp["y"], sinp["X"], sinp["z"], opt)
+        sec_it = (time.perf_counter() - t0) / 3
+        fits_obj["cpu_port"] = {"seconds_per_iteration": sec_it, "fits_per_hour_one_process": 3600.0 / (sec_it * fits_obj["iterations_mean"]),
+                                "cores": host_threads(),
+                                "what": "oracle port of para_update at n=672, p=25 (reference-faithful), scaled by iterations_mean"}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
