@@ -394,7 +394,9 @@ def run_ours(args, rank, world, local_rank):
             "grad": {"bound": "hbm", "achieved": b_grad / (phases["grad"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                      "frac": b_grad / (phases["grad"] * 1e-3) / 1e9 / hbm_peak, "ms": phases["grad"],
                      "fp64_tflops": (n * n / 2.0) * (10 * p + 12) / (phases["grad"] * 1e-3) / 1e12},
-            "note": "at p=25 both kernels are FP64-issue-bound, not HBM-bound (SURVEY.md 8d)",
+            "note": "at p=25 both kernels are FP64-issue-bound, not HBM-bound (SURVEY.md 8d); ncu --set full (profiles/r01_s2_ncu_gram.txt, "
+                    "r01_s2_ncu_grad.txt): DRAM traffic 213 MB (Gram) / 283 MB (gradient) per launch = the algorithmic bytes, "
+                    "fp64 pipe 65 % / 53 % of peak while active",
         }
         line_extra["phases_ms"] = phases
         # ---- CPU baseline on the host cores (rank 0, N=1 only) ----

@@ -410,13 +410,14 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
     }
     acc[0 * ETH + tid] += wgt * tm;
     acc[1 * ETH + tid] += wgt * ta;
-    for (int i = 0; i < p; ++i) {
+    // two dimensions per trip: with two warps per scheduler the FP64 latency is only hidden by independent work
+    // inside the warp (eight partial sums per kernel in flight)
+    auto one_dim = [&](int i, double& om, double& oa) {
       double xa[4], xb[4];
 #pragma unroll
       for (int a = 0; a < 4; ++a) xa[a] = xr[i * TB + tx + 16 * a];
 #pragma unroll
       for (int b = 0; b < 4; ++b) xb[b] = xc[i * TB + ty + 16 * b];
-      // four independent partial sums per kernel: no 16-long dependent FMA chain
       double gm[4] = {0.0, 0.0, 0.0, 0.0}, ga[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
       for (int a = 0; a < 4; ++a)
@@ -427,8 +428,24 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
           gm[b] = fma(km[a][b], d2, gm[b]);
           ga[b] = fma(ka[a][b], d2, ga[b]);
         }
-      acc[(2 + i) * ETH + tid] += wgt * ((gm[0] + gm[1]) + (gm[2] + gm[3]));
-      acc[(2 + p + i) * ETH + tid] += wgt * ((ga[0] + ga[1]) + (ga[2] + ga[3]));
+      om = (gm[0] + gm[1]) + (gm[2] + gm[3]);
+      oa = (ga[0] + ga[1]) + (ga[2] + ga[3]);
+    };
+    int i = 0;
+    for (; i + 1 < p; i += 2) {
+      double m0, a0, m1, a1;
+      one_dim(i, m0, a0);
+      one_dim(i + 1, m1, a1);
+      acc[(2 + i) * ETH + tid] += wgt * m0;
+      acc[(2 + p + i) * ETH + tid] += wgt * a0;
+      acc[(3 + i) * ETH + tid] += wgt * m1;
+      acc[(3 + p + i) * ETH + tid] += wgt * a1;
+    }
+    if (i < p) {
+      double m0, a0;
+      one_dim(i, m0, a0);
+      acc[(2 + i) * ETH + tid] += wgt * m0;
+      acc[(2 + p + i) * ETH + tid] += wgt * a0;
     }
     // K*alpha partials: rows (reduce over ty) and columns (reduce over tx)
 #pragma unroll

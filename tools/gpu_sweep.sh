@@ -1,4 +1,5 @@
 cd "${GRAFT_REPO_ROOT:-.}"
-for b in 16 32 64; do
-timeout 300 python tools/fits_scaling.py 256 512 --batch=$b 2>&1 | tail -2 | cut -c1-330
-done
+timeout 900 python bench.py --steps 20 --warmup 3 --no-fits --no-cpu 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(round(d['value'],2), round(d['ms_per_step'],3), {k:round(v,3) for k,v in d['phases_ms'].items()})"
+timeout 500 python tools/batch_phases.py 2>&1 | grep "tile= 64" | grep "B=32\|B=64"
