@@ -372,7 +372,7 @@ static int fit_create_impl(const cs_fit_config* cfg, int nbatch, int n, int p, c
   *out = nullptr;
   f->cfg = *cfg;
   f->cfg.tile = tile;
-  if (nbatch > 1) f->cfg.inv_pipeline = 0;  // the pipelined inverse re-zeroes X and C per member and evaluation
+  if (nbatch > 1) f->cfg.inv_pipeline = std::getenv("CS_BATCH_PIPE") ? 1 : 0;  // experiment knob; sequential inverse measured best for small-n batches
   f->lay.kind = cfg->kind;
   f->lay.p = p;
   f->n = n;
