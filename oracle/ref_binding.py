@@ -42,11 +42,29 @@ def _p(a):
     return a.ctypes.data_as(dp)
 
 
+def build_glue(c_abi_lib, out):
+    """Compiles the R-side glue of the drop-in (causalstump_b200/r/src/b200_glue.cpp) against oracle/shim/Rcpp.h and links
+    it to `c_abi_lib`, a library exporting the C ABI of include/cs_b200.h (the SIMT-emulated one on CPU, the CUDA one on
+    the GPU box).  Returns `out`."""
+    root = os.path.dirname(HERE)
+    d, f = os.path.split(os.path.abspath(c_abi_lib))
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-I" + os.path.join(HERE, "shim"),
+           "-I" + os.path.join(root, "include"), os.path.join(root, "causalstump_b200", "r", "src", "b200_glue.cpp"),
+           os.path.join(HERE, "glue_driver.cpp"), "-o", out, "-L" + d, "-l:" + f, "-Wl,-rpath," + d]
+    subprocess.check_call(cmd)
+    return out
+
+
 class RefLib:
-    def __init__(self, path=LIB):
+    """prefix "ref": the reference's own compiled routines; prefix "glue": the drop-in's R glue -> C ABI -> kernels."""
+
+    def __init__(self, path=LIB, prefix="ref"):
         self.dll = C.CDLL(path)
-        for name in ("ref_kernmat", "ref_invkernel", "ref_mu_solution", "ref_grad", "ref_stats", "ref_opt_step"):
-            getattr(self.dll, name).restype = C.c_int
+        self.prefix = prefix
+        for name in ("kernmat", "invkernel", "mu_solution", "grad", "stats", "opt_step"):
+            fn = getattr(self.dll, prefix + "_" + name)
+            fn.restype = C.c_int
+            setattr(self.dll, "ref_" + name, fn)  # the methods below call ref_*
 
     def kernmat(self, kind, X1, X2, Z1, Z2, Lm, La, lambdam, lambda_a):
         X1, X2, Z1, Z2, Lm, La = map(_f, (X1, X2, Z1, Z2, Lm, La))

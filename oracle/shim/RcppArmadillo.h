@@ -19,7 +19,9 @@
 #include <cstddef>
 #include <memory>
 #include <stdexcept>
+#include <initializer_list>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -235,6 +237,14 @@ struct NumericVector {
   double operator()(size_t i) const { return d[i]; }
   double& operator[](size_t i) { return d[i]; }
   double operator[](size_t i) const { return d[i]; }
+  double* begin() { return d.data(); }
+  double* end() { return d.data() + d.size(); }
+  const double* begin() const { return d.data(); }
+  const double* end() const { return d.data() + d.size(); }
+  // attributes (only "dim" is ever set, by the R glue)
+  struct AttrProxy { std::vector<int>* dims; template <class T> void operator=(const T& v) { dims->assign(v.d.begin(), v.d.end()); } };
+  std::vector<int> dims;
+  AttrProxy attr(const char*) { return AttrProxy{&dims}; }
 };
 #define CS_SHIM_VV(op) \
   inline NumericVector operator op(const NumericVector& a, const NumericVector& b) { NumericVector o(a.size()); for (size_t i = 0; i < a.size(); ++i) o.d[i] = a.d[i] op b.d[i]; return o; }
@@ -260,6 +270,7 @@ struct NumericMatrix {
   NumericMatrix(int r, int c) : d((size_t)r * c, 0.0), nr(r), nc(c) {}
   int nrow() const { return nr; }
   int ncol() const { return nc; }
+  double* begin() { return d.data(); }
   double& operator()(int r, int c) { return d[(size_t)c * nr + r]; }
   double operator()(int r, int c) const { return d[(size_t)c * nr + r]; }
   MatrixColumn operator()(internal::NamedPlaceHolder, int c) const { return MatrixColumn{*this, c}; }
@@ -278,6 +289,9 @@ struct Value {  // an R object: numeric vector (optionally with dim) or a list
   std::shared_ptr<List> lst;
   Value() {}
   Value(double x) : num(1, x) {}
+  Value(int x) : num(1, (double)x) {}
+  template <class IV, class = decltype(std::declval<IV>().d), class = typename std::enable_if<std::is_same<decltype(std::declval<IV>().d), std::vector<int>>::value>::type>
+  Value(const IV& v) : num(v.d.begin(), v.d.end()) {}
   Value(const std::vector<double>& v) : num(v) {}
   Value(const NumericVector& v) : num(v.d) {}
   Value(const NumericMatrix& m) : num(m.d), nrow(m.nr), ncol(m.nc) {}
@@ -294,9 +308,24 @@ struct Named {
 };
 
 struct ListProxy;
+struct ConstListProxy { const Value& v; };
 struct List {
   std::vector<std::pair<std::string, Value>> items;
-  size_t size() const { return items.size(); }
+  List() {}
+  explicit List(int k) : items((size_t)k) {}
+  int size() const { return (int)items.size(); }
+  bool containsElementNamed(const char* name) const { for (const auto& it : items) if (it.first == name) return true; return false; }
+  ConstListProxy operator[](int i) const { return ConstListProxy{items.at((size_t)i).second}; }
+  ConstListProxy operator[](const char* name) const {
+    for (const auto& it : items) if (it.first == name) return ConstListProxy{it.second};
+    throw std::runtime_error(std::string("Index out of bounds: [index='") + name + "']");
+  }
+  template <class... Ns> static List create(const Named& a, const Named& b, const Named& c, const Named& d, const Ns&... rest) {
+    List l = create(a, b, c);
+    l.items.push_back({d.name, d.val});
+    (void)std::initializer_list<int>{(l.items.push_back({rest.name, rest.val}), 0)...};
+    return l;
+  }
   ListProxy operator[](const char* name);
   ListProxy operator[](const std::string& name);
   ListProxy operator[](int i);
@@ -314,6 +343,9 @@ inline Value::Value(const List& l) : lst(std::make_shared<List>(l)) {}
 struct ListProxy {
   Value& v;
   template <class T> ListProxy& operator=(const T& x) { v = Value(x); return *this; }
+  ListProxy& operator=(const ListProxy& o) { v = o.v; return *this; }
+  ListProxy& operator=(const ConstListProxy& o) { v = o.v; return *this; }
+  operator NumericVector() const { return NumericVector(v.num); }
 };
 inline ListProxy List::operator[](const char* name) { return ListProxy{slot(name)}; }
 inline ListProxy List::operator[](const std::string& name) { return ListProxy{slot(name)}; }
@@ -336,6 +368,7 @@ template <> struct AsImpl<NumericVector> { static NumericVector get(const Value&
 template <> struct AsImpl<std::vector<double>> { static std::vector<double> get(const Value& v) { return v.num; } };
 template <> struct AsImpl<arma::vec> { static arma::vec get(const Value& v) { return arma::vec(v.num); } };
 template <class T> T as(const ListProxy& p) { return AsImpl<T>::get(p.v); }
+template <class T> T as(const ConstListProxy& p) { return AsImpl<T>::get(p.v); }
 template <class T> T as(const Value& v) { return AsImpl<T>::get(v); }
 
 }  // namespace Rcpp

@@ -192,6 +192,23 @@ def test_real_ihdp_covariates(gpulib):
     assert abs(M["E.ate.train"]) < 0.6 and 0.7 < M["RMSE.all.test"] < 2.5
 
 
+def test_r_glue_on_the_cuda_library(gpulib, tmp_path):
+    """tests/test_r_glue.py with the glue linked to the CUDA library instead of the emulated one: the reference's 11 .Call
+    routines and the b200_* fast path, re-implemented on the C ABI, against the reference's own compiled routines."""
+    import shutil
+    from oracle import ref_binding as rb
+    from tests import test_r_glue as trg
+    if not shutil.which("g++") or not rb.available():
+        pytest.skip("g++ or oracle/_ref/libcausalstump_ref.so not present")
+    out = rb.build_glue(_lib.DEFAULT_LIB, str(tmp_path / "libglue_cuda.so"))
+    libs = (rb.RefLib(), rb.RefLib(out, prefix="glue"))
+    trg.test_glue_routines_equal_the_reference_routines(libs, "GP", 300, 25, True)
+    trg.test_glue_routines_equal_the_reference_routines(libs, "TP", 130, 4, False)
+    for optim in (0, 1, 2):
+        trg.test_glue_optimizers_equal_the_reference_optimizers(libs, optim)
+    trg.test_glue_fast_path_equals_the_restated_r_loop(libs)
+
+
 def test_stateless_mirrors_vs_compiled_reference(gpulib):
     """The stateless C-ABI mirrors against oracle/_ref (the reference's C++ compiled with the header shim),
     which travels to the GPU box as a prebuilt .so; skipped when it is absent."""
