@@ -26,6 +26,11 @@ SEXP b200_fit_create(int kind, int optim, double lr, double beta1, double beta2,
 List b200_fit_run(SEXP handle, int maxiter, double tol, List parameters);
 List b200_treat(SEXP handle, NumericMatrix X2, double jitter, bool want_cov);
 List b200_predict(SEXP handle, NumericMatrix X2, NumericVector z2, bool want_cov);
+SEXP b200_fit_create_batch(int kind, int optim, double lr, double beta1, double beta2, double momentum, List ys, List Xs, List zs,
+                           Nullable<List> ws, List inits);
+List b200_fit_run_batch(SEXP handle, int maxiter, double tol);
+void b200_fit_select(SEXP handle, int member);
+List b200_fit_get_params(SEXP handle, List parameters);
 
 namespace {
 
@@ -145,6 +150,30 @@ int glue_fit_run(int kind, int optim, int n, int p, const double* y, const doubl
       List tr = b200_treat(h, mknm(X2, n2, p), kind == 1 ? 1e-6 : 0.0, false);
       std::memcpy(treat_map, get(tr, "map").num.data(), sizeof(double) * n2);
       *ate = get(tr, "ate").num[0];
+    }
+    return 0;
+  } catch (const std::exception& e) { g_msg = e.what(); return -1; }
+}
+
+// batched handle as the R side would drive it: B members stored back to back (y: B x n, X: B x n x p column-major, ...)
+int glue_fit_run_batch(int kind, int optim, int B, int n, int p, const double* ys, const double* Xs, const double* zs,
+                       const double* params, double lr, int maxiter, double tol, int* iters, double* params_out) {
+  try {
+    const int NP = 2 * p + (kind == 0 ? 4 : 5);
+    List ly(B), lX(B), lz(B), li(B);
+    for (int b = 0; b < B; ++b) {
+      ly[b] = mknv(ys + (size_t)b * n, n);
+      lX[b] = mknm(Xs + (size_t)b * n * p, n, p);
+      lz[b] = mknv(zs + (size_t)b * n, n);
+      li[b] = mklist(kind, p, params + (size_t)b * NP);
+    }
+    SEXP h = b200_fit_create_batch(kind, optim, lr, 0.9, 0.999, 0.0, ly, lX, lz, Nullable<List>(), li);
+    List res = b200_fit_run_batch(h, maxiter, tol);
+    const Value& it = get(res, "iter");
+    for (int b = 0; b < B; ++b) {
+      iters[b] = (int)it.num[b];
+      b200_fit_select(h, b);
+      flatten(b200_fit_get_params(h, mklist(kind, p, params)), params_out + (size_t)b * NP);
     }
     return 0;
   } catch (const std::exception& e) { g_msg = e.what(); return -1; }

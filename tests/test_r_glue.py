@@ -106,3 +106,32 @@ def test_glue_fast_path_equals_the_restated_r_loop(libs):
     assert rc == 0 and it.value == iters
     assert cs.rel(pout, parR, 1e-9) < 1e-8 and cs.rel(trace[1, 1:], traceR[1, 1:]) < 1e-9
     assert cs.relm(tmap, tmR) < 1e-8 and abs(ate.value - ateR) < 1e-8 * max(abs(ateR), 1e-3)
+
+
+def test_glue_batched_handle(libs):
+    """b200_fit_create_batch / b200_fit_run_batch / b200_fit_select / b200_fit_get_params: every member equals the
+    single-handle fast path on its own data."""
+    ref, glue = libs
+    B, n, p, iters = 3, 60, 2, 4
+    Ps = [cs.make_problem("GP", n, p, replicate=r, draws=(0.4 + 0.1 * r, 0.7)) for r in range(B)]
+    ys = np.ascontiguousarray(np.stack([P["y"] for P in Ps]))
+    Xs = np.ascontiguousarray(np.stack([np.asfortranarray(P["X"]).ravel(order="F") for P in Ps]))
+    zs = np.ascontiguousarray(np.stack([P["z"] for P in Ps]))
+    p0 = np.ascontiguousarray(np.stack([o.pack_params(P["par"]) for P in Ps]))
+    its = (C.c_int * B)()
+    pout = np.zeros_like(p0)
+    f = glue.dll.glue_fit_run_batch
+    f.restype = C.c_int
+    rc = f(0, 1, B, n, p, ys.ctypes.data_as(dp), Xs.ctypes.data_as(dp), zs.ctypes.data_as(dp), p0.ctypes.data_as(dp), C.c_double(0.01),
+           iters, C.c_double(0.0), its, pout.ctypes.data_as(dp))
+    assert rc == 0 and list(its) == [iters] * B
+    g = glue.dll.glue_fit_run
+    g.restype = C.c_int
+    for b, P in enumerate(Ps):
+        it, ate = C.c_int(0), C.c_double(0.0)
+        trace, single, dummy = np.zeros((2, iters + 2), order="F"), np.zeros_like(p0[b]), np.zeros(1)
+        Xb, w = np.asfortranarray(P["X"]), np.ones(n)
+        rc = g(0, 1, n, p, P["y"].ctypes.data_as(dp), Xb.ctypes.data_as(dp), P["z"].ctypes.data_as(dp), w.ctypes.data_as(dp),
+               p0[b].ctypes.data_as(dp), C.c_double(0.01), C.c_double(0.0), iters, C.c_double(0.0), C.byref(it), trace.ctypes.data_as(dp),
+               single.ctypes.data_as(dp), 0, dummy.ctypes.data_as(dp), dummy.ctypes.data_as(dp), C.byref(ate))
+        assert rc == 0 and cs.rel(pout[b], single, 1e-9) < 1e-9
