@@ -3,8 +3,9 @@
 // libcausalstump_b200.so (include/cs_b200.h).  Replaces src/kernel_GP_SE_cpp.cpp,
 // src/kernel_TP_SE_cpp.cpp and src/optimizer_cpp.cpp of the reference package; run
 // Rcpp::compileAttributes() to regenerate RcppExports.{R,cpp} (names and arities are
-// unchanged, four b200_* routines are added).  NOT compiled in the build image (no R /
-// Rcpp headers there) -- see INTEGRATION.md.  Only Rcpp is needed (RcppArmadillo is dropped).
+// unchanged, the b200_* routines are added).  The build image has no R / Rcpp headers: this file is
+// compiled there against oracle/shim/Rcpp.h and run next to the reference's own routines (tests/test_r_glue.py) --
+// see INTEGRATION.md.  Only Rcpp is needed (RcppArmadillo is dropped).
 #include <Rcpp.h>
 #include "cs_b200.h"
 using namespace Rcpp;
