@@ -293,7 +293,7 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
     f->eng.set_status_max(st, skip);
     f->eng.run_seq(f->eng.potrf, st, skip, true);
     if (phase_ev) rt::event_record(phase_ev[ph++], st);
-    f->eng.run_seq(f->eng.trtri, st, skip);
+    if (!f->eng.single_panel) f->eng.run_seq(f->eng.trtri, st, skip);
     if (phase_ev) rt::event_record(phase_ev[ph++], st);
     f->eng.run_seq(f->eng.xtx, st, skip);
     if (phase_ev) rt::event_record(phase_ev[ph++], st);

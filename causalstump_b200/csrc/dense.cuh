@@ -321,6 +321,7 @@ struct DenseEngine {
   int nbatch = 1;
   long long bstride = 0;
   bool external_buffers = false;  // G, X, C, logdet_part, status, Pbuf belong to the caller's slab
+  bool single_panel = false;      // one panel = the whole matrix: X = L^-1 is complete after the Cholesky plan
   bool reset_status = true;       // false while the optimisation loop runs: a non-PD pivot of ANY iteration must survive
   int panel_blocks = 4;             // outer panel width in blocks (maximum)
   std::vector<int> bounds;          // plan v2: panel boundaries in blocks (graded: narrow first and last panels)
@@ -380,6 +381,12 @@ struct DenseEngine {
     inv_pipeline = inv_pipe;
     panel_blocks = panel_width();
     n = n_; tile = tile_; N = (n + tile - 1) / tile; np = N * tile;
+    // A single small fit (the README / Hill n = 747 configurations) is bound by the latency of its launch chain, not by
+    // throughput: one panel spanning the whole matrix removes the panel / trailing-update launches, and the chain's
+    // second stream then produces the complete L^-1, so the recursive inverse is skipped (n = 672: 0.88 -> 0.70 ms per
+    // evaluation).  Batched handles keep W = 4 (measured best for throughput).
+    single_panel = nbatch == 1 && N <= 12 && N > 1 && std::getenv("CS_PANEL") == nullptr && std::getenv("CS_PLAN") == nullptr;
+    if (single_panel) panel_blocks = N;
     gt = (gemm_tile == 128 && tile == 128) ? 128 : 64;
     rr = tile / gt;
     const size_t bytes = (size_t)np * np * sizeof(double);
@@ -988,7 +995,7 @@ struct DenseEngine {
 
   // G (lower) must hold K_n; X and the upper triangle of G must be zero outside diagonal tiles.
   void factor(cudaStream_t st, const int* skip = nullptr) { set_status_max(st, skip); run_seq(potrf, st, skip, true); }
-  void invert(cudaStream_t st, const int* skip = nullptr) { run_seq(trtri, st, skip); run_seq(xtx, st, skip); }
+  void invert(cudaStream_t st, const int* skip = nullptr) { if (!single_panel) run_seq(trtri, st, skip); run_seq(xtx, st, skip); }
   // K_n (in G) -> L, L^-1, K_n^-1.  With inv_pipeline the inverse trails the factorization on its
   // own stream; X and C are accumulated into and must start from zero.
   void factor_and_invert(cudaStream_t st, const int* skip = nullptr) {
