@@ -385,7 +385,8 @@ struct DenseEngine {
     // throughput: one panel spanning the whole matrix removes the panel / trailing-update launches, and the chain's
     // second stream then produces the complete L^-1, so the recursive inverse is skipped (n = 672: 0.88 -> 0.70 ms per
     // evaluation).  Batched handles keep W = 4 (measured best for throughput).
-    single_panel = nbatch == 1 && N <= 12 && N > 1 && std::getenv("CS_PANEL") == nullptr && std::getenv("CS_PLAN") == nullptr;
+    single_panel = (nbatch == 1 || std::getenv("CS_SINGLE_PANEL") != nullptr) && N <= 12 && N > 1 && std::getenv("CS_PANEL") == nullptr &&
+                   std::getenv("CS_PLAN") == nullptr;
     if (single_panel) panel_blocks = N;
     gt = (gemm_tile == 128 && tile == 128) ? 128 : 64;
     rr = tile / gt;
