@@ -611,9 +611,10 @@ static int fit_run_begin(cs_fit* f, int maxiter, double tol) {
   f->run_launched = 0;
   f->run_chunk = f->cfg.chunk;
   if (f->run_chunk <= 0) {
-    // keep each poll interval around a few milliseconds of device work
+    // keep each poll interval around 5-10 milliseconds of device work (iterations past convergence are skipped on the
+    // device, so a longer chunk only costs launch latency, while every poll drains the handle's stream)
     const double flops = (double)f->np * f->np * f->np * B;
-    f->run_chunk = (int)std::max(1.0, std::min(64.0, 2.0e9 / std::max(flops, 1.0)));
+    f->run_chunk = (int)std::max(1.0, std::min(64.0, 4.0e10 / std::max(flops, 1.0)));
   }
   if (!f->graph_tried && f->cfg.use_graph >= 0) {
     f->graph_tried = true;

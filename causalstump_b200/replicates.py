@@ -86,7 +86,7 @@ def update_results(testindex, y_hat_all, tau_hat_all, tau_ci_all, ate_ci_train, 
 
 
 def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1e-1, lr=0.01, prior=False, nu=2000,
-                          batch=32, tile=0, covariates=None):
+                          batch=32, tile=0, covariates=None, chunk=0):
     """The same fits as `hill_unit`, but all `units` = [(replicate, restart), ...] are optimised
     together on this GPU, which is how the small n ~ 700 fits fill a B200: groups of `batch` fits share
     one batched handle (cs_fit_create_batch: every launch serves the whole group) and the groups are
@@ -127,7 +127,7 @@ def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1
         prep.append((d, nr["moments"], train, test, replicate, restart))
     t_prep = _t.perf_counter()
     if batch > 1:
-        handles = [_lib.FitBatch(lib, kind, members[i:i + batch], optim=_lib.CS_OPT_NADAM, lr=lr, tile=tile)
+        handles = [_lib.FitBatch(lib, kind, members[i:i + batch], optim=_lib.CS_OPT_NADAM, lr=lr, tile=tile, chunk=chunk)
                    for i in range(0, len(members), batch)]
         t_create = _t.perf_counter()
         res = _lib.run_many(handles, maxiter, tol)
