@@ -721,13 +721,15 @@ int cs_fit_run_many(cs_fit** fits, int nfits, int maxiter, double tol, int* iter
   for (int i = 0; i < nfits; ++i) if ((e = fit_run_begin(fits[i], maxiter, tol))) return e;
   std::vector<int> active(nfits, 1);
   int nactive = nfits;
+  // every handle is re-fed right after its own poll, so its stream never waits for the polls of the others
+  for (int i = 0; i < nfits; ++i) if ((e = fit_run_enqueue(fits[i]))) return e;
   while (nactive > 0) {
-    for (int i = 0; i < nfits; ++i) if (active[i]) { if ((e = fit_run_enqueue(fits[i]))) return e; }
     for (int i = 0; i < nfits; ++i)
       if (active[i]) {
         int fin = 0;
         if ((e = fit_run_poll(fits[i], &fin))) return e;
         if (fin) { active[i] = 0; --nactive; if ((e = fit_run_finish_enqueue(fits[i]))) return e; }
+        else if ((e = fit_run_enqueue(fits[i]))) return e;
       }
   }
   int off = 0;
