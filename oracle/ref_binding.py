@@ -55,6 +55,23 @@ def build_glue(c_abi_lib, out):
     return out
 
 
+def host_lapack():
+    """(ctypes library, description) of an LP64 LAPACK in this process: SciPy's bundled OpenBLAS (`scipy_dpotrf_`, ...)."""
+    import scipy.linalg  # noqa: F401  (loads the library)
+    from threadpoolctl import threadpool_info
+    for info in threadpool_info():
+        if info.get("user_api") != "blas":
+            continue
+        try:
+            dll = C.CDLL(info["filepath"])
+            for pre, suf in (("scipy_", "_"), ("", "_")):
+                if all(hasattr(dll, pre + f + suf) for f in ("dpotrf", "dpotri", "dgetrf")):
+                    return dll, pre, suf, "%s %s (%s)" % (info.get("internal_api"), info.get("version"), info.get("architecture"))
+        except OSError:
+            continue
+    return None
+
+
 class RefLib:
     """prefix "ref": the reference's own compiled routines; prefix "glue": the drop-in's R glue -> C ABI -> kernels."""
 
@@ -65,6 +82,32 @@ class RefLib:
             fn = getattr(self.dll, prefix + "_" + name)
             fn.restype = C.c_int
             setattr(self.dll, "ref_" + name, fn)  # the methods below call ref_*
+        self.lapack = None
+
+    def use_host_lapack(self, on=True):
+        """inv_sympd / log_det through the host LAPACK (what Armadillo links) instead of the shim's plain loops."""
+        if not on:
+            self.dll.ref_set_lapack(None, None, None)
+            self.lapack = None
+            return None
+        found = host_lapack()
+        if found is None:
+            raise RuntimeError("no LP64 LAPACK (dpotrf_/dpotri_/dgetrf_) found in this process")
+        dll, pre, suf, desc = found
+        self._lapack_dll = dll
+        ptr = [C.cast(getattr(dll, pre + f + suf), C.c_void_p) for f in ("dpotrf", "dpotri", "dgetrf")]
+        self.dll.ref_set_lapack.argtypes = [C.c_void_p] * 3
+        self.dll.ref_set_lapack.restype = None
+        self.dll.ref_set_lapack(*ptr)
+        self.lapack = desc
+        return desc
+
+    def log_det(self, A):
+        A = _f(A)
+        val, sign = C.c_double(0.0), C.c_double(0.0)
+        rc = self.dll.ref_log_det(A.shape[0], _p(A), C.byref(val), C.byref(sign))
+        assert rc == 0
+        return val.value, sign.value
 
     def kernmat(self, kind, X1, X2, Z1, Z2, Lm, La, lambdam, lambda_a):
         X1, X2, Z1, Z2, Lm, La = map(_f, (X1, X2, Z1, Z2, Lm, La))

@@ -54,6 +54,19 @@ const Rcpp::Value& get(const Rcpp::List& l, const char* name) {
 
 extern "C" {
 
+// Optional: host LAPACK for arma::inv_sympd / arma::log_det (LP64 Fortran dpotrf_, dpotri_, dgetrf_); nulls switch
+// back to the shim's plain loops.
+void ref_set_lapack(void* dpotrf, void* dpotri, void* dgetrf) {
+  arma::lapack_hook::potrf = (arma::lapack_hook::potrf_t)dpotrf;
+  arma::lapack_hook::potri = (arma::lapack_hook::potrf_t)dpotri;
+  arma::lapack_hook::getrf = (arma::lapack_hook::getrf_t)dgetrf;
+}
+
+// arma::log_det alone (the LU that grad_*_SE_cpp / stats_*_SE run on K^-1), for the bounded-sample timing of bench.py
+int ref_log_det(int n, const double* A, double* val, double* sign) {
+  try { arma::log_det(*val, *sign, mkmat(A, n, n)); return 0; } catch (const std::exception&) { return -1; }
+}
+
 int ref_kernmat(int kind, int n1, int n2, int p, const double* X1, const double* X2, const double* Z1, const double* Z2,
                 const double* Lm, const double* La, double lambdam, double lambda_a, double* K, double* Km, double* Ka) {
   try {

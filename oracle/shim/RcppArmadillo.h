@@ -13,6 +13,9 @@
 //   arma::trace(A*B)  sum_k sum_i A(k,i) B(i,k) without forming the product (Armadillo
 //                     special-cases the same way)
 //   Rcpp::List        ordered (name, value) pairs, value = numeric vector (+dims) or list
+// inv_sympd / log_det use the host's LAPACK (dpotrf + dpotri, dgetrf -- the calls Armadillo makes for them)
+// when arma::lapack_hook holds the three entry points (ref_set_lapack in oracle/ref_driver.cpp; the timing
+// legs of bench.py set it to SciPy's OpenBLAS), else the plain loops below.
 // Nothing here is shipped or linked into the product library.
 #pragma once
 #include <cmath>
@@ -166,9 +169,27 @@ inline double trace(const matprod& p) {
 }
 inline double trace(const mat& A) { double s = 0.0; for (uword i = 0; i < A.n_rows && i < A.n_cols; ++i) s += A(i, i); return s; }
 
+// LP64 Fortran entry points of the host LAPACK (optional)
+namespace lapack_hook {
+typedef void (*potrf_t)(const char* uplo, const int* n, double* a, const int* lda, int* info);
+typedef void (*getrf_t)(const int* m, const int* n, double* a, const int* lda, int* ipiv, int* info);
+inline potrf_t potrf = nullptr, potri = nullptr;
+inline getrf_t getrf = nullptr;
+}  // namespace lapack_hook
+
 // inv_sympd: A = L L^T (lower, unblocked), X = L^-1, A^-1 = X^T X
 inline mat inv_sympd(const mat& Ain) {
   const uword n = Ain.n_rows;
+  if (lapack_hook::potrf && lapack_hook::potri) {
+    mat A = Ain;
+    const int N = (int)n; int info = 0;
+    lapack_hook::potrf("L", &N, A.d.data(), &N, &info);
+    if (info != 0) throw std::runtime_error("inv_sympd(): matrix is singular or not positive definite");
+    lapack_hook::potri("L", &N, A.d.data(), &N, &info);
+    if (info != 0) throw std::runtime_error("inv_sympd(): matrix is singular or not positive definite");
+    for (uword c = 1; c < n; ++c) for (uword r = 0; r < c; ++r) A(r, c) = A(c, r);  // lower -> full
+    return A;
+  }
   mat L = Ain;
   for (uword j = 0; j < n; ++j) {
     double djj = L(j, j);
@@ -206,6 +227,20 @@ inline void log_det(double& val, double& sign, const mat& Ain) {
   const uword n = Ain.n_rows;
   mat A = Ain;
   val = 0.0; sign = 1.0;
+  if (lapack_hook::getrf) {
+    const int N = (int)n; int info = 0;
+    std::vector<int> ipiv(n);
+    lapack_hook::getrf(&N, &N, A.d.data(), &N, ipiv.data(), &info);
+    if (info < 0) throw std::runtime_error("log_det(): dgetrf failed");
+    for (uword j = 0; j < n; ++j) {
+      const double u = A(j, j);
+      if (u == 0.0) { val = -INFINITY; sign = 0.0; return; }
+      if (u < 0.0) sign = -sign;
+      if ((uword)ipiv[j] != j + 1) sign = -sign;
+      val += std::log(std::fabs(u));
+    }
+    return;
+  }
   for (uword j = 0; j < n; ++j) {
     uword piv = j; double best = std::fabs(A(j, j));
     for (uword i = j + 1; i < n; ++i) if (std::fabs(A(i, j)) > best) { best = std::fabs(A(i, j)); piv = i; }

@@ -12,6 +12,7 @@ import bench  # noqa: E402
 
 def test_reference_arm_line(monkeypatch, capsys):
     monkeypatch.setattr(bench, "cpu_eval_seconds", lambda inp, budget: (100.0, "stub sample"))
+    monkeypatch.setattr(bench, "ref_eval_seconds", lambda inp, budget: None)   # compiled reference absent -> oracle port
     monkeypatch.setattr(bench, "make_inputs", lambda n, p, r, kind="GP": {})
     args = types.SimpleNamespace(steps=2, warmup=1, gpus=4)
     assert bench.run_reference(args, rank=1, world=4) == 0 and capsys.readouterr().out == ""   # only rank 0 works and prints
@@ -24,6 +25,29 @@ def test_reference_arm_line(monkeypatch, capsys):
     assert abs(line["value"] - 0.01) < 1e-12 and line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "workload" in line["config"]
     assert line["vs_baseline"] is None and line["dtype"] == "f64" and line["higher_is_better"] is True
+
+
+def test_reference_arm_uses_the_compiled_reference(monkeypatch, capsys):
+    """with oracle/_ref present the arm times the reference's own C++ (kind "reference") and reports the port beside it"""
+    monkeypatch.setattr(bench, "cpu_eval_seconds", lambda inp, budget: (100.0, "stub port"))
+    monkeypatch.setattr(bench, "ref_eval_seconds", lambda inp, budget: (250.0, "stub reference"))
+    monkeypatch.setattr(bench, "make_inputs", lambda n, p, r, kind="GP": {})
+    assert bench.run_reference(types.SimpleNamespace(steps=2, warmup=1, gpus=1), rank=0, world=1) == 0
+    line = json.loads(capsys.readouterr().out.strip())
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "reference" and abs(line["value"] - 0.004) < 1e-12 and cb["value"] == line["value"]
+    assert abs(cb["oracle_port"]["value"] - 0.01) < 1e-12 and line["e2e"]["value"] == line["value"]
+
+
+def test_reference_timing_sample_on_a_small_case():
+    """ref_eval_seconds runs the compiled reference end to end (LAPACK hooked in) and extrapolates a positive time"""
+    import pytest
+    from oracle import ref_binding as rb
+    if not rb.available():
+        pytest.skip("oracle/_ref not built")
+    inp = bench.make_inputs(512, 25, 0)
+    secs, desc = bench.ref_eval_seconds(inp, 1.0)   # n_s = 128
+    assert secs > 0 and "n_s=128" in desc and "openblas" in desc.lower()
 
 
 def test_ours_fails_loudly_without_a_gpu():

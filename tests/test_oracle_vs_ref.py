@@ -99,3 +99,24 @@ def test_reference_inv_sympd_rejects_non_pd(ref):
         ref.invkernel(np.zeros(2), np.ones(2), A, -40.0)
     with pytest.raises(o.NotPositiveDefinite):
         o.invkernel_cpp(np.zeros(2), np.ones(2), A, dict(sigma=-40.0))
+
+
+def test_host_lapack_hook_matches_the_plain_loops(ref):
+    """inv_sympd / log_det through the host LAPACK (dpotrf + dpotri, dgetrf: the calls Armadillo makes; used by the
+    timing legs of bench.py) give the same routine outputs as the shim's plain loops, and still reject non-PD input."""
+    P = cs.make_problem("GP", 211, 7)
+    par, y, X, z, w = P["par"], P["y"], P["X"], P["z"], P["w"]
+    flat = o.pack_params(par)
+    try:
+        g0, st0, mu0, m0 = ref.eval_lml_grad(0, y, X, z, w, flat)
+        ld0 = ref.log_det(m0["invK"])
+        assert "openblas" in ref.use_host_lapack().lower()
+        g1, st1, mu1, m1 = ref.eval_lml_grad(0, y, X, z, w, flat)
+        ld1 = ref.log_det(m1["invK"])
+        assert np.allclose(m1["invK"], m0["invK"], rtol=1e-9, atol=1e-11 * np.abs(m0["invK"]).max())
+        assert np.allclose(g1, g0, rtol=1e-8, atol=1e-10) and np.allclose(st1, st0, rtol=1e-10)
+        assert abs(mu1 - mu0) <= 1e-9 * max(1.0, abs(mu0)) and ld1[1] == ld0[1] and abs(ld1[0] - ld0[0]) <= 1e-9 * abs(ld0[0])
+        with pytest.raises(np.linalg.LinAlgError):
+            ref.invkernel(np.zeros(2), np.ones(2), np.array([[1.0, 2.0], [2.0, 1.0]]), -40.0)
+    finally:
+        ref.use_host_lapack(False)
