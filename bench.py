@@ -545,6 +545,32 @@ def run_ours(args, rank, world, local_rank):
         fits_obj["cpu_port"] = {"seconds_per_iteration": sec_it, "fits_per_hour_one_process": 3600.0 / (sec_it * fits_obj["iterations_mean"]),
                                 "cores": host_threads(),
                                 "what": "oracle port of para_update at n=672, p=25 (reference-faithful), scaled by iterations_mean"}
+        from oracle import ref_binding as rb
+        if rb.available():
+            # the same iteration by the reference's own compiled routines, chained as para_update chains them:
+            # kernmat + invkernel, grad, optimizer step, mu, then kernmat + invkernel + stats again (:48-58)
+            ref = rb.RefLib()
+            ref.use_host_lapack()
+            par, ys, Xs, zs, ws = sinp["par"], sinp["y"], sinp["X"], sinp["z"], sinp["w"]
+            flat = np.array(sinp["params"], dtype=np.float64)
+            t0 = time.perf_counter()
+            reps = 2
+            for it in range(reps):
+                for second in (False, True):
+                    Kr, Kmr, Kar = ref.kernmat(0, Xs, Xs, zs, zs, par["Lm"], par["La"], par["lambdam"], par["lambdaa"])
+                    invr = ref.invkernel(zs, ws, Kr, par["sigma"])
+                    if not second:
+                        gr, _ = ref.grad(0, ys, Xs, zs, ws, Kr, Kmr, Kar, invr, flat)
+                        ref.opt_step(1, 0, P_METRIC, it + 1.0, 0.01, 0.9, 0.999, 1e-8, np.zeros_like(flat), np.zeros_like(flat), gr, flat)
+                        ref.mu_solution(ys, zs, invr)
+                    else:
+                        ref.stats(0, P_METRIC, ys, Kr, invr, flat)
+            sec_ref = (time.perf_counter() - t0) / reps
+            fits_obj["cpu_reference"] = {"seconds_per_iteration": sec_ref,
+                                         "fits_per_hour_one_process": 3600.0 / (sec_ref * fits_obj["iterations_mean"]),
+                                         "cores": host_threads(),
+                                         "what": "the reference's own C++ routines (oracle/_ref, host LAPACK) chained as one para_update "
+                                                 "iteration at n=672, p=25, scaled by iterations_mean"}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
