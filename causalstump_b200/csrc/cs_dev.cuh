@@ -54,6 +54,29 @@ __device__ __forceinline__ void cp_async_wait() {
 #endif
 }
 
+// Streaming 8-byte load whose position in the instruction stream is kept (asm volatile): lets a loop put a batch of
+// independent loads in flight before the first use, where the scheduler would otherwise pair each load with its FMA.
+__device__ __forceinline__ double ld_stream(const double* p) {
+#ifdef CS_EMU
+  return *p;
+#else
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+#endif
+}
+
+__device__ __forceinline__ double2 ld_stream2(const double* p) {  // 16-byte aligned pair
+#ifdef CS_EMU
+  double2 v; v.x = p[0]; v.y = p[1];
+  return v;
+#else
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+#endif
+}
+
 // Batched launches (cs_fit_create_batch): every per-fit device buffer sits at the same offset of a
 // per-fit slab, so one launch serves B fits with blockIdx.z selecting the slab (bstride bytes apart).
 template <class T>

@@ -202,7 +202,8 @@ gram_cross_kernel(const double* __restrict__ X1, long long ldx1, const double* _
 
 // ---------------------------------------------------------------------------------
 // Mat-vec panel: out_part[split][k][r] = sum_{c in split} A[r,c] * v_k[c], k < NV.
-// A is rows x cols column-major (ld), rows/cols multiples of 64; CTA = 64 rows x 4 lanes.
+// A is rows x cols column-major (ld), rows/cols multiples of 64, 16-byte aligned; CTA = 64 rows as 32 row pairs
+// (one 16-byte load each) x 8 column lanes.
 // ---------------------------------------------------------------------------------
 template <int NV>
 __global__ void __launch_bounds__(ETH)
@@ -214,28 +215,41 @@ matvec_kernel(const double* __restrict__ A, long long ld, int cols_per_split, in
   if (skip && *skip) return;
   A = csd::bshift(A, bstride); v0 = csd::bshift(v0, bstride); v1 = csd::bshift(v1, bstride); v2 = csd::bshift(v2, bstride);
   shift0 = csd::bshift(shift0, bstride); out_part = csd::bshift(out_part, bstride);
-  __shared__ double red[3][4][TB];
+  constexpr int CL = 8;  // column lanes
+  __shared__ double red[3][CL][TB];
   const double sh = shift0 ? *shift0 : 0.0;  // v0 is used as (v0 - *shift0): ybar = y - mu
-  const int tid = threadIdx.x, rl = tid & 63, cl = tid >> 6;
-  const int r = (int)blockIdx.x * TB + rl;
+  const int tid = threadIdx.x, rp = tid & 31, cl = tid >> 5;
+  const double* Ar = A + (int)blockIdx.x * TB + 2 * rp;
   const int cbeg = (int)blockIdx.y * cols_per_split;
   int cend = cbeg + cols_per_split;
   if (cend > cols) cend = cols;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-  for (int c = cbeg + cl; c < cend; c += 4) {
-    const double a = A[(long long)c * ld + r];
-    s0 = fma(a, v0[c] - sh, s0);
-    if (NV > 1) s1 = fma(a, v1[c], s1);
-    if (NV > 2) s2 = fma(a, v2[c], s2);
+  double s0x = 0.0, s0y = 0.0, s1x = 0.0, s1y = 0.0, s2x = 0.0, s2y = 0.0;
+  auto use = [&](double2 a, int cc) {
+    const double w0 = v0[cc] - sh;
+    s0x = fma(a.x, w0, s0x); s0y = fma(a.y, w0, s0y);
+    if (NV > 1) { const double w1 = v1[cc]; s1x = fma(a.x, w1, s1x); s1y = fma(a.y, w1, s1y); }
+    if (NV > 2) { const double w2 = v2[cc]; s2x = fma(a.x, w2, s2x); s2y = fma(a.y, w2, s2y); }
+  };
+  int c = cbeg + cl;
+  // four 16-byte matrix loads are requested before the first one is used: with one load in flight per thread the
+  // pass is bound by HBM latency, not bandwidth
+  for (; c + 3 * CL < cend; c += 4 * CL) {
+    double2 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = csd::ld_stream2(Ar + (long long)(c + CL * u) * ld);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) use(a[u], c + CL * u);
   }
-  red[0][cl][rl] = s0;
-  if (NV > 1) red[1][cl][rl] = s1;
-  if (NV > 2) red[2][cl][rl] = s2;
+  for (; c < cend; c += CL) use(csd::ld_stream2(Ar + (long long)c * ld), c);
+  red[0][cl][2 * rp] = s0x; red[0][cl][2 * rp + 1] = s0y;
+  if (NV > 1) { red[1][cl][2 * rp] = s1x; red[1][cl][2 * rp + 1] = s1y; }
+  if (NV > 2) { red[2][cl][2 * rp] = s2x; red[2][cl][2 * rp + 1] = s2y; }
   __syncthreads();
   if (tid < TB) {
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      const double s = (red[k][0][tid] + red[k][1][tid]) + (red[k][2][tid] + red[k][3][tid]);
+      const double s = ((red[k][0][tid] + red[k][1][tid]) + (red[k][2][tid] + red[k][3][tid])) +
+                       ((red[k][4][tid] + red[k][5][tid]) + (red[k][6][tid] + red[k][7][tid]));
       out_part[(long long)blockIdx.y * out_stride_split + k * out_stride_k + (int)blockIdx.x * TB + tid] = s;
     }
   }

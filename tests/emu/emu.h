@@ -16,6 +16,7 @@
 #include <functional>
 
 struct emu_uint3 { unsigned x, y, z; };
+struct alignas(16) double2 { double x, y; };
 struct dim3 {
   unsigned x, y, z;
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
