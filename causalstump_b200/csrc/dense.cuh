@@ -275,10 +275,20 @@ inline void launch_gemm_t(int kind, const GemmProblem* dprobs, int nprob, int nt
   }
 }
 
+// 32 x 32 CTA tiles (NT only): four times the CTAs of a 64-tile launch, for the two small multiplies the Cholesky chain
+// waits for at every panel boundary -- they share their SMs with resident bulk CTAs, so their latency is set by how
+// thinly they spread, not by per-CTA efficiency
+inline void launch_gemm_32(const GemmProblem* dprobs, int nprob, int ntiles_, cudaStream_t st, const int* skip, int nbatch) {
+  if (ntiles_ <= 0) return;
+  auto k = csg::gemm_kernel<32, 2, 2, false, false, 16, 3>;
+  CS_LAUNCH(k, dim3(ntiles_, 1, nbatch), 128, (csg::gemm_smem_bytes<32, false, false, 16, 3>()), st, dprobs, nprob, skip);
+}
+
 inline void launch_gemm(int tile, int kind, const GemmProblem* dprobs, int nprob, int ntiles, cudaStream_t st,
                         const int* skip = nullptr, int nbatch = 1) {
   ++g_launches;
-  if (tile == 128) launch_gemm_t<128>(kind, dprobs, nprob, ntiles, st, skip, nbatch);
+  if (tile == 32 && kind == GK_NT) launch_gemm_32(dprobs, nprob, ntiles, st, skip, nbatch);
+  else if (tile == 128) launch_gemm_t<128>(kind, dprobs, nprob, ntiles, st, skip, nbatch);
   else launch_gemm_t<64>(kind, dprobs, nprob, ntiles, st, skip, nbatch);
 }
 
@@ -317,6 +327,11 @@ struct DenseEngine {
   std::vector<Launch> potrf_inv;    // Cholesky with the inverse pipelined behind it (inv_pipeline)
   int inv_pipeline = 0;
   int plan_version = 2;
+  int tail_a_max = 0, tail_from = 0;                 // tile columns of K^-1 accumulated on the chain stream after the chain (0 = off): tail_a_max from panel tail_from on, one fewer before
+  struct TailPiece { int ev_rows, ev_prev; std::vector<GemmProblem> probs; };
+  std::vector<TailPiece> tail_pieces;
+  bool split_u2b = false;                            // look-ahead of depth three: U2b-rest on its own stream S7
+  bool top32 = false;                                // Ltop / U1top with 32 x 32 CTA tiles (tile 128 plans of single fits)
   // batched engine (cs_fit_create_batch): nbatch fits share the plan; their buffers are bstride bytes apart
   int nbatch = 1;
   long long bstride = 0;
@@ -327,8 +342,8 @@ struct DenseEngine {
   std::vector<int> bounds;          // plan v2: panel boundaries in blocks (graded: narrow first and last panels)
   int n_events = 0;
   std::vector<cudaEvent_t> events;
-  cudaStream_t aux{}, aux2{}, aux3{}, aux4{}, aux5{}, aux6{};  // S6: second chain stream (X_PP), partition A;  // S4: K^-1 accumulation (lowest); S5: Acc rows below the next panel; S1: bulk trailing updates (low); S2: panel rest (high); S3: pipelined inverse (low)
-  bool aux_ok = false, aux2_ok = false, aux3_ok = false, aux4_ok = false, aux5_ok = false, aux6_ok = false;
+  cudaStream_t aux{}, aux2{}, aux3{}, aux4{}, aux5{}, aux6{}, aux7{};  // S7: U2b-rest (bulk trailing update behind the look-ahead);  // S6: second chain stream (X_PP), partition A;  // S4: K^-1 accumulation (lowest); S5: Acc rows below the next panel; S1: bulk trailing updates (low); S2: panel rest (high); S3: pipelined inverse (low)
+  bool aux_ok = false, aux2_ok = false, aux3_ok = false, aux4_ok = false, aux5_ok = false, aux6_ok = false, aux7_ok = false;
   // SM partition (rt::partition_streams): the critical chain of the Cholesky (leaf + one-tile GEMMs, plan
   // stream 0) runs on `crit`, a stream of the small partition A; S1..S3 live on partition B.
   cudaStream_t crit{};
@@ -592,7 +607,7 @@ struct DenseEngine {
       Launch o{}; o.is_leaf = OP_COPY; o.stream = stream; o.cp_dst = dst; o.cp_src = src; o.cp_rows = rows; o.cp_cols = cols;
       o.cp_ldd = ldd; o.cp_lds = lds; seq.push_back(o);
     };
-    int last_aux_ev = -1, last_inv_ev = -1, last_inv3_ev = -1, last_rest_ev = -1, ev_u1top_prev = -1, last_s6_ev = -1, last_u2b_ev = -1;
+    int last_aux_ev = -1, last_inv_ev = -1, last_inv3_ev = -1, last_rest_ev = -1, ev_u1top_prev = -1, last_s6_ev = -1, last_u2b_ev = -1, last_u2brest_ev = -1;
     auto push_panel = [&](int k, int r0, int nb, int stream) {  // in-place L = A X_kk^T for nb block rows of column k
       if (nb <= 0) return;
       double* pan = G + (long long)r0 * T + (long long)k * T * ld;
@@ -612,6 +627,7 @@ struct DenseEngine {
       const int pw = p1 - p0;
       const int w_next = pi + 2 < bounds.size() ? bounds[pi + 2] - bounds[pi + 1] : 0;   // width of the next panel
       const int w_next2 = pi + 3 < bounds.size() ? bounds[pi + 3] - bounds[pi + 2] : 0;  // and of the one after
+      const int w_next3 = pi + 4 < bounds.size() ? bounds[pi + 4] - bounds[pi + 3] : 0;  // and of the third ahead
       double* Xpp = X + (long long)p0 * T * (ld + 1);   // diagonal block of X = inverse of the diagonal block of L
       // ---- D(P) on the chain (S0): factor the diagonal block; S6 builds the off-diagonal tiles of X_PP
       if (ev_u1top_prev >= 0) op(OP_WAIT, 0, ev_u1top_prev);
@@ -651,22 +667,27 @@ struct DenseEngine {
         const long long kw = (long long)pw * tile;
         double* pan = G + (long long)p1 * T + (long long)p0 * T * ld;
         op(OP_WAIT, 2, ev_xpp);
-        auto lmul = [&](int r0, int nb_rows) {
+        // the two multiplies the chain waits for (Ltop, U1top) use 32 x 32 CTA tiles when the plan tile is 128
+        const int qf = (top32 && tile % 32 == 0) ? tile / 32 : rr;
+        auto lmul = [&](int r0, int nb_rows, bool fine) {
           double* src = G + (long long)r0 * T + (long long)p0 * T * ld;
           double* dst = Pbuf + (long long)r0 * T;
-          grp.push_back(mk(src, ld, Xpp, ld, dst, ld, nb_rows * rr, pw * rr, (int)kw, csg::KM_LE_J, csg::ORD_COL, 0, 1.0, 0.0));
+          const int q = fine ? qf : rr;
+          grp.push_back(mk(src, ld, Xpp, ld, dst, ld, nb_rows * q, pw * q, (int)kw, csg::KM_LE_J, csg::ORD_COL, 0, 1.0, 0.0));
           add_group(seq, GK_NT, grp); seq.back().stream = 2;
+          if (fine && qf != rr) seq.back().gtile = 32;
           copy_op(2, src, ld, dst, ld, (long long)nb_rows * tile, kw);
         };
-        lmul(p1, n1);
+        lmul(p1, n1, true);
         // U1top: next diagonal block (lower tiles), K = panel width
         if (last_aux_ev >= 0) op(OP_WAIT, 2, last_aux_ev);  // U2 of the previous panel also wrote these columns
-        grp.push_back(mk(pan, ld, pan, ld, G + (long long)p1 * T * (ld + 1), ld, n1 * rr, n1 * rr, (int)kw, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
+        grp.push_back(mk(pan, ld, pan, ld, G + (long long)p1 * T * (ld + 1), ld, n1 * qf, n1 * qf, (int)kw, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
         add_group(seq, GK_NT, grp); seq.back().stream = 2;
+        if (qf != rr) seq.back().gtile = 32;
         ev_u1top_prev = nev++;
         op(OP_RECORD, 2, ev_u1top_prev);
         if (mt > n1) {
-          lmul(p1 + n1, mt - n1);
+          lmul(p1 + n1, mt - n1, false);
           // U1rest: rectangle below the next diagonal block (next panel's columns)
           grp.push_back(mk(pan + (long long)n1 * T, ld, pan, ld, G + (long long)(p1 + n1) * T + (long long)p1 * T * ld, ld, (mt - n1) * rr, n1 * rr, (int)kw,
                            csg::KM_FULL, csg::ORD_COL, 0, -1.0, 1.0));
@@ -689,11 +710,32 @@ struct DenseEngine {
           last_aux_ev = nev++;
           op(OP_RECORD, 1, last_aux_ev);
           if (m2 > n2) {
+            // U2b.  Look-ahead of depth three: the columns of the third panel ahead (U2b-first) stay on S1, the rest
+            // (U2b-rest) goes to S7.  U2a of the NEXT panel touches exactly the tiles of U2b-first, so it no longer
+            // queues behind the whole trailing update of this panel (which cost the chain ~190 us per boundary).
+            const int m3 = m2 - n2;
+            const int n3 = split_u2b ? w_next3 : 0;
             double* pan3 = pan2 + (long long)n2 * T;
-            grp.push_back(mk(pan3, ld, pan3, ld, D2 + (long long)n2 * T * (ld + 1), ld, (m2 - n2) * rr, (m2 - n2) * rr, (int)kw, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
-            add_group(seq, GK_NT, grp); seq.back().stream = 1;
-            last_u2b_ev = nev++;
-            op(OP_RECORD, 1, last_u2b_ev);
+            double* D3 = D2 + (long long)n2 * T * (ld + 1);
+            if (last_u2brest_ev >= 0) op(OP_WAIT, 1, last_u2brest_ev);  // U2b-rest of the previous panel wrote these columns
+            if (n3 > 0 && m3 > n3) {
+              grp.push_back(mk(pan3, ld, pan3, ld, D3, ld, n3 * rr, n3 * rr, (int)kw, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
+              grp.push_back(mk(pan3 + (long long)n3 * T, ld, pan3, ld, D3 + (long long)n3 * T, ld, (m3 - n3) * rr, n3 * rr, (int)kw, csg::KM_FULL, csg::ORD_COL, 0, -1.0, 1.0));
+              add_group(seq, GK_NT, grp); seq.back().stream = 1;
+              last_u2b_ev = nev++;
+              op(OP_RECORD, 1, last_u2b_ev);
+              double* pan4 = pan3 + (long long)n3 * T;
+              op(OP_WAIT, 7, ev_lpanel);
+              grp.push_back(mk(pan4, ld, pan4, ld, D3 + (long long)n3 * T * (ld + 1), ld, (m3 - n3) * rr, (m3 - n3) * rr, (int)kw, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
+              add_group(seq, GK_NT, grp); seq.back().stream = 7;
+              last_u2brest_ev = nev++;
+              op(OP_RECORD, 7, last_u2brest_ev);
+            } else {
+              grp.push_back(mk(pan3, ld, pan3, ld, D3, ld, m3 * rr, m3 * rr, (int)kw, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
+              add_group(seq, GK_NT, grp); seq.back().stream = 1;
+              last_u2b_ev = nev++;
+              op(OP_RECORD, 1, last_u2b_ev);
+            }
           }
         }
       }
@@ -713,7 +755,23 @@ struct DenseEngine {
         {  // S4: C_IJ += sum_{k in P} X_kI^T X_kJ  (mirrored store keeps C symmetric)
           double* Xp = X + (long long)p0 * T;
           if (p0 > 0) {
-            grp.push_back(mk(Xp, ld, Xp, ld, C, ld, p0 * rr, p0 * rr, pw * tile, csg::KM_FULL, csg::ORD_LOWER, 1, 1.0, 1.0));
+            const int m1 = p0 * rr;
+            const int tail_a = (int)pi >= tail_from ? tail_a_max : tail_a_max - 1;  // nondecreasing in the panel index
+            if (tail_a > 0 && m1 > tail_a) {
+              // The first tail_a tile columns of the leading square belong to the chain stream (partition A, idle once
+              // the Cholesky is done): their accumulations are queued behind the last leaf (emitted after the panel loop).
+              const long long o = (long long)tail_a * gt;
+              TailPiece tp;
+              tp.ev_rows = ev_rows; tp.ev_prev = last_inv_ev;
+              tp.probs.push_back(mk(Xp, ld, Xp, ld, C, ld, tail_a, tail_a, pw * tile, csg::KM_FULL, csg::ORD_LOWER, 1, 1.0, 1.0));
+              GemmProblem r = mk(Xp + o * ld, ld, Xp, ld, C + o, ld, m1 - tail_a, tail_a, pw * tile, csg::KM_FULL, csg::ORD_COL, 2, 1.0, 1.0);
+              r.Cm = C + o * ld;
+              tp.probs.push_back(r);
+              tail_pieces.push_back(tp);
+              grp.push_back(mk(Xp + o * ld, ld, Xp + o * ld, ld, C + o * (ld + 1), ld, m1 - tail_a, m1 - tail_a, pw * tile, csg::KM_FULL, csg::ORD_LOWER, 1, 1.0, 1.0));
+            } else {
+              grp.push_back(mk(Xp, ld, Xp, ld, C, ld, m1, m1, pw * tile, csg::KM_FULL, csg::ORD_LOWER, 1, 1.0, 1.0));
+            }
             // rows P of K^-1 are touched for the first time here: beta = 0 (no memset of C per evaluation)
             GemmProblem q = mk(Xpp, ld, Xp, ld, C + (long long)p0 * T, ld, pw * rr, p0 * rr, pw * tile, csg::KM_GE_I, csg::ORD_COL, 2, 1.0, 0.0);
             q.Cm = C + (long long)p0 * T * ld;
@@ -749,12 +807,30 @@ struct DenseEngine {
         }
       }
     }
+    // share of the K^-1 accumulation that runs on the chain stream once the chain is done, in panel order
+    for (TailPiece& tp : tail_pieces) {
+      op(OP_WAIT, 0, tp.ev_rows);
+      if (tp.ev_prev >= 0) op(OP_WAIT, 0, tp.ev_prev);
+      for (auto& q : tp.probs) grp.push_back(q);
+      add_group(seq, GK_TN, grp);
+    }
+    tail_pieces.clear();
     // the chain stream rejoins every other stream before anything reads the results
-    for (int ev : {last_aux_ev, last_u2b_ev, last_inv_ev, last_inv3_ev, last_rest_ev, last_s6_ev, ev_u1top_prev})
+    for (int ev : {last_aux_ev, last_u2b_ev, last_u2brest_ev, last_inv_ev, last_inv3_ev, last_rest_ev, last_s6_ev, ev_u1top_prev})
       if (ev >= 0) op(OP_WAIT, 0, ev);
     };
     plan_version = 2;
     if (const char* pv = std::getenv("CS_PLAN")) plan_version = std::atoi(pv);
+    top32 = tile == 128 && gt == 64 && nbatch == 1 && !std::getenv("CS_NO_TOP32");
+    split_u2b = nbatch == 1 && !std::getenv("CS_NO_U2B_SPLIT");
+    tail_a_max = (nbatch == 1 && np >= 4096) ? 3 : 0;
+    tail_from = (N / W) / 2;
+    if (const char* ta = std::getenv("CS_TAIL_A")) {
+      int a = 0, f = 0;
+      const int got = std::sscanf(ta, "%d,%d", &a, &f);
+      tail_a_max = nbatch == 1 ? a : 0;
+      tail_from = got > 1 ? f : 0;
+    }
     {
       // Panel widths: uniform W by default.  CS_GRADED=1 selects a narrow first panel (the bulk streams start after
       // two leaves instead of four) and narrow last panels (a shorter tail); measured on the B200 at n = 8192 it is
@@ -824,11 +900,11 @@ struct DenseEngine {
     const bool want_part = partition > 0 || (partition == 0 && np >= 4096 && !under_ncu && std::getenv("CS_NO_PARTITION") == nullptr);
     // priorities: S2 (panel work the Cholesky chain waits for) highest, then S3 (row chain of the inverse),
     // S1 (trailing update), then S5 (Acc of the rows below the next panel) and S4 (K^-1 accumulation) lowest
-    cudaStream_t* bulk[5] = {&aux, &aux2, &aux3, &aux4, &aux5};
-    int level[5] = {2, 0, 1, 5, 5};  // 0 = highest (swept on the B200: tools/gpu_sweep.sh)
-    if (const char* ev = std::getenv("CS_PRIO")) std::sscanf(ev, "%d,%d,%d,%d,%d", &level[0], &level[1], &level[2], &level[3], &level[4]);
-    if (want_part && rt::partition_streams(8, &crit, &aux6, bulk, level, 5, &sm_crit, &sm_bulk) == 0) {
-      crit_ok = aux_ok = aux2_ok = aux3_ok = aux4_ok = aux5_ok = aux6_ok = true;
+    cudaStream_t* bulk[6] = {&aux, &aux2, &aux3, &aux4, &aux5, &aux7};
+    int level[6] = {2, 0, 1, 5, 5, 3};  // 0 = highest (swept on the B200: tools/gpu_sweep.sh); last: S7
+    if (const char* ev = std::getenv("CS_PRIO")) std::sscanf(ev, "%d,%d,%d,%d,%d,%d", &level[0], &level[1], &level[2], &level[3], &level[4], &level[5]);
+    if (want_part && rt::partition_streams(8, &crit, &aux6, bulk, level, 6, &sm_crit, &sm_bulk) == 0) {
+      crit_ok = aux_ok = aux2_ok = aux3_ok = aux4_ok = aux5_ok = aux6_ok = aux7_ok = true;
       if ((e = rt::event_create_fast(&ev_in))) return e;
       if ((e = rt::event_create_fast(&ev_out))) return e;
     } else {
@@ -844,6 +920,8 @@ struct DenseEngine {
       aux5_ok = true;
       if ((e = rt::stream_create_level(&aux6, 0))) return e;
       aux6_ok = true;
+      if ((e = rt::stream_create_level(&aux7, level[5]))) return e;
+      aux7_ok = true;
     }
     if ((e = rt::event_create_fast(&ev_gram))) return e;
     ev_gram_ok = true;
@@ -872,6 +950,7 @@ struct DenseEngine {
     if (aux4_ok) { rt::stream_sync(aux4); rt::stream_destroy(aux4); aux4_ok = false; }
     if (aux5_ok) { rt::stream_sync(aux5); rt::stream_destroy(aux5); aux5_ok = false; }
     if (aux6_ok) { rt::stream_sync(aux6); rt::stream_destroy(aux6); aux6_ok = false; }
+    if (aux7_ok) { rt::stream_sync(aux7); rt::stream_destroy(aux7); aux7_ok = false; }
     if (crit_ok) { rt::stream_sync(crit); rt::stream_destroy(crit); rt::event_destroy(ev_in); rt::event_destroy(ev_out); crit_ok = false; }
     G = X = C = logdet_part = nullptr; status = nullptr; d_probs = nullptr;
   }
@@ -891,7 +970,7 @@ struct DenseEngine {
       s0 = crit;
     }
     for (const Launch& L : seq) {
-      cudaStream_t s = L.stream == 1 ? aux : (L.stream == 2 ? aux2 : (L.stream == 3 ? aux3 : (L.stream == 4 ? aux4 : (L.stream == 5 ? aux5 : (L.stream == 6 ? aux6 : s0)))));
+      cudaStream_t s = L.stream == 1 ? aux : (L.stream == 2 ? aux2 : (L.stream == 3 ? aux3 : (L.stream == 4 ? aux4 : (L.stream == 5 ? aux5 : (L.stream == 6 ? aux6 : (L.stream == 7 ? aux7 : s0))))));
       const bool timed = tl && (L.is_leaf == OP_LEAF || L.is_leaf == OP_GEMM || L.is_leaf == OP_COPY);
       if (timed) { cudaEvent_t e0; rt::event_create(&e0); rt::event_record(e0, s); tl->push_back(e0); }
       if (L.is_leaf == OP_LEAF) {
@@ -963,7 +1042,7 @@ struct DenseEngine {
     const int n_ops = (int)seq.size();
     const int words = (n_ops + 63) / 64;
     std::vector<std::vector<unsigned long long>> anc(n_ops, std::vector<unsigned long long>(words, 0ULL));
-    int last_on_stream[7] = {-1, -1, -1, -1, -1, -1, -1};
+    int last_on_stream[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
     std::vector<int> last_record(n_events + 1, -1);
     auto add_pred = [&](int j, int i) {
       if (i < 0) return;

@@ -77,6 +77,33 @@ def test_multistream_cholesky_plan_has_no_races(emulib, n, tile, gt):
     assert emulib.dll.cs_debug_check_plan(n, tile, gt, 1) == 0
 
 
+@pytest.mark.parametrize("tail", ["3,2"])
+def test_chain_stream_takes_a_share_of_the_inverse(emulib, monkeypatch, tail):
+    """Large single fits (n >= 4096) give the first tile columns of the K^-1 accumulation to the chain stream once the
+    Cholesky is done (CS_TAIL_A, default 3 from the middle panel on) and split the trailing update over two streams
+    (look-ahead of depth three); forced here at a size the emulator handles.  Tile ownership is static, so the result
+    is bitwise the one of the plain plan."""
+    P = cs.make_problem("GP", 1100, 3)
+    p0 = o.pack_params(P["par"])
+    for t in ("2", tail):
+        monkeypatch.setenv("CS_TAIL_A", t)
+        assert emulib.dll.cs_debug_check_plan(3000, 128, 64, 1) == 0
+    monkeypatch.setenv("CS_TAIL_A", tail)
+    assert emulib.dll.cs_debug_check_plan(1536, 128, 64, 1) == 0 and emulib.dll.cs_debug_check_plan(2048, 128, 64, 1) == 0
+    f = _lib.Fit(emulib, 0, P["y"], P["X"], P["z"], P["w"], p0, tile=128, inv_pipeline=1)
+    g1, st1, mu1 = f.eval()
+    f.close()
+    monkeypatch.setenv("CS_TAIL_A", "0")
+    monkeypatch.setenv("CS_NO_U2B_SPLIT", "1")
+    monkeypatch.setenv("CS_NO_TOP32", "1")
+    f = _lib.Fit(emulib, 0, P["y"], P["X"], P["z"], P["w"], p0, tile=128, inv_pipeline=1)
+    g0, st0, mu0 = f.eval()
+    f.close()
+    assert np.array_equal(g1, g0) and np.array_equal(st1, st0) and mu1 == mu0
+    g, st, mu = o.eval_lml_grad("GP", P["y"], P["X"], P["z"], P["w"], P["par"])
+    assert cs.rel(g1, o.pack_params(g), 1e-9) < cs.TOL_GRAD and abs(st1[1] - st[1]) < cs.TOL_LML * abs(st[1])
+
+
 def test_concurrent_fits_match_sequential(emulib):
     Ps = [cs.make_problem("GP", 90, 3, replicate=r) for r in range(3)]
     fits = [_lib.Fit(emulib, 0, P["y"], P["X"], P["z"], P["w"], o.pack_params(P["par"]), chunk=2) for P in Ps]

@@ -35,7 +35,7 @@ def main():
         np.savetxt(a.out, tl, fmt="%.4f", delimiter=",", header="stream,type,tiles,K_or_blk,t0_ms,t1_ms")
     end = tl[:, 5].max()
     print("launches %d, span %.3f ms" % (len(tl), end))
-    for s in range(7):
+    for s in range(8):
         m = tl[:, 0] == s
         if not m.any():
             continue
