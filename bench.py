@@ -406,7 +406,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- per-phase device times and the roofline of the dominant kernel ----
     # `phases` comes from the plan that was timed above.  With the pipelined plan the three dense
-    # phases overlap on four streams (their total is reported under "potrf"), so the per-launch
+    # phases overlap on eight streams (their total is reported under "potrf"), so the per-launch
     # duration of the dominant kernel is measured on a second handle that runs the same kernels
     # back to back on one stream (inv_pipeline=0): K^-1 = X^T X there is ONE launch.
     phases = None
@@ -447,7 +447,7 @@ def run_ours(args, rank, world, local_rank):
         line_extra["roofline_dense_path"] = {
             "what": "Cholesky + triangular inverse + X^T X of the plan timed in `value` (n^3 algorithmic flops, every launch "
                     "an instance of csg::gemm_kernel or the leaf kernel; %s)" %
-                    ("inverse pipelined behind the Cholesky on 4 streams" if args.inv_pipeline else "phases back to back"),
+                    ("inverse pipelined behind the Cholesky on 8 streams (look-ahead of depth three, chain on its own SM partition)" if args.inv_pipeline else "phases back to back"),
             "bound": "tensor", "achieved": dense_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": dense_tflops / fp64_peak, "ms": dense_ms,
         }
