@@ -823,14 +823,6 @@ struct DenseEngine {
     if (const char* pv = std::getenv("CS_PLAN")) plan_version = std::atoi(pv);
     top32 = tile == 128 && gt == 64 && nbatch == 1 && !std::getenv("CS_NO_TOP32");
     split_u2b = nbatch == 1 && !std::getenv("CS_NO_U2B_SPLIT");
-    tail_a_max = (nbatch == 1 && np >= 4096) ? 3 : 0;
-    tail_from = (N / W) / 2;
-    if (const char* ta = std::getenv("CS_TAIL_A")) {
-      int a = 0, f = 0;
-      const int got = std::sscanf(ta, "%d,%d", &a, &f);
-      tail_a_max = nbatch == 1 ? a : 0;
-      tail_from = got > 1 ? f : 0;
-    }
     {
       // Panel widths: uniform W by default.  CS_GRADED=1 selects a narrow first panel (the bulk streams start after
       // two leaves instead of four) and narrow last panels (a shorter tail); measured on the B200 at n = 8192 it is
@@ -859,6 +851,28 @@ struct DenseEngine {
       } else {
         for (int pos = W; pos < N; pos += W) bounds.push_back(pos);
         bounds.push_back(N);
+      }
+    }
+    {
+      // Tail share of the chain partition (plan v2, single fits): once the chain of N leaves is done (about 186 us per
+      // leaf step on the B200) its 8 SMs are idle until the bulk streams finish (about np^3 flops at 28 TFLOP/s), and
+      // in that window they accumulate about 1.6 TFLOP/s of K^-1 tiles.  One tile column costs
+      // 2 * gt * tile^2 * sum_P p0 * pw flops over the run.  n = 8192: 3 columns (measured: 2 -> 19.72, 3 -> 19.60,
+      // 4 -> 21.2 ms, the chain partition becomes the last to finish); n <= 6144: chain-bound, no share.
+      tail_a_max = 0;
+      tail_from = ((int)bounds.size() - 1) / 2;
+      if (nbatch == 1 && np >= 4096) {
+        double sum = 0.0;
+        for (size_t pi = 0; pi + 1 < bounds.size(); ++pi) sum += (double)bounds[pi] * (bounds[pi + 1] - bounds[pi]);
+        const double window = (double)np * np * np / 28.0e12 - (double)N * 186e-6;
+        const double per_col = 2.0 * gt * (double)tile * tile * sum;
+        if (window > 0.0 && per_col > 0.0) tail_a_max = std::min((int)(window * 1.6e12 / per_col), N * rr / 8);
+      }
+      if (const char* ta = std::getenv("CS_TAIL_A")) {
+        int a = 0, f = 0;
+        const int got = std::sscanf(ta, "%d,%d", &a, &f);
+        tail_a_max = nbatch == 1 ? a : 0;
+        tail_from = got > 1 ? f : 0;
       }
     }
     if (plan_version == 1) {
