@@ -16,6 +16,7 @@ DEFAULT_LIB = os.path.join(_HERE, "csrc", "libcausalstump_b200.so")
 CS_GP, CS_TP = 0, 1
 CS_OPT_ADAM, CS_OPT_NADAM, CS_OPT_NESTEROV = 0, 1, 2
 CS_NPHASE = 7
+CS_ERR_NONFINITE = -6
 CS_MAX_P = 40
 PHASES = ("gram", "potrf", "trtri", "xtx", "matvec", "grad", "final")
 
@@ -67,6 +68,8 @@ _SIGS = {
     "cs_fit_run": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_int), dp]),
     "cs_fit_run_many": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int),
                                   C.POINTER(dp)]),
+    "cs_fit_member_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "cs_release_scratch": (C.c_int, []),
     "cs_fit_set_data": (C.c_int, [C.c_void_p, dp, dp, dp, dp]),
     "cs_fit_get_params": (C.c_int, [C.c_void_p, dp]),
     "cs_fit_set_params": (C.c_int, [C.c_void_p, dp]),
@@ -359,6 +362,11 @@ class Fit:
     def flush_l2(self):
         self.lib.check(self.lib.dll.cs_flush_l2(self.h))
 
+    def member_status(self):
+        st = (C.c_int * max(getattr(self, "B", 1), 1))()
+        self.lib.check(self.lib.dll.cs_fit_member_status(self.h, st))
+        return [int(x) for x in st]
+
 
 class FitBatch(Fit):
     """Batched handle (cs_fit_create_batch): B independent fits of the same (n, p, kind) advance with every
@@ -391,17 +399,28 @@ class FitBatch(Fit):
         self.lib.check(self.lib.dll.cs_fit_select(self.h, int(member)))
         return self
 
-    def run(self, maxiter, tol):
-        """-> [(iters, trace[2, iters+2]), ...] per member"""
+    def member_status(self):
+        """Per member after run(): 0 OK, > 0 failing pivot (not positive definite), CS_ERR_NONFINITE (-6)."""
+        st = (C.c_int * self.B)()
+        self.lib.check(self.lib.dll.cs_fit_member_status(self.h, st))
+        return [int(x) for x in st]
+
+    def run(self, maxiter, tol, strict=True):
+        """-> [(iters, trace[2, iters+2]), ...] per member.  A failing member (K_n not positive definite, non-finite LML)
+        stops alone; the others run to completion.  strict=True raises afterwards like the reference's failing
+        CausalStump() call would; strict=False returns everything and leaves the verdict to member_status()."""
         its = (C.c_int * self.B)()
         traces = np.zeros((self.B, maxiter + 2, 2))
-        self.lib.check(self.lib.dll.cs_fit_run(self.h, int(maxiter), float(tol), its, _ptr(traces)))
+        code = self.lib.dll.cs_fit_run(self.h, int(maxiter), float(tol), its, _ptr(traces))
+        if strict or (code < 0 and code != CS_ERR_NONFINITE):
+            self.lib.check(code)
         return [(int(its[b]), traces[b, : int(its[b]) + 2].T.copy()) for b in range(self.B)]
 
 
-def run_many(fits, maxiter, tol):
+def run_many(fits, maxiter, tol, strict=True):
     """cs_fit_run_many: drive several handles (Fit or FitBatch) concurrently; returns [(iters, trace), ...]
-    with one entry per fit, batched handles expanded member by member in order."""
+    with one entry per fit, batched handles expanded member by member in order.  strict=False: a failing member does
+    not raise (see FitBatch.run); query member_status() of the handles."""
     lib = fits[0].lib
     n = len(fits)
     sizes = [getattr(f, "B", 1) for f in fits]
@@ -410,7 +429,9 @@ def run_many(fits, maxiter, tol):
     iters = (C.c_int * total)()
     traces = [np.zeros((b, maxiter + 2, 2)) for b in sizes]
     tp = (dp * n)(*[_ptr(t) for t in traces])
-    lib.check(lib.dll.cs_fit_run_many(hs, n, int(maxiter), float(tol), iters, tp))
+    code = lib.dll.cs_fit_run_many(hs, n, int(maxiter), float(tol), iters, tp)
+    if strict or (code < 0 and code != CS_ERR_NONFINITE):
+        lib.check(code)
     out, k = [], 0
     for t, b in zip(traces, sizes):
         for m in range(b):

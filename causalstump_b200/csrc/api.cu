@@ -98,7 +98,22 @@ struct Arena {
     return c.base;
   }
   void release() { for (auto& c : chunks) rt::dev_free(c.base); chunks.clear(); }
+  // keep at most `cap` bytes for the next call (largest chunks go first): a replicate loop at n ~ 700 keeps its few
+  // MB, one predict at n = 8192 (1.5 GB of scratch) does not stay resident for the life of the host thread
+  void trim(size_t cap) {
+    size_t total = 0;
+    for (auto& c : chunks) total += c.cap;
+    while (total > cap && !chunks.empty()) {
+      size_t big = 0;
+      for (size_t i = 1; i < chunks.size(); ++i) if (chunks[i].cap > chunks[big].cap) big = i;
+      total -= chunks[big].cap;
+      rt::dev_free(chunks[big].base);
+      chunks.erase(chunks.begin() + big);
+    }
+  }
+  ~Arena() { release(); }  // thread exit: the scratch of this host thread goes back to the device
 };
+static constexpr size_t ARENA_KEEP_BYTES = (size_t)256 << 20;
 static thread_local Arena* g_arena = nullptr;
 // one arena per host thread and device, shared by every handle: replicate loops create and destroy handles,
 // the scratch survives them (predict / treatment calls are synchronous, so it is idle between calls)
@@ -113,7 +128,7 @@ static Arena* thread_arena() {
 struct ArenaScope {
   Arena* prev;
   explicit ArenaScope(Arena* a) : prev(g_arena) { g_arena = a; if (a) a->reset(); }
-  ~ArenaScope() { g_arena = prev; }
+  ~ArenaScope() { if (g_arena) g_arena->trim(ARENA_KEEP_BYTES); g_arena = prev; }
 };
 
 struct DevBuf {
@@ -209,6 +224,7 @@ struct cs_fit {
   char* slab = nullptr;
   std::vector<std::pair<void**, size_t>> slab_req;
   bool trace_in_slab = false;
+  std::vector<int> member_status;  // per member, after cs_fit_run: 0 OK, > 0 failing pivot, < 0 CS_ERR_*
 
   void want(void** field, size_t bytes) { slab_req.emplace_back(field, bytes); }
   int commit_slab() {
@@ -335,7 +351,7 @@ static void fit_enqueue_loop_step(cs_fit* f) {
   auto k = csk::loop_step_kernel;
   ++g_launches;
   CS_LAUNCH(k, dim3(1, 1, (unsigned)f->nbatch), 64, 0, f->st, f->cfg.optim, f->lay, f->cfg.lr, f->cfg.beta1, f->cfg.beta2, f->cfg.eps,
-            f->cfg.momentum, f->m, f->v, f->grad, f->params, f->sc, f->ls, f->trace);
+            f->cfg.momentum, f->m, f->v, f->grad, f->params, f->sc, f->ls, f->trace, (const int*)f->eng.status);
 }
 
 extern "C" {
@@ -353,6 +369,11 @@ int cs_set_device(int device) {
   return 0;
 }
 long long cs_launch_count(void) { return g_launches; }
+int cs_release_scratch(void) {  // predict / treatment scratch retained by the calling host thread on the current device
+  if (need_device()) return CS_ERR_NODEVICE;
+  thread_arena()->release();
+  return 0;
+}
 
 static int fit_create_impl(const cs_fit_config* cfg, int nbatch, int n, int p, const double* const* ys,
                            const double* const* Xs, const double* const* zs, const double* const* ws,
@@ -602,11 +623,13 @@ static int fit_run_begin(cs_fit* f, int maxiter, double tol) {
     HostLoop& h = f->h_ls[b];
     h = HostLoop{};
     h.ls.it = 1; h.ls.done = 0; h.ls.iters = 0; h.ls.maxiter = maxiter; h.ls.tol = tol; h.ls.prev_lml = 0.0;  // stats[,1] = 0 (R/main.R:77)
+    h.ls.err = 0;
     RT(rt::h2d(reinterpret_cast<char*>(f->ls) + b * f->bstride, &h.ls, sizeof(LoopState), st));
     static const int status_ok = 0x7fffffff;
     RT(rt::h2d(reinterpret_cast<char*>(f->eng.status) + b * f->bstride, &status_ok, sizeof(int), st));
   }
   RT(rt::stream_sync(st));
+  f->member_status.assign(B, 0);
   f->run_maxiter = maxiter;
   f->run_launched = 0;
   f->run_chunk = f->cfg.chunk;
@@ -654,19 +677,26 @@ static int fit_run_enqueue(cs_fit* f) {
   return 0;
 }
 
-// wait for the chunk; *finished = 1 when every member has stopped; <0 / >0 on error
+// wait for the chunk; *finished = 1 when every member has stopped.  A member that failed (non positive definite K_n,
+// non-finite LML) has stopped itself on the device with LoopState.err set (loop_step_kernel); the others keep running --
+// in the reference only the failing CausalStump() call errors, not the other replicates of the cluster.
 static int fit_run_poll(cs_fit* f, int* finished) {
   RT(rt::stream_sync(f->st));
   int all_done = 1;
-  for (int b = 0; b < f->nbatch; ++b) {
-    const int stt = f->h_ls[b].status;
-    if (stt != 0x7fffffff && stt > 0)
-      return fail(stt, "inv_sympd(): matrix is singular or not positive definite (pivot %d) at iteration %d (member %d)", stt,
-                  f->h_ls[b].ls.it - 1, b);
+  for (int b = 0; b < f->nbatch; ++b)
     if (!f->h_ls[b].ls.done) all_done = 0;
-  }
   *finished = (all_done || f->run_launched >= f->run_maxiter) ? 1 : 0;
   return 0;
+}
+
+static int member_fail(int code, int member, int iteration) {
+  if (code > 0)
+    return fail(code, "inv_sympd(): matrix is singular or not positive definite (pivot %d) at iteration %d (member %d)", code,
+                iteration, member);
+  if (code == CS_ERR_NONFINITE)
+    return fail(code, "log marginal likelihood is not finite at iteration %d (member %d): missing value where TRUE/FALSE needed",
+                iteration, member);
+  return code;
 }
 
 static int fit_run_finish_enqueue(cs_fit* f) {
@@ -677,27 +707,30 @@ static int fit_run_finish_enqueue(cs_fit* f) {
   return 0;
 }
 
-// iters[nbatch]; stats_trace = nbatch consecutive 2 x (maxiter+2) column-major blocks
+// iters[nbatch]; stats_trace = nbatch consecutive 2 x (maxiter+2) column-major blocks.  Every member is fetched; the
+// status of each lands in f->member_status (cs_fit_member_status) and the first failure is the return value.
 static int fit_run_finish_fetch(cs_fit* f, int* iters, double* stats_trace) {
   const int keep = f->cur;
   const int cap = 2 * (f->run_maxiter + 2);
-  int rc = 0;
-  for (int b = 0; b < f->nbatch && rc == 0; ++b) {
+  int first = 0, first_member = -1, first_it = 0;
+  for (int b = 0; b < f->nbatch; ++b) {
     f->select(b);
     const int it = f->h_ls[b].ls.done ? f->h_ls[b].ls.iters : f->run_maxiter;
-    double st2[2];
-    rc = cs_fit_fetch(f, nullptr, st2, nullptr);
-    if (rc) break;
+    double st2[2] = {0.0, 0.0};
+    int rc = f->h_ls[b].ls.err;
+    if (rc == 0) rc = cs_fit_fetch(f, nullptr, st2, nullptr);  // > 0: the final get_train_stats was not positive definite
+    if (rc < 0 && rc != CS_ERR_NONFINITE) { f->select(keep); return rc; }  // CUDA / transfer failure: not a property of the member
+    f->member_status[b] = rc;
+    if (rc != 0 && first == 0) { first = rc; first_member = b; first_it = it; }
     if (iters) iters[b] = it;
     if (stats_trace) {
       double* tr = stats_trace + (size_t)b * cap;
-      if ((rc = rt::d2h(tr, f->trace, sizeof(double) * cap, f->st)) || (rc = rt::stream_sync(f->st))) { rc = fail(CS_ERR_CUDA, "trace download failed"); break; }
-      tr[2 * (it + 1) + 0] = st2[0];
-      tr[2 * (it + 1) + 1] = st2[1];
+      if (rt::d2h(tr, f->trace, sizeof(double) * cap, f->st) || rt::stream_sync(f->st)) { f->select(keep); return fail(CS_ERR_CUDA, "trace download failed"); }
+      if (rc == 0) { tr[2 * (it + 1) + 0] = st2[0]; tr[2 * (it + 1) + 1] = st2[1]; }
     }
   }
   f->select(keep);
-  return rc;
+  return first ? member_fail(first, first_member, first_it) : 0;
 }
 
 int cs_fit_run(cs_fit* f, int maxiter, double tol, int* iters, double* stats_trace) {
@@ -711,6 +744,12 @@ int cs_fit_run(cs_fit* f, int maxiter, double tol, int* iters, double* stats_tra
   }
   if ((e = fit_run_finish_enqueue(f))) return e;
   return fit_run_finish_fetch(f, iters, stats_trace);
+}
+
+int cs_fit_member_status(const cs_fit* f, int* status) {
+  if (!f || !status) return fail(CS_ERR_ARG, "cs_fit_member_status: null argument");
+  for (int b = 0; b < f->nbatch; ++b) status[b] = b < (int)f->member_status.size() ? f->member_status[b] : 0;
+  return 0;
 }
 
 // handles may be batched: iters then holds sum(batch sizes) entries in handle order, stats_traces[i] nbatch_i blocks
@@ -732,12 +771,18 @@ int cs_fit_run_many(cs_fit** fits, int nfits, int maxiter, double tol, int* iter
         else if ((e = fit_run_enqueue(fits[i]))) return e;
       }
   }
-  int off = 0;
+  // every handle is fetched even when a member of an earlier one failed; the first failure is the return value and
+  // cs_fit_member_status tells which members of which handle are affected
+  int off = 0, first = 0;
+  std::string first_msg;
   for (int i = 0; i < nfits; ++i) {
-    if ((e = fit_run_finish_fetch(fits[i], iters ? iters + off : nullptr, stats_traces ? stats_traces[i] : nullptr))) return e;
+    e = fit_run_finish_fetch(fits[i], iters ? iters + off : nullptr, stats_traces ? stats_traces[i] : nullptr);
+    if (e < 0 && e != CS_ERR_NONFINITE) return e;
+    if (e != 0 && first == 0) { first = e; first_msg = g_err + " (handle " + std::to_string(i) + ")"; }
     off += fits[i]->nbatch;
   }
-  return 0;
+  if (first) g_err = first_msg;
+  return first;
 }
 
 int cs_fit_get_matrices(cs_fit* f, double* Kmat, double* Km, double* Ka, double* invK) {

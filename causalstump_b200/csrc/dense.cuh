@@ -864,9 +864,14 @@ struct DenseEngine {
       if (nbatch == 1 && np >= 4096) {
         double sum = 0.0;
         for (size_t pi = 0; pi + 1 < bounds.size(); ++pi) sum += (double)bounds[pi] * (bounds[pi + 1] - bounds[pi]);
-        const double window = (double)np * np * np / 28.0e12 - (double)N * 186e-6;
+        // the three constants were measured on a 148-SM B200 at 1965 MHz (bulk 28 TFLOP/s on 140 SMs, chain partition
+        // 1.6 TFLOP/s on 8 SMs, 186 us per leaf step); the bulk rate scales with the SM count of the device in use.
+        // CS_TAIL_A overrides the model.
+        const double bulk = 28.0e12 * std::max(rt::sm_count() - 8, 8) / 140.0;
+        const double window = (double)np * np * np / bulk - (double)N * 186e-6;
         const double per_col = 2.0 * gt * (double)tile * tile * sum;
-        if (window > 0.0 && per_col > 0.0) tail_a_max = std::min((int)(window * 1.6e12 / per_col), N * rr / 8);
+        if (window > 0.0 && per_col > 0.0)
+          tail_a_max = (int)std::min(window * 1.6e12 / per_col, (double)(N * rr / 8));  // clamped in double: no int overflow
       }
       if (const char* ta = std::getenv("CS_TAIL_A")) {
         int a = 0, f = 0;

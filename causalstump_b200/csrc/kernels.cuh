@@ -54,7 +54,11 @@ struct LoopState {
   int maxiter;
   double tol;
   double prev_lml; // stats[2, iter] of the previous iteration (0 before the first)
+  int err;         // 0, or why this member stopped: > 0 = failing pivot of a non positive definite K_n (arma::inv_sympd
+                   // throws, src/kernel_GP_SE_cpp.cpp:56), LOOP_ERR_NONFINITE = |dLML| is NaN (R stops at R/main.R:82)
+  int pad;
 };
+constexpr int LOOP_ERR_NONFINITE = -6;  // == CS_ERR_NONFINITE (include/cs_b200.h)
 
 // ---------------------------------------------------------------------------------
 // shared micro-tile: thread (tx,ty) owns rows tx+16a, cols ty+16b (a,b = 0..3) of a 64x64 tile
@@ -615,11 +619,24 @@ __global__ void opt_step_kernel(int optim, int nparam, double iter, double lr, d
 
 __global__ void loop_step_kernel(int optim, Layout lay, double lr, double b1, double b2, double eps, double momentum,
                                  double* m, double* v, const double* grad, double* para, EvalScalars* sc,
-                                 LoopState* ls, double* trace) {
+                                 LoopState* ls, double* trace, const int* status) {
   CS_BS(ls);
   if (ls->done) return;
-  CS_BS(m); CS_BS(v); CS_BS(grad); CS_BS(para); CS_BS(sc); CS_BS(trace);
+  CS_BS(m); CS_BS(v); CS_BS(grad); CS_BS(para); CS_BS(sc); CS_BS(trace); CS_BS(status);
   const int it = ls->it;
+  // A member whose K_n was not positive definite stops HERE, before the optimizer step, with the failing pivot (the
+  // reference throws inside getinv_kernel, R/kernel_GP_SE_class.R:42); the other members of the batch keep running.
+  // |dLML| = NaN stops it too: `if (change < tol && iter > 3)` is an R error on NA (R/main.R:82).
+  const int stt = status ? *status : 0x7fffffff;
+  const double change_now = fabs(sc->stats[1] - ls->prev_lml);
+  if ((stt != 0x7fffffff && stt > 0) || change_now != change_now) {
+    if (threadIdx.x == 0) {
+      ls->err = (stt != 0x7fffffff && stt > 0) ? stt : LOOP_ERR_NONFINITE;
+      ls->iters = it;
+      ls->done = 1;
+    }
+    return;
+  }
   const int nparam = lay.np();
   for (int i = threadIdx.x; i < nparam; i += blockDim.x)
     opt_update(optim, i, (double)it, lr, b1, b2, eps, momentum, m, v, grad, para);

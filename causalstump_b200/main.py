@@ -129,10 +129,33 @@ class _KernelBase:
         self._fit_key = None
 
     # -- device handle ------------------------------------------------------------
+    @staticmethod
+    def _fingerprint(*arrays):
+        """Cheap content check (Adler-32 of the bytes, ~1 GB/s): catches in-place edits of y, X or z between calls."""
+        import zlib
+        h = 1
+        for a in arrays:
+            h = zlib.adler32(np.ascontiguousarray(a).view(np.uint8), h)
+        return h
+
+    def invalidate(self):
+        """Drop the device handle: the next call re-uploads y, X, z (call after changing them in place if the
+        content check below is bypassed, or to release the device memory)."""
+        if self._fit is not None:
+            self._fit.close()
+        self._fit, self._fit_key = None, None
+
     def _handle(self, y, X, z, Optim=None, need_inverse=False):
-        X = rx._mat(X)
-        key = (id(y), id(X), id(z), X.shape)
-        fresh = self._fit is None or self._fit_key != key
+        # The cache entry keeps STRONG references to the caller's arrays (identity compared with `is`, so a freed
+        # array whose id() is reused can never alias) plus a content fingerprint (so an in-place edit re-uploads).
+        # X is keyed on the object the caller passed: a 1-D X gets a fresh 2-D view per call, which is not what is keyed.
+        src = (y, X, z)
+        Xm = rx._mat(X)
+        fp = (Xm.shape, self._fingerprint(np.asarray(y, dtype=np.float64), Xm, np.asarray(z, dtype=np.float64)))
+        k = self._fit_key
+        fresh = self._fit is None or k is None or not (k[0][0] is src[0] and k[0][1] is src[1] and k[0][2] is src[2]) or k[1] != fp
+        key = (src, fp)
+        X = Xm
         if fresh:
             if self._fit is not None:
                 self._fit.close()

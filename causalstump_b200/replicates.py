@@ -130,16 +130,25 @@ def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1
         handles = [_lib.FitBatch(lib, kind, members[i:i + batch], optim=_lib.CS_OPT_NADAM, lr=lr, tile=tile, chunk=chunk)
                    for i in range(0, len(members), batch)]
         t_create = _t.perf_counter()
-        res = _lib.run_many(handles, maxiter, tol)
+        res = _lib.run_many(handles, maxiter, tol, strict=False)
         views = [(h, b) for h in handles for b in range(h.B)]
     else:
         handles = fits
         t_create = _t.perf_counter()
-        res = _lib.run_many(fits, maxiter, tol)
+        res = _lib.run_many(fits, maxiter, tol, strict=False)
         views = [(f, None) for f in fits]
+    # a unit whose K_n stopped being positive definite (or whose LML became NaN) fails ALONE, as the one CausalStump() call
+    # of that replicate would in the reference; its row says so and the other units of the shard are unaffected
+    status = [st for h in handles for st in h.member_status()]
     t_run = _t.perf_counter()
     out = []
-    for (d, mom, train, test, replicate, restart), (f, member), (iters, trace) in zip(prep, views, res):
+    for (d, mom, train, test, replicate, restart), (f, member), (iters, trace), stt in zip(prep, views, res, status):
+        if stt != 0:
+            nan = float("nan")
+            out.append(dict(replicate=replicate, restart=restart, iters=int(iters), lml=-float("inf"), failed=True, status=int(stt),
+                            metrics={k: nan for k in METRICS}, pehe_train=nan, pehe_test=nan, rmse_train=nan, rmse_test=nan,
+                            e_ate_train=nan, e_ate_test=nan))
+            continue
         if member is not None:
             f.select(member)
         sd = _m.sqrt(mom["varY"])
@@ -156,10 +165,12 @@ def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1
             tau_hat[idx] = sd * t["map"]
             tau_ci[idx, 0] = vy * (-1.96 * t["var"]) + sd * t["map"]
             tau_ci[idx, 1] = vy * (1.96 * t["var"]) + sd * t["map"]
-        ate_ci = [(vy * (-1.96 * _m.sqrt(max(t["ate_var"], 0.0))) + sd * t["ate"], vy * (1.96 * _m.sqrt(max(t["ate_var"], 0.0))) + sd * t["ate"])
-                  for t in (t_tr, t_te)]
+        # sqrt of a negative ate_var is NaN as in R (R/treatment.R:31): a broken fit must not show up as a zero-width interval
+        with np.errstate(invalid="ignore"):
+            half = [float(np.sqrt(np.float64(t["ate_var"]))) for t in (t_tr, t_te)]
+        ate_ci = [(vy * (-1.96 * h) + sd * t["ate"], vy * (1.96 * h) + sd * t["ate"]) for h, t in zip(half, (t_tr, t_te))]
         metrics = update_results(test, pred, tau_hat, tau_ci, ate_ci[0], ate_ci[1], d["y"], d["z"], d["y1"], d["y0"])
-        out.append(dict(replicate=replicate, restart=restart, iters=int(iters), lml=float(trace[1, -1]), metrics=metrics,
+        out.append(dict(replicate=replicate, restart=restart, iters=int(iters), lml=float(trace[1, -1]), metrics=metrics, failed=False, status=0,
                         pehe_train=float(np.sqrt(np.mean((tau[train] - sd * t_tr["map"]) ** 2))),
                         pehe_test=float(np.sqrt(np.mean((tau[test] - sd * t_te["map"]) ** 2))),
                         rmse_train=float(np.sqrt(np.mean((d["y"][train] - pred[train]) ** 2))),

@@ -39,6 +39,7 @@ extern "C" {
 #define CS_ERR_NOMEM (-3)
 #define CS_ERR_NODEVICE (-4)
 #define CS_ERR_UNSUPPORTED (-5)
+#define CS_ERR_NONFINITE (-6) /* |dLML| is NaN inside the optimisation loop: R stops at `if (change < tol ...)`, R/main.R:82 */
 
 #define CS_MAX_P 40
 
@@ -147,6 +148,11 @@ int cs_fit_fetch(cs_fit* f, double* grad, double* stats, double* mu_solution);
  * iter > 3), then the final get_train_stats.  stats_trace (nullable) is 2 x (maxiter+2)
  * column-major like `stats` in R/main.R:77; *iters receives the last iteration run. */
 int cs_fit_run(cs_fit* f, int maxiter, double tol, int* iters, double* stats_trace);
+/* Failure of one member (K_n not positive definite: the reference's inv_sympd throws, src/kernel_GP_SE_cpp.cpp:56; or a
+ * non-finite LML) stops THAT member on the device; the others run to completion and all outputs are filled.  cs_fit_run /
+ * cs_fit_run_many then return the first failing member's code (> 0 pivot, CS_ERR_NONFINITE) and status[nbatch] tells
+ * which members are affected (0 = OK), so a replicate driver drops or retries only those units. */
+int cs_fit_member_status(const cs_fit* f, int* status);
 /* The same loop for several independent fits at once (replicates x restarts of config 4):
  * their iterations are interleaved on separate streams so the small kernels of one fit
  * fill the SMs another leaves idle.  iters[nfits]; stats_traces[i] nullable. */
@@ -209,6 +215,9 @@ int cs_fit_event_elapsed_ms(cs_fit* f, int slot_a, int slot_b, float* ms);
 int cs_fit_eval_profile(cs_fit* f, float phase_ms[CS_NPHASE]);
 /* kernels launched by this library since load (claimed launch count for bench.py) */
 long long cs_launch_count(void);
+/* cs_predict / cs_treat keep up to 256 MiB of device scratch per host thread and device for the next call (a
+ * replicate loop makes three such calls per fit); this releases it.  It is also released when the host thread exits. */
+int cs_release_scratch(void);
 /* test hook: happens-before check of the multi-stream Cholesky launch plan (0 = no races) */
 int cs_debug_check_plan(int n, int tile, int gemm_tile, int verbose);
 /* debug: per-launch timeline of the dense plan (rows of 6 floats: stream, type, tiles, K | block,

@@ -313,6 +313,51 @@ def test_public_api_end_to_end(gpulib):
             assert np.all(np.abs(U / ref - 1.0) < 0.08)
 
 
+def _expected_order_stat(df, k=900, n=1000):
+    """E[k-th of n order statistic] of a standard t_df variable (exact, by quadrature over the Beta(k, n-k+1) law
+    of the uniform order statistic): what `mean_j sort(rmvt(1000, ...))[900]` estimates (R/kernel_TP_SE_class.R:90)."""
+    from scipy import integrate, stats as ss
+    b = ss.beta(k, n - k + 1)
+    return integrate.quad(lambda u: ss.t.ppf(u, df) * b.pdf(u), b.ppf(1e-14), b.ppf(1 - 1e-14), limit=400,
+                          epsabs=1e-13, epsrel=1e-12)[0]
+
+
+@pytest.mark.parametrize("which,df,nsampling,vs_oracle", [("treat672", 2000.0, 400000, True), ("predict747", 2000.0, 100000, False),
+                                                           ("treat672", 3.0, 200000, False)])
+def test_tp_sampler_at_config3_size(gpulib, which, df, nsampling, vs_oracle):
+    """cs_tp_sample (Philox + Box-Muller + Marsaglia-Tsang + bitonic order statistic on the device) at the sizes of
+    config 3: the 672 x 672 treatment covariance of a Student-t fit (R/kernel_TP_SE_class.R:112-124, incl. ate_U) and the
+    747 x 747 predictive covariance (:84-93).  mvnfast's sitmo stream is not reproducible, so parity is distributional:
+    every U_i within 2 % of sqrt(cov_ii) * E[900th of 1000 t_df order statistic] (exact quadrature; Monte-Carlo error of
+    the estimate is 0.2-0.4 % at these draw counts), ate_U within 2 % of the same law for the row means (a univariate
+    t_df with scale sqrt(sum cov)/n2), and -- 400 000 draws on both sides -- within 2 % of the oracle's restatement of
+    rmvt + apply(..., sort) run with NumPy's generator."""
+    import bench
+    tinp = bench.make_inputs(672, 25, 1, kind="TP")
+    f = _lib.Fit(gpulib, _lib.CS_TP, tinp["y"], tinp["X"], tinp["z"], tinp["w"], tinp["params"])
+    f.run(5, 0.0)
+    if which == "treat672":
+        cov = f.treat(tinp["X"], cov_jitter=1e-6, want_cov=True)["cov"]
+    else:
+        pinp = bench.make_inputs(747, 25, 2, kind="TP")
+        cov = f.predict(pinp["X"], pinp["z"], want_cov=True)["cov"]
+    f.close()
+    n2 = cov.shape[0]
+    assert n2 == int(which[-3:]) and np.array_equal(cov, cov.T)
+    U, aU = gpulib.tp_sample(cov, df, nsampling, 2026, want_ate=True)
+    U2, aU2 = gpulib.tp_sample(cov, df, nsampling, 2026, want_ate=True)
+    assert np.array_equal(U, U2) and aU == aU2                       # counter-based RNG: reproducible per seed
+    e = _expected_order_stat(df)
+    assert np.max(np.abs(U / (np.sqrt(np.diag(cov)) * e) - 1.0)) < 0.02
+    assert abs(aU / (np.sqrt(cov.sum()) / n2 * e) - 1.0) < 0.02
+    assert not np.array_equal(U, gpulib.tp_sample(cov, df, nsampling, 2027))
+    if vs_oracle:
+        K = o.KernelClass_TP_SE(25, np.ones(672), nsampling=nsampling)
+        K.parameters = dict(nu=np.log(df))
+        Uo, aUo = K._sample_U(cov, np.random.default_rng(11), want_ate=True)
+        assert np.max(np.abs(U / Uo - 1.0)) < 0.02 and abs(aU / aUo - 1.0) < 0.02
+
+
 def test_full_size_properties_n8192(gpulib):
     """n=8192, p=25 (the metric's size): the oracle is too slow here, so check
     size-independent properties: gradient == central finite difference of the LML,
