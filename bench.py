@@ -11,8 +11,14 @@ batch: Gram -> Cholesky -> inverse -> fused trace gradients -> LM
 parameters, D2H of gradient + stats every step).  N > 1 runs one replica per GPU
 ("replicas only", no collective on the data path).
 
---impl reference times the CPU restatement of the reference (oracle/, kind "port": R and
-RcppArmadillo are not available) on the host cores.
+--impl reference times the reference's OWN C++ (oracle/_ref: src/kernel_GP_SE_cpp.cpp compiled unmodified against the
+header shim of oracle/shim, arma::inv_sympd / log_det through the host LAPACK; kind "reference") on the host cores: ONE
+full n=8192, p=25 evaluation, chained as para_update chains the routines.  R and RcppArmadillo are not installed in this
+image; where oracle/_ref is absent the NumPy oracle port stands in (kind "port").
+
+N > 1 additionally reports the two sharded configurations of BASELINE.json: `config4` (100 replicates x 4 restarts = 400
+fits SPLIT over the N GPUs, no collective) and `config5` (one n=32768 evaluation on a P x Q grid, 2-D block-cyclic
+Cholesky with NCCL panel broadcasts).
 """
 from __future__ import annotations
 
@@ -38,6 +44,24 @@ XTX_TRAFFIC_SOURCE = ("profiles/r01_s2_ncu_xtx.txt: ncu --set full of this kerne
                       "(dram__bytes_read.sum 4.108 GB + dram__bytes_write.sum 485.4 MB per launch)")
 METRIC = "fp64 LML+gradient evals/sec at n=8192,p=25"
 UNIT = "evals/s"
+# time-weighted DMMA sub-pipe activity of the K = 512 bulk launches of the timed plan (ncu --set full over every GEMM launch
+# of one evaluation, plain priority streams -- ncu cannot attach to green-context streams); updated with each capture
+DMMA_ACTIVE_K512 = {"pct": 85.4, "source": "profiles/r01_s2_gemm_launches.md (launches with >= 592 CTA tiles, time-weighted)"}
+
+
+def workload_config():
+    """The `config` object: identical in both arms (ours / --impl reference) at every N."""
+    return {"workload": "Hill-(2011)-shaped synthetic n=8192 p=25, GP (prior=FALSE), one LML+gradient evaluation per step",
+            "n": N_METRIC, "p": P_METRIC, "l2": "working set 3 x 512 MiB per evaluation, larger than the 126 MB L2 (no flush needed)"}
+
+
+def check_fracs(obj, path="line"):
+    """No roofline fraction above 1.2 may be printed (a bracket that does not contain the work it claims)."""
+    if isinstance(obj, dict):
+        for k, v in obj.items():
+            if k == "frac" and isinstance(v, (int, float)):
+                assert v <= 1.2, "%s.frac = %.3f: the timed bracket does not contain the work" % (path, v)
+            check_fracs(v, path + "." + str(k))
 
 
 def make_inputs(n, p, replicate, kind="GP"):
@@ -213,7 +237,8 @@ def ref_eval_seconds(inp, budget_s):
     ref.mu_solution(ys, zs, invK)
     t_mu = (time.perf_counter() - t0) * r2
     total = t_kern + t_inv + t_grad + t_mu
-    desc = ("the reference's own C++ (src/kernel_GP_SE_cpp.cpp compiled unmodified against oracle/shim, LAPACK = %s) on the "
+    desc = ("the reference's own C++ (src/kernel_GP_SE_cpp.cpp compiled unmodified against oracle/shim -- an eager stand-in for Armadillo: "
+            "the reference's loops run verbatim, Armadillo's expression templates do not; LAPACK = %s) on the "
             "first n_s=%d rows of the n=%d p=%d workload: kernmat and grad timed with 1 and 2 covariate columns (per-column cost "
             "scaled to p=%d), n^2 parts scaled by (n/n_s)^2, invkernel and log_det by (n/n_s)^3; components at n: kernmat %.1f s, "
             "invkernel %.1f s, grad %.1f s, mu %.2f s; %.1f s of CPU work"
@@ -247,47 +272,104 @@ def host_threads():
     return os.cpu_count() or 1
 
 
+def ref_available():
+    from oracle import ref_binding as rb
+    return rb.available()
+
+
+def ref_full_eval(inp, threads):
+    """ONE full evaluation by the reference's own compiled routines, chained as para_update chains them
+    (R/kernel_GP_SE_class.R:45-60): kernmat -> invkernel -> grad -> mu_solution.  Returns per-routine seconds, the LML,
+    the LAPACK description, and the two LAPACK-bound parts (inv_sympd inside invkernel, log_det inside grad) re-timed alone
+    at `threads` and at 2 BLAS threads (OMP_NUM_THREADS=2 is the reference's documented setting, README.md:13)."""
+    from oracle import ref_binding as rb
+    from threadpoolctl import threadpool_limits
+    ref = rb.RefLib()
+    t = {"lapack": ref.use_host_lapack()}
+    y, X, z, w, par = inp["y"], inp["X"], inp["z"], inp["w"], inp["par"]
+    flat = np.asarray(inp["params"], dtype=np.float64)
+    with threadpool_limits(limits=threads, user_api="blas"):
+        t0 = time.perf_counter()
+        K, Km, Ka = ref.kernmat(0, X, X, z, z, par["Lm"], par["La"], par["lambdam"], par["lambdaa"])
+        t["kernmat"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        invK = ref.invkernel(z, w, K, par["sigma"])
+        t["invkernel"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        g, st = ref.grad(0, y, X, z, w, K, Km, Ka, invK, flat)
+        t["grad"] = time.perf_counter() - t0
+        del Km, Ka
+        t0 = time.perf_counter()
+        ref.mu_solution(y, z, invK)
+        t["mu_solution"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ref.log_det(invK)
+        t["log_det_alone"] = time.perf_counter() - t0
+    with threadpool_limits(limits=2, user_api="blas"):
+        t0 = time.perf_counter()
+        ref.invkernel(z, w, K, par["sigma"])
+        t["invkernel_2threads"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ref.log_det(invK)
+        t["log_det_2threads"] = time.perf_counter() - t0
+    t["lml"] = float(st[1])
+    return t
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return 0
-    total_steps = args.steps + args.warmup
-    budget = max(6.0, min(30.0, 150.0 / max(total_steps, 1)))
+    ncores = os.cpu_count() or 1
     try:  # torchrun exports OMP_NUM_THREADS=1 to every rank: give the reference arm all host threads back
         import scipy.linalg  # noqa: F401  (load SciPy's OpenBLAS before limits are applied)
         from oracle import causalstump_oracle  # noqa: F401
         from threadpoolctl import threadpool_limits
-        threadpool_limits(limits=os.cpu_count() or 1, user_api="blas")
+        threadpool_limits(limits=ncores, user_api="blas")
     except Exception:
         pass
     inp = make_inputs(N_METRIC, P_METRIC, 0)
-    secs = []
-    desc = ""
-    kind = "reference"
-    for i in range(total_steps):
-        got = ref_eval_seconds(inp, budget)
-        if got is None:  # oracle/_ref was not built (no /root/reference at build time): the oracle port stands in
-            kind = "port"
-            got = cpu_eval_seconds(inp, budget)
-        s, desc = got
-        if i >= args.warmup:
-            secs.append(s)
-    ms = 1e3 * float(np.mean(secs))
-    value = 1e3 / ms
-    port = None
-    if kind == "reference":
-        ps, pdesc = cpu_eval_seconds(inp, 12.0)
-        port = {"value": 1.0 / ps, "unit": UNIT, "sample": pdesc}
+    extra = {}
+    if ref_available():
+        # The whole budget of this arm goes into ONE honest full-size evaluation (about 3 minutes on 16 host cores);
+        # --steps / --warmup are not multiplied into it: the line says how many steps were really run.
+        kind = "reference"
+        t = ref_full_eval(inp, ncores)
+        secs = t["kernmat"] + t["invkernel"] + t["grad"] + t["mu_solution"]
+        desc = ("ONE full evaluation at n=%d p=%d by the reference's own C++ (src/kernel_GP_SE_cpp.cpp compiled unmodified, -O2) chained "
+                "as para_update chains it: kernmat %.1f s, invkernel %.1f s, grad %.1f s (of which log_det %.1f s), mu_solution %.2f s; "
+                "arma::inv_sympd / log_det = host LAPACK dpotrf+dpotri / dgetrf (%s, %d threads); every other Armadillo operation is "
+                "the EAGER stand-in of oracle/shim/RcppArmadillo.h (the reference's own loops run verbatim, Armadillo's expression "
+                "templates -- which fuse some temporaries of the O(p n^2) passes -- do not), single-threaded like Armadillo's"
+                % (N_METRIC, P_METRIC, t["kernmat"], t["invkernel"], t["grad"], t["log_det_alone"], t["mu_solution"], t["lapack"], ncores))
+        secs2 = secs - t["invkernel"] - t["log_det_alone"] + t["invkernel_2threads"] + t["log_det_2threads"]
+        extra["omp_num_threads_2"] = {"value": 1.0 / secs2, "unit": UNIT, "seconds": secs2,
+                                      "how": "the full run above with invkernel (%.1f s) and log_det (%.1f s) re-timed at 2 BLAS threads; "
+                                             "the element-wise passes are single-threaded at any setting"
+                                             % (t["invkernel_2threads"], t["log_det_2threads"])}
+        m = ref_eval_seconds(inp, 8.0)  # the round-1 bounded-sample model, kept beside the measurement
+        if m is not None:
+            extra["model"] = {"value": 1.0 / m[0], "unit": UNIT, "seconds": m[0], "ratio_to_measured": m[0] / secs, "sample": m[1]}
+        extra["lml"] = t["lml"]
+        steps_run, sample_kind = 1, "full"
+    else:  # oracle/_ref was not built (no /root/reference at build time): the oracle port stands in, bounded sample
+        kind = "port"
+        secs, desc = cpu_eval_seconds(inp, 30.0)
+        steps_run, sample_kind = 1, "bounded sample"
+    ms = 1e3 * secs
+    value = 1.0 / secs
+    ps, pdesc = cpu_eval_seconds(inp, 12.0)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps_run, "warmup": 0,
+        "steps_requested": args.steps, "warmup_requested": args.warmup, "step_is": sample_kind,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "impl": "reference",
-        "config": {"workload": "Hill-(2011)-shaped synthetic n=8192 p=25, GP (prior=FALSE), one LML+gradient evaluation per step",
-                   "n": N_METRIC, "p": P_METRIC},
+        "config": workload_config(), "parallelism": "rank 0 only: one host process, all host threads",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads(), "kind": kind, "sample": desc, "host": host_env(),
-                         "oracle_port": port},
+                         "oracle_port": {"value": 1.0 / ps, "unit": UNIT, "sample": pdesc}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    line["cpu_baseline"].update(extra)
     print(json.dumps(line), flush=True)
     return 0
 
@@ -372,6 +454,7 @@ def run_ours(args, rank, world, local_rank):
     fit.sync()
     barrier()
     l0 = lib.launch_count()
+    fit.dense_timing(True)   # event pair around the dense phase of every timed evaluation (the `roofline` object)
     fit.event_record(0)
     for _ in range(K):
         fit.eval_async()
@@ -379,6 +462,9 @@ def run_ours(args, rank, world, local_rank):
     fit.sync()
     barrier()
     launches = lib.launch_count() - l0
+    dense_ms_total, dense_evals = fit.dense_ms()
+    fit.dense_timing(False)
+    assert dense_evals == K
     ms_total = max_over_ranks(fit.event_elapsed_ms(0, 1))
     g, st, mu = fit.fetch()
     assert np.isfinite(st).all() and np.isfinite(g).all(), "non-finite evaluation"
@@ -432,40 +518,51 @@ def run_ours(args, rank, world, local_rank):
         npad = n
         f_xtx = npad ** 3 / 3.0
         xtx_tflops = f_xtx / (seq_phases["xtx"] * 1e-3) / 1e12
-        dense_ms = phases["potrf"] + phases["trtri"] + phases["xtx"]
+        dense_ms = dense_ms_total / K        # measured INSIDE the timed region, on the handle's stream
         dense_tflops = float(npad) ** 3 / (dense_ms * 1e-3) / 1e12
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         line_extra["roofline"] = {
-            "kernel": "csg::gemm_kernel<64,2,2,true,true,16,2> (K^-1 = X^T X as one launch of 8256 CTA tiles, DMMA.8x8x4), "
-                      "timed alone on its stream (sequential plan, second handle)",
-            "bound": "tensor", "achieved": xtx_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": xtx_tflops / fp64_peak, "traffic": XTX_TRAFFIC_BYTES,
-            "traffic_source": XTX_TRAFFIC_SOURCE,
-            "peak_source": "cuBLAS DGEMM 8192^3 fp64 burst measured live in this run (MEASURED_PEAKS.json has no fp64 entry)",
-            "flops_per_launch": f_xtx, "ms_per_launch": seq_phases["xtx"],
-        }
-        line_extra["roofline_dense_path"] = {
-            "what": "Cholesky + triangular inverse + X^T X of the plan timed in `value` (n^3 algorithmic flops, every launch "
-                    "an instance of csg::gemm_kernel or the leaf kernel; %s)" %
-                    ("inverse pipelined behind the Cholesky on 8 streams (look-ahead of depth three, chain on its own SM partition)" if args.inv_pipeline else "phases back to back"),
+            "kernel": "csg::gemm_kernel (DMMA.8x8x4) + leaf kernel: the dense path of the TIMED plan -- Cholesky, triangular inverse and "
+                      "K^-1 = X^T X, %s; every launch is an instance of the GEMM kernel template or the leaf kernel" %
+                      ("inverse pipelined behind the Cholesky on 8 streams (look-ahead of depth three, chain on its own SM partition)"
+                       if args.inv_pipeline else "phases back to back"),
             "bound": "tensor", "achieved": dense_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": dense_tflops / fp64_peak, "ms": dense_ms,
+            "frac": dense_tflops / fp64_peak, "traffic": None,
+            "flops_per_launch": float(npad) ** 3, "ms_per_launch": dense_ms,
+            "launch": "one launch = the dense phase of one evaluation (about 460 GEMM / leaf launches overlapping on 8 streams); "
+                      "algorithmic flops n^3 (n^3/3 potrf + 2n^3/3 potri); duration = CUDA event pair on the handle's stream around "
+                      "that phase, averaged over the %d timed steps" % K,
+            "dmma_active_pct_k512_launches": DMMA_ACTIVE_K512,
+            "peak_source": "cuBLAS DGEMM 8192^3 fp64 burst measured live in this run (MEASURED_PEAKS.json has no fp64 entry)",
+        }
+        line_extra["roofline_kernel_isolated"] = {
+            "kernel": "csg::gemm_kernel<64,2,2,true,true,16,2> (K^-1 = X^T X as ONE launch of 8256 CTA tiles, K = 8192), timed alone on its "
+                      "stream on a second handle running the sequential plan -- NOT a launch of the timed step, kept as the ceiling "
+                      "the K = 512 slices of the timed plan are compared with",
+            "bound": "tensor", "achieved": xtx_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": xtx_tflops / fp64_peak, "traffic": XTX_TRAFFIC_BYTES, "traffic_source": XTX_TRAFFIC_SOURCE,
+            "flops_per_launch": f_xtx, "ms_per_launch": seq_phases["xtx"],
         }
         if args.inv_pipeline:
             line_extra["phases_ms_sequential_plan"] = seq_phases
+        # Gram / trace-gradient kernels: FP64-issue-bound at p = 25 (19 / 14 flop per byte against a ridge
+        # of ~6), so the bound is the DFMA issue rate; the HBM figure north_star asks for is reported beside it.
+        # cs_fit_eval_profile builds the whole Gram matrix on the handle's stream (no split), so `gram` brackets all of it.
         b_gram = 8.0 * n * n / 2 + 8.0 * n * (p + 2)   # lower triangle written once
         b_grad = 8.0 * n * n / 2 + 8.0 * n * (p + 3)   # lower triangle of K^-1 read once
-        line_extra["roofline_elementwise"] = {
-            "gram": {"bound": "hbm", "achieved": b_gram / (phases["gram"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": b_gram / (phases["gram"] * 1e-3) / 1e9 / hbm_peak, "ms": phases["gram"],
-                     "fp64_tflops": (n * n / 2.0) * (6 * p + 6) / (phases["gram"] * 1e-3) / 1e12},
-            "grad": {"bound": "hbm", "achieved": b_grad / (phases["grad"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": b_grad / (phases["grad"] * 1e-3) / 1e9 / hbm_peak, "ms": phases["grad"],
-                     "fp64_tflops": (n * n / 2.0) * (10 * p + 12) / (phases["grad"] * 1e-3) / 1e12},
-            "note": "at p=25 both kernels are FP64-issue-bound, not HBM-bound (SURVEY.md 8d); ncu --set full (profiles/r01_s2_ncu_gram.txt, "
-                    "r01_s2_ncu_grad.txt): DRAM traffic 213 MB (Gram) / 283 MB (gradient) per launch = the algorithmic bytes, "
-                    "fp64 pipe 65 % / 53 % of peak while active",
-        }
+        dfma_peak = 33.0  # TFLOP/s, DFMA-only issue rate measured by tools/pipe_probe.cu (profiles/r01_s2_pipe_probe.txt)
+        f_gram = (n * n / 2.0) * (6 * p + 6)
+        f_grad = (n * n / 2.0) * (10 * p + 12)
+        ew = {}
+        for nm, fl, by in (("gram", f_gram, b_gram), ("grad", f_grad, b_grad)):
+            ms_k = seq_phases[nm]
+            tf = fl / (ms_k * 1e-3) / 1e12
+            ew[nm] = {"bound": "fp64-issue", "achieved": tf, "peak": dfma_peak, "unit": "TFLOP/s", "frac": tf / dfma_peak, "ms": ms_k,
+                      "hbm_gbs": by / (ms_k * 1e-3) / 1e9, "hbm_frac": by / (ms_k * 1e-3) / 1e9 / hbm_peak}
+        ew["note"] = ("both kernels timed as ONE launch each on the sequential-plan handle (the Gram build is not split there); fp64 flops "
+                      "exclude the two exp per entry; peak = DFMA-only issue rate of tools/pipe_probe.cu (vector and tensor FP64 share "
+                      "one pipe on sm_100a); hbm_* = algorithmic bytes / time against MEASURED_PEAKS.json hbm_gbs")
+        line_extra["roofline_elementwise"] = ew
         line_extra["phases_ms"] = phases
         # ---- CPU baseline on the host cores (rank 0, N=1 only) ----
         if world == 1 and not args.no_cpu:
@@ -473,7 +570,9 @@ def run_ours(args, rank, world, local_rank):
             got = ref_eval_seconds(inp, 15.0)
             secs, desc = got if got is not None else (psecs, pdesc)
             line_extra["cpu_baseline"] = {"value": 1.0 / secs, "unit": UNIT, "cores": host_threads(),
-                                          "kind": "reference" if got is not None else "port", "sample": desc, "host": host_env(),
+                                          "kind": "reference" if got is not None else "port",
+                                          "sample": desc + ("; a full-size evaluation of the same library is what `bench.py --impl reference` times" if got is not None else ""),
+                                          "host": host_env(),
                                           "oracle_port": {"value": 1.0 / psecs, "unit": UNIT, "sample": pdesc}}
     fit.close()
 
@@ -576,13 +675,12 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "Hill-(2011)-shaped synthetic n=8192 p=25, GP (prior=FALSE), one LML+gradient evaluation per step; one replica per GPU",
-                       "n": n, "p": p, "l2": "working set 3 x 512 MiB per evaluation, larger than the 126 MB L2 (no flush needed)",
-                       "parallelism": "replicas x%d, no collective" % world},
+            "config": workload_config(), "parallelism": "replicas x%d (one per GPU), no collective on the data path" % world,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
             "lml": float(st[1]),
         }
         line.update(line_extra)
+        check_fracs(line)
         if fits_obj:
             line["fits"] = fits_obj
         if tp_obj:

@@ -87,6 +87,8 @@ _SIGS = {
     "cs_fit_event_record": (C.c_int, [C.c_void_p, C.c_int]),
     "cs_fit_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "cs_fit_eval_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "cs_fit_dense_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "cs_fit_dense_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "cs_debug_check_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "cs_debug_timeline": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     "cs_launch_count": (C.c_longlong, []),
@@ -351,6 +353,15 @@ class Fit:
         arr = (C.c_float * CS_NPHASE)()
         self.lib.check(self.lib.dll.cs_fit_eval_profile(self.h, arr))
         return dict(zip(PHASES, [float(x) for x in arr]))
+
+    def dense_timing(self, on=True):
+        self.lib.check(self.lib.dll.cs_fit_dense_timing(self.h, 1 if on else 0))
+
+    def dense_ms(self):
+        """(summed ms, evaluations) of the dense phase since dense_timing(True) / the last call"""
+        ms, k = C.c_float(0.0), C.c_int(0)
+        self.lib.check(self.lib.dll.cs_fit_dense_ms(self.h, C.byref(ms), C.byref(k)))
+        return ms.value, k.value
 
     def timeline(self, cap=4096):
         """Per-launch timeline of the dense plan: rows (stream, type, tiles, K|block, t0_ms, t1_ms)."""

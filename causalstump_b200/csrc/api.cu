@@ -225,6 +225,10 @@ struct cs_fit {
   std::vector<std::pair<void**, size_t>> slab_req;
   bool trace_in_slab = false;
   std::vector<int> member_status;  // per member, after cs_fit_run: 0 OK, > 0 failing pivot, < 0 CS_ERR_*
+  // cs_fit_dense_timing: event pairs around the dense phase (Cholesky + inverse) of every evaluation enqueued while on
+  bool dense_timing = false;
+  std::vector<cudaEvent_t> dense_ev;
+  size_t dense_used = 0;
 
   void want(void** field, size_t bytes) { slab_req.emplace_back(field, bytes); }
   int commit_slab() {
@@ -286,7 +290,9 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
     const int total = csg::lower_tiles(f->nblk);
     int first = total;
     static const bool no_split = std::getenv("CS_NO_GRAM_SPLIT") != nullptr;
-    if (f->eng.plan_version == 2 && f->eng.aux2_ok && !no_split) {
+    // profile mode (cs_fit_eval_profile) builds the whole matrix on the handle's stream so that the "gram" phase brackets
+    // ALL of the build (with the split, 8220 of the 8256 tiles at n = 8192 run on S2, outside any bracket on `st`)
+    if (f->eng.plan_version == 2 && f->eng.aux2_ok && !no_split && !phase_ev) {
       const int bw = std::min(f->nblk, (f->eng.bounds.size() > 1 ? f->eng.bounds[1] : f->eng.panel_blocks) * f->eng.tile / csk::TB);
       first = csg::lower_tiles(bw);
     }
@@ -302,6 +308,18 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
     }
   }
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
+  const bool dtime = f->dense_timing && !phase_ev && skip == nullptr;
+  if (dtime) {
+    if (f->dense_used + 2 > f->dense_ev.size()) {
+      cudaEvent_t a, b;
+      if (rt::event_create(&a) == 0 && rt::event_create(&b) == 0) { f->dense_ev.push_back(a); f->dense_ev.push_back(b); }
+    }
+    if (f->dense_used + 2 <= f->dense_ev.size()) rt::event_record(f->dense_ev[f->dense_used], st);
+  }
+  struct DenseStop {  // closes the bracket when the dense phase has been enqueued (both plan branches below)
+    cs_fit* f; bool on; cudaStream_t st;
+    void stop() { if (on && f->dense_used + 2 <= f->dense_ev.size()) { rt::event_record(f->dense_ev[f->dense_used + 1], st); f->dense_used += 2; } on = false; }
+  } dstop{f, dtime, st};
   if (f->eng.inv_pipeline) {
     f->eng.factor_and_invert(st, skip);  // Cholesky with the inverse pipelined behind it
     if (phase_ev) { rt::event_record(phase_ev[ph++], st); rt::event_record(phase_ev[ph++], st); rt::event_record(phase_ev[ph++], st); }
@@ -314,6 +332,7 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
     f->eng.run_seq(f->eng.xtx, st, skip);
     if (phase_ev) rt::event_record(phase_ev[ph++], st);
   }
+  dstop.stop();
   {  // alpha, u, s
     auto k = csk::matvec_kernel<3>;
     ++g_launches;
@@ -494,6 +513,7 @@ void cs_fit_destroy(cs_fit* f) {
   if (f->pinned) rt::host_free(f->pinned);
   if (f->h_ls) rt::host_free(f->h_ls);
   if (f->graph_ok) rt::graph_destroy(f->iter_graph);
+  for (cudaEvent_t e : f->dense_ev) rt::event_destroy(e);
   f->eng.destroy();
   if (f->ev_ok) for (int i = 0; i < 16; ++i) rt::event_destroy(f->ev[i]);
   rt::stream_destroy(f->st);
@@ -744,6 +764,28 @@ int cs_fit_run(cs_fit* f, int maxiter, double tol, int* iters, double* stats_tra
   }
   if ((e = fit_run_finish_enqueue(f))) return e;
   return fit_run_finish_fetch(f, iters, stats_trace);
+}
+
+int cs_fit_dense_timing(cs_fit* f, int on) {
+  if (!f) return fail(CS_ERR_ARG, "null handle");
+  f->dense_timing = on != 0;
+  f->dense_used = 0;
+  return 0;
+}
+
+int cs_fit_dense_ms(cs_fit* f, float* total_ms, int* evaluations) {
+  if (!f || !total_ms || !evaluations) return fail(CS_ERR_ARG, "cs_fit_dense_ms: null argument");
+  RT(rt::stream_sync(f->st));
+  float sum = 0.f;
+  for (size_t i = 0; i + 1 < f->dense_used; i += 2) {
+    float ms = 0.f;
+    RT(rt::event_elapsed(&ms, f->dense_ev[i], f->dense_ev[i + 1]));
+    sum += ms;
+  }
+  *total_ms = sum;
+  *evaluations = (int)(f->dense_used / 2);
+  f->dense_used = 0;
+  return 0;
 }
 
 int cs_fit_member_status(const cs_fit* f, int* status) {

@@ -213,6 +213,11 @@ int cs_fit_event_elapsed_ms(cs_fit* f, int slot_a, int slot_b, float* ms);
 /* per-phase device time of one evaluation: gram, potrf, trtri, xtx, matvec, grad, final */
 #define CS_NPHASE 7
 int cs_fit_eval_profile(cs_fit* f, float phase_ms[CS_NPHASE]);
+/* Dense phase (Cholesky + inverse: every launch an instance of the DMMA GEMM kernel or the leaf kernel) of the plan that is
+ * actually being timed: while on, every cs_fit_eval_async / cs_fit_eval brackets that phase with a pair of CUDA events on the
+ * handle's stream; cs_fit_dense_ms synchronises, returns the summed duration and the number of evaluations, and resets. */
+int cs_fit_dense_timing(cs_fit* f, int on);
+int cs_fit_dense_ms(cs_fit* f, float* total_ms, int* evaluations);
 /* kernels launched by this library since load (claimed launch count for bench.py) */
 long long cs_launch_count(void);
 /* cs_predict / cs_treat keep up to 256 MiB of device scratch per host thread and device for the next call (a

@@ -12,7 +12,7 @@ import bench  # noqa: E402
 
 def test_reference_arm_line(monkeypatch, capsys):
     monkeypatch.setattr(bench, "cpu_eval_seconds", lambda inp, budget: (100.0, "stub sample"))
-    monkeypatch.setattr(bench, "ref_eval_seconds", lambda inp, budget: None)   # compiled reference absent -> oracle port
+    monkeypatch.setattr(bench, "ref_available", lambda: False)   # compiled reference absent -> oracle port
     monkeypatch.setattr(bench, "make_inputs", lambda n, p, r, kind="GP": {})
     args = types.SimpleNamespace(steps=2, warmup=1, gpus=4)
     assert bench.run_reference(args, rank=1, world=4) == 0 and capsys.readouterr().out == ""   # only rank 0 works and prints
@@ -30,13 +30,28 @@ def test_reference_arm_line(monkeypatch, capsys):
 def test_reference_arm_uses_the_compiled_reference(monkeypatch, capsys):
     """with oracle/_ref present the arm times the reference's own C++ (kind "reference") and reports the port beside it"""
     monkeypatch.setattr(bench, "cpu_eval_seconds", lambda inp, budget: (100.0, "stub port"))
-    monkeypatch.setattr(bench, "ref_eval_seconds", lambda inp, budget: (250.0, "stub reference"))
+    monkeypatch.setattr(bench, "ref_eval_seconds", lambda inp, budget: (200.0, "stub model"))
+    monkeypatch.setattr(bench, "ref_available", lambda: True)
+    full = dict(kernmat=60.0, invkernel=10.0, grad=179.0, mu_solution=1.0, log_det_alone=4.0, invkernel_2threads=30.0,
+                log_det_2threads=14.0, lapack="stub lapack", lml=-1.0)
+    monkeypatch.setattr(bench, "ref_full_eval", lambda inp, threads: dict(full))
     monkeypatch.setattr(bench, "make_inputs", lambda n, p, r, kind="GP": {})
-    assert bench.run_reference(types.SimpleNamespace(steps=2, warmup=1, gpus=1), rank=0, world=1) == 0
+    assert bench.run_reference(types.SimpleNamespace(steps=20, warmup=5, gpus=1), rank=0, world=1) == 0
     line = json.loads(capsys.readouterr().out.strip())
     cb = line["cpu_baseline"]
     assert cb["kind"] == "reference" and abs(line["value"] - 0.004) < 1e-12 and cb["value"] == line["value"]
     assert abs(cb["oracle_port"]["value"] - 0.01) < 1e-12 and line["e2e"]["value"] == line["value"]
+    # one honest full-size evaluation: the line reports the steps it really ran, so ms_per_step x steps is the run time
+    assert line["steps"] == 1 and line["warmup"] == 0 and line["steps_requested"] == 20 and abs(line["ms_per_step"] - 250e3) < 1e-6
+    assert abs(cb["omp_num_threads_2"]["seconds"] - 280.0) < 1e-9 and abs(cb["model"]["ratio_to_measured"] - 0.8) < 1e-12
+    assert line["config"] == bench.workload_config()   # same `config` object as the product arm at N = 1
+
+
+def test_no_roofline_fraction_above_the_bracket():
+    import pytest
+    bench.check_fracs({"roofline": {"frac": 0.84}, "x": {"y": {"frac": 1.1}}})
+    with pytest.raises(AssertionError):
+        bench.check_fracs({"roofline_elementwise": {"gram": {"frac": 2.7}}})
 
 
 def test_reference_timing_sample_on_a_small_case():
