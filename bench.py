@@ -413,6 +413,99 @@ def measure_fits(lib, rank, world, nfit, batch=32):
     return secs, nfit, [r["iters"] for r in res], float(np.mean([w["pehe_test"] for w in win]))
 
 
+GRIDS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (2, 4)}
+
+
+def measure_config4(lib, rank, world, dist, barrier, max_over_ranks, batch):
+    """Config 4 AS STATED (test/sec5-3_Hill2011.R:611-616): 100 replicates x 4 restarts = 400 independent fits SPLIT over the
+    N GPUs (static round-robin of (replicate, restart) units, no collective; the result rows are gathered on rank 0 and the
+    restart with the highest final LML wins per replicate).  Strong scaling: 400 / N fits per GPU."""
+    from causalstump_b200 import replicates as rp
+    units = rp.shard(rp.unit_list(100, 4), rank, world)
+    rp.hill_units_concurrent(units[:2], batch=batch)  # warm-up: graph capture, allocator
+    barrier()
+    t0 = time.perf_counter()
+    res = rp.hill_units_concurrent(units, batch=batch)
+    secs_local = time.perf_counter() - t0
+    tim = dict(rp.LAST_TIMING)
+    secs = max_over_ranks(secs_local)
+    rows = [(r["replicate"], r["restart"], r["lml"], r["iters"], r["pehe_test"], r["failed"]) for r in res]
+    util = [(tim["iterations"], tim["iterations"] / max(tim["slot_utilisation"], 1e-12), secs_local)]
+    if dist is not None:
+        allr, allu = [None] * world, [None] * world
+        dist.all_gather_object(allr, rows)
+        dist.all_gather_object(allu, util)
+        rows = [x for part in allr for x in part]
+        util = [x for part in allu for x in part]
+    if rank != 0:
+        return None
+    assert sorted((a, b) for a, b, *_ in rows) == rp.unit_list(100, 4), "every (replicate, restart) unit exactly once"
+    win = rp.select_winners([dict(replicate=a, restart=b, lml=c, pehe_test=e) for a, b, c, d, e, f in rows if not f])
+    its = [d for a, b, c, d, e, f in rows]
+    return {"what": "config 4 as stated: 100 Hill surface-B replicates x 4 restarts = 400 GP fits (672 x 25 training split, reference stopping "
+                    "rule maxiter 3000 / tol 1e-1 / lr .01 Nadam, + predict(747) + treatment(672, 75) + the 22 metrics) split over "
+                    "%d GPU(s), %d fits per GPU in batched handles of %d; wall time incl. host data generation and handle creation, "
+                    "max over ranks" % (world, len(units), batch),
+            "fits": len(rows), "fits_per_gpu": len(units), "seconds": secs, "value": len(rows) / secs * 3600.0, "unit": "fits/hour",
+            "scaling": "strong", "iterations_mean": float(np.mean(its)), "iterations_max": int(np.max(its)),
+            "slot_utilisation": float(sum(u[0] for u in util) / max(sum(u[1] for u in util), 1e-12)),
+            "seconds_per_rank": [round(u[2], 3) for u in util], "failed_units": int(sum(1 for r in rows if r[5])),
+            "pehe_test_winners_mean": float(np.mean([w["pehe_test"] for w in win])), "phases_s_rank0": {k: round(v, 3) for k, v in tim.items()}}
+
+
+def measure_config5(lib, torch, dev, rank, world, dist, barrier, steps=2, n=32768, parity_n=1500):
+    """Config 5: ONE large evaluation (n=32768, p=25) on a P x Q grid of ranks: tiles 2-D block-cyclic, every rank builds its
+    own Gram tiles, right-looking Cholesky / inverse / X^T X sweeps with NCCL panel broadcasts on row / column communicators
+    (csrc/dist.cuh).  Parity of the same code path against the oracle at n=1500 first."""
+    from causalstump_b200 import _lib
+    P, Q = GRIDS[world]
+
+    def make(nn):
+        inp = make_inputs(nn, P_METRIC, 0)
+        ids = [lib.dist_unique_id() if rank == 0 else None]
+        if dist is not None:
+            dist.broadcast_object_list(ids, src=0)
+        return inp, _lib.DistFit(lib, 0, inp["y"], inp["X"], inp["z"], inp["w"], inp["params"], rank, world, P, Q, ids[0])
+
+    out = {"what": "config 5: one LML+gradient evaluation at n=%d, p=%d, 2-D block-cyclic (128 x 128 tiles) over a %dx%d grid, NCCL panel "
+                   "broadcasts; time = max over ranks of the device time of one evaluation" % (n, P_METRIC, P, Q),
+           "n": n, "p": P_METRIC, "n_gpus": world, "grid": [P, Q]}
+    inp, f = make(parity_n)
+    g, st, mu, _ = f.eval()
+    f.close()
+    gathered = [(g.tolist(), st.tolist())]
+    if dist is not None:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (g.tolist(), st.tolist()))
+    if rank == 0:
+        from oracle import causalstump_oracle as o   # the checker, outside every timed region
+        go, sto, muo = o.eval_lml_grad("GP", inp["y"], inp["X"], inp["z"], inp["w"], inp["par"])
+        gref = o.pack_params(go)
+        out["parity"] = {"n": parity_n, "vs": "oracle",
+                         "grad_rel": float(np.max(np.abs(g - gref) / np.maximum(np.abs(gref), 1e-6 * np.max(np.abs(gref))))),
+                         "lml_rel": float(abs(st[1] - sto[1]) / abs(sto[1])), "mu_rel": float(abs(mu - muo) / abs(muo)),
+                         "ranks_agree": bool(all(np.allclose(gathered[0][0], x[0], rtol=1e-12, atol=0) for x in gathered))}
+    inp, f = make(n)
+    f.eval()  # warm-up
+    barrier()
+    ms = []
+    for _ in range(steps):
+        g, st, mu, m = f.eval()
+        ms.append(m)
+    barrier()
+    t = torch.tensor([float(np.mean(ms))], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    f.close()
+    if rank != 0:
+        return None
+    ms_eval = float(t[0])
+    out.update({"ms_per_eval": ms_eval, "evals_per_s": 1e3 / ms_eval, "tflops_n3": float(n) ** 3 / (ms_eval * 1e-3) / 1e12,
+                "steps": steps, "lml": float(st[1]), "finite": bool(np.isfinite(g).all() and np.isfinite(st).all()),
+                "nccl_ranks": world, "scaling": "strong"})
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     from causalstump_b200 import _lib
@@ -626,6 +719,13 @@ def run_ours(args, rank, world, local_rank):
                             "members (cs_fit_create_batch, every launch serves a whole batch), handles driven concurrently "
                             "(cs_fit_run_many); includes host data generation and handle creation" % (nf, args.fit_batch)}
 
+    # ---- the two sharded configurations of BASELINE.json (extra objects; SCALE records them at N = 1, 2, 4, 8) ----
+    c4_obj = c5_obj = None
+    if not args.no_configs:
+        c4_obj = measure_config4(lib, rank, world, dist, barrier, max_over_ranks, args.fit_batch)
+        if world in GRIDS:
+            c5_obj = measure_config5(lib, torch, dev, rank, world, dist, barrier)
+
     if rank == 0 and fits_obj and world == 1 and not args.no_cpu:
         # the same fit on the host: one reference-faithful optimizer iteration of the oracle port (para_update, which
         # builds Gram + inverse twice for the GP class, R/kernel_GP_SE_class.R:48,58) at the replicate size, timed
@@ -685,6 +785,10 @@ def run_ours(args, rank, world, local_rank):
             line["fits"] = fits_obj
         if tp_obj:
             line["student_t"] = tp_obj
+        if c4_obj:
+            line["config4"] = c4_obj
+        if c5_obj:
+            line["config5"] = c5_obj
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -701,6 +805,7 @@ def main():
     ap.add_argument("--fits", type=int, default=256, help="(replicate, restart) fits per GPU for the fits/hour object")
     ap.add_argument("--fit-batch", type=int, default=32, help="members per batched handle (cs_fit_create_batch); 1 = one handle per fit")
     ap.add_argument("--no-fits", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the config4 (400 fits split over N) and config5 (n=32768 on a P x Q grid) objects")
     ap.add_argument("--inv-pipeline", type=int, default=1, help="1: inverse pipelined behind the Cholesky (default); 0: recursive inverse after it")
     ap.add_argument("--partition", type=int, default=0, help="SM partition for the Cholesky chain: 0 auto, 1 on, -1 off")
     ap.add_argument("--no-cpu", action="store_true")

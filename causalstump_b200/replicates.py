@@ -179,7 +179,16 @@ def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1
                         e_ate_test=float(np.mean(tau[test]) - sd * t_te["ate"])))
     for h in handles:
         h.close()
-    LAST_TIMING.update(prep=t_prep - t_start, create=t_create - t_prep, run=t_run - t_create, post=_t.perf_counter() - t_run)
+    # slot utilisation of the batched handles: a member that has converged keeps its blockIdx.z slot (as early-exit CTAs)
+    # until the slowest member of ITS handle stops -- sum(iterations) / sum_h(B_h * max iterations in h)
+    used = cap = 0
+    k = 0
+    for h in handles:
+        its = [res[k + b][0] for b in range(getattr(h, "B", 1))]
+        k += len(its)
+        used += sum(its); cap += len(its) * max(its)
+    LAST_TIMING.update(prep=t_prep - t_start, create=t_create - t_prep, run=t_run - t_create, post=_t.perf_counter() - t_run,
+                       slot_utilisation=used / max(cap, 1), iterations=used, failed=sum(1 for s in status if s != 0))
     return out
 
 
