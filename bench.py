@@ -416,6 +416,51 @@ def measure_fits(lib, rank, world, nfit, batch=32):
 GRIDS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (2, 4)}
 
 
+def measure_stateless_boundary(sizes=((747, 3), (8192, 1))):
+    """What a user gets who swaps the library in but leaves the R package untouched (INTEGRATION.md step 2 without step 3):
+    the RefClass methods keep issuing the 8 stateless `.Call`s of one GP iteration (R/kernel_GP_SE_class.R:45-60: kernmat,
+    invkernel, grad, Nadam, mu_solution, then get_train_stats = kernmat, invkernel, stats), each shipping its n x n matrices
+    over PCIe in both directions.  Timed through the host mirrors of those routines (causalstump_b200/rcpp_exports.py), wall
+    clock, host buffers; next to it the same iteration on the device handle (the fast path CausalStump() uses)."""
+    from causalstump_b200 import _lib, rcpp_exports as rx
+    from causalstump_b200.main import list2zero
+    out = {"what": "one GP optimizer iteration through the 8 stateless .Call mirrors (n x n matrices cross PCIe on every call) vs the "
+                   "same iteration on the device-resident handle; seconds per iteration, wall clock", "sizes": []}
+    for n, reps in sizes:
+        inp = make_inputs(n, P_METRIC, 1)
+        y, X, z, w, par = inp["y"], inp["X"], inp["z"], inp["w"], inp["par"]
+        m, v = list2zero(par), list2zero(par)
+
+        def iteration(it, par, m, v):
+            Kl = rx.kernmat_GP_SE_cpp(X, X, z, z, par)
+            inv = rx.invkernel_cpp(z, w, Kl["Kmat"], par)
+            gl = rx.grad_GP_SE_cpp(y, X, z, w, Kl["Kmat"], Kl["Km"], Kl["Ka"], inv, par)
+            o = rx.Nadam_cpp(it, 0.01, 0.9, 0.999, 1e-8, m, v, gl["gradients"], par)
+            par = o["parameters"]
+            par["mu"] = rx.mu_solution_cpp(y, z, inv, par)
+            Kl = rx.kernmat_GP_SE_cpp(X, X, z, z, par)          # get_train_stats (:58)
+            inv = rx.invkernel_cpp(z, w, Kl["Kmat"], par)
+            st = rx.stats_GP_SE(y, Kl["Kmat"], inv, par)
+            return par, o["m"], o["v"], st
+
+        par1, m1, v1, _ = iteration(1, par, m, v)  # warm-up
+        t0 = time.perf_counter()
+        for it in range(reps):
+            par1, m1, v1, st = iteration(it + 2, par1, m1, v1)
+        sec_stateless = (time.perf_counter() - t0) / reps
+        f = _lib.Fit(rx.lib(), _lib.CS_GP, y, X, z, w, inp["params"])
+        f.run(3, 0.0)
+        iters = 20 if n < 4096 else 5
+        t0 = time.perf_counter()
+        f.run(iters, 0.0)
+        sec_handle = (time.perf_counter() - t0) / (iters + 1)   # + the final get_train_stats evaluation
+        f.close()
+        pcie = 8.0 * n * n * (3 + 1 + 1 + 4 + 1 + 3 + 1 + 1 + 2)   # matrices out/in per iteration: 3, 1+1, 4, 1, 3, 1+1, 2
+        out["sizes"].append({"n": n, "p": P_METRIC, "stateless_s_per_iteration": sec_stateless, "handle_s_per_iteration": sec_handle,
+                             "ratio": sec_stateless / sec_handle, "pcie_bytes_per_iteration": pcie, "lml_after": float(st[1])})
+    return out
+
+
 def measure_config4(lib, rank, world, dist, barrier, max_over_ranks, batch):
     """Config 4 AS STATED (test/sec5-3_Hill2011.R:611-616): 100 replicates x 4 restarts = 400 independent fits SPLIT over the
     N GPUs (static round-robin of (replicate, restart) units, no collective; the result rows are gathered on rank 0 and the
@@ -726,6 +771,10 @@ def run_ours(args, rank, world, local_rank):
         if world in GRIDS:
             c5_obj = measure_config5(lib, torch, dev, rank, world, dist, barrier)
 
+    stateless_obj = None
+    if rank == 0 and world == 1 and not args.no_fits:
+        stateless_obj = measure_stateless_boundary()
+
     if rank == 0 and fits_obj and world == 1 and not args.no_cpu:
         # the same fit on the host: one reference-faithful optimizer iteration of the oracle port (para_update, which
         # builds Gram + inverse twice for the GP class, R/kernel_GP_SE_class.R:48,58) at the replicate size, timed
@@ -785,6 +834,8 @@ def run_ours(args, rank, world, local_rank):
             line["fits"] = fits_obj
         if tp_obj:
             line["student_t"] = tp_obj
+        if stateless_obj:
+            line["boundary_stateless"] = stateless_obj
         if c4_obj:
             line["config4"] = c4_obj
         if c5_obj:

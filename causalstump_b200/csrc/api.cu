@@ -12,6 +12,7 @@
 #include "kernels.cuh"
 #include "predict.cuh"
 #include "dist.cuh"
+#include "sim.cuh"
 #ifndef CS_EMU
 #include <dlfcn.h>
 #endif
@@ -157,6 +158,26 @@ static int upload_matrix(double* dst, long long ldd, int rows_pad, int cols_pad,
 #endif
 }
 
+// same, source with its own leading dimension, on the host OR on the device (cudaMemcpyDefault: unified addressing)
+static int stage_matrix(double* dst, long long ldd, int cols_pad, const double* src, long long lds, int rows, int cols, cudaStream_t st) {
+  int e;
+  if ((e = rt::memset0(dst, sizeof(double) * (size_t)ldd * cols_pad, st))) return e;
+#ifdef CS_EMU
+  for (int c = 0; c < cols; ++c) std::memcpy(dst + (size_t)c * ldd, src + (size_t)c * lds, sizeof(double) * rows);
+  return 0;
+#else
+  return (int)cudaMemcpy2DAsync(dst, sizeof(double) * ldd, src, sizeof(double) * lds, sizeof(double) * rows, cols, cudaMemcpyDefault, st);
+#endif
+}
+static int copy_any(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+#ifdef CS_EMU
+  std::memcpy(dst, src, bytes);
+  return 0;
+#else
+  return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st);
+#endif
+}
+
 static int download_matrix(double* dst, int rows, int cols, const double* src, long long lds, cudaStream_t st) {
 #ifdef CS_EMU
   for (int c = 0; c < cols; ++c) std::memcpy(dst + (size_t)c * rows, src + (size_t)c * lds, sizeof(double) * rows);
@@ -190,6 +211,7 @@ struct cs_fit {
   cudaStream_t st{};
   DenseEngine eng;
   double *X = nullptr, *y = nullptr, *z = nullptr, *w = nullptr, *ones = nullptr;
+  rt::XTma xt{};  // TMA descriptor of X over all members (kernels stage their covariate tiles with it); on == 0: plain loads
   double *params = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr;
   double *alpha = nullptr, *u = nullptr, *s = nullptr;
   double* mv_part = nullptr;
@@ -292,19 +314,19 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
     static const bool no_split = std::getenv("CS_NO_GRAM_SPLIT") != nullptr;
     // profile mode (cs_fit_eval_profile) builds the whole matrix on the handle's stream so that the "gram" phase brackets
     // ALL of the build (with the split, 8220 of the 8256 tiles at n = 8192 run on S2, outside any bracket on `st`)
-    if (f->eng.plan_version == 2 && f->eng.aux2_ok && !no_split && !phase_ev) {
+    if (f->eng.plan_version == 2 && f->eng.aux2_ok && !no_split && !phase_ev && !f->eng.left_looking) {
       const int bw = std::min(f->nblk, (f->eng.bounds.size() > 1 ? f->eng.bounds[1] : f->eng.panel_blocks) * f->eng.tile / csk::TB);
       first = csg::lower_tiles(bw);
     }
     ++g_launches;
     CS_LAUNCH(k, dim3(first, 1, B), csk::ETH, csk::gram_smem_bytes(p), st, f->X, ld, f->z, f->w, f->params,
-              f->lay, n, f->eng.G, ld, skip, 0);
+              f->lay, n, f->eng.G, ld, skip, 0, f->xt);
     if (first < total) {
       rt::event_record(f->eng.ev_gram, st);   // orders S2 behind everything already on the handle's stream
       rt::stream_wait_event(f->eng.aux2, f->eng.ev_gram);
       ++g_launches;
       CS_LAUNCH(k, dim3(total - first, 1, B), csk::ETH, csk::gram_smem_bytes(p), f->eng.aux2, f->X, ld, f->z, f->w, f->params,
-                f->lay, n, f->eng.G, ld, skip, first);
+                f->lay, n, f->eng.G, ld, skip, first, f->xt);
     }
   }
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
@@ -347,9 +369,9 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
   {  // K3 / K4
     auto k = csk::grad_trace_kernel<false>;
     ++g_launches;
-    CS_LAUNCH(k, dim3(f->ncta_grad, 1, B), csk::ETH, csk::grad_smem_bytes(p), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
+    CS_LAUNCH(k, dim3(f->ncta_grad, 1, B), csk::ETH, csk::grad_smem_bytes(p, f->xt.on != 0), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
               f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)nullptr,
-              (const double*)nullptr, (const double*)nullptr, skip, (const int*)nullptr);
+              (const double*)nullptr, (const double*)nullptr, skip, (const int*)nullptr, f->xt);
   }
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
   {
@@ -452,6 +474,7 @@ static int fit_create_impl(const cs_fit_config* cfg, int nbatch, int n, int p, c
   f->trace_in_slab = true;
   if (f->commit_slab()) return bail(fail(CS_ERR_NOMEM, "device allocation failed (%lld bytes x %d members)", f->slab_bytes, nbatch));
   f->lay.bstride = f->bstride;
+  if (csk::grad_prefetch_fits(p)) rt::make_x_tensormap(&f->xt, f->X, np, p, nbatch, f->slab_bytes);  // member 0 is selected here
   E.external_buffers = true;
   E.nbatch = nbatch;
   E.bstride = f->bstride;
@@ -474,7 +497,7 @@ static int fit_create_impl(const cs_fit_config* cfg, int nbatch, int n, int p, c
   f->select(0);
   { auto k = csk::gram_train_kernel; CS_SET_SMEM(k, csk::gram_smem_bytes(csk::PMAX)); }
   { auto k = csk::gram_cross_kernel; CS_SET_SMEM(k, csk::gram_smem_bytes(csk::PMAX)); }
-  { auto k = csk::grad_trace_kernel<false>; CS_SET_SMEM(k, csk::grad_smem_bytes(csk::PMAX)); }
+  { auto k = csk::grad_trace_kernel<false>; CS_SET_SMEM(k, std::max(csk::grad_smem_bytes(csk::PMAX), csk::grad_smem_bytes(p, f->xt.on != 0))); }
   { auto k = csk::grad_trace_kernel<true>; CS_SET_SMEM(k, csk::grad_smem_bytes(csk::PMAX)); }
   { auto k = csp::gram_sum_kernel; CS_SET_SMEM(k, csk::gram_smem_bytes(csk::PMAX)); }
   for (int i = 0; i < 16; ++i)
@@ -898,7 +921,7 @@ int cs_debug_timeline(cs_fit* f, int cap, int* n_out, float* rows) {
     auto k = csk::gram_train_kernel;
     ++g_launches;
     CS_LAUNCH(k, csg::lower_tiles(f->nblk), csk::ETH, csk::gram_smem_bytes(f->p), st, f->X, (long long)f->np, f->z, f->w,
-              f->params, f->lay, f->n, f->eng.G, (long long)f->np, (const int*)nullptr, 0);
+              f->params, f->lay, f->n, f->eng.G, (long long)f->np, (const int*)nullptr, 0, f->xt);
   }
   RT(rt::stream_sync(st));
   cudaEvent_t base;
@@ -959,7 +982,9 @@ struct CrossWork {
 };
 
 // shared by cs_predict (use_m = 1, z2 given) and cs_treat (use_m = 0, z2 = 1, Ka only)
-static int cross_common(cs_fit* f, CrossWork& W, int n2, const double* X2, const double* z2, bool treat,
+// dev_io: X2 (leading dimension ldx2), z2, map and var_diag may live on the device (zero-copy callers: the simulation
+// driver, handle-based wrappers); then nothing here waits for the stream -- the scratch comes from the caller's arena
+static int cross_common(cs_fit* f, CrossWork& W, int n2, const double* X2, long long ldx2, const double* z2, bool dev_io, bool treat,
                         double* map, double* var_diag, double add_sigma, double add_const, double* cov_out) {
   const int n = f->n, np = f->np, p = f->p, tile = f->eng.gt;
   cudaStream_t st = f->st;
@@ -969,13 +994,14 @@ static int cross_common(cs_fit* f, CrossWork& W, int n2, const double* X2, const
   if (W.X2.alloc(vb2 * p) || W.z2.alloc(vb2) || W.Kc.alloc(vb2 * np) || W.V.alloc(vb2 * np) || W.q.alloc(vb2) ||
       W.tmp.alloc(vb2))
     return fail(CS_ERR_NOMEM, "predict workspace allocation failed");
-  RT(upload_matrix(W.X2.d(), n2p, n2p, p, X2, n2, p, st));
+  RT(stage_matrix(W.X2.d(), n2p, p, X2, ldx2, n2, p, st));
   if (treat) {
     auto k = fill_kernel;
     ++g_launches;
     CS_LAUNCH(k, (n2p + 255) / 256, 256, 0, st, W.z2.d(), (long long)n2p, 1.0);
   } else {
-    RT(upload_vector(W.z2.d(), n2p, z2, n2, 0.0, st));
+    if (n2p > n2) { auto kf = fill_kernel; ++g_launches; CS_LAUNCH(kf, (n2p + 255) / 256, 256, 0, st, W.z2.d(), (long long)n2p, 0.0); }
+    RT(copy_any(W.z2.d(), z2, sizeof(double) * n2, st));
   }
   const int rb2 = n2p / csk::TB;
   {  // K_xX (or Ka_xX) : n2p x np
@@ -998,7 +1024,7 @@ static int cross_common(cs_fit* f, CrossWork& W, int n2, const double* X2, const
     ++g_launches;
     CS_LAUNCH(k2, (n2p + 255) / 256, 256, 0, st, W.part.d(), W.nsplit, (long long)n2p, n2p,
               treat ? nul : (const double*)(f->params + f->lay.i_mu()), W.tmp.d());
-    if (map) RT(rt::d2h(map, W.tmp.d(), sizeof(double) * n2, st));
+    if (map) RT(copy_any(map, W.tmp.d(), sizeof(double) * n2, st));
   }
   {  // V = Kc * K^-1  (NT GEMM on the DMMA path; K^-1 is full symmetric)
     csg::GemmProblem P = DenseEngine::mk(W.Kc.d(), n2p, f->eng.C, np, W.V.d(), n2p, n2p / tile, np / tile, np,
@@ -1020,8 +1046,8 @@ static int cross_common(cs_fit* f, CrossWork& W, int n2, const double* X2, const
     ++g_launches;
     CS_LAUNCH(k3, (n2p + 255) / 256, 256, 0, st, W.q.d(), W.z2.d(), f->params, f->lay, treat ? 0 : 1, add_sigma,
               add_const, n2, W.tmp.d());
-    if (var_diag) RT(rt::d2h(var_diag, W.tmp.d(), sizeof(double) * n2, st));
-    RT(rt::stream_sync(st));  // dP must outlive the launch
+    if (var_diag) RT(copy_any(var_diag, W.tmp.d(), sizeof(double) * n2, st));
+    if (!dev_io || !g_arena) RT(rt::stream_sync(st));  // dP must outlive the launch (arena scratch does)
   }
   if (cov_out) {
     if (W.cov.alloc(vb2 * n2p)) return fail(CS_ERR_NOMEM, "cov allocation failed");
@@ -1048,11 +1074,48 @@ static int cross_common(cs_fit* f, CrossWork& W, int n2, const double* X2, const
   return 0;
 }
 
+// sum(cov) of the treatment block without n2 x n2 temporaries: scal_dev[0] = c' K^-1 c with c_j = sum_i Ka_xX[i,j],
+// scal_dev[1] = sum(Ka_xx); sum(cov) = scal[1] - scal[0] (+ jitter * n2).  Enqueue only.
+static int treat_sumcov_enqueue(cs_fit* f, CrossWork& W, int n2, double* scal_dev) {
+  cudaStream_t st = f->st;
+  const int np = f->np, n2p = W.n2p, p = f->p;
+  DevBuf c, t, part, gs;
+  const int rb2 = n2p / csk::TB;
+  int ns = 1, cps = 0;
+  split_plan(f->nblk, np, &ns, &cps);
+  if (c.alloc(sizeof(double) * np) || t.alloc(sizeof(double) * np) || part.alloc(sizeof(double) * np * ns) ||
+      gs.alloc(sizeof(double) * rb2 * rb2))
+    return fail(CS_ERR_NOMEM, "alloc failed");
+  auto k = csp::colsum_kernel;
+  ++g_launches;
+  CS_LAUNCH(k, (np * 32 + 255) / 256, 256, 0, st, W.Kc.d(), (long long)n2p, n2, np, c.d());
+  auto k2 = csk::matvec_kernel<1>;
+  ++g_launches;
+  const double* nul = nullptr;
+  CS_LAUNCH(k2, dim3(f->nblk, ns), csk::ETH, 0, st, f->eng.C, (long long)np, cps, np, c.d(), nul, nul, nul, part.d(),
+            (long long)np, (long long)np, (const int*)nullptr, 0LL);
+  auto k3 = csp::reduce_parts_kernel;
+  ++g_launches;
+  CS_LAUNCH(k3, (np + 255) / 256, 256, 0, st, part.d(), ns, (long long)np, np, nul, t.d());
+  auto k4 = csp::dot_kernel;
+  ++g_launches;
+  CS_LAUNCH(k4, 1, csk::ETH, 0, st, c.d(), t.d(), f->n, scal_dev);
+  auto k5 = csp::gram_sum_kernel;
+  ++g_launches;
+  CS_LAUNCH(k5, dim3(rb2, rb2), csk::ETH, csk::gram_smem_bytes(p), st, W.X2.d(), (long long)n2p, n2, f->params, f->lay,
+            gs.d());
+  ++g_launches;
+  CS_LAUNCH(k4, 1, csk::ETH, 0, st, gs.d(), nul, rb2 * rb2, scal_dev + 1);
+  KCHECK();
+  if (!g_arena) RT(rt::stream_sync(st));  // the scratch above is freed on return unless it comes from the arena
+  return 0;
+}
+
 int cs_predict(cs_fit* f, int n2, const double* X2, const double* z2, double* map, double* var_diag, double* cov) {
   if (!f || !X2 || !z2 || n2 < 1) return fail(CS_ERR_ARG, "cs_predict: bad argument");
   ArenaScope scope(thread_arena());
   CrossWork W;
-  int e = cross_common(f, W, n2, X2, z2, false, map, var_diag, 1.0, 0.0, cov);
+  int e = cross_common(f, W, n2, X2, n2, z2, false, false, map, var_diag, 1.0, 0.0, cov);
   if (e) return e;
   RT(rt::stream_sync(f->st));
   return 0;
@@ -1064,10 +1127,9 @@ int cs_treat(cs_fit* f, int n2, const double* X2, double cov_jitter, double* map
   ArenaScope scope(thread_arena());
   CrossWork W;
   std::vector<double> hmap(n2);
-  int e = cross_common(f, W, n2, X2, nullptr, true, hmap.data(), var_diag, 0.0, cov_jitter, cov);
+  int e = cross_common(f, W, n2, X2, n2, nullptr, false, true, hmap.data(), var_diag, 0.0, cov_jitter, cov);
   if (e) return e;
   cudaStream_t st = f->st;
-  const int np = f->np, n2p = W.n2p, p = f->p;
   RT(rt::stream_sync(st));
   if (map) std::copy(hmap.begin(), hmap.end(), map);
   if (ate) {
@@ -1076,35 +1138,9 @@ int cs_treat(cs_fit* f, int n2, const double* X2, double cov_jitter, double* map
     *ate = s / n2;  // mean(map), R/kernel_GP_SE_class.R:96
   }
   if (ate_var) {
-    // sum(cov) = sum(Ka_xx) - c' K^-1 c,  c_j = sum_i Ka_xX[i,j]   (no n2 x n2 temporaries)
-    DevBuf c, t, part, scal, gs;
-    const int rb2 = n2p / csk::TB;
-    int ns = 1, cps = 0;
-    split_plan(f->nblk, np, &ns, &cps);
-    if (c.alloc(sizeof(double) * np) || t.alloc(sizeof(double) * np) || part.alloc(sizeof(double) * np * ns) ||
-        scal.alloc(sizeof(double) * 2) || gs.alloc(sizeof(double) * rb2 * rb2))
-      return fail(CS_ERR_NOMEM, "alloc failed");
-    auto k = csp::colsum_kernel;
-    ++g_launches;
-    CS_LAUNCH(k, (np * 32 + 255) / 256, 256, 0, st, W.Kc.d(), (long long)n2p, n2, np, c.d());
-    auto k2 = csk::matvec_kernel<1>;
-    ++g_launches;
-    const double* nul = nullptr;
-    CS_LAUNCH(k2, dim3(f->nblk, ns), csk::ETH, 0, st, f->eng.C, (long long)np, cps, np, c.d(), nul, nul, nul, part.d(),
-              (long long)np, (long long)np, (const int*)nullptr, 0LL);
-    auto k3 = csp::reduce_parts_kernel;
-    ++g_launches;
-    CS_LAUNCH(k3, (np + 255) / 256, 256, 0, st, part.d(), ns, (long long)np, np, nul, t.d());
-    auto k4 = csp::dot_kernel;
-    ++g_launches;
-    CS_LAUNCH(k4, 1, csk::ETH, 0, st, c.d(), t.d(), f->n, scal.d());
-    auto k5 = csp::gram_sum_kernel;
-    ++g_launches;
-    CS_LAUNCH(k5, dim3(rb2, rb2), csk::ETH, csk::gram_smem_bytes(p), st, W.X2.d(), (long long)n2p, n2, f->params, f->lay,
-              gs.d());
-    ++g_launches;
-    CS_LAUNCH(k4, 1, csk::ETH, 0, st, gs.d(), nul, rb2 * rb2, scal.d() + 1);
-    KCHECK();
+    DevBuf scal;
+    if (scal.alloc(sizeof(double) * 2)) return fail(CS_ERR_NOMEM, "alloc failed");
+    if ((e = treat_sumcov_enqueue(f, W, n2, scal.d()))) return e;
     double h[2];
     RT(rt::d2h(h, scal.d(), sizeof h, st));
     RT(rt::stream_sync(st));
@@ -1358,12 +1394,12 @@ static int grad_stats_common(int kind, int n, int p, const double* y, const doub
       auto k3 = csk::grad_trace_kernel<true>;
       CS_LAUNCH(k3, f->ncta_grad, csk::ETH, csk::grad_smem_bytes(p), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
                 f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)dK.d(), (const double*)dM.d(),
-                (const double*)dA.d(), (const int*)nullptr, (const int*)nullptr);
+                (const double*)dA.d(), (const int*)nullptr, (const int*)nullptr, rt::XTma{});
     } else {
       auto k3 = csk::grad_trace_kernel<false>;
       CS_LAUNCH(k3, f->ncta_grad, csk::ETH, csk::grad_smem_bytes(p), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
                 f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)nullptr,
-                (const double*)nullptr, (const double*)nullptr, (const int*)nullptr, (const int*)nullptr);
+                (const double*)nullptr, (const double*)nullptr, (const int*)nullptr, (const int*)nullptr, rt::XTma{});
     }
     auto k40 = csk::rowstats_kernel;
     ++g_launches;

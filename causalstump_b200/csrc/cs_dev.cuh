@@ -77,6 +77,34 @@ __device__ __forceinline__ double2 ld_stream2(const double* p) {  // 16-byte ali
 #endif
 }
 
+// ---- TMA (cp.async.bulk.tensor, SASS UTMALDG) + mbarrier: one elected thread stages a whole operand tile into shared
+// memory with a single instruction; the consumers wait on the transaction barrier.  Product build only: the SIMT
+// emulator keeps the plain copy loops (its thread blocks run to completion one after another, nothing to overlap).
+#ifndef CS_EMU
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// generic-proxy reads of a shared-memory buffer are ordered before the async-proxy (TMA) writes that refill it
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, unsigned long long* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+#endif
+
 // Batched launches (cs_fit_create_batch): every per-fit device buffer sits at the same offset of a
 // per-fit slab, so one launch serves B fits with blockIdx.z selecting the slab (bstride bytes apart).
 template <class T>

@@ -19,6 +19,7 @@ typedef int cudaError_t;
 #define CS_LAUNCH(kfn, grid, block, smem, stream, ...) \
   emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kfn(__VA_ARGS__); })
 #define CS_SET_SMEM(kfn, bytes) ((void)0)
+#define __grid_constant__
 namespace rt {
 inline int check(int e, const char*, int) { return e; }
 inline int dev_malloc(void** p, size_t bytes) { *p = std::malloc(bytes ? bytes : 1); return *p ? 0 : 2; }
@@ -51,6 +52,8 @@ inline int copy2d(double* dst, long long ldd, const double* src, long long lds, 
   return 0;
 }
 inline int stream_create_level(cudaStream_t* s, int) { *s = 0; return 0; }
+struct XTma { int on; };  // no TMA on the emulator (see cs_dev.cuh)
+inline int make_x_tensormap(XTma* out, const double*, long long, int, int, long long) { out->on = 0; return 1; }
 typedef int graph_exec_t;
 inline int graph_begin(cudaStream_t) { return 1; }  // no graphs on the emulator: eager launches
 inline int graph_end(cudaStream_t, graph_exec_t*) { return 1; }
@@ -63,7 +66,7 @@ inline int graph_destroy(graph_exec_t) { return 0; }
 
 #include <mutex>
 #define CS_DYN_SMEM(T, name) \
-  extern __shared__ __align__(16) unsigned char cs_dyn_smem_raw[]; \
+  extern __shared__ __align__(128) unsigned char cs_dyn_smem_raw[]; \
   T* name = reinterpret_cast<T*>(cs_dyn_smem_raw)
 #define CS_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define CS_SET_SMEM(kfn, bytes) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
@@ -192,6 +195,29 @@ inline int partition_streams(int sm_crit, cudaStream_t* crit_hi, cudaStream_t* c
   }
   if (sm_a) *sm_a = P.sm_a;
   if (sm_b) *sm_b = P.sm_b;
+  return 0;
+}
+// TMA descriptor of a covariate matrix X (np rows x p columns, column-major, one per member of a batched handle `slab`
+// bytes apart): a 3-D tensor {np, p, members} with box {64, p, 1}, so ONE cp.async.bulk.tensor instruction brings the
+// [p][64] X tile of a 64-row block into shared memory in exactly the layout the element-wise kernels index (xs[i*64 + r]).
+// Passed to the kernels by value as a __grid_constant__ parameter.  on == 0: the kernels use their plain copy loops.
+struct XTma { CUtensorMap map; int on; };
+inline int make_x_tensormap(XTma* out, const double* X, long long np, int p, int members, long long slab_bytes) {
+  out->on = 0;
+  if (p < 1 || p > 256 || np % 64 != 0 || (reinterpret_cast<unsigned long long>(X) & 15ull) || std::getenv("CS_NO_TMA")) return 1;
+  CUresult (*f_enc)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
+  if (!drv_sym("cuTensorMapEncodeTiled", &f_enc)) return 1;
+  const cuuint64_t dims[3] = {(cuuint64_t)np, (cuuint64_t)p, (cuuint64_t)(members > 0 ? members : 1)};
+  const cuuint64_t col = (cuuint64_t)np * sizeof(double);
+  const cuuint64_t strides[2] = {col, members > 1 ? (cuuint64_t)slab_bytes : col * (cuuint64_t)p};
+  if (strides[1] % 16 != 0) return 1;
+  const cuuint32_t box[3] = {64u, (cuuint32_t)p, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  if (f_enc(&out->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(X), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return 1;
+  out->on = 1;
   return 0;
 }
 // CUDA graphs: one optimizer iteration (all its launches, both streams) is captured once

@@ -337,6 +337,7 @@ struct DenseEngine {
   long long bstride = 0;
   bool external_buffers = false;  // G, X, C, logdet_part, status, Pbuf belong to the caller's slab
   bool single_panel = false;      // one panel = the whole matrix: X = L^-1 is complete after the Cholesky plan
+  bool left_looking = false;      // batched handles: left-looking Cholesky (one growing-K update per block column)
   bool reset_status = true;       // false while the optimisation loop runs: a non-PD pivot of ANY iteration must survive
   int panel_blocks = 4;             // outer panel width in blocks (maximum)
   std::vector<int> bounds;          // plan v2: panel boundaries in blocks (graded: narrow first and last panels)
@@ -819,8 +820,39 @@ struct DenseEngine {
     for (int ev : {last_aux_ev, last_u2b_ev, last_u2brest_ev, last_inv_ev, last_inv3_ev, last_rest_ev, last_s6_ev, ev_u1top_prev})
       if (ev >= 0) op(OP_WAIT, 0, ev);
     };
+    // ---- left-looking plan for batched small-n handles: block column k is first brought up to date with ONE multiply whose
+    // k-extent is everything to its left, C[k:N, k] -= L[k:N, 0:k] L[k, 0:k]^T (K = k*TILE), then the diagonal tile is
+    // factored and inverted (leaf) and the column below it multiplied by X_kk^T.  The flops are those of the right-looking
+    // plan, but they sit in N-1 launches of growing K instead of ~N^2/2 rank-TILE updates whose pipeline fill is as long as
+    // their main loop (K = 64: 5.5 TFLOP/s effective).  One stream: the members of the batch (blockIdx.z) are the
+    // parallelism.  3 launches per block step.
+    auto build_chol_ll = [&](std::vector<Launch>& seq) {
+      for (int k = 0; k < N; ++k) {
+        if (k > 0) {
+          double* rows = G + (long long)k * T;                               // block rows k.., column 0
+          grp.push_back(mk(rows, ld, rows, ld, G + (long long)k * T * (ld + 1), ld, (N - k) * rr, rr, k * tile, csg::KM_FULL, csg::ORD_COL, 0, -1.0, 1.0));
+          add_group(seq, GK_NT, grp);
+        }
+        { Launch L{}; L.is_leaf = OP_LEAF; L.blk = k; seq.push_back(L); }
+        const int nb = N - 1 - k;
+        if (nb > 0) {
+          double* pan = G + (long long)(k + 1) * T + (long long)k * T * ld;
+          double* Xkk = X + (long long)k * T * (ld + 1);
+          if (rr == 2) {  // see push_panel: right half first, then the left half with K = 64 (in-place safe per CTA)
+            grp.push_back(mk(pan, ld, Xkk + gt, ld, pan + gt * ld, ld, nb * rr, 1, tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
+            add_group(seq, GK_NT, grp);
+            grp.push_back(mk(pan, ld, Xkk, ld, pan, ld, nb * rr, 1, gt, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
+            add_group(seq, GK_NT, grp);
+          } else {
+            grp.push_back(mk(pan, ld, Xkk, ld, pan, ld, nb, 1, tile, csg::KM_FULL, csg::ORD_COL, 0, 1.0, 0.0));
+            add_group(seq, GK_NT, grp); seq.back().gtile = tile;
+          }
+        }
+      }
+    };
     plan_version = 2;
     if (const char* pv = std::getenv("CS_PLAN")) plan_version = std::atoi(pv);
+    left_looking = nbatch > 1 && !inv_pipeline && N > 1 && std::getenv("CS_PLAN") == nullptr && std::getenv("CS_BATCH_RIGHT") == nullptr;
     top32 = tile == 128 && gt == 64 && nbatch == 1 && !std::getenv("CS_NO_TOP32");
     split_u2b = nbatch == 1 && !std::getenv("CS_NO_U2B_SPLIT");
     {
@@ -880,7 +912,9 @@ struct DenseEngine {
         tail_from = got > 1 ? f : 0;
       }
     }
-    if (plan_version == 1) {
+    if (left_looking) {
+      build_chol_ll(potrf);
+    } else if (plan_version == 1) {
       build_chol(potrf, false);
       if (inv_pipeline) build_chol(potrf_inv, true);
     } else {

@@ -592,7 +592,7 @@ struct DistEval {
       auto k3 = csk::grad_trace_kernel<false>; ++g_launches;
       CS_LAUNCH(k3, R.ncta_grad, csk::ETH, csk::grad_smem_bytes(R.lay.p), R.st, R.X, ld, R.z, R.params, R.lay, g.n, R.n_k3,
                 R.C, g.ldl, R.alpha, R.sc, R.gpart, kal, (long long)0, (const double*)nullptr, (const double*)nullptr,
-                (const double*)nullptr, (const int*)nullptr, (const int*)R.d_k3);
+                (const double*)nullptr, (const int*)nullptr, (const int*)R.d_k3, rt::XTma{});
       auto k4 = csk::reduce_gpart_kernel; ++g_launches;
       CS_LAUNCH(k4, 1, 128, 0, R.st, R.gpart, R.ncta_grad, nacc, R.red);
       if (!R.diag_tiles.empty()) {

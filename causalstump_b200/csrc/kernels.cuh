@@ -106,9 +106,11 @@ inline int gram_smem_bytes(int p) { return (2 * p * TB + 2 * PMAX + 3 * TB) * (i
 __global__ void __launch_bounds__(ETH)
 gram_train_kernel(const double* __restrict__ X, long long ldx, const double* __restrict__ z,
                   const double* __restrict__ w, const double* __restrict__ params, Layout lay, int n,
-                  double* __restrict__ G, long long ldg, const int* __restrict__ skip, int tile0) {
+                  double* __restrict__ G, long long ldg, const int* __restrict__ skip, int tile0,
+                  const __grid_constant__ rt::XTma xt) {
   // tile0: first lower-triangular tile of this launch (the Gram build is split so that the first diagonal
   // block of the Cholesky can start while the rest of the matrix is still being built)
+  // xt: TMA descriptor of X (rt::make_x_tensormap): the two [p][64] covariate tiles arrive by one bulk tensor copy each
   CS_BS(skip);
   if (skip && *skip) return;
   CS_BS(X); CS_BS(z); CS_BS(w); CS_BS(params); CS_BS(G);
@@ -129,11 +131,28 @@ gram_train_kernel(const double* __restrict__ X, long long ldx, const double* __r
   while ((long long)I * (I + 1) / 2 > t) --I;
   const int J = t - I * (I + 1) / 2;
   const int r0 = I * TB, c0 = J * TB;
-  load_x_tile(xr, X, ldx, r0, p, tid);
-  load_x_tile(xc, X, ldx, c0, p, tid);
+#ifndef CS_EMU
+  __shared__ unsigned long long xbar;
+  if (xt.on) {
+    if (tid == 0) {
+      csd::mbar_init(&xbar, 1);
+      csd::mbar_fence_init();
+      csd::mbar_expect_tx(&xbar, 2u * (unsigned)p * TB * (unsigned)sizeof(double));
+      csd::tma_load_3d(xr, &xt.map, &xbar, r0, 0, (int)blockIdx.z);
+      csd::tma_load_3d(xc, &xt.map, &xbar, c0, 0, (int)blockIdx.z);
+    }
+  } else
+#endif
+  {
+    load_x_tile(xr, X, ldx, r0, p, tid);
+    load_x_tile(xc, X, ldx, c0, p, tid);
+  }
   if (tid < p) { ea[tid] = exp(-params[lay.i_Lm() + tid]); eb[tid] = exp(-params[lay.i_La() + tid]); }
   if (tid < TB) { zr[tid] = z[r0 + tid]; zc[tid] = z[c0 + tid]; wr[tid] = w[r0 + tid]; }
   __syncthreads();
+#ifndef CS_EMU
+  if (xt.on) csd::mbar_wait(&xbar, 0);
+#endif
   const double lam_m = params[lay.i_lm()], lam_a = params[lay.i_la()];
   const double esig = exp(params[lay.i_sigma()]);
   double sm[4][4], sa[4][4];
@@ -323,8 +342,16 @@ scalars_kernel(const double* __restrict__ mv_part, int nsplit, long long stride_
 //   gpart[cta][2+p+i]    = sum T .* Ka .* d_i^2
 // and K*alpha row partials go to kal_part[slot][row] (each slot/row written exactly once).
 // ---------------------------------------------------------------------------------
-inline int grad_smem_bytes(int p) {
-  return ((2 * p + 2) * ETH + 2 * p * TB + 2 * PMAX + 5 * TB + 8 * TB + 32) * (int)sizeof(double);
+inline int grad_smem_bytes(int p, bool prefetch = false) {  // prefetch: a second pair of X tiles (TMA double buffering)
+  return ((2 * p + 2) * ETH + (prefetch ? 4 : 2) * p * TB + 2 * PMAX + 5 * TB + 8 * TB + 32) * (int)sizeof(double);
+}
+inline bool grad_prefetch_fits(int p) { return grad_smem_bytes(p, true) <= 227 * 1024; }
+
+__host__ __device__ inline void lower_tile_of(int t, int& I, int& J) {
+  I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((long long)(I + 1) * (I + 2) / 2 <= t) ++I;
+  while ((long long)I * (I + 1) / 2 > t) --I;
+  J = t - I * (I + 1) / 2;
 }
 
 template <bool FROM_MEM>
@@ -335,7 +362,9 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
                   const EvalScalars* __restrict__ sc, double* __restrict__ gpart, double* __restrict__ kal_part,
                   long long kal_stride, const double* __restrict__ Kmat_in, const double* __restrict__ Km_in,
                   const double* __restrict__ Ka_in, const int* __restrict__ skip,
-                  const int* __restrict__ tile_tab) {
+                  const int* __restrict__ tile_tab, const __grid_constant__ rt::XTma xt) {
+  // xt.on (never together with tile_tab): the X tiles of the NEXT tile of this persistent CTA are fetched by TMA into a
+  // second pair of buffers while the current tile is being processed (grad_smem_bytes(p, true))
   // tile_tab != null (distributed mode): nblk is the number of table entries
   // (I64, J64, coff_lo, coff_hi); Cinv + coff is the local 64 x 64 tile and K*alpha is
   // accumulated into the vector kal_part with atomics (kal_stride is ignored).
@@ -358,6 +387,26 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
   double* rred = csum + TB;             // [8][TB]
   double* red = rred + 8 * TB;          // [32]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, wid = tid >> 5;
+#ifndef CS_EMU
+  double* const xbase = xr;                                  // buffer b: row tile at xbase + b * xoff, column tile p*TB behind it
+  const long long xoff = (red + 32) - xr;                   // (all 128-byte aligned)
+  __shared__ unsigned long long xbar[2];
+  const bool tma = xt.on && !tile_tab;
+  if (tma && tid == 0) {
+    csd::mbar_init(&xbar[0], 1);
+    csd::mbar_init(&xbar[1], 1);
+    csd::mbar_fence_init();
+    const int t0 = (int)blockIdx.x;
+    if (t0 < nblk * (nblk + 1) / 2) {
+      int I0, J0;
+      lower_tile_of(t0, I0, J0);
+      csd::mbar_expect_tx(&xbar[0], 2u * (unsigned)p * TB * (unsigned)sizeof(double));
+      csd::tma_load_3d(xbase, &xt.map, &xbar[0], I0 * TB, 0, (int)blockIdx.z);
+      csd::tma_load_3d(xbase + p * TB, &xt.map, &xbar[0], J0 * TB, 0, (int)blockIdx.z);
+    }
+  }
+  int local_tile = 0;
+#endif
   for (int k = 0; k < nacc; ++k) acc[k * ETH + tid] = 0.0;
   if (tid < p) { ea[tid] = exp(-params[lay.i_Lm() + tid]); eb[tid] = exp(-params[lay.i_La() + tid]); }
   const double lam_m = params[lay.i_lm()], lam_a = params[lay.i_la()];
@@ -381,10 +430,33 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
     const int r0 = I * TB, c0 = J * TB;
     const double wgt = (I == J) ? 1.0 : 2.0;
     __syncthreads();  // previous tile fully consumed
-    load_x_tile(xr, X, ldx, r0, p, tid);
-    load_x_tile(xc, X, ldx, c0, p, tid);
+#ifndef CS_EMU
+    if (tma) {
+      const int b = local_tile & 1;
+      if (tid == 0) {  // the buffers of the previous tile are free now: refill them with the next tile of this CTA
+        const int tn = t + (int)gridDim.x;
+        if (tn < ntiles) {
+          int In, Jn;
+          lower_tile_of(tn, In, Jn);
+          csd::fence_proxy_async();
+          csd::mbar_expect_tx(&xbar[b ^ 1], 2u * (unsigned)p * TB * (unsigned)sizeof(double));
+          double* nxt = xbase + (b ^ 1) * xoff;
+          csd::tma_load_3d(nxt, &xt.map, &xbar[b ^ 1], In * TB, 0, (int)blockIdx.z);
+          csd::tma_load_3d(nxt + p * TB, &xt.map, &xbar[b ^ 1], Jn * TB, 0, (int)blockIdx.z);
+        }
+      }
+      xr = xbase + b * xoff; xc = xr + p * TB;
+    } else
+#endif
+    {
+      load_x_tile(xr, X, ldx, r0, p, tid);
+      load_x_tile(xc, X, ldx, c0, p, tid);
+    }
     if (tid < TB) { zr[tid] = z[r0 + tid]; zc[tid] = z[c0 + tid]; ar[tid] = alpha[r0 + tid]; ac[tid] = alpha[c0 + tid]; }
     __syncthreads();
+#ifndef CS_EMU
+    if (tma) { csd::mbar_wait(&xbar[local_tile & 1], (unsigned)((local_tile >> 1) & 1)); ++local_tile; }
+#endif
     // the K^-1 entries of this tile are requested first so that their HBM latency hides behind the
     // distance / exponent arithmetic
     double tv[4][4];

@@ -59,6 +59,7 @@ def test_distributed_engine_against_the_compiled_reference(gpulib, gold, mode):
     y, X, z, w, par = mk.case_inputs("GP", 8192, False)
     assert mk.digest(y, X, z, w, par) == str(gold["gp8192/digest"])
     if mode == "nccl_1x1":
+        import torch  # noqa: F401  (loads the NCCL that cs_dist binds to by soname, as bench.py does)
         f = _lib.DistFit(gpulib, 0, y, X, z, w, par, 0, 1, 1, 1, gpulib.dist_unique_id())
         try:
             g, st, mu, _ = f.eval()
