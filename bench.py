@@ -397,7 +397,14 @@ def measure_fp64_peak(torch, dev):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def measure_fits(lib, rank, world, nfit, batch=32):
+def run_units(units, batch, host_sim):
+    """The replicate loop: on the device end to end (cs_sim_run: generator, split, fits, predict / treatment, metrics) or,
+    with --host-sim, with the generator / split / metrics in host NumPy around the device fits (the round-1 driver)."""
+    from causalstump_b200 import replicates as rp
+    return rp.hill_units_concurrent(units, batch=batch) if host_sim else rp.hill_units_device(units, batch=batch)
+
+
+def measure_fits(lib, rank, world, nfit, batch=32, host_sim=False):
     """Metric ii: one 'fit' = CausalStump() on a 672 x 25 training split to the reference's
     stopping rule (maxiter=3000, tol=1e-1, lr=.01, Nadam; test/sec5-3_Hill2011.R:344-345)
     + predict on 747 + treatment on 672 and 75.  The nfit fits of this rank (replicates x
@@ -405,9 +412,9 @@ def measure_fits(lib, rank, world, nfit, batch=32):
     Returns (seconds, fits, iterations, mean PEHE of the restart winners)."""
     from causalstump_b200 import replicates as rp
     units = [(rank * ((nfit + 3) // 4) + k // 4, k % 4) for k in range(nfit)]
-    rp.hill_units_concurrent(units[:2], batch=batch)  # warm-up: library load, graph capture, allocator
+    run_units(units[:2], batch, host_sim)  # warm-up: library load, graph capture, allocator
     t0 = time.perf_counter()
-    res = rp.hill_units_concurrent(units, batch=batch)
+    res = run_units(units, batch, host_sim)
     secs = time.perf_counter() - t0
     win = rp.select_winners(res)
     return secs, nfit, [r["iters"] for r in res], float(np.mean([w["pehe_test"] for w in win]))
@@ -461,16 +468,16 @@ def measure_stateless_boundary(sizes=((747, 3), (8192, 1))):
     return out
 
 
-def measure_config4(lib, rank, world, dist, barrier, max_over_ranks, batch):
+def measure_config4(lib, rank, world, dist, barrier, max_over_ranks, batch, host_sim=False):
     """Config 4 AS STATED (test/sec5-3_Hill2011.R:611-616): 100 replicates x 4 restarts = 400 independent fits SPLIT over the
     N GPUs (static round-robin of (replicate, restart) units, no collective; the result rows are gathered on rank 0 and the
     restart with the highest final LML wins per replicate).  Strong scaling: 400 / N fits per GPU."""
     from causalstump_b200 import replicates as rp
     units = rp.shard(rp.unit_list(100, 4), rank, world)
-    rp.hill_units_concurrent(units[:2], batch=batch)  # warm-up: graph capture, allocator
+    run_units(units[:2], batch, host_sim)  # warm-up: graph capture, allocator
     barrier()
     t0 = time.perf_counter()
-    res = rp.hill_units_concurrent(units, batch=batch)
+    res = run_units(units, batch, host_sim)
     secs_local = time.perf_counter() - t0
     tim = dict(rp.LAST_TIMING)
     secs = max_over_ranks(secs_local)
@@ -489,8 +496,10 @@ def measure_config4(lib, rank, world, dist, barrier, max_over_ranks, batch):
     its = [d for a, b, c, d, e, f in rows]
     return {"what": "config 4 as stated: 100 Hill surface-B replicates x 4 restarts = 400 GP fits (672 x 25 training split, reference stopping "
                     "rule maxiter 3000 / tol 1e-1 / lr .01 Nadam, + predict(747) + treatment(672, 75) + the 22 metrics) split over "
-                    "%d GPU(s), %d fits per GPU in batched handles of %d; wall time incl. host data generation and handle creation, "
-                    "max over ranks" % (world, len(units), batch),
+                    "%d GPU(s), %d fits per GPU in batched handles of %d; %s; wall time of the whole loop incl. handle creation, "
+                    "max over ranks" % (world, len(units), batch, "generator / split / metrics in host NumPy (--host-sim)" if host_sim else
+                                        "simulation driver on the device (cs_sim_run: Philox response-surface generator, split, "
+                                        "normalisation, fits, predict / treatment and the metric block never leave the GPU)"),
             "fits": len(rows), "fits_per_gpu": len(units), "seconds": secs, "value": len(rows) / secs * 3600.0, "unit": "fits/hour",
             "scaling": "strong", "iterations_mean": float(np.mean(its)), "iterations_max": int(np.max(its)),
             "slot_utilisation": float(sum(u[0] for u in util) / max(sum(u[1] for u in util), 1e-12)),
@@ -751,7 +760,7 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_fits:
         nfit = args.fits
         barrier()
-        secs, nf, iters, pehe = measure_fits(lib, rank, world, nfit, args.fit_batch)
+        secs, nf, iters, pehe = measure_fits(lib, rank, world, nfit, args.fit_batch, args.host_sim)
         secs = max_over_ranks(secs)
         if dist is not None:
             all_it = [None] * world
@@ -762,12 +771,13 @@ def run_ours(args, rank, world, local_rank):
                     "what": "GP fit on a 672x25 Hill surface-B split to the reference stopping rule (maxiter 3000, tol 1e-1, "
                             "lr .01, Nadam) + predict(747) + treatment(672, 75); %d (replicate, restart) fits per GPU in batched handles of %d "
                             "members (cs_fit_create_batch, every launch serves a whole batch), handles driven concurrently "
-                            "(cs_fit_run_many); includes host data generation and handle creation" % (nf, args.fit_batch)}
+                            "(cs_fit_run_many); %s; includes handle creation" % (nf, args.fit_batch, "host generator / metrics (--host-sim)" if args.host_sim
+                                                                                else "simulation driver on the device (cs_sim_run)")}
 
     # ---- the two sharded configurations of BASELINE.json (extra objects; SCALE records them at N = 1, 2, 4, 8) ----
     c4_obj = c5_obj = None
     if not args.no_configs:
-        c4_obj = measure_config4(lib, rank, world, dist, barrier, max_over_ranks, args.fit_batch)
+        c4_obj = measure_config4(lib, rank, world, dist, barrier, max_over_ranks, args.fit_batch, args.host_sim)
         if world in GRIDS:
             c5_obj = measure_config5(lib, torch, dev, rank, world, dist, barrier)
 
@@ -856,6 +866,7 @@ def main():
     ap.add_argument("--fits", type=int, default=256, help="(replicate, restart) fits per GPU for the fits/hour object")
     ap.add_argument("--fit-batch", type=int, default=32, help="members per batched handle (cs_fit_create_batch); 1 = one handle per fit")
     ap.add_argument("--no-fits", action="store_true")
+    ap.add_argument("--host-sim", action="store_true", help="replicate loop with the generator / split / metrics in host NumPy (round-1 driver) instead of cs_sim_run")
     ap.add_argument("--no-configs", action="store_true", help="skip the config4 (400 fits split over N) and config5 (n=32768 on a P x Q grid) objects")
     ap.add_argument("--inv-pipeline", type=int, default=1, help="1: inverse pipelined behind the Cholesky (default); 0: recursive inverse after it")
     ap.add_argument("--partition", type=int, default=0, help="SM partition for the Cholesky chain: 0 auto, 1 on, -1 off")

@@ -30,6 +30,14 @@ class cs_fit_config(C.Structure):
                 ("partition", C.c_int)]
 
 
+class cs_sim_config(C.Structure):
+    _fields_ = [("n", C.c_int), ("p", C.c_int), ("test_frac", C.c_double), ("maxiter", C.c_int), ("tol", C.c_double),
+                ("lr", C.c_double), ("optim", C.c_int), ("batch", C.c_int), ("seed", C.c_ulonglong)]
+
+
+CS_SIM_NMETRIC = 22
+
+
 class CsError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"cs_b200 error {code}: {msg}")
@@ -70,6 +78,10 @@ _SIGS = {
                                   C.POINTER(dp)]),
     "cs_fit_member_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "cs_release_scratch": (C.c_int, []),
+    "cs_sim_run": (C.c_int, [C.POINTER(cs_sim_config), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), dp, dp, dp, C.POINTER(C.c_int), dp,
+                             C.POINTER(C.c_int)]),
+    "cs_sim_generate": (C.c_int, [C.POINTER(cs_sim_config), C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_int), dp, dp, dp,
+                                  dp, dp, dp]),
     "cs_fit_set_data": (C.c_int, [C.c_void_p, dp, dp, dp, dp]),
     "cs_fit_get_params": (C.c_int, [C.c_void_p, dp]),
     "cs_fit_set_params": (C.c_int, [C.c_void_p, dp]),
@@ -198,6 +210,45 @@ class CsLib:
 
     def launch_count(self):
         return int(self.dll.cs_launch_count())
+
+    # -- simulation driver on the device (cs_sim_*) ------------------------------------------
+    @staticmethod
+    def _sim_cfg(n, p, test_frac, maxiter, tol, lr, optim, batch, seed):
+        return cs_sim_config(int(n), int(p), float(test_frac), int(maxiter), float(tol), float(lr), int(optim), int(batch), int(seed))
+
+    def sim_run(self, units, n=747, p=25, X=None, z=None, test_frac=0.1, maxiter=3000, tol=1e-1, lr=0.01, optim=CS_OPT_NADAM,
+                batch=32, seed=565):
+        """units = [(replicate, restart), ...] -> dict(metrics[nunits, 22], iters, lml, status): generator, split, normalisation,
+        fits, predict / treatment and the 22-metric block all on the device (cs_sim_run)."""
+        nu = len(units)
+        rep = (C.c_int * nu)(*[int(u[0]) for u in units])
+        rs = (C.c_int * nu)(*[int(u[1]) for u in units])
+        if X is not None:
+            X = _f64(X); z = _f64(z)
+            n, p = X.shape
+        cfg = self._sim_cfg(n, p, test_frac, maxiter, tol, lr, optim, batch, seed)
+        met = np.empty((nu, CS_SIM_NMETRIC))
+        its, st = (C.c_int * nu)(), (C.c_int * nu)()
+        lml = np.empty(nu)
+        self.check(self.dll.cs_sim_run(C.byref(cfg), nu, rep, rs, _ptr(X), _ptr(z), _ptr(met), its, _ptr(lml), st))
+        return dict(metrics=met, iters=np.array(list(its)), lml=lml, status=np.array(list(st)))
+
+    def sim_generate(self, replicate, restart, n=747, p=25, X=None, z=None, test_frac=0.1, seed=565, kind=CS_GP):
+        """The device generator alone for one unit (test hook, cs_sim_generate)."""
+        if X is not None:
+            X = _f64(X); z = _f64(z)
+            n, p = X.shape
+        import math
+        ntr = n - int(math.ceil(n * test_frac))
+        cfg = self._sim_cfg(n, p, test_frac, 1, 0.0, 0.01, CS_OPT_NADAM, 1, seed)
+        o = dict(Xraw=np.empty((n, p), order="F"), z=np.empty(n), y=np.empty(n), y1=np.empty(n), y0=np.empty(n),
+                 is_test=np.empty(n, dtype=np.int32), Xtrain=np.empty((ntr, p), order="F"), ytrain=np.empty(ntr), ztrain=np.empty(ntr),
+                 Xall=np.empty((n, p), order="F"), moments=np.empty(2 * p + 2), params=np.empty(2 * p + 4))
+        self.check(self.dll.cs_sim_generate(C.byref(cfg), int(replicate), int(restart), _ptr(X), _ptr(z), _ptr(o["Xraw"]), _ptr(o["z"]),
+                                            _ptr(o["y"]), _ptr(o["y1"]), _ptr(o["y0"]), o["is_test"].ctypes.data_as(C.POINTER(C.c_int)),
+                                            _ptr(o["Xtrain"]), _ptr(o["ytrain"]), _ptr(o["ztrain"]), _ptr(o["Xall"]), _ptr(o["moments"]),
+                                            _ptr(o["params"])))
+        return o
 
     # -- config 5: distributed evaluation -------------------------------------------------
     def dist_sim_eval(self, kind, y, X, z, w, params, P, Q, T=128):

@@ -231,6 +231,9 @@ struct cs_fit {
   size_t pinned_bytes = 0;
   rt::graph_exec_t iter_graph{};   // one captured optimizer iteration
   bool graph_ok = false, graph_tried = false;
+  rt::graph_exec_t loop_graph{};   // the whole optimisation loop as one conditional WHILE graph (no host polling)
+  bool loop_ok = false;
+  bool loop_running = false;
   long long launches_per_iter = 0;
   HostLoop* h_ls = nullptr;  // pinned: loop state + status read-back, one per member
   double* trace_unused = nullptr;
@@ -419,9 +422,12 @@ int cs_release_scratch(void) {  // predict / treatment scratch retained by the c
 static int fit_create_impl(const cs_fit_config* cfg, int nbatch, int n, int p, const double* const* ys,
                            const double* const* Xs, const double* const* zs, const double* const* ws,
                            const double* const* inits, cs_fit** out) {
-  if (!cfg || !ys || !Xs || !zs || !inits || !out) return fail(CS_ERR_ARG, "cs_fit_create: null argument");
+  // ys == nullptr: "device fill" -- the slabs are allocated and zeroed, the caller's kernels write the training data and the
+  // initial parameters of every member (the simulation driver, sim.cuh)
+  const bool device_fill = (ys == nullptr);
+  if (!cfg || !out || (!device_fill && (!Xs || !zs || !inits))) return fail(CS_ERR_ARG, "cs_fit_create: null argument");
   if (nbatch < 1) return fail(CS_ERR_ARG, "cs_fit_create_batch: nbatch must be positive");
-  for (int b = 0; b < nbatch; ++b)
+  for (int b = 0; b < nbatch && !device_fill; ++b)
     if (!ys[b] || !Xs[b] || !zs[b] || !inits[b]) return fail(CS_ERR_ARG, "cs_fit_create: null argument (member %d)", b);
   if (n < 1 || p < 1) return fail(CS_ERR_ARG, "cs_fit_create: n and p must be positive");
   if (p > CS_MAX_P) return fail(CS_ERR_UNSUPPORTED, "cs_fit_create: p=%d exceeds CS_MAX_P=%d", p, CS_MAX_P);
@@ -481,7 +487,7 @@ static int fit_create_impl(const cs_fit_config* cfg, int nbatch, int n, int p, c
   if (int e = E.init(n, tile, cfg->gemm_tile, f->cfg.inv_pipeline, cfg->partition)) return bail(fail(e == 2 ? CS_ERR_NOMEM : CS_ERR_CUDA, "dense engine init failed: %s", rt::err_str(e)));
   cudaStream_t st = f->st;
   if (rt::memset0(f->slab, (size_t)f->slab_bytes * nbatch, st)) return bail(fail(CS_ERR_CUDA, "memset failed"));
-  for (int b = 0; b < nbatch; ++b) {
+  for (int b = 0; b < nbatch && !device_fill; ++b) {
     f->select(b);
     if (upload_matrix(f->X, np, np, p, Xs[b], n, p, st)) return bail(fail(CS_ERR_CUDA, "upload X failed"));
     if (upload_vector(f->y, np, ys[b], n, 0.0, st) || upload_vector(f->z, np, zs[b], n, 0.0, st))
@@ -511,11 +517,13 @@ static int fit_create_impl(const cs_fit_config* cfg, int nbatch, int n, int p, c
 int cs_fit_create(const cs_fit_config* cfg, int n, int p, const double* y, const double* X, const double* z,
                   const double* w, const double* init_params, cs_fit** out) {
   const double* ws[1] = {w};
+  if (!y) return fail(CS_ERR_ARG, "cs_fit_create: null argument");
   return fit_create_impl(cfg, 1, n, p, &y, &X, &z, ws, &init_params, out);
 }
 
 int cs_fit_create_batch(const cs_fit_config* cfg, int nbatch, int n, int p, const double* const* y, const double* const* X,
                         const double* const* z, const double* const* w, const double* const* init_params, cs_fit** out) {
+  if (!y) return fail(CS_ERR_ARG, "cs_fit_create_batch: null argument");
   return fit_create_impl(cfg, nbatch, n, p, y, X, z, w, init_params, out);
 }
 
@@ -536,6 +544,7 @@ void cs_fit_destroy(cs_fit* f) {
   if (f->pinned) rt::host_free(f->pinned);
   if (f->h_ls) rt::host_free(f->h_ls);
   if (f->graph_ok) rt::graph_destroy(f->iter_graph);
+  if (f->loop_ok) rt::graph_destroy(f->loop_graph);
   for (cudaEvent_t e : f->dense_ev) rt::event_destroy(e);
   f->eng.destroy();
   if (f->ev_ok) for (int i = 0; i < 16; ++i) rt::event_destroy(f->ev[i]);
@@ -658,6 +667,7 @@ static int fit_run_begin(cs_fit* f, int maxiter, double tol) {
     RT(rt::dev_malloc((void**)&f->trace, sizeof(double) * cap));
     f->trace_cap = cap;
     if (f->graph_ok) { rt::graph_destroy(f->iter_graph); f->graph_ok = false; }  // graph holds the old pointer
+    if (f->loop_ok) { rt::graph_destroy(f->loop_graph); f->loop_ok = false; }
     f->graph_tried = false;
   }
   if (!f->h_ls) RT(rt::host_alloc((void**)&f->h_ls, sizeof(HostLoop) * B));
@@ -692,6 +702,22 @@ static int fit_run_begin(cs_fit* f, int maxiter, double tol) {
       f->launches_per_iter = g_launches - l0;
       g_launches = l0;  // captured, not executed
     }
+#ifndef CS_EMU
+    // The loop itself on the device: WHILE(any member running) { evaluation; optimizer step; stopping rule }.  Kernels of a
+    // conditional body must share one context, so handles whose Cholesky chain runs on green-context streams (padded
+    // n >= 4096, iterations of >= 6 ms) keep the chunked host loop.
+    static const bool no_while = std::getenv("CS_NO_WHILE") != nullptr;
+    if (f->graph_ok && !f->eng.crit_ok && !no_while) {
+      const long long l1 = g_launches;
+      f->loop_ok = rt::graph_while_build(st, [&](rt::graph_cond_t h) {
+        fit_enqueue_eval(f, &f->ls->done, nullptr);
+        fit_enqueue_loop_step(f);
+        auto kc = csk::loop_cond_kernel;
+        CS_LAUNCH(kc, 1, 32, 0, st, (const LoopState*)f->ls, f->bstride, f->nbatch, h);
+      }, &f->loop_graph) == 0;
+      g_launches = l1;
+    }
+#endif
   }
   return 0;
 }
@@ -700,7 +726,13 @@ static int fit_run_begin(cs_fit* f, int maxiter, double tol) {
 static int fit_run_enqueue(cs_fit* f) {
   BaseMember base(f);
   cudaStream_t st = f->st;
-  const int todo = std::min(f->run_chunk, f->run_maxiter - f->run_launched);
+  const bool whole_loop = f->loop_ok && f->run_launched == 0;
+  if (whole_loop) {  // ONE launch runs every iteration up to convergence / maxiter of every member
+    if (rt::graph_launch(f->loop_graph, st) != 0) return fail(CS_ERR_CUDA, "loop graph launch failed: %s", rt::err_str(rt::last_error()));
+    f->loop_running = true;
+  }
+  const int todo = whole_loop ? 0 : std::min(f->run_chunk, f->run_maxiter - f->run_launched);
+  if (whole_loop) f->run_launched = f->run_maxiter;
   for (int i = 0; i < todo; ++i) {
     if (f->graph_ok) {
       if (rt::graph_launch(f->iter_graph, st) != 0)
@@ -725,6 +757,12 @@ static int fit_run_enqueue(cs_fit* f) {
 // in the reference only the failing CausalStump() call errors, not the other replicates of the cluster.
 static int fit_run_poll(cs_fit* f, int* finished) {
   RT(rt::stream_sync(f->st));
+  if (f->loop_running) {  // claimed launch count of the device-side loop: iterations actually run x launches of one iteration
+    int its = 0;
+    for (int b = 0; b < f->nbatch; ++b) its = std::max(its, f->h_ls[b].ls.it - 1);
+    g_launches += (f->launches_per_iter + 1) * (long long)its;
+    f->loop_running = false;
+  }
   int all_done = 1;
   for (int b = 0; b < f->nbatch; ++b)
     if (!f->h_ls[b].ls.done) all_done = 0;
@@ -1499,10 +1537,226 @@ int cs_opt_step(int optim, int nparam, double iter, double lr, double beta1, dou
 }
 
 
+}  // extern "C" (reopened below)
+
+// ------------------------------------------------------------------------------------
+// simulation driver on the device (kernels in sim.cuh)
+// ------------------------------------------------------------------------------------
+struct SimGroup {  // the units that share one batched fit handle
+  cs_fit* f = nullptr;
+  int B = 0, first = 0;
+  char* buf = nullptr;  // one allocation: everything below
+  css::SimArgs ga{};
+  css::MetricArgs ma{};
+  double *pred_map = nullptr, *tr_map = nullptr, *tr_var = nullptr, *te_map = nullptr, *te_var = nullptr, *scal = nullptr, *metrics = nullptr;
+  int* units = nullptr;
+  ~SimGroup() { if (f) cs_fit_destroy(f); if (buf) rt::dev_free(buf); }
+};
+
+static int sim_group_create(SimGroup& g, const cs_sim_config* cfg, int B, const int* replicate, const int* restart,
+                            const double* dXshared, const double* dzshared) {
+  const int n = cfg->n, p = cfg->p;
+  const int nte = (int)std::ceil(n * cfg->test_frac), ntr = n - nte;
+  cs_fit_config fc{};
+  fc.kind = CS_GP; fc.optim = cfg->optim; fc.lr = cfg->lr; fc.beta1 = 0.9; fc.beta2 = 0.999; fc.eps = 1e-8; fc.momentum = 0.0;
+  int e = fit_create_impl(&fc, B, ntr, p, nullptr, nullptr, nullptr, nullptr, nullptr, &g.f);
+  if (e) return e;
+  g.B = B;
+  cs_fit* f = g.f;
+  // carve the group's buffer
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t dn = sizeof(double) * n, dnp = dn * p;
+  const size_t o_units = take(sizeof(int) * 2 * B), o_Xraw = take(dnp * B), o_z = take(dn * B), o_y = take(dn * B), o_y1 = take(dn * B),
+               o_y0 = take(dn * B), o_ist = take(sizeof(int) * n * B), o_tri = take(sizeof(int) * ntr * B), o_tei = take(sizeof(int) * nte * B),
+               o_Xall = take(dnp * B), o_Xte = take(sizeof(double) * nte * p * B), o_mom = take(sizeof(double) * (2 * p + 2) * B),
+               o_pm = take(dn * B), o_trm = take(sizeof(double) * ntr * B), o_trv = take(sizeof(double) * ntr * B),
+               o_tem = take(sizeof(double) * nte * B), o_tev = take(sizeof(double) * nte * B), o_scal = take(sizeof(double) * 4 * B),
+               o_met = take(sizeof(double) * css::NMETRIC * B);
+  if (rt::dev_malloc((void**)&g.buf, off)) return fail(CS_ERR_NOMEM, "simulation buffers: allocation of %zu bytes failed", off);
+  auto D = [&](size_t o) { return reinterpret_cast<double*>(g.buf + o); };
+  auto I = [&](size_t o) { return reinterpret_cast<int*>(g.buf + o); };
+  g.units = I(o_units);
+  std::vector<int> hu(2 * (size_t)B);
+  for (int b = 0; b < B; ++b) { hu[2 * b] = replicate[b]; hu[2 * b + 1] = restart[b]; }
+  RT(rt::h2d(g.units, hu.data(), sizeof(int) * hu.size(), f->st));
+  RT(rt::stream_sync(f->st));
+  css::SimArgs& a = g.ga;
+  a.n = n; a.p = p; a.ntr = ntr; a.nte = nte; a.np_fit = f->np; a.seed = cfg->seed; a.units = g.units;
+  a.Xshared = dXshared; a.zshared = dzshared;
+  a.Xraw = D(o_Xraw); a.zraw = D(o_z); a.y = D(o_y); a.y1 = D(o_y1); a.y0 = D(o_y0);
+  a.is_test = I(o_ist); a.train_idx = I(o_tri); a.test_idx = I(o_tei); a.Xall = D(o_Xall); a.Xte = D(o_Xte); a.moments = D(o_mom);
+  f->select(0);
+  a.fX = f->X; a.fy = f->y; a.fz = f->z; a.fw = f->w; a.fones = f->ones; a.fparams = f->params; a.bstride = f->bstride; a.lay = f->lay;
+  a.lay.bstride = 0;
+  g.pred_map = D(o_pm); g.tr_map = D(o_trm); g.tr_var = D(o_trv); g.te_map = D(o_tem); g.te_var = D(o_tev); g.scal = D(o_scal);
+  g.metrics = D(o_met);
+  css::MetricArgs& m = g.ma;
+  m.n = n; m.p = p; m.ntr = ntr; m.nte = nte; m.y = a.y; m.z = a.zraw; m.y1 = a.y1; m.y0 = a.y0; m.train_idx = a.train_idx;
+  m.test_idx = a.test_idx; m.moments = a.moments; m.pred_map = g.pred_map; m.tr_map = g.tr_map; m.tr_var = g.tr_var;
+  m.te_map = g.te_map; m.te_var = g.te_var; m.scal = g.scal; m.metrics = g.metrics;
+  return 0;
+}
+
+static int sim_group_generate(SimGroup& g) {
+  auto k = css::sim_generate_kernel;
+  const int smem = css::sim_smem_bytes(g.ga.n, g.ga.p);
+  if (smem > 227 * 1024) return fail(CS_ERR_UNSUPPORTED, "simulation generator: n=%d does not fit the shared-memory staging", g.ga.n);
+  CS_SET_SMEM(k, smem);
+  ++g_launches;
+  CS_LAUNCH(k, g.B, css::SIM_THREADS, smem, g.f->st, g.ga);
+  KCHECK();
+  return 0;
+}
+
+// predict on all rows, treatment on the training and on the test rows of every member (inputs and outputs stay on the
+// device), then the metric block of the whole group as one kernel
+static int sim_group_post(SimGroup& g, const std::vector<int>& status) {
+  cs_fit* f = g.f;
+  const css::SimArgs& a = g.ga;
+  const int n = a.n, p = a.p, ntr = a.ntr, nte = a.nte;
+  ArenaScope scope(thread_arena());
+  const int keep = f->cur;
+  for (int b = 0; b < g.B; ++b) {
+    if (status[g.first + b] != 0) continue;
+    f->select(b);
+    if (g_arena) g_arena->reset();  // the previous member's scratch is reusable: same stream, launches are ordered
+    int e;
+    {
+      CrossWork W;
+      if ((e = cross_common(f, W, n, a.Xall + (size_t)b * n * p, n, a.zraw + (size_t)b * n, true, false, g.pred_map + (size_t)b * n,
+                            nullptr, 1.0, 0.0, nullptr))) { f->select(keep); return e; }
+    }
+    for (int sub = 0; sub < 2; ++sub) {
+      CrossWork W;
+      const int n2 = sub == 0 ? ntr : nte;
+      const double* X2 = sub == 0 ? f->X : a.Xte + (size_t)b * nte * p;
+      const long long ld2 = sub == 0 ? f->np : nte;
+      double* mp = sub == 0 ? g.tr_map + (size_t)b * ntr : g.te_map + (size_t)b * nte;
+      double* vr = sub == 0 ? g.tr_var + (size_t)b * ntr : g.te_var + (size_t)b * nte;
+      if ((e = cross_common(f, W, n2, X2, ld2, nullptr, true, true, mp, vr, 0.0, 0.0, nullptr))) { f->select(keep); return e; }
+      DevBuf h2;
+      if (h2.alloc(sizeof(double) * 2)) { f->select(keep); return fail(CS_ERR_NOMEM, "alloc failed"); }
+      if ((e = treat_sumcov_enqueue(f, W, n2, h2.d()))) { f->select(keep); return e; }
+      auto k = css::treat_scalars_kernel;
+      ++g_launches;
+      CS_LAUNCH(k, 1, csk::ETH, 0, f->st, (const double*)mp, n2, (const double*)h2.d(), 0.0, f->n, g.scal + 4 * (size_t)b + 2 * sub);
+    }
+  }
+  f->select(keep);
+  auto km = css::sim_metrics_kernel;
+  ++g_launches;
+  CS_LAUNCH(km, g.B, css::SIM_THREADS, 0, f->st, g.ma);
+  KCHECK();
+  RT(rt::stream_sync(f->st));
+  return 0;
+}
+
+extern "C" {
+
+int cs_sim_run(const cs_sim_config* cfg, int nunits, const int* replicate, const int* restart, const double* X, const double* z,
+               double* metrics, int* iters, double* lml, int* status) {
+  if (!cfg || nunits < 1 || !replicate || !restart || !metrics) return fail(CS_ERR_ARG, "cs_sim_run: null argument");
+  if (cfg->n < 8 || cfg->p < 1 || cfg->p > CS_MAX_P || !(cfg->test_frac > 0.0 && cfg->test_frac < 0.9) || cfg->maxiter < 1)
+    return fail(CS_ERR_ARG, "cs_sim_run: bad configuration");
+  if ((X == nullptr) != (z == nullptr)) return fail(CS_ERR_ARG, "cs_sim_run: X and z are given together or not at all");
+  if (need_device()) return CS_ERR_NODEVICE;
+  const int n = cfg->n, p = cfg->p;
+  const int batch = cfg->batch > 0 ? cfg->batch : 32;
+  DevBuf dX, dz;
+  if (X) {
+    if (dX.alloc(sizeof(double) * (size_t)n * p) || dz.alloc(sizeof(double) * n)) return fail(CS_ERR_NOMEM, "alloc failed");
+    RT(rt::h2d(dX.p, X, sizeof(double) * (size_t)n * p, 0));
+    RT(rt::h2d(dz.p, z, sizeof(double) * n, 0));
+    RT(rt::stream_sync(0));
+  }
+  std::vector<std::unique_ptr<SimGroup>> groups;
+  int e = 0;
+  for (int u0 = 0; u0 < nunits; u0 += batch) {
+    const int B = std::min(batch, nunits - u0);
+    groups.emplace_back(new SimGroup());
+    SimGroup& g = *groups.back();
+    g.first = u0;
+    if ((e = sim_group_create(g, cfg, B, replicate + u0, restart + u0, X ? dX.d() : nullptr, z ? dz.d() : nullptr))) return e;
+    if ((e = sim_group_generate(g))) return e;
+  }
+  std::vector<cs_fit*> fits;
+  for (auto& g : groups) fits.push_back(g->f);
+  std::vector<int> its(nunits, 0), stat(nunits, 0);
+  e = cs_fit_run_many(fits.data(), (int)fits.size(), cfg->maxiter, cfg->tol, its.data(), nullptr);
+  if (e < 0 && e != CS_ERR_NONFINITE) return e;   // e > 0 / non-finite: properties of single members, reported through `status`
+  for (auto& g : groups) {
+    std::vector<int> ms(g->B, 0);
+    cs_fit_member_status(g->f, ms.data());
+    for (int b = 0; b < g->B; ++b) stat[g->first + b] = ms[b];
+  }
+  for (auto& g : groups)
+    if ((e = sim_group_post(*g, stat))) return e;
+  const double nanv = std::nan("");
+  for (auto& g : groups) {
+    RT(rt::d2h(metrics + (size_t)g->first * css::NMETRIC, g->metrics, sizeof(double) * css::NMETRIC * g->B, g->f->st));
+    RT(rt::stream_sync(g->f->st));
+    for (int b = 0; b < g->B; ++b) {
+      const int u = g->first + b;
+      if (stat[u] != 0) for (int k = 0; k < css::NMETRIC; ++k) metrics[(size_t)u * css::NMETRIC + k] = nanv;
+      if (lml) {
+        csk::EvalScalars h{};
+        g->f->select(b);
+        RT(rt::d2h(&h, g->f->sc, sizeof h, g->f->st));
+        RT(rt::stream_sync(g->f->st));
+        lml[u] = stat[u] == 0 ? h.stats[1] : -HUGE_VAL;
+      }
+    }
+  }
+  if (iters) std::copy(its.begin(), its.end(), iters);
+  if (status) std::copy(stat.begin(), stat.end(), status);
+  return 0;
+}
+
+// test hook: the generator alone for ONE unit -- everything sim_generate_kernel produces, downloaded
+int cs_sim_generate(const cs_sim_config* cfg, int replicate, int restart, const double* X, const double* z, double* Xraw,
+                    double* zraw, double* y, double* y1, double* y0, int* is_test, double* Xtrain, double* ytrain, double* ztrain,
+                    double* Xall, double* moments, double* params) {
+  if (!cfg) return fail(CS_ERR_ARG, "cs_sim_generate: null argument");
+  if ((X == nullptr) != (z == nullptr)) return fail(CS_ERR_ARG, "cs_sim_generate: X and z are given together or not at all");
+  if (need_device()) return CS_ERR_NODEVICE;
+  const int n = cfg->n, p = cfg->p;
+  DevBuf dX, dz;
+  if (X) {
+    if (dX.alloc(sizeof(double) * (size_t)n * p) || dz.alloc(sizeof(double) * n)) return fail(CS_ERR_NOMEM, "alloc failed");
+    RT(rt::h2d(dX.p, X, sizeof(double) * (size_t)n * p, 0));
+    RT(rt::h2d(dz.p, z, sizeof(double) * n, 0));
+    RT(rt::stream_sync(0));
+  }
+  SimGroup g;
+  int e = sim_group_create(g, cfg, 1, &replicate, &restart, X ? dX.d() : nullptr, z ? dz.d() : nullptr);
+  if (e) return e;
+  if ((e = sim_group_generate(g))) return e;
+  cs_fit* f = g.f;
+  cudaStream_t st = f->st;
+  const css::SimArgs& a = g.ga;
+  const size_t dn = sizeof(double) * n;
+  if (Xraw) RT(rt::d2h(Xraw, a.Xraw, dn * p, st));
+  if (zraw) RT(rt::d2h(zraw, a.zraw, dn, st));
+  if (y) RT(rt::d2h(y, a.y, dn, st));
+  if (y1) RT(rt::d2h(y1, a.y1, dn, st));
+  if (y0) RT(rt::d2h(y0, a.y0, dn, st));
+  if (is_test) RT(rt::d2h(is_test, a.is_test, sizeof(int) * n, st));
+  if (Xall) RT(rt::d2h(Xall, a.Xall, dn * p, st));
+  if (moments) RT(rt::d2h(moments, a.moments, sizeof(double) * (2 * p + 2), st));
+  if (Xtrain) RT(download_matrix(Xtrain, a.ntr, p, f->X, f->np, st));
+  if (ytrain) RT(rt::d2h(ytrain, f->y, sizeof(double) * a.ntr, st));
+  if (ztrain) RT(rt::d2h(ztrain, f->z, sizeof(double) * a.ntr, st));
+  if (params) RT(rt::d2h(params, f->params, sizeof(double) * f->lay.np(), st));
+  RT(rt::stream_sync(st));
+  return 0;
+}
+
+}  // extern "C"
+
 // ------------------------------------------------------------------------------------
 // config 5: distributed evaluation over a P x Q process grid
 // ------------------------------------------------------------------------------------
-}  // extern "C" (reopened below)
 
 #ifndef CS_EMU
 // NCCL is resolved at run time (dlopen) so the library has no link-time dependency on it and

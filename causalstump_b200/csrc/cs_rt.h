@@ -59,6 +59,8 @@ inline int graph_begin(cudaStream_t) { return 1; }  // no graphs on the emulator
 inline int graph_end(cudaStream_t, graph_exec_t*) { return 1; }
 inline int graph_launch(graph_exec_t, cudaStream_t) { return 1; }
 inline int graph_destroy(graph_exec_t) { return 0; }
+typedef int graph_cond_t;
+template <class Body> inline int graph_while_build(cudaStream_t, Body, graph_exec_t*) { return 1; }
 }  // namespace rt
 #else
 #include <cuda.h>
@@ -235,5 +237,38 @@ inline int graph_end(cudaStream_t s, graph_exec_t* exec) {
 }
 inline int graph_launch(graph_exec_t exec, cudaStream_t s) { return (int)cudaGraphLaunch(exec, s); }
 inline int graph_destroy(graph_exec_t exec) { return (int)cudaGraphExecDestroy(exec); }
+// Device-side loop: a graph whose only node is a conditional WHILE node (CUDA 12.4+); `body(handle)` enqueues one
+// iteration on `s` (captured into the body graph) and must end with a kernel that calls cudaGraphSetConditional(handle, go_on).
+// The condition starts at 1 on every launch.  All kernels of the body must belong to one context (no green-context streams).
+typedef cudaGraphConditionalHandle graph_cond_t;
+template <class Body>
+inline int graph_while_build(cudaStream_t s, Body body, graph_exec_t* exec) {
+  cudaGraph_t g = nullptr;
+  if (cudaGraphCreate(&g, 0) != cudaSuccess) { cudaGetLastError(); return 1; }
+  cudaGraphConditionalHandle h;
+  cudaGraphNode_t node;
+  cudaGraphNodeParams np{};
+  int e = (int)cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault);
+  if (e == 0) {
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = h;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    e = (int)cudaGraphAddNode(&node, g, nullptr, 0, &np);
+  }
+  if (e == 0) {
+    cudaGraph_t bodyg = np.conditional.phGraph_out[0];
+    e = (int)cudaStreamBeginCaptureToGraph(s, bodyg, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+    if (e == 0) {
+      body(h);
+      cudaGraph_t got = nullptr;
+      e = (int)cudaStreamEndCapture(s, &got);
+    }
+  }
+  if (e == 0) e = (int)cudaGraphInstantiate(exec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != 0) cudaGetLastError();
+  return e;
+}
 }  // namespace rt
 #endif

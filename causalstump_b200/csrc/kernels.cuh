@@ -727,6 +727,20 @@ __global__ void loop_step_kernel(int optim, Layout lay, double lr, double b1, do
   }
 }
 
+// Last node of the WHILE-loop body (rt::graph_while_build): the loop goes on while any member of the handle is still
+// running.  With it one cs_fit_run is ONE graph launch; the host only waits for the result (R/main.R:79-84 on the device).
+#ifndef CS_EMU
+__global__ void loop_cond_kernel(const LoopState* __restrict__ ls, long long bstride, int nbatch, cudaGraphConditionalHandle h) {
+  int active = 0;
+  for (int b = threadIdx.x; b < nbatch; b += 32) {
+    const LoopState* l = reinterpret_cast<const LoopState*>(reinterpret_cast<const char*>(ls) + (long long)b * bstride);
+    active |= l->done ? 0 : 1;
+  }
+  active = __any_sync(0xffffffffu, active);
+  if (threadIdx.x == 0) cudaGraphSetConditional(h, active ? 1u : 0u);
+}
+#endif
+
 // out[k] = sum over CTAs of gpart[cta][k]  (distributed mode: feeds the all-reduce)
 __global__ void reduce_gpart_kernel(const double* __restrict__ gpart, int ncta, int nacc, double* __restrict__ out) {
   for (int k = threadIdx.x; k < nacc; k += blockDim.x) {

@@ -85,3 +85,92 @@ def restart_draws(replicate, restart, prior=False):
     a = rng.uniform(0.2, 1.0)
     b = rng.uniform(0.1, 0.7) if prior else rng.uniform(0.2, 1.0)
     return float(a), float(b)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Host mirror of the DEVICE generator (csrc/sim.cuh, cs_sim_run): the same Philox-4x32-10 counters, so a replicate
+# produced on the GPU can be re-created here draw for draw.  Discrete draws (beta categories, Bernoulli covariates,
+# treatment, the train / test split) are identical; normals and sums agree to rounding (libm vs CUDA exp / log / cos,
+# reduction order).  Input generation only -- nothing here is on the measured path.
+# --------------------------------------------------------------------------------------------------------------
+_S_BETA, _S_XNORM, _S_XBIN, _S_Z, _S_N0, _S_N1, _S_SPLIT, _S_RESTART = range(8)
+_SIM_TAG = 0x48494C4C
+
+
+def philox4x32(c0, c1, c2, c3, seed):
+    """Philox-4x32-10 (csrc/predict.cuh: csp::Philox::block) on uint32 arrays; key = (seed & 0xffffffff, seed >> 32)."""
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    c = [np.asarray(x, dtype=np.uint64) & np.uint64(0xFFFFFFFF) for x in np.broadcast_arrays(c0, c1, c2, c3)]
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        h0, l0, h1, l1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = [h1 ^ c[1] ^ k0, l1, h0 ^ c[3] ^ k1, l0]
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & mask, (k1 + np.uint64(0xBB67AE85)) & mask
+    return c
+
+
+def _u01(hi, lo):
+    bits = ((hi << np.uint64(32)) | lo) >> np.uint64(11)
+    return (bits.astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+
+
+def _sim_uniform(index, stream, rep, seed):
+    o = philox4x32(index, stream, rep, _SIM_TAG, seed)
+    return _u01(o[0], o[1])
+
+
+def _sim_normal(index, stream, rep, seed):
+    o = philox4x32(index, stream, rep, _SIM_TAG, seed)
+    u1, u2 = _u01(o[0], o[1]), _u01(o[2], o[3])
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(6.283185307179586476925 * u2)
+
+
+def hill_unit_philox(replicate, restart, n=747, p=25, X=None, z=None, test_frac=0.1, seed=565):
+    """One (replicate, restart) unit exactly as sim_generate_kernel builds it: response surface B
+    (test/sec5-3_Hill2011.R:49-66), the 10 % test split (:171), norm_variables on the training rows (R/utilities.R:1-33)
+    and parainit (R/kernel_GP_SE_class.R:10-20).  Returns raw and normalised pieces plus the initial parameter vector."""
+    import math
+    if X is None:
+        ncont = min(6, p)
+        idx = np.arange(n * p, dtype=np.uint64)
+        j = (idx // np.uint64(n)).astype(np.int64)
+        xn = _sim_normal(idx, _S_XNORM, replicate, seed)
+        means = np.array(_BIN_MEANS)[np.maximum(j - ncont, 0) % 19]
+        xb = (_sim_uniform(idx, _S_XBIN, replicate, seed) < means).astype(np.float64) + ((j - ncont) == 7)
+        X = np.where(j < ncont, xn, xb).reshape(p, n).T.copy()
+        z = (_sim_uniform(np.arange(n, dtype=np.uint64), _S_Z, replicate, seed) < 0.186).astype(np.float64)
+        if z.sum() == 0:
+            z[0] = 1.0
+    else:
+        X = np.array(X, dtype=np.float64)
+        z = np.array(z, dtype=np.float64)
+        n, p = X.shape
+    u = _sim_uniform(np.arange(p + 1, dtype=np.uint64), _S_BETA, replicate, seed)
+    beta = np.select([u < 0.6, u < 0.7, u < 0.8, u < 0.9], [0.0, 0.1, 0.2, 0.3], 0.4)
+    lin = np.full(n, beta[0])
+    for jj in range(p):
+        lin = (X[:, jj] + 0.5) * beta[jj + 1] + lin        # two roundings per term, like the device (no FMA)
+    y0 = np.exp(lin)
+    offset = float(np.mean((lin - y0)[z == 1])) - 4.0
+    y1 = lin - offset
+    ii = np.arange(n, dtype=np.uint64)
+    e0, e1 = _sim_normal(ii, _S_N0, replicate, seed), _sim_normal(ii, _S_N1, replicate, seed)
+    y = np.where(z == 1, y1 + e1, y0 + e0)
+    key = _sim_uniform(ii, _S_SPLIT, replicate, seed)
+    nte = int(math.ceil(n * test_frac))
+    order = np.lexsort((np.arange(n), key))
+    is_test = np.zeros(n, dtype=bool)
+    is_test[order[:nte]] = True
+    train, test = np.flatnonzero(~is_test), np.flatnonzero(is_test)
+    from .main import norm_variables
+    nr = norm_variables(y[train], X[train])
+    mom = nr["moments"]
+    Xall = norm_variables(X=X, moments=mom)["X"]
+    yn = nr["y"]
+    ab = _sim_uniform(np.array([2 * restart, 2 * restart + 1], dtype=np.uint64), _S_RESTART, replicate, seed)
+    params = np.concatenate([[math.log(float(np.var(yn, ddof=1))), math.log(0.2 + 0.8 * ab[0]), math.log(0.2 + 0.8 * ab[1])],
+                             np.full(p, -0.1), np.full(p, 0.1), [float(np.mean(yn))]])
+    return dict(y=y, X=X, z=z, tau=y1 - y0, y1=y1, y0=y0, is_test=is_test, train=train, test=test, moments=mom,
+                Xtrain=np.asfortranarray(nr["X"]), ytrain=yn, ztrain=z[train], Xall=Xall, params=params, beta=beta)

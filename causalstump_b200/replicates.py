@@ -192,6 +192,36 @@ def hill_units_concurrent(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1
     return out
 
 
+def hill_units_device(units, n=747, p=25, test_frac=0.1, maxiter=3000, tol=1e-1, lr=0.01, batch=32, covariates=None, seed=565):
+    """The replicate loop with NOTHING but the unit list going in and the metric block coming out (cs_sim_run, csrc/sim.cuh):
+    response surface B, the 10 % split, norm_variables and parainit are generated on the device straight into the members of
+    batched fit handles, the fits run as in `hill_units_concurrent`, predict / treatment keep their inputs and outputs on the
+    device, and update.results (:104-152) is one kernel per batch.  Draws come from Philox counters (host mirror:
+    hill.hill_unit_philox), so a unit is NOT the same data as hill.hill_surface_b(replicate) -- same law, different stream.
+    Returns the same per-unit dicts as `hill_units_concurrent` (GP arm)."""
+    import time as _t
+    from . import rcpp_exports as rx
+    lib = rx.lib()
+    t0 = _t.perf_counter()
+    X, z = (None, None) if covariates is None else covariates
+    out = lib.sim_run(units, n=n, p=p, X=X, z=z, test_frac=test_frac, maxiter=maxiter, tol=tol, lr=lr, batch=batch, seed=seed)
+    res = []
+    for u, (replicate, restart) in enumerate(units):
+        m = dict(zip(METRICS, out["metrics"][u].tolist()))
+        res.append(dict(replicate=replicate, restart=restart, iters=int(out["iters"][u]), lml=float(out["lml"][u]), metrics=m,
+                        failed=bool(out["status"][u] != 0), status=int(out["status"][u]), pehe_train=m["PEHE.all.train"],
+                        pehe_test=m["PEHE.all.test"], rmse_train=m["RMSE.all.train"], rmse_test=m["RMSE.all.test"],
+                        e_ate_train=m["E.ate.train"], e_ate_test=m["E.ate.test"]))
+    used = cap = 0
+    for i in range(0, len(units), batch):
+        its = [int(x) for x in out["iters"][i:i + batch]]
+        used += sum(its); cap += len(its) * max(its)
+    LAST_TIMING.clear()
+    LAST_TIMING.update(total=_t.perf_counter() - t0, slot_utilisation=used / max(cap, 1), iterations=used,
+                       failed=int(np.sum(out["status"] != 0)), prep=0.0, post=0.0)
+    return res
+
+
 LAST_TIMING = {}  # seconds spent by the last hill_units_concurrent call: host data prep / handle creation / device loop / predict+treat
 
 

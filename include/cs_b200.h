@@ -188,6 +188,33 @@ int cs_treat(cs_fit* f, int n2, const double* X2, double cov_jitter, double* map
 int cs_tp_sample(int n2, const double* cov, double df, int nsampling, unsigned long long seed, double* U,
                  double* ate_U);
 
+/* ---- simulation driver on the device: the replicate loop of the reference's simulation scripts
+ * (test/sec5-3_Hill2011.R: Hill11_surfaceB :49-66, run(i) :157-176, update.results :104-152; norm_variables R/utilities.R:1-33;
+ * parainit R/kernel_GP_SE_class.R:10-20) for a list of (replicate, restart) units.  Response surface, 10 % test split,
+ * normalisation and initial parameters are produced by one kernel per batch straight into the members of batched fit
+ * handles; the fits run as cs_fit_run_many; predict(all rows) / treatment(train) / treatment(test) keep their inputs and
+ * outputs on the device; one kernel per batch evaluates the 22 metrics.  Only the metric block comes back.
+ * Random numbers: Philox-4x32-10 counters keyed by `seed` (host mirror: causalstump_b200/hill.py).  GP (prior=FALSE) arm. */
+typedef struct cs_sim_config {
+  int n, p;          /* rows / covariates of one replicate before the split (747 x 25)          */
+  double test_frac;  /* 0.1: idx.test = sample.int(n, ceiling(n*0.1)), :171                     */
+  int maxiter;       /* fit settings of the GP arm (:344-345: 3000, tol 1e-1, lr .01, Nadam)    */
+  double tol, lr;
+  int optim;         /* CS_OPT_*                                                                */
+  int batch;         /* members per batched fit handle (0 = 32)                                 */
+  unsigned long long seed;
+} cs_sim_config;
+#define CS_SIM_NMETRIC 22 /* row order of result.item, :163-164: 11 train rows then 11 test rows */
+/* X (n x p, raw) and z (n) = covariates / treatment shared by every replicate, like the reference's fixed IHDP data; both
+ * NULL: drawn per replicate with the IHDP marginals.  metrics[nunits][22]; iters, lml, status (0 OK, > 0 pivot of a non
+ * positive definite K_n, CS_ERR_NONFINITE) nullable, per unit.  A failing unit fails alone (its metrics are NaN). */
+int cs_sim_run(const cs_sim_config* cfg, int nunits, const int* replicate, const int* restart, const double* X, const double* z,
+               double* metrics, int* iters, double* lml, int* status);
+/* the generator alone for one unit (tests): every output nullable; Xtrain is ntr x p with ntr = n - ceil(n*test_frac) */
+int cs_sim_generate(const cs_sim_config* cfg, int replicate, int restart, const double* X, const double* z, double* Xraw,
+                    double* zraw, double* y, double* y1, double* y0, int* is_test, double* Xtrain, double* ytrain, double* ztrain,
+                    double* Xall, double* moments, double* params);
+
 /* ---- config 5: one large evaluation over a P x Q process grid (2-D block-cyclic tiles,
  * NCCL panel broadcasts; no reference equivalent) --------------------- */
 typedef struct cs_dist cs_dist;

@@ -5,13 +5,19 @@ TEST INFRASTRUCTURE ONLY.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
 module.  The product package ``causalstump_b200`` never imports it and has no
 CPU fallback.
 
-PARITY UNPINNED.  The reference (mazphilip/CausalStump, R + RcppArmadillo)
-ships no unit tests, golden vectors or known-answer fixtures for this path
- and cannot be built in this image (no R, Rcpp,
-Armadillo or gfortran).  This file is therefore a line-by-line *restatement*
-of the reference arithmetic in NumPy + SciPy-LAPACK, pinned only by
-self-consistency known-answer tests (closed forms for n=1,2, finite-difference
-gradient checks, optimizer single-step vectors; see tests/test_oracle.py).
+PARITY PINNED against the reference's own C++.  The reference (mazphilip/CausalStump, R + RcppArmadillo)
+ships no unit tests, golden vectors or known-answer fixtures for this path (SURVEY.md
+section 4 / 8c) and its R build cannot run in this image (no R, Rcpp, Armadillo), but
+its three hot-path source files compile unmodified against the header shim of
+oracle/shim (oracle/Makefile -> oracle/_ref/libcausalstump_ref.so).  This restatement is
+held to that library routine by routine (tests/test_oracle_vs_ref.py) and to golden
+vectors it produced: tests/golden/golden_ref_v1.npz (five small cases incl. optimizer
+trajectories, predict / treatment) and tests/golden/golden_ref_8192.npz (n=8192 GP and
+Student-t, n=4000: tests/test_golden_ref.py checks the n=4000 case here).  What stays
+unpinned: the R-level glue (restated with line numbers, not executed), R's RNG stream and
+mvnfast's sitmo stream (sampling parity is distributional).  Self-consistency known-answer
+tests (closed forms for n=1,2, finite-difference gradients, optimizer single-step vectors)
+are in tests/test_oracle.py.
 
 Third-party arithmetic that lives outside /root/reference and is restated here
 (versions unpinned by the reference, DESCRIPTION:10-15):

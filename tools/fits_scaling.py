@@ -16,6 +16,7 @@ def main():
     rp.hill_units_concurrent([(0, 0)])
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     batch, tile, chunk = 32, 0, 0
+    device = "--device" in sys.argv
     for a in sys.argv[1:]:
         if a.startswith("--batch="):
             batch = int(a.split("=")[1])
@@ -28,10 +29,10 @@ def main():
         units = [(k // 4, k % 4) for k in range(nf)]
         l0 = lib.launch_count()
         t0 = time.perf_counter()
-        res = rp.hill_units_concurrent(units, batch=batch, tile=tile, chunk=chunk)
+        res = rp.hill_units_device(units, batch=batch) if device else rp.hill_units_concurrent(units, batch=batch, tile=tile, chunk=chunk)
         s = time.perf_counter() - t0
         it = [r["iters"] for r in res]
-        print(json.dumps({"fits": nf, "batch": batch, "tile": tile, "chunk": chunk, "seconds": s, "fits_per_hour": nf / s * 3600, "iters_mean": float(np.mean(it)),
+        print(json.dumps({"fits": nf, "driver": "device (cs_sim_run)" if device else "host generator / metrics", "batch": batch, "tile": tile, "chunk": chunk, "seconds": s, "fits_per_hour": nf / s * 3600, "iters_mean": float(np.mean(it)),
                           "iters_total": int(np.sum(it)), "us_per_fit_iter": 1e6 * s / np.sum(it), "launches": lib.launch_count() - l0,
                           "phases_s": {k: round(v, 3) for k, v in rp.LAST_TIMING.items()}}), flush=True)
 
