@@ -551,9 +551,27 @@ def measure_config5(lib, torch, dev, rank, world, dist, barrier, steps=2, n=3276
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     f.close()
+    single = None
+    if world == 1:
+        # the same evaluation on the single-GPU engine (cs_fit: 512-column panels, SM partition, pipelined inverse) -- what a
+        # user with one GPU would run; the distributed engine above still advances in 128-column steps
+        inp1 = make_inputs(n, P_METRIC, 0)
+        f1 = _lib.Fit(lib, _lib.CS_GP, inp1["y"], inp1["X"], inp1["z"], inp1["w"], inp1["params"], inv_pipeline=1)
+        f1.eval_async(); f1.sync()
+        f1.event_record(6)
+        for _ in range(steps):
+            f1.eval_async()
+        f1.event_record(7)
+        f1.sync()
+        ms1 = f1.event_elapsed_ms(6, 7) / steps
+        _, st1, _ = f1.fetch()
+        f1.close()
+        single = {"ms_per_eval": ms1, "tflops_n3": float(n) ** 3 / (ms1 * 1e-3) / 1e12, "lml": float(st1[1])}
     if rank != 0:
         return None
     ms_eval = float(t[0])
+    if single:
+        out["single_gpu_engine"] = single
     out.update({"ms_per_eval": ms_eval, "evals_per_s": 1e3 / ms_eval, "tflops_n3": float(n) ** 3 / (ms_eval * 1e-3) / 1e12,
                 "steps": steps, "lml": float(st[1]), "finite": bool(np.isfinite(g).all() and np.isfinite(st).all()),
                 "nccl_ranks": world, "scaling": "strong"})
