@@ -359,7 +359,7 @@ struct DenseEngine {
     GemmProblem p{};
     p.A = A; p.B = B; p.C = C; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
     p.mt = mt; p.nt = nt; p.K = K; p.kmode = kmode; p.order = order; p.mirror = mirror;
-    p.alpha = alpha; p.beta = beta; p.tile_base = 0;
+    p.set_scale(alpha, beta); p.tile_base = 0;
     p.ntiles = (order == csg::ORD_LOWER) ? csg::lower_tiles(mt) : mt * nt;
     return p;
   }

@@ -422,7 +422,7 @@ static int rank_init(DistRank& R, int n, int p, int kind, int T, int P, int Q, i
     auto mkp = [&](const double* A, long long lda, const double* B, long long ldb, double* Cc, StepTab& tab, int first, int count,
                    double alpha, double beta) {
       GemmProblem p_{};
-      p_.A = A; p_.B = B; p_.C = Cc; p_.lda = lda; p_.ldb = ldb; p_.ldc = g.ldl; p_.K = T; p_.alpha = alpha; p_.beta = beta;
+      p_.A = A; p_.B = B; p_.C = Cc; p_.lda = lda; p_.ldb = ldb; p_.ldc = g.ldl; p_.K = T; p_.set_scale(alpha, beta);
       p_.ntiles = count; p_.tile_base = 0; p_.table = tab.d + 3LL * (tab.start[k] + first);
       p_.mt = p_.ntiles; p_.nt = 1;
       return p_;

@@ -29,7 +29,14 @@ struct GemmProblem {
   int mirror;       // 1: also store C(j,i) = C(i,j) for I != J (square, diagonal origin); 2: always (rectangular)
   int tile_base;    // first linear tile id of this problem inside the launch
   int ntiles;
-  double alpha, beta;  // C = beta*C + alpha*acc   (beta in {0,1})
+  double alpha, beta;  // C = beta*C + alpha*acc   (alpha in {+1,-1}, beta in {0,1}: every contraction of the fit)
+  // What the kernel reads: sign masks / flags derived from (alpha, beta) by set_scale().  The prologue and epilogue of a
+  // tile must not touch the FP64 pipe -- it is saturated by the DMMAs of the co-resident CTAs, and every dependent
+  // DMUL / DFMA / fp64 divide issued there queues behind them (ncu, K = 512 launches: 14 % of all warp time sat in a
+  // `beta / alpha` divide and an fp64 sqrt of the tile decode).  +-1 scaling is an integer XOR on the sign bit.
+  unsigned neg_mask;   // 0x80000000 if alpha < 0
+  int beta_one;        // 1: accumulate into C
+  __host__ __device__ void set_scale(double a, double b) { alpha = a; beta = b; neg_mask = a < 0.0 ? 0x80000000u : 0u; beta_one = b != 0.0 ? 1 : 0; }
   // Table mode (distributed block-cyclic sweeps): tile t uses element offsets
   // table[3t] into A, table[3t+1] into B, table[3t+2] into C and the full k-range.
   const long long* table;
@@ -43,17 +50,33 @@ constexpr int GEMM_STAGES = 4;
 
 __host__ __device__ inline int lower_tiles(int n) { return n * (n + 1) / 2; }
 
+// row i of the lower-triangular enumeration t = i(i+1)/2 + j: single-precision estimate, exact integer correction
+// (no fp64 arithmetic: see GemmProblem::neg_mask)
+__host__ __device__ inline int lower_row(int t) {
+  int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+  while ((long long)(i + 1) * (i + 2) / 2 <= t) ++i;
+  while ((long long)i * (i + 1) / 2 > t) --i;
+  return i;
+}
+
 __host__ __device__ inline void decode_tile(int order, int mt, int nt, int t, int& I, int& J) {
   if (order == ORD_COL) {
     J = t / mt; I = t - J * mt;
   } else if (order == ORD_ROW_DESC) {
     int r = t / nt; I = mt - 1 - r; J = t - r * nt;
   } else {
-    int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((long long)(i + 1) * (i + 2) / 2 <= t) ++i;
-    while ((long long)i * (i + 1) / 2 > t) --i;
+    const int i = lower_row(t);
     I = i; J = t - i * (i + 1) / 2;
   }
+}
+
+// x or -x without the FP64 pipe
+__device__ __forceinline__ double flip_sign(double x, unsigned mask) {
+#ifdef CS_EMU
+  return mask ? -x : x;
+#else
+  return __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x));
+#endif
 }
 
 __host__ __device__ inline void tile_krange(int kmode, int K, int TILE, int I, int J, int& kbeg, int& kend) {
@@ -145,16 +168,16 @@ gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restr
   // Accumulators start from (beta/alpha)*C so the read of C overlaps the pipeline fill and
   // the epilogue is store-only:  C = alpha * ((beta/alpha) C + sum_k A B^T).
   double acc[FM][FN][2];
-  if (P.beta != 0.0) {
-    const double sc0 = P.beta / P.alpha;
+  const unsigned neg = P.neg_mask;
+  if (P.beta_one) {  // acc = (beta / alpha) C = +-C
 #pragma unroll
     for (int a = 0; a < FM; ++a) {
       const long long r = i0 + wm + a * 8 + g;
 #pragma unroll
       for (int b = 0; b < FN; ++b) {
         const double* p0 = P.C + r + (long long)(j0 + wn + b * 8 + 2 * t) * P.ldc;
-        acc[a][b][0] = sc0 * p0[0];
-        acc[a][b][1] = sc0 * p0[P.ldc];
+        acc[a][b][0] = flip_sign(p0[0], neg);
+        acc[a][b][1] = flip_sign(p0[P.ldc], neg);
       }
     }
   } else {
@@ -205,8 +228,7 @@ gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restr
   }
   csd::cp_async_wait<0>();
 
-  // epilogue: C = alpha*acc (+ mirrored store)
-  const double alpha = P.alpha;
+  // epilogue: C = alpha*acc = +-acc (+ mirrored store)
 #pragma unroll
   for (int a = 0; a < FM; ++a) {
     const long long r = i0 + wm + a * 8 + g;
@@ -215,7 +237,7 @@ gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restr
       const long long cc = j0 + wn + b * 8 + 2 * t;
       double* p0 = P.C + r + cc * P.ldc;
       double* p1 = p0 + P.ldc;
-      const double v0 = alpha * acc[a][b][0], v1 = alpha * acc[a][b][1];
+      const double v0 = flip_sign(acc[a][b][0], neg), v1 = flip_sign(acc[a][b][1], neg);
       *p0 = v0; *p1 = v1;
       if (P.mirror == 2 || (P.mirror == 1 && I != J)) {
         double* q = (P.Cm ? P.Cm : P.C) + cc + r * P.ldc;  // (cc, r) and (cc+1, r) are adjacent

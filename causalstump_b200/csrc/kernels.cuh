@@ -12,6 +12,14 @@
 
 namespace csk {
 
+// row of the lower-triangular tile enumeration (same as csg::lower_row in gemm.cuh, which includes this header's users later)
+__host__ __device__ inline int csg_lower_row(int t) {
+  int i = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+  while ((long long)(i + 1) * (i + 2) / 2 <= t) ++i;
+  while ((long long)i * (i + 1) / 2 > t) --i;
+  return i;
+}
+
 constexpr int TB = 64;        // tile edge of the element-wise kernels
 constexpr int ETH = 256;      // threads per CTA (16 x 16, 4 x 4 entries each)
 constexpr int PMAX = 40;      // max covariates supported by the fused gradient kernel
@@ -126,9 +134,7 @@ gram_train_kernel(const double* __restrict__ X, long long ldx, const double* __r
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   // lower-triangular tile enumeration
   const int t = (int)blockIdx.x + tile0;
-  int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-  while ((long long)(I + 1) * (I + 2) / 2 <= t) ++I;
-  while ((long long)I * (I + 1) / 2 > t) --I;
+  const int I = csg_lower_row(t);   // integer / single-precision decode: the FP64 pipe belongs to the tile arithmetic
   const int J = t - I * (I + 1) / 2;
   const int r0 = I * TB, c0 = J * TB;
 #ifndef CS_EMU
@@ -348,9 +354,7 @@ inline int grad_smem_bytes(int p, bool prefetch = false) {  // prefetch: a secon
 inline bool grad_prefetch_fits(int p) { return grad_smem_bytes(p, true) <= 227 * 1024; }
 
 __host__ __device__ inline void lower_tile_of(int t, int& I, int& J) {
-  I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-  while ((long long)(I + 1) * (I + 2) / 2 <= t) ++I;
-  while ((long long)I * (I + 1) / 2 > t) --I;
+  I = csg_lower_row(t);
   J = t - I * (I + 1) / 2;
 }
 
@@ -421,10 +425,7 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
       const long long coff = (long long)(unsigned)tile_tab[4 * t + 2] | ((long long)tile_tab[4 * t + 3] << 32);
       Ct = Cinv + coff;
     } else {
-      I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-      while ((long long)(I + 1) * (I + 2) / 2 <= t) ++I;
-      while ((long long)I * (I + 1) / 2 > t) --I;
-      J = t - I * (I + 1) / 2;
+      lower_tile_of(t, I, J);
       Ct = Cinv + (long long)J * TB * ldc + (long long)I * TB;
     }
     const int r0 = I * TB, c0 = J * TB;

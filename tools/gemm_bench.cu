@@ -85,7 +85,7 @@ int main() {
   }
   auto mk = [&](int TILE, int mt, int nt, int K, int kmode, int order, int mirror, double alpha, double beta) {
     GemmProblem P{}; P.A = A; P.B = B; P.C = C; P.lda = ld; P.ldb = ld; P.ldc = ld; P.mt = mt; P.nt = nt; P.K = K; P.kmode = kmode;
-    P.order = order; P.mirror = mirror; P.alpha = alpha; P.beta = beta; P.tile_base = 0; P.ntiles = order == ORD_LOWER ? lower_tiles(mt) : mt * nt;
+    P.order = order; P.mirror = mirror; P.set_scale(alpha, beta); P.tile_base = 0; P.ntiles = order == ORD_LOWER ? lower_tiles(mt) : mt * nt;
     return P; };
   printf("\n== TN  K^-1 = X^T X  (n=8192, k >= i, lower + mirror): n^3/3 flops\n");
   { double fl = (double)n * n * n / 3.0;
