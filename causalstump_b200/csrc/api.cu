@@ -10,6 +10,7 @@
 #include "../../include/cs_b200.h"
 #include "dense.cuh"
 #include "kernels.cuh"
+#include "kernels_mma.cuh"
 #include "predict.cuh"
 #include "dist.cuh"
 #include "sim.cuh"
@@ -298,6 +299,44 @@ static int split_plan(int row_blocks, int cols, int* nsplit, int* cols_per_split
   return 0;
 }
 
+// K1 / K3 launchers: the tensor-path kernels (kernels_mma.cuh) for p <= 32, the element-wise ones (kernels.cuh) otherwise
+// or with CS_GRAD_OLD=1 (A/B switch)
+static bool use_mma_kernels(int p) {
+  static const bool old_k = std::getenv("CS_GRAD_OLD") != nullptr;
+  return csk::mma_kernels_ok(p) && !old_k;
+}
+static int use_bulk_copies() {
+  static const int on = std::getenv("CS_NO_TMA") == nullptr ? 1 : 0;
+  return on;
+}
+static void launch_gram_train(cs_fit* f, cudaStream_t st, const int* skip, int tile0, int ntiles, unsigned B) {
+  const long long ld = f->np;
+  ++g_launches;
+  if (use_mma_kernels(f->p)) {
+    auto k = csk::gram_train_mma_kernel;
+    CS_LAUNCH(k, dim3(ntiles, 1, B), csk::ETH, csk::gram_mma_smem_bytes(), st, f->X, ld, f->z, f->w, f->params, f->lay, f->n, f->eng.G, ld,
+              skip, tile0, use_bulk_copies());
+  } else {
+    auto k = csk::gram_train_kernel;
+    CS_LAUNCH(k, dim3(ntiles, 1, B), csk::ETH, csk::gram_smem_bytes(f->p), st, f->X, ld, f->z, f->w, f->params, f->lay, f->n, f->eng.G, ld,
+              skip, tile0, f->xt);
+  }
+}
+static void launch_grad_trace(cs_fit* f, cudaStream_t st, const int* skip, unsigned B) {
+  const long long ld = f->np;
+  const double* nul = nullptr;
+  ++g_launches;
+  if (use_mma_kernels(f->p)) {
+    auto k = csk::grad_trace_mma_kernel<false>;
+    CS_LAUNCH(k, dim3(f->ncta_grad, 1, B), csk::ETH, csk::grad_mma_smem_bytes(), st, f->X, ld, f->z, f->params, f->lay, f->n, f->nblk,
+              f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, nul, nul, nul, skip, (const int*)nullptr, use_bulk_copies());
+  } else {
+    auto k = csk::grad_trace_kernel<false>;
+    CS_LAUNCH(k, dim3(f->ncta_grad, 1, B), csk::ETH, csk::grad_smem_bytes(f->p, f->xt.on != 0), st, f->X, ld, f->z, f->params, f->lay, f->n,
+              f->nblk, f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, nul, nul, nul, skip, (const int*)nullptr, f->xt);
+  }
+}
+
 static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
   const int n = f->n, np = f->np, p = f->p;
   cudaStream_t st = f->st;
@@ -311,7 +350,6 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
   {  // K1.  With the v2 plan the build is split: the tiles of the first diagonal block (rows < W*TILE) on the
      // handle's stream, the rest on the panel stream S2, which every other consumer of G is ordered behind
      // (DenseEngine::build_chol2) -- so the first diagonal block is factored while the rest is still built.
-    auto k = csk::gram_train_kernel;
     const int total = csg::lower_tiles(f->nblk);
     int first = total;
     static const bool no_split = std::getenv("CS_NO_GRAM_SPLIT") != nullptr;
@@ -321,15 +359,11 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
       const int bw = std::min(f->nblk, (f->eng.bounds.size() > 1 ? f->eng.bounds[1] : f->eng.panel_blocks) * f->eng.tile / csk::TB);
       first = csg::lower_tiles(bw);
     }
-    ++g_launches;
-    CS_LAUNCH(k, dim3(first, 1, B), csk::ETH, csk::gram_smem_bytes(p), st, f->X, ld, f->z, f->w, f->params,
-              f->lay, n, f->eng.G, ld, skip, 0, f->xt);
+    launch_gram_train(f, st, skip, 0, first, B);
     if (first < total) {
       rt::event_record(f->eng.ev_gram, st);   // orders S2 behind everything already on the handle's stream
       rt::stream_wait_event(f->eng.aux2, f->eng.ev_gram);
-      ++g_launches;
-      CS_LAUNCH(k, dim3(total - first, 1, B), csk::ETH, csk::gram_smem_bytes(p), f->eng.aux2, f->X, ld, f->z, f->w, f->params,
-                f->lay, n, f->eng.G, ld, skip, first, f->xt);
+      launch_gram_train(f, f->eng.aux2, skip, first, total - first, B);
     }
   }
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
@@ -369,13 +403,7 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
               f->eng.logdet_part, f->eng.N, f->alpha, f->u, f->s, f->sc, skip);
   }
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
-  {  // K3 / K4
-    auto k = csk::grad_trace_kernel<false>;
-    ++g_launches;
-    CS_LAUNCH(k, dim3(f->ncta_grad, 1, B), csk::ETH, csk::grad_smem_bytes(p, f->xt.on != 0), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
-              f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)nullptr,
-              (const double*)nullptr, (const double*)nullptr, skip, (const int*)nullptr, f->xt);
-  }
+  launch_grad_trace(f, st, skip, B);  // K3 / K4
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
   {
     auto k0 = csk::rowstats_kernel;
@@ -506,6 +534,9 @@ static int fit_create_impl(const cs_fit_config* cfg, int nbatch, int n, int p, c
   { auto k = csk::grad_trace_kernel<false>; CS_SET_SMEM(k, std::max(csk::grad_smem_bytes(csk::PMAX), csk::grad_smem_bytes(p, f->xt.on != 0))); }
   { auto k = csk::grad_trace_kernel<true>; CS_SET_SMEM(k, csk::grad_smem_bytes(csk::PMAX)); }
   { auto k = csp::gram_sum_kernel; CS_SET_SMEM(k, csk::gram_smem_bytes(csk::PMAX)); }
+  { auto k = csk::gram_train_mma_kernel; CS_SET_SMEM(k, csk::gram_mma_smem_bytes()); }
+  { auto k = csk::grad_trace_mma_kernel<false>; CS_SET_SMEM(k, csk::grad_mma_smem_bytes()); }
+  { auto k = csk::grad_trace_mma_kernel<true>; CS_SET_SMEM(k, csk::grad_mma_smem_bytes()); }
   for (int i = 0; i < 16; ++i)
     if (rt::event_create(&f->ev[i])) return bail(fail(CS_ERR_CUDA, "event create failed"));
   f->ev_ok = true;
@@ -955,12 +986,7 @@ int cs_debug_timeline(cs_fit* f, int cap, int* n_out, float* rows) {
   if (!f || !n_out || !rows) return fail(CS_ERR_ARG, "null argument");
   cudaStream_t st = f->st;
   std::vector<cudaEvent_t> evs;
-  {  // Gram first so the factorization sees a valid matrix
-    auto k = csk::gram_train_kernel;
-    ++g_launches;
-    CS_LAUNCH(k, csg::lower_tiles(f->nblk), csk::ETH, csk::gram_smem_bytes(f->p), st, f->X, (long long)f->np, f->z, f->w,
-              f->params, f->lay, f->n, f->eng.G, (long long)f->np, (const int*)nullptr, 0, f->xt);
-  }
+  launch_gram_train(f, st, nullptr, 0, csg::lower_tiles(f->nblk), (unsigned)f->nbatch);  // Gram first so the factorization sees a valid matrix
   RT(rt::stream_sync(st));
   cudaEvent_t base;
   RT(rt::event_create(&base));
@@ -1427,17 +1453,21 @@ static int grad_stats_common(int kind, int n, int p, const double* y, const doub
     ++g_launches;
     CS_LAUNCH(k2, 1, csk::SCALARS_THREADS, 0, st, f->mv_part, f->nsplit, ld, 3 * ld, n, np, f->y, f->params, f->lay,
               f->eng.logdet_part, f->eng.N, f->alpha, f->u, f->s, f->sc, (const int*)nullptr);
-    ++g_launches;
     if (from_mem) {
-      auto k3 = csk::grad_trace_kernel<true>;
-      CS_LAUNCH(k3, f->ncta_grad, csk::ETH, csk::grad_smem_bytes(p), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
-                f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)dK.d(), (const double*)dM.d(),
-                (const double*)dA.d(), (const int*)nullptr, (const int*)nullptr, rt::XTma{});
+      ++g_launches;
+      if (use_mma_kernels(p)) {
+        auto k3 = csk::grad_trace_mma_kernel<true>;
+        CS_LAUNCH(k3, f->ncta_grad, csk::ETH, csk::grad_mma_smem_bytes(), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
+                  f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)dK.d(), (const double*)dM.d(),
+                  (const double*)dA.d(), (const int*)nullptr, (const int*)nullptr, use_bulk_copies());
+      } else {
+        auto k3 = csk::grad_trace_kernel<true>;
+        CS_LAUNCH(k3, f->ncta_grad, csk::ETH, csk::grad_smem_bytes(p), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
+                  f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)dK.d(), (const double*)dM.d(),
+                  (const double*)dA.d(), (const int*)nullptr, (const int*)nullptr, rt::XTma{});
+      }
     } else {
-      auto k3 = csk::grad_trace_kernel<false>;
-      CS_LAUNCH(k3, f->ncta_grad, csk::ETH, csk::grad_smem_bytes(p), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
-                f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)nullptr,
-                (const double*)nullptr, (const double*)nullptr, (const int*)nullptr, (const int*)nullptr, rt::XTma{});
+      launch_grad_trace(f, st, nullptr, 1u);
     }
     auto k40 = csk::rowstats_kernel;
     ++g_launches;

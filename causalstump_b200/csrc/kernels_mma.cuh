@@ -1,0 +1,456 @@
+// Gram (K1) and fused trace-gradient (K3/K4) kernels with their O(p) inner loops on the FP64 tensor path.
+// Same arithmetic as kernels.cuh (reference: kernmat_*_SE_cpp, grad_*_SE_cpp + evid_scale_gradients), reorganised so that
+// the two O(p n^2) passes are small matrix products issued as DMMA.8x8x4 instead of per-entry subtract / square / FMA chains:
+//
+//   pass 1 (exponents)   E[r,c] = sum_i a_i (x_ri - x_ci)^2 = u_r + v_c - 2 sum_i (a_i x_ri) x_ci            (64 x 64 x p product)
+//   pass 2 (traces)      sum_{r,c} W[r,c] (x_ri - x_ci)^2 = sum_r x_ri (x_ri R[r] - 2 P[r,i]) + sum_c x_ci^2 C[c],
+//                        P = W Xc (64 x p x 64 product), R / C = row / column sums of W = T o Km (and T o Ka)
+//
+// Vector and tensor FP64 share one pipe on sm_100a (tools/pipe_probe.cu), so the gain is not a second pipe: a DMMA retires
+// 512 flops per issue against 64 for a warp-wide DFMA, the subtract / square of every (entry, dimension) pair disappears,
+// and the per-dimension accumulators become 16 registers per thread instead of 2p+2 shared-memory slots per thread (106 KB).
+//
+// Thread layout of a 64 x 64 tile (8 warps): warp w owns rows 8w..8w+7; lane (g = lane>>2, t = lane&3) owns row 8w+g and the
+// 16 columns 8cb + 2t + i (cb = 0..7, i = 0,1) -- exactly the accumulator fragment of DMMA.8x8x4, so the pass-1 result is used
+// in place and W = T o K feeds pass 2 as the A fragment without leaving the registers.
+// Covariate tiles are staged as [32 dims][XS = 68] (rows >= p are zero): fragment loads of pass 1 are bank-conflict-free.
+// They arrive by bulk asynchronous copies (cp.async.bulk + mbarrier, SASS UBLKCP), the tile after next being prefetched while
+// the current one is processed.  p <= 32; larger p uses the kernels of kernels.cuh.
+#pragma once
+#include "kernels.cuh"
+
+namespace csk {
+
+constexpr int XS = 68;         // doubles per staged dimension row
+constexpr int XD = 32;         // staged dimensions
+constexpr int XT = XD * XS;    // doubles per staged tile
+
+inline bool mma_kernels_ok(int p) { return p <= XD; }
+
+__device__ __forceinline__ void stage_x_coop(double* __restrict__ xs, const double* __restrict__ X, long long ldx, int row0, int p,
+                                             int tid) {
+  for (int idx = tid; idx < p * TB; idx += ETH) {
+    const int d = idx / TB, r = idx - d * TB;
+    xs[d * XS + r] = X[(long long)d * ldx + row0 + r];
+  }
+}
+
+#ifndef CS_EMU
+// one thread: p bulk copies of one 512-byte dimension row each, completing on `bar`
+__device__ __forceinline__ void stage_x_bulk(double* xs, const double* X, long long ldx, int row0, int p, unsigned long long* bar) {
+  for (int d = 0; d < p; ++d) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(csd::smem_u32(xs + d * XS)), "l"(X + (long long)d * ldx + row0), "r"((unsigned)(TB * sizeof(double))),
+                   "r"(csd::smem_u32(bar)) : "memory");
+  }
+}
+#endif
+
+// u[idx] = sum_k e_k x[k][idx]^2 for the row tile (ea, eb) and the column tile (ea, eb): 4 x 64 values, one per thread
+__device__ __forceinline__ void tile_norms(const double* __restrict__ xr, const double* __restrict__ xc, const double* __restrict__ ea,
+                                           const double* __restrict__ eb, int p, int tid, double* __restrict__ uv) {
+  const int which = tid >> 6, idx = tid & 63;
+  const double* xs = which < 2 ? xr : xc;
+  const double* e = (which & 1) ? eb : ea;
+  double s = 0.0;
+  for (int k = 0; k < p; ++k) {
+    const double x = xs[k * XS + idx];
+    s = fma(e[k] * x, x, s);
+  }
+  uv[which * TB + idx] = s;   // um | ua | vm | va
+}
+
+// D[cb][i] = sum_k e_k x_rk x_ck for the thread's row and 16 columns, both scalings at once
+__device__ __forceinline__ void pass1_mma(const double* __restrict__ xr, const double* __restrict__ xc, const double* __restrict__ ea,
+                                          const double* __restrict__ eb, int p, int r, int g, int t, double (&Dm)[8][2],
+                                          double (&Da)[8][2]) {
+#pragma unroll
+  for (int cb = 0; cb < 8; ++cb) { Dm[cb][0] = Dm[cb][1] = 0.0; Da[cb][0] = Da[cb][1] = 0.0; }
+  const int ks = (p + 3) >> 2;
+  for (int s = 0; s < ks; ++s) {
+    const int k = 4 * s + t;
+    const double xrk = xr[k * XS + r];
+    const double am = ea[k] * xrk, aa = eb[k] * xrk;
+    const double* xck = xc + k * XS + g;
+#pragma unroll
+    for (int cb = 0; cb < 8; ++cb) {
+      const double b = xck[8 * cb];
+      csd::dmma8x8x4(Dm[cb], am, b);
+      csd::dmma8x8x4(Da[cb], aa, b);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// K1 on the tensor path
+// ---------------------------------------------------------------------------------
+inline int gram_mma_smem_bytes() { return (2 * XT + 2 * XD + 4 * TB + 3 * TB) * (int)sizeof(double); }
+
+__global__ void __launch_bounds__(ETH, 3)
+gram_train_mma_kernel(const double* __restrict__ X, long long ldx, const double* __restrict__ z, const double* __restrict__ w,
+                      const double* __restrict__ params, Layout lay, int n, double* __restrict__ G, long long ldg,
+                      const int* __restrict__ skip, int tile0, int use_bulk) {
+  CS_BS(skip);
+  if (skip && *skip) return;
+  CS_BS(X); CS_BS(z); CS_BS(w); CS_BS(params); CS_BS(G);
+  CS_DYN_SMEM(double, sm_);
+  const int p = lay.p;
+  double* xr = sm_;
+  double* xc = xr + XT;
+  double* ea = xc + XT;
+  double* eb = ea + XD;
+  double* uv = eb + XD;          // um | ua | vm | va
+  double* zr = uv + 4 * TB;
+  double* zc = zr + TB;
+  double* wr = zc + TB;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int tl = (int)blockIdx.x + tile0;
+  const int I = csg_lower_row(tl), J = tl - I * (I + 1) / 2;
+  const int r0 = I * TB, c0 = J * TB;
+  for (int idx = tid; idx < (XD - p) * XS; idx += ETH) { xr[p * XS + idx] = 0.0; xc[p * XS + idx] = 0.0; }
+#ifndef CS_EMU
+  __shared__ unsigned long long xbar;
+  if (use_bulk) {
+    if (tid == 0) {
+      csd::mbar_init(&xbar, 1);
+      csd::mbar_fence_init();
+      csd::mbar_expect_tx(&xbar, 2u * (unsigned)p * TB * (unsigned)sizeof(double));
+      stage_x_bulk(xr, X, ldx, r0, p, &xbar);
+      stage_x_bulk(xc, X, ldx, c0, p, &xbar);
+    }
+  } else
+#endif
+  {
+    stage_x_coop(xr, X, ldx, r0, p, tid);
+    stage_x_coop(xc, X, ldx, c0, p, tid);
+  }
+  if (tid < XD) {
+    ea[tid] = tid < p ? exp(-params[lay.i_Lm() + tid]) : 0.0;
+    eb[tid] = tid < p ? exp(-params[lay.i_La() + tid]) : 0.0;
+  }
+  if (tid < TB) { zr[tid] = z[r0 + tid]; zc[tid] = z[c0 + tid]; wr[tid] = w[r0 + tid]; }
+  __syncthreads();
+#ifndef CS_EMU
+  if (use_bulk) csd::mbar_wait(&xbar, 0);
+#endif
+  tile_norms(xr, xc, ea, eb, p, tid, uv);
+  const int r = 8 * wid + g;
+  double Dm[8][2], Da[8][2];
+  pass1_mma(xr, xc, ea, eb, p, r, g, t, Dm, Da);
+  __syncthreads();
+  const double lam_m = params[lay.i_lm()], lam_a = params[lay.i_la()];
+  const double esig = exp(params[lay.i_sigma()]);
+  const int gr = r0 + r;
+  const double umr = uv[r], uar = uv[TB + r], zrr = zr[r];
+#pragma unroll
+  for (int cb = 0; cb < 8; ++cb)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int cl = 8 * cb + 2 * t + i, gc = c0 + cl;
+      double v;
+      if (gr >= n || gc >= n) v = (gr == gc) ? 1.0 : 0.0;
+      else if (gr < gc) v = 0.0;
+      else {
+        const double em = fma(-2.0, Dm[cb][i], umr + uv[2 * TB + cl]);
+        const double ea_ = fma(-2.0, Da[cb][i], uar + uv[3 * TB + cl]);
+        v = exp(lam_m - em) + exp(lam_a - ea_) * zrr * zc[cl];
+        if (gr == gc) v += esig / wr[r];
+      }
+      G[(long long)gc * ldg + gr] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// K3 / K4 on the tensor path
+// ---------------------------------------------------------------------------------
+inline int grad_mma_smem_bytes() {
+  return (4 * XT + 2 * XD + 8 * TB + 24 * TB + 3 * TB + 16 * XD + 32) * (int)sizeof(double);
+}
+
+// column sums over the 8 rows of a warp (lanes that differ in g) of a 16-vector indexed e = 2cb + i: recursive halving, after
+// which lane (g, t) holds the sums of the two columns 8g + 2t + {0, 1}.  42 shuffles instead of 48 x 3.  Deterministic.
+__device__ __forceinline__ void col_butterfly(const double (&v)[16], int g, double& o0, double& o1) {
+  const bool b2 = (g & 4) != 0, b1 = (g & 2) != 0, b0 = (g & 1) != 0;
+  double a[8], b[4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const double keep = b2 ? v[j + 8] : v[j], send = b2 ? v[j] : v[j + 8];
+    a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double keep = b1 ? a[j + 4] : a[j], send = b1 ? a[j] : a[j + 4];
+    b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    const double k0 = b0 ? b[2] : b[0], s0 = b0 ? b[0] : b[2];
+    const double k1 = b0 ? b[3] : b[1], s1 = b0 ? b[1] : b[3];
+    o0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 4);
+    o1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 4);
+  }
+}
+
+template <bool FROM_MEM>
+__global__ void __launch_bounds__(ETH, 1)
+grad_trace_mma_kernel(const double* __restrict__ X, long long ldx, const double* __restrict__ z,
+                      const double* __restrict__ params, Layout lay, int n, int nblk,
+                      const double* __restrict__ Cinv, long long ldc, const double* __restrict__ alpha,
+                      const EvalScalars* __restrict__ sc, double* __restrict__ gpart, double* __restrict__ kal_part,
+                      long long kal_stride, const double* __restrict__ Kmat_in, const double* __restrict__ Km_in,
+                      const double* __restrict__ Ka_in, const int* __restrict__ skip,
+                      const int* __restrict__ tile_tab, int use_bulk) {
+  // outputs and the tile_tab (distributed) mode exactly as grad_trace_kernel (kernels.cuh)
+  CS_BS(skip);
+  if (skip && *skip) return;
+  CS_BS(X); CS_BS(z); CS_BS(params); CS_BS(Cinv); CS_BS(alpha); CS_BS(sc); CS_BS(gpart); CS_BS(kal_part);
+  CS_DYN_SMEM(double, sm_);
+  const int p = lay.p;
+  const int nacc = 2 * p + 2;
+  double* xbuf = sm_;                  // [2 buffers][row tile | column tile][XT]
+  double* ea = xbuf + 4 * XT;
+  double* eb = ea + XD;
+  double* uv = eb + XD;                // um | ua | vm | va
+  double* zr = uv + 4 * TB;
+  double* zc = zr + TB;
+  double* ar = zc + TB;                // alpha rows
+  double* ac = ar + TB;                // alpha cols
+  double* colred = ac + TB;            // [8 warps][3][TB]: column sums of T o Km, T o Ka, K alpha_r per warp
+  double* colsum = colred + 24 * TB;   // [3][TB]
+  double* fin = colsum + 3 * TB;       // [8][2][XD] final reduction scratch
+  double* red = fin + 16 * XD;         // [32]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+  for (int idx = tid; idx < 4 * XT; idx += ETH) xbuf[idx] = 0.0;   // rows >= p stay zero for the whole kernel
+#ifndef CS_EMU
+  csd::fence_proxy_async();   // these generic-proxy writes precede the bulk copies into the same buffers
+#endif
+  if (tid < XD) {
+    ea[tid] = tid < p ? exp(-params[lay.i_Lm() + tid]) : 0.0;
+    eb[tid] = tid < p ? exp(-params[lay.i_La() + tid]) : 0.0;
+  }
+  const double lam_m = params[lay.i_lm()], lam_a = params[lay.i_la()];
+  const double coef = sc->coef;
+  const int ntiles = tile_tab ? nblk : nblk * (nblk + 1) / 2;
+  __syncthreads();
+#ifndef CS_EMU
+  __shared__ unsigned long long xbar[2];
+  const bool bulk = use_bulk && !tile_tab;
+  if (bulk && tid == 0) {
+    csd::mbar_init(&xbar[0], 1);
+    csd::mbar_init(&xbar[1], 1);
+    csd::mbar_fence_init();
+    csd::fence_proxy_async();
+    const int t0 = (int)blockIdx.x;
+    if (t0 < ntiles) {
+      int I0, J0;
+      lower_tile_of(t0, I0, J0);
+      csd::mbar_expect_tx(&xbar[0], 2u * (unsigned)p * TB * (unsigned)sizeof(double));
+      stage_x_bulk(xbuf, X, ldx, I0 * TB, p, &xbar[0]);
+      stage_x_bulk(xbuf + XT, X, ldx, J0 * TB, p, &xbar[0]);
+    }
+  }
+  int local_tile = 0;
+#else
+  const bool bulk = false;
+#endif
+  // per-thread accumulators over all tiles of this CTA: dims 8nb + 2t + ii of the row-side terms, one (matrix, dim,
+  // column quarter) of the column-side term, and the two plain traces
+  double acc_m[4][2], acc_a[4][2];
+#pragma unroll
+  for (int nb = 0; nb < 4; ++nb) { acc_m[nb][0] = acc_m[nb][1] = 0.0; acc_a[nb][0] = acc_a[nb][1] = 0.0; }
+  double acc_col = 0.0, tm_acc = 0.0, ta_acc = 0.0;
+  const int r = 8 * wid + g;
+  const int nbk = (p + 7) >> 3;
+
+  for (int tl = (int)blockIdx.x; tl < ntiles; tl += (int)gridDim.x) {
+    int I, J;
+    const double* Ct;
+    if (tile_tab) {
+      I = tile_tab[4 * tl]; J = tile_tab[4 * tl + 1];
+      const long long coff = (long long)(unsigned)tile_tab[4 * tl + 2] | ((long long)tile_tab[4 * tl + 3] << 32);
+      Ct = Cinv + coff;
+    } else {
+      lower_tile_of(tl, I, J);
+      Ct = Cinv + (long long)J * TB * ldc + (long long)I * TB;
+    }
+    const int r0 = I * TB, c0 = J * TB;
+    const double wgt = (I == J) ? 1.0 : 2.0;
+    __syncthreads();  // previous tile fully consumed
+    double* xr = xbuf;
+    double* xc = xbuf + XT;
+#ifndef CS_EMU
+    if (bulk) {
+      const int b = local_tile & 1;
+      if (tid == 0) {
+        const int tn = tl + (int)gridDim.x;
+        if (tn < ntiles) {
+          int In, Jn;
+          lower_tile_of(tn, In, Jn);
+          csd::fence_proxy_async();
+          csd::mbar_expect_tx(&xbar[b ^ 1], 2u * (unsigned)p * TB * (unsigned)sizeof(double));
+          stage_x_bulk(xbuf + (b ^ 1) * 2 * XT, X, ldx, In * TB, p, &xbar[b ^ 1]);
+          stage_x_bulk(xbuf + (b ^ 1) * 2 * XT + XT, X, ldx, Jn * TB, p, &xbar[b ^ 1]);
+        }
+      }
+      xr = xbuf + b * 2 * XT; xc = xr + XT;
+    } else
+#endif
+    {
+      stage_x_coop(xr, X, ldx, r0, p, tid);
+      stage_x_coop(xc, X, ldx, c0, p, tid);
+    }
+    if (tid < TB) { zr[tid] = z[r0 + tid]; zc[tid] = z[c0 + tid]; ar[tid] = alpha[r0 + tid]; ac[tid] = alpha[c0 + tid]; }
+    // the K^-1 entries of this tile are requested before anything waits (HBM latency hides behind the staging and pass 1)
+    const int gr = r0 + r;
+    double tv[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int cl = 8 * (e >> 1) + 2 * t + (e & 1);
+      tv[e] = (gr < n && c0 + cl < n) ? Ct[(long long)cl * ldc + r] : 0.0;
+    }
+    __syncthreads();
+#ifndef CS_EMU
+    if (bulk) { csd::mbar_wait(&xbar[local_tile & 1], (unsigned)((local_tile >> 1) & 1)); ++local_tile; }
+#endif
+    double Wm[16], Wa[16];   // pass-1 products, then T o Km and T o Ka
+    if (!FROM_MEM) {
+      tile_norms(xr, xc, ea, eb, p, tid, uv);
+      double Dm[8][2], Da[8][2];
+      pass1_mma(xr, xc, ea, eb, p, r, g, t, Dm, Da);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) { Wm[e] = Dm[e >> 1][e & 1]; Wa[e] = Da[e >> 1][e & 1]; }
+      __syncthreads();  // u / v visible
+    }
+    // ---- per entry: Km, Ka, T = K^-1 - coef alpha alpha^T, W = T o K; row / column pieces of K alpha
+    double kc[16];           // K[r,c] alpha_r: column partials of K alpha
+    double rm = 0.0, ra = 0.0, rk = 0.0;
+    {
+      const double umr = uv[r], uar = uv[TB + r], zrr = zr[r], arr = ar[r];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int cl = 8 * (e >> 1) + 2 * t + (e & 1), gc = c0 + cl;
+        double vkm = 0.0, vka = 0.0, T = 0.0, kfull = 0.0;
+        if (gr < n && gc < n) {
+          if (FROM_MEM) {
+            vkm = Km_in[(long long)gc * ldc + gr];
+            vka = Ka_in[(long long)gc * ldc + gr];
+            kfull = Kmat_in[(long long)gc * ldc + gr];
+          } else {
+            vkm = exp(lam_m - fma(-2.0, Wm[e], umr + uv[2 * TB + cl]));
+            vka = exp(lam_a - fma(-2.0, Wa[e], uar + uv[3 * TB + cl])) * zrr * zc[cl];
+            kfull = vkm + vka;
+          }
+          T = tv[e] - coef * arr * ac[cl];
+        }
+        rk = fma(kfull, ac[cl], rk);
+        kc[e] = kfull * arr;
+        Wm[e] = T * vkm;
+        Wa[e] = T * vka;
+        rm += Wm[e];
+        ra += Wa[e];
+      }
+    }
+    tm_acc = fma(wgt, rm, tm_acc);
+    ta_acc = fma(wgt, ra, ta_acc);
+    // full row sums over the 64 columns: the four lanes of a quad hold the same row
+    rm += __shfl_xor_sync(0xffffffffu, rm, 1); rm += __shfl_xor_sync(0xffffffffu, rm, 2);
+    ra += __shfl_xor_sync(0xffffffffu, ra, 1); ra += __shfl_xor_sync(0xffffffffu, ra, 2);
+    rk += __shfl_xor_sync(0xffffffffu, rk, 1); rk += __shfl_xor_sync(0xffffffffu, rk, 2);
+    if (t == 0) {  // K alpha, row part: every row of the tile belongs to exactly one quad
+      if (tile_tab) atomicAdd(kal_part + r0 + r, rk);
+      else kal_part[(long long)J * kal_stride + r0 + r] = rk;
+    }
+    // column sums over this warp's 8 rows, then across the warps through shared memory
+    {
+      double o0, o1;
+      double* cr = colred + wid * 3 * TB + 8 * g + 2 * t;
+      col_butterfly(Wm, g, o0, o1); cr[0] = o0; cr[1] = o1;
+      col_butterfly(Wa, g, o0, o1); cr[TB] = o0; cr[TB + 1] = o1;
+      col_butterfly(kc, g, o0, o1); cr[2 * TB] = o0; cr[2 * TB + 1] = o1;
+    }
+    // ---- pass 2: P = W Xc on the tensor path (A fragments straight from the registers), then the row-side terms
+    {
+      double Pm[4][2], Pa[4][2];
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) { Pm[nb][0] = Pm[nb][1] = 0.0; Pa[nb][0] = Pa[nb][1] = 0.0; }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const double* xce = xc + g * XS + 8 * (e >> 1) + 2 * t + (e & 1);
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+          if (nb < nbk) {
+            const double b = xce[8 * nb * XS];
+            csd::dmma8x8x4(Pm[nb], Wm[e], b);
+            csd::dmma8x8x4(Pa[nb], Wa[e], b);
+          }
+        }
+      }
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {
+          const int d = 8 * nb + 2 * t + ii;
+          const double x = xr[d * XS + r];          // zero for d >= p
+          acc_m[nb][ii] = fma(wgt * x, fma(x, rm, -2.0 * Pm[nb][ii]), acc_m[nb][ii]);
+          acc_a[nb][ii] = fma(wgt * x, fma(x, ra, -2.0 * Pa[nb][ii]), acc_a[nb][ii]);
+        }
+    }
+    __syncthreads();  // colred complete
+    if (tid < 3 * TB) {
+      const int q = tid >> 6, c = tid & 63;
+      double s = 0.0;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) s += colred[w8 * 3 * TB + q * TB + c];
+      colsum[q * TB + c] = s;
+      if (q == 2 && I != J) {  // K alpha, column part
+        if (tile_tab) atomicAdd(kal_part + c0 + c, s);
+        else kal_part[(long long)I * kal_stride + c0 + c] = s;
+      }
+    }
+    __syncthreads();
+    {  // column-side terms: thread = (matrix m, dim d, column quarter q4): sum_c x_cd^2 C_m[c] over the columns 4j + q4
+      const int m = tid >> 7, d = (tid >> 2) & 31, q4 = tid & 3;
+      const double* cs_ = colsum + m * TB;
+      const double* xd = xc + d * XS;
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const double x = xd[4 * j + q4];
+        s = fma(x * x, cs_[4 * j + q4], s);
+      }
+      acc_col = fma(wgt, s, acc_col);
+    }
+  }
+  // ---- reductions over the CTA: gpart[cta][0] = sum T o Km, [1] = sum T o Ka, [2+i] / [2+p+i] = sums weighted by d_i^2
+  __syncthreads();
+#pragma unroll
+  for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+    for (int ii = 0; ii < 2; ++ii) {
+      double vm = acc_m[nb][ii], va = acc_a[nb][ii];
+#pragma unroll
+      for (int o = 4; o <= 16; o <<= 1) { vm += __shfl_xor_sync(0xffffffffu, vm, o); va += __shfl_xor_sync(0xffffffffu, va, o); }
+      if (g == 0) {
+        const int d = 8 * nb + 2 * t + ii;
+        fin[(wid * 2 + 0) * XD + d] = vm;
+        fin[(wid * 2 + 1) * XD + d] = va;
+      }
+    }
+  acc_col += __shfl_xor_sync(0xffffffffu, acc_col, 1);
+  acc_col += __shfl_xor_sync(0xffffffffu, acc_col, 2);
+  if ((tid & 3) == 0) colsum[(tid >> 7) * XD + ((tid >> 2) & 31)] = acc_col;   // [matrix][dim]
+  __syncthreads();
+  if (tid < 2 * XD) {
+    const int m = tid >> 5, d = tid & 31;
+    if (d < p) {
+      double s = colsum[m * XD + d];
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) s += fin[(w8 * 2 + m) * XD + d];
+      gpart[(long long)blockIdx.x * nacc + 2 + m * p + d] = s;
+    }
+  }
+  const double tms = csd::block_sum(tm_acc, red);
+  const double tas = csd::block_sum(ta_acc, red);
+  if (tid == 0) { gpart[(long long)blockIdx.x * nacc] = tms; gpart[(long long)blockIdx.x * nacc + 1] = tas; }
+}
+
+}  // namespace csk
