@@ -902,8 +902,12 @@ struct DenseEngine {
         const double bulk = 28.0e12 * std::max(rt::sm_count() - 8, 8) / 140.0;
         const double window = (double)np * np * np / bulk - (double)N * 186e-6;
         const double per_col = 2.0 * gt * (double)tile * tile * sum;
+        // Round 2: the window model over-assigns at large n (measured on the B200, best a: n = 8192: 3 of 128 tile
+        // columns; 12288: 3..5 of 192; 16384: 6..8 of 256, 10 already slower; 32768: 16 of 512, 24 slower -- the model said
+        // 12 at 16384 and 64 at 32768 and cost 10 % / 19 % there): the pieces of the late panels carry most of the work and
+        // pile up behind the chain.  So the share is capped at 1/36 of the tile columns.
         if (window > 0.0 && per_col > 0.0)
-          tail_a_max = (int)std::min(window * 1.6e12 / per_col, (double)(N * rr / 8));  // clamped in double: no int overflow
+          tail_a_max = (int)std::min(std::min(window * 1.6e12 / per_col, (double)(N * rr / 8)), (double)(N * rr / 36));  // in double: no int overflow
       }
       if (const char* ta = std::getenv("CS_TAIL_A")) {
         int a = 0, f = 0;

@@ -95,6 +95,19 @@ int main() {
   { double fl = 2.0 * 128 * 128 * 512.0 * lower_tiles(60);
     auto MK = [&](int T) { return mk(T, 7680 / T, 7680 / T, 512, KM_FULL, ORD_LOWER, 0, -1.0, 1.0); };
     ALLCFG(false, false, MK, fl, "NT512") }
+  printf("\n== layout vs K: the same 64 x 64 kernel, 4096 rows lower, K = 4096 and K = 512, NT / TN / NN, beta = 1 and beta = 0\n");
+  for (int K : {4096, 512}) {
+    double fl = 2.0 * 64 * 64 * (double)K * lower_tiles(4096 / 64);
+    char nm[64];
+    for (int beta = 1; beta >= 0; --beta) {
+      auto MKb = [&](int T) { return mk(T, 4096 / T, 4096 / T, K, KM_FULL, ORD_LOWER, 0, -1.0, (double)beta); };
+      snprintf(nm, sizeof nm, "NT K=%d beta=%d s3", K, beta); run<64, 2, 2, false, false, 16, 3>(nm, MKb(64), fl);
+      snprintf(nm, sizeof nm, "NT K=%d beta=%d s2", K, beta); run<64, 2, 2, false, false, 16, 2>(nm, MKb(64), fl);
+      snprintf(nm, sizeof nm, "TN K=%d beta=%d s2", K, beta); run<64, 2, 2, true, true, 16, 2>(nm, MKb(64), fl);
+      snprintf(nm, sizeof nm, "TN K=%d beta=%d s3", K, beta); run<64, 2, 2, true, true, 16, 3>(nm, MKb(64), fl);
+      snprintf(nm, sizeof nm, "NN K=%d beta=%d s3", K, beta); run<64, 2, 2, false, true, 16, 3>(nm, MKb(64), fl);
+    }
+  }
   printf("\n== NT  inner update k=128, 7680 x 384 rectangle (beta=1)\n");
   { double fl = 2.0 * 7680.0 * 384 * 128;
     auto MK = [&](int T) { return mk(T, 7680 / T, 384 / T, 128, KM_FULL, ORD_COL, 0, -1.0, 1.0); };

@@ -16,10 +16,10 @@ timeout 1200 ncu --set full --clock-control none --import-source on --kernel-nam
    -k 'regex:gemm_kernel<.int.64, .int.2, .int.2, .bool.1, .bool.1' -s 2 -c 1 -o gpurun_out/prof_xtx -f $S > gpurun_out/ncu_full_xtx.log 2>&1
 echo "ncu_xtx_exit=$?" | tee -a gpurun_out/status.txt
 timeout 1200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-   -k 'regex:grad_trace_kernel' -s 1 -c 1 -o gpurun_out/prof_grad -f $S > gpurun_out/ncu_full_grad.log 2>&1
+   -k 'regex:grad_trace_mma_kernel' -s 1 -c 1 -o gpurun_out/prof_grad -f $S > gpurun_out/ncu_full_grad.log 2>&1
 echo "ncu_grad_exit=$?" | tee -a gpurun_out/status.txt
 timeout 1200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-   -k 'regex:gram_train_kernel' -s 1 -c 1 -o gpurun_out/prof_gram -f $S > gpurun_out/ncu_full_gram.log 2>&1
+   -k 'regex:gram_train_mma_kernel' -s 1 -c 1 -o gpurun_out/prof_gram -f $S > gpurun_out/ncu_full_gram.log 2>&1
 echo "ncu_gram_exit=$?" | tee -a gpurun_out/status.txt
 timeout 1200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
    -k 'regex:leaf_kernel' -s 10 -c 1 -o gpurun_out/prof_leaf -f $S > gpurun_out/ncu_full_leaf.log 2>&1
