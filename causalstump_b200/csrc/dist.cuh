@@ -486,6 +486,10 @@ struct DistEval {
                   R.lay, g.n, (const int*)R.d_lower, T, P, Q, R.G, g.ldl);
       }
     });
+    static const bool two_sweeps = std::getenv("CS_DIST_TWO_SWEEPS") != nullptr;
+    if (!two_sweeps) {
+      if ((e = fused_sweep())) return e;
+    } else {
     // ---- sweep 1: Cholesky, with look-ahead.  The update of step k is split: block column k+1 on the main
     // stream (the next leaf / panel multiply wait for nothing else), the rest on the side stream st2 where it
     // overlaps the leaf, the panel multiply and the communication of step k+1.
@@ -568,6 +572,7 @@ struct DistEval {
       side_pending = true;
     }
     join_side();
+    }  // two sweeps
     // ---- reductions: alpha/u/s, scalars, trace gradients, stats ----
     each([&](DistRank& R) {
       const Geom& g = R.g;
@@ -611,6 +616,77 @@ struct DistEval {
       auto k7 = csk::finalize_kernel; ++g_launches;
       CS_LAUNCH(k7, 1, csk::ETH, 0, R.st, R.red, 1, R.rs_part, 1, R.params, R.lay, g.n, R.sc, R.grad, (const int*)nullptr);
     });
+    return 0;
+  }
+
+  // Round 2: ONE sweep.  Row k of X = L^-1 can be finalised as soon as block column k of L and X_kk exist (its Acc_kJ only
+  // collects contributions of the steps before k), so the inverse / K^-1 step k is issued right behind the Cholesky step k
+  // instead of in a second pass over the matrix: the column panel of L is shared once instead of twice, the chain of
+  // leaf + collectives is walked N times instead of 2N, and the bulk work of the inverse (2/3 of all flops: Acc and C updates,
+  // side stream) overlaps the latency-bound Cholesky chain of the following steps -- the same idea as the pipelined inverse of
+  // the single-GPU engine.  Tables, problems and buffers are those of the two-sweep driver (CS_DIST_TWO_SWEEPS=1 keeps it).
+  int fused_sweep() {
+    const size_t T2 = (size_t)T * T;
+    int e;
+    bool side_pending = false;
+    auto join_side = [&]() {
+      if (!side_pending) return;
+      each([&](DistRank& R) { rt::stream_wait_event(R.st, R.ev_side); });
+    };
+    for (int k = 0; k < N; ++k) {
+      const int prk = k % P, pck = k % Q;
+      const int par = k & 1;
+      const bool last = (k == N - 1);
+      each([&](DistRank& R) {
+        if (R.g.pr == prk && R.g.pc == pck) {
+          const long long o = R.g.off(k, k);
+          csdense::launch_leaf(T, R.G + o, R.g.ldl, R.Xl + o, R.g.ldl, k * T, R.logdet_part + k, R.status, n, R.st, nullptr);
+          pack(R, R.Xl + o, R.g.ldl, 0, R.xkk, 1);
+        }
+      });
+      // X_kk to the process column (panel multiply) and to the process row (row k of X)
+      if (!last && (e = comm->bcast(L, G_COL, pck, prk, [](DistRank& R) { return R.xkk; }, T2))) return e;
+      if ((e = comm->bcast(L, G_ROW, prk, pck, [](DistRank& R) { return R.xkk; }, T2))) return e;
+      const int li0 = k / P;
+      const int cntr = k / Q + 1;
+      if (!last)
+        each([&](DistRank& R) {
+          if (R.g.pc != pck) return;
+          const GemmProblem& pp = R.probs[NPK * (size_t)N + k];
+          if (pp.ntiles > 0) csdense::launch_gemm(T, csdense::GK_NT, R.d_panel + k, 1, pp.ntiles, R.st);
+          pack(R, R.G + (long long)li0 * T + (long long)R.g.lj(k) * T * R.g.ldl, R.g.ldl, T, R.colsend, R.g.mt - li0);
+        });
+      each([&](DistRank& R) {
+        if (R.g.pr != prk) return;
+        const GemmProblem& pf = R.probs[NPK * (size_t)k + 1];
+        if (pf.ntiles > 0) csdense::launch_gemm(T, csdense::GK_NN, R.d_probs + NPK * k + 1, 1, pf.ntiles, R.st);
+        pack(R, R.Xl + (long long)R.g.li(k) * T, R.g.ldl, (long long)T * R.g.ldl, R.rowsend, cntr);
+      });
+      if (!last && (e = share_col_panel(k))) return e;
+      if ((e = comm->share_panel(L, G_ROW, prk, [](DistRank& R) { return R.rowsend; }, [par](DistRank& R) { return R.ROWb[par]; }, cntr * T2, Q))) return e;
+      join_side();  // the side stream has finished step k-1 (it updated block column / row k+1 and read the other buffers)
+      each([&](DistRank& R) {
+        rt::event_record(R.ev_share, R.st);
+        if (!last) {
+          const GemmProblem& pa = R.probs[NPK * (size_t)k + 0];
+          if (pa.ntiles > 0) csdense::launch_gemm(R.gt, csdense::GK_NT, R.d_probs + NPK * k + 0, 1, pa.ntiles, R.st);
+        }
+        const GemmProblem& pa2 = R.probs[NPK * (size_t)k + 2];
+        if (pa2.ntiles > 0) csdense::launch_gemm(R.gt, csdense::GK_NN, R.d_probs + NPK * k + 2, 1, pa2.ntiles, R.st);
+        rt::stream_wait_event(R.st2, R.ev_share);
+        if (!last) {
+          const GemmProblem& pb = R.probs[NPK * (size_t)k + 4];
+          if (pb.ntiles > 0) csdense::launch_gemm(R.gt, csdense::GK_NT, R.d_probs + NPK * k + 4, 1, pb.ntiles, R.st2);
+        }
+        const GemmProblem& pb2 = R.probs[NPK * (size_t)k + 5];
+        if (pb2.ntiles > 0) csdense::launch_gemm(R.gt, csdense::GK_NN, R.d_probs + NPK * k + 5, 1, pb2.ntiles, R.st2);
+        const GemmProblem& pcx = R.probs[NPK * (size_t)k + 3];
+        if (pcx.ntiles > 0) csdense::launch_gemm(R.gt, csdense::GK_TN, R.d_probs + NPK * k + 3, 1, pcx.ntiles, R.st2);
+        rt::event_record(R.ev_side, R.st2);
+      });
+      side_pending = true;
+    }
+    join_side();
     return 0;
   }
 

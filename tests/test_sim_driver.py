@@ -94,3 +94,22 @@ def test_device_simulation_loop_on_gpu(gpulib):
     rng = np.random.default_rng(5)
     X = np.column_stack([rng.normal(size=(200, 3)), (rng.random((200, 2)) < 0.4).astype(float)])
     check_run(gpulib, [(1, 0), (2, 1)], n=200, p=5, maxiter=25, tol=1e-1, rtol=1e-6, X=X, z=(rng.random(200) < 0.25).astype(float))
+
+
+def test_replicate_driver_on_the_device_driver(emulib):
+    """replicates.hill_units_device: the Python face of cs_sim_run returns the same row shape as the host driver
+    (metrics dict over METRICS, iteration count, final LML, failure flag) and restart winners can be selected from it."""
+    from causalstump_b200 import rcpp_exports as rx
+    rx.use_library(emulib)
+    try:
+        units = [(0, 0), (0, 1), (1, 0)]
+        res = rp.hill_units_device(units, n=64, p=3, maxiter=5, tol=0.0, batch=2, seed=11)
+        assert [(r["replicate"], r["restart"]) for r in res] == units
+        for r in res:
+            assert set(r["metrics"]) == set(rp.METRICS) and r["iters"] == 5 and not r["failed"] and np.isfinite(r["lml"])
+            assert r["pehe_test"] == r["metrics"]["PEHE.all.test"] and 0.0 <= r["metrics"]["coverage.ite.train"] <= 1.0
+        win = rp.select_winners(res)
+        assert [w["replicate"] for w in win] == [0, 1] and win[0]["lml"] == max(res[0]["lml"], res[1]["lml"])
+        assert 0.0 < rp.LAST_TIMING["slot_utilisation"] <= 1.0 and rp.LAST_TIMING["iterations"] == 15
+    finally:
+        rx.use_library(None)
