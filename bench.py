@@ -39,14 +39,15 @@ if ROOT not in sys.path:
 N_METRIC, P_METRIC = 8192, 25
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
 # `ncu --set full` capture (per launch; None until a capture of the current kernel exists)
-XTX_TRAFFIC_BYTES = 4.107949e9 + 485.392896e6
-XTX_TRAFFIC_SOURCE = ("profiles/r01_s2_ncu_xtx.txt: ncu --set full of this kernel in `bench.py --inv-pipeline 0` "
-                      "(dram__bytes_read.sum 4.108 GB + dram__bytes_write.sum 485.4 MB per launch)")
+XTX_TRAFFIC_BYTES = 4.086840e9 + 485.787392e6
+XTX_TRAFFIC_SOURCE = ("profiles/r02_ncu_xtx.txt: ncu --set full of this kernel in `bench.py --inv-pipeline 0` "
+                      "(dram__bytes_read.sum 4.087 GB + dram__bytes_write.sum 485.8 MB per launch)")
 METRIC = "fp64 LML+gradient evals/sec at n=8192,p=25"
 UNIT = "evals/s"
 # time-weighted DMMA sub-pipe activity of the K = 512 bulk launches of the timed plan (ncu --set full over every GEMM launch
 # of one evaluation, plain priority streams -- ncu cannot attach to green-context streams); updated with each capture
-DMMA_ACTIVE_K512 = {"pct": 85.4, "source": "profiles/r01_s2_gemm_launches.md (launches with >= 592 CTA tiles, time-weighted)"}
+DMMA_ACTIVE_K512 = {"pct": 86.3, "all_gemm_launches_pct": 77.9,
+                    "source": "profiles/r02_gemm_launches.md (71 launches with >= 592 CTA tiles, time-weighted; 77.9 % over all 460 GEMM launches)"}
 
 
 def workload_config():
