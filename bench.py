@@ -475,6 +475,9 @@ def measure_config4(lib, rank, world, dist, barrier, max_over_ranks, batch, host
     restart with the highest final LML wins per replicate).  Strong scaling: 400 / N fits per GPU."""
     from causalstump_b200 import replicates as rp
     units = rp.shard(rp.unit_list(100, 4), rank, world)
+    # few units per GPU: smaller batched handles keep more handles in flight (measured on one B200, device driver:
+    # 50 units 1.54 s at batch 8 vs 1.68 s at 32; 100 units 2.46 s at 16 vs 2.67 s at 32; 200 units: 32 as good as 8)
+    batch = batch if len(units) > 128 else (16 if len(units) > 64 else 8)
     run_units(units[:2], batch, host_sim)  # warm-up: graph capture, allocator
     barrier()
     t0 = time.perf_counter()

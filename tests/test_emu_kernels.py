@@ -195,36 +195,7 @@ def test_first_generation_plan_still_works(emulib, monkeypatch, pipe):
 
 
 def test_failing_member_stops_alone(emulib):
-    """a non positive definite member (or one whose LML turns NaN) must not discard the healthy members of
-    the batch.  In the reference only the failing CausalStump() call errors (inv_sympd throws inside that call,
-    src/kernel_GP_SE_cpp.cpp:56; `if (change < tol ...)` on NA, R/main.R:82)."""
-    good = cs.make_problem("GP", 40, 2)
-    bad = cs.make_problem("GP", 40, 2, replicate=1)
-    nanp = cs.make_problem("GP", 40, 2, replicate=2)
-    Xb = bad["X"].copy(); Xb[7] = Xb[3]
-    zb = bad["z"].copy(); zb[7] = zb[3]
-    pb = o.pack_params(bad["par"]); pb[0] = -80.0
-    yn = nanp["y"].copy(); yn[5] = np.nan
-    single = _lib.Fit(emulib, 0, good["y"], good["X"], good["z"], None, o.pack_params(good["par"]))
-    it0, tr0 = single.run(6, 1e-12)
-    p0 = single.get_params()
-    single.close()
-    fb = _lib.FitBatch(emulib, 0, [(bad["y"], Xb, zb, None, pb), (good["y"], good["X"], good["z"], None, o.pack_params(good["par"])),
-                                   (yn, nanp["X"], nanp["z"], None, o.pack_params(nanp["par"]))])
-    res = fb.run(6, 1e-12, strict=False)
-    st = fb.member_status()
-    assert 1 <= st[0] <= 40 and st[1] == 0 and st[2] == _lib.CS_ERR_NONFINITE
-    assert res[1][0] == it0 and np.array_equal(res[1][1], tr0) and np.array_equal(fb.select(1).get_params(), p0)
-    assert res[0][0] <= 2 and res[2][0] == 1     # stopped at the iteration the reference would error in, not at maxiter
-    with pytest.raises(_lib.NotPositiveDefinite) as ei:
-        fb.run(6, 1e-12)                         # strict: the first failing member is the error, after all members ran
-    assert "member 0" in str(ei.value)
-    fb.close()
-    f = _lib.Fit(emulib, 0, yn, nanp["X"], nanp["z"], None, o.pack_params(nanp["par"]))
-    with pytest.raises(_lib.CsError) as ei:
-        f.run(6, 1e-12)
-    assert ei.value.code == _lib.CS_ERR_NONFINITE
-    f.close()
+    cs.check_failing_member(emulib)
 
 
 def test_kernel_handle_cache_follows_the_data(emulib):

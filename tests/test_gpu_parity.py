@@ -123,6 +123,12 @@ def test_limits_and_failure_reporting(gpulib):
     cs.check_limits(gpulib)
 
 
+def test_failing_member_stops_alone_on_gpu(gpulib):
+    """same body as the emulator test: a non positive definite member and a NaN member stop alone, the healthy member of the
+    batch finishes bit-identically to a single handle (device-side WHILE loop included)"""
+    cs.check_failing_member(gpulib)
+
+
 def test_batched_handle(gpulib):
     """cs_fit_create_batch at the size of config 4 (672 x 25 training splits): all members advance with every
     launch; each must equal its own single-handle fit (to rounding: the per-fit CTA count of the trace-gradient
