@@ -17,7 +17,7 @@ CS_GP, CS_TP = 0, 1
 CS_OPT_ADAM, CS_OPT_NADAM, CS_OPT_NESTEROV = 0, 1, 2
 CS_NPHASE = 7
 CS_ERR_NONFINITE = -6
-CS_MAX_P = 40
+CS_MAX_P = 128
 PHASES = ("gram", "potrf", "trtri", "xtx", "matvec", "grad", "final")
 
 dp = C.POINTER(C.c_double)

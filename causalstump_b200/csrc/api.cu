@@ -331,9 +331,18 @@ static void launch_grad_trace(cs_fit* f, cudaStream_t st, const int* skip, unsig
     CS_LAUNCH(k, dim3(f->ncta_grad, 1, B), csk::ETH, csk::grad_mma_smem_bytes(), st, f->X, ld, f->z, f->params, f->lay, f->n, f->nblk,
               f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, nul, nul, nul, skip, (const int*)nullptr, use_bulk_copies());
   } else {
+    // element-wise kernel; p beyond what its shared-memory accumulators hold runs as several launches, one dimension window each
     auto k = csk::grad_trace_kernel<false>;
-    CS_LAUNCH(k, dim3(f->ncta_grad, 1, B), csk::ETH, csk::grad_smem_bytes(f->p, f->xt.on != 0), st, f->X, ld, f->z, f->params, f->lay, f->n,
-              f->nblk, f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, nul, nul, nul, skip, (const int*)nullptr, f->xt);
+    const int dwmax = csk::grad_window(f->p);
+    --g_launches;
+    for (int d0 = 0; d0 < f->p; d0 += dwmax) {
+      const int dw = std::min(dwmax, f->p - d0);
+      const bool pre = f->xt.on != 0 && dwmax >= f->p;
+      ++g_launches;
+      CS_LAUNCH(k, dim3(f->ncta_grad, 1, B), csk::ETH, csk::grad_smem_bytes(f->p, pre, dw), st, f->X, ld, f->z, f->params, f->lay, f->n,
+                f->nblk, f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, nul, nul, nul, skip, (const int*)nullptr,
+                pre ? f->xt : rt::XTma{}, d0, dw);
+    }
   }
 }
 
@@ -531,8 +540,8 @@ static int fit_create_impl(const cs_fit_config* cfg, int nbatch, int n, int p, c
   f->select(0);
   { auto k = csk::gram_train_kernel; CS_SET_SMEM(k, csk::gram_smem_bytes(csk::PMAX)); }
   { auto k = csk::gram_cross_kernel; CS_SET_SMEM(k, csk::gram_smem_bytes(csk::PMAX)); }
-  { auto k = csk::grad_trace_kernel<false>; CS_SET_SMEM(k, std::max(csk::grad_smem_bytes(csk::PMAX), csk::grad_smem_bytes(p, f->xt.on != 0))); }
-  { auto k = csk::grad_trace_kernel<true>; CS_SET_SMEM(k, csk::grad_smem_bytes(csk::PMAX)); }
+  { auto k = csk::grad_trace_kernel<false>; CS_SET_SMEM(k, csk::SMEM_LIMIT); }
+  { auto k = csk::grad_trace_kernel<true>; CS_SET_SMEM(k, csk::SMEM_LIMIT); }
   { auto k = csp::gram_sum_kernel; CS_SET_SMEM(k, csk::gram_smem_bytes(csk::PMAX)); }
   { auto k = csk::gram_train_mma_kernel; CS_SET_SMEM(k, csk::gram_mma_smem_bytes()); }
   { auto k = csk::grad_trace_mma_kernel<false>; CS_SET_SMEM(k, csk::grad_mma_smem_bytes()); }
@@ -1462,9 +1471,15 @@ static int grad_stats_common(int kind, int n, int p, const double* y, const doub
                   (const double*)dA.d(), (const int*)nullptr, (const int*)nullptr, use_bulk_copies());
       } else {
         auto k3 = csk::grad_trace_kernel<true>;
-        CS_LAUNCH(k3, f->ncta_grad, csk::ETH, csk::grad_smem_bytes(p), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
-                  f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)dK.d(), (const double*)dM.d(),
-                  (const double*)dA.d(), (const int*)nullptr, (const int*)nullptr, rt::XTma{});
+        const int dwmax = csk::grad_window(p);
+        --g_launches;
+        for (int d0 = 0; d0 < p; d0 += dwmax) {
+          const int dw = std::min(dwmax, p - d0);
+          ++g_launches;
+          CS_LAUNCH(k3, f->ncta_grad, csk::ETH, csk::grad_smem_bytes(p, false, dw), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
+                    f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)dK.d(), (const double*)dM.d(),
+                    (const double*)dA.d(), (const int*)nullptr, (const int*)nullptr, rt::XTma{}, d0, dw);
+        }
       }
     } else {
       launch_grad_trace(f, st, nullptr, 1u);
@@ -1909,7 +1924,7 @@ int cs_dist_create(int kind, int n, int p, const double* y, const double* X, con
 #else
   if (!y || !X || !z || !params || !id128 || !out) return fail(CS_ERR_ARG, "cs_dist_create: null argument");
   if (P * Q != world || rank < 0 || rank >= world) return fail(CS_ERR_ARG, "cs_dist_create: P*Q must equal world");
-  if (p > CS_MAX_P) return fail(CS_ERR_UNSUPPORTED, "p exceeds CS_MAX_P");
+  if (p > 40) return fail(CS_ERR_UNSUPPORTED, "cs_dist_create: p=%d exceeds 40, the limit of the distributed engine", p);
   if (need_device()) return CS_ERR_NODEVICE;
   if (!g_nccl.load()) return fail(CS_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
   std::unique_ptr<cs_dist> d(new cs_dist());

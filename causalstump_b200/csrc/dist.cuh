@@ -454,7 +454,7 @@ static int rank_init(DistRank& R, int n, int p, int kind, int T, int P, int Q, i
   if ((e = rt::stream_sync(st))) return e;
   csdense::configure_kernels();
   { auto kf = gram_dist_kernel; CS_SET_SMEM(kf, csk::gram_smem_bytes(csk::PMAX)); }
-  { auto kf = csk::grad_trace_kernel<false>; CS_SET_SMEM(kf, csk::grad_smem_bytes(csk::PMAX)); }
+  { auto kf = csk::grad_trace_kernel<false>; CS_SET_SMEM(kf, csk::SMEM_LIMIT); }
   return 0;
 }
 
@@ -597,7 +597,7 @@ struct DistEval {
       auto k3 = csk::grad_trace_kernel<false>; ++g_launches;
       CS_LAUNCH(k3, R.ncta_grad, csk::ETH, csk::grad_smem_bytes(R.lay.p), R.st, R.X, ld, R.z, R.params, R.lay, g.n, R.n_k3,
                 R.C, g.ldl, R.alpha, R.sc, R.gpart, kal, (long long)0, (const double*)nullptr, (const double*)nullptr,
-                (const double*)nullptr, (const int*)nullptr, (const int*)R.d_k3, rt::XTma{});
+                (const double*)nullptr, (const int*)nullptr, (const int*)R.d_k3, rt::XTma{}, 0, R.lay.p);
       auto k4 = csk::reduce_gpart_kernel; ++g_launches;
       CS_LAUNCH(k4, 1, 128, 0, R.st, R.gpart, R.ncta_grad, nacc, R.red);
       if (!R.diag_tiles.empty()) {

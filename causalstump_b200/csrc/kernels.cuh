@@ -22,7 +22,8 @@ __host__ __device__ inline int csg_lower_row(int t) {
 
 constexpr int TB = 64;        // tile edge of the element-wise kernels
 constexpr int ETH = 256;      // threads per CTA (16 x 16, 4 x 4 entries each)
-constexpr int PMAX = 40;      // max covariates supported by the fused gradient kernel
+constexpr int PMAX = 128;     // max covariates (== CS_MAX_P): sizes of the per-dimension shared-memory vectors
+constexpr int SMEM_LIMIT = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100a
 
 enum Kind { KIND_GP = 0, KIND_TP = 1 };
 enum Optim { OPT_ADAM = 0, OPT_NADAM = 1, OPT_NESTEROV = 2 };
@@ -348,10 +349,20 @@ scalars_kernel(const double* __restrict__ mv_part, int nsplit, long long stride_
 //   gpart[cta][2+p+i]    = sum T .* Ka .* d_i^2
 // and K*alpha row partials go to kal_part[slot][row] (each slot/row written exactly once).
 // ---------------------------------------------------------------------------------
-inline int grad_smem_bytes(int p, bool prefetch = false) {  // prefetch: a second pair of X tiles (TMA double buffering)
-  return ((2 * p + 2) * ETH + (prefetch ? 4 : 2) * p * TB + 2 * PMAX + 5 * TB + 8 * TB + 32) * (int)sizeof(double);
+// prefetch: a second pair of X tiles (TMA double buffering); dw: dimensions whose trace sums this launch accumulates
+// (the per-thread accumulators are the large term: 2 KB per accumulated quantity)
+inline int grad_smem_bytes(int p, bool prefetch = false, int dw = -1) {
+  if (dw < 0) dw = p;
+  return ((2 * dw + 2) * ETH + (prefetch ? 4 : 2) * p * TB + 2 * PMAX + 5 * TB + 8 * TB + 32) * (int)sizeof(double);
 }
-inline bool grad_prefetch_fits(int p) { return grad_smem_bytes(p, true) <= 227 * 1024; }
+inline bool grad_prefetch_fits(int p) { return grad_smem_bytes(p, true) <= SMEM_LIMIT; }
+// largest dimension window that fits beside the X tiles of all p dimensions (p > ~43 needs several launches: every launch
+// recomputes the exponents over all p dimensions and accumulates the 2 dw trace sums of its window)
+inline int grad_window(int p) {
+  int dw = p;
+  while (dw > 1 && grad_smem_bytes(p, false, dw) > SMEM_LIMIT) --dw;
+  return dw;
+}
 
 __host__ __device__ inline void lower_tile_of(int t, int& I, int& J) {
   I = csg_lower_row(t);
@@ -366,7 +377,9 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
                   const EvalScalars* __restrict__ sc, double* __restrict__ gpart, double* __restrict__ kal_part,
                   long long kal_stride, const double* __restrict__ Kmat_in, const double* __restrict__ Km_in,
                   const double* __restrict__ Ka_in, const int* __restrict__ skip,
-                  const int* __restrict__ tile_tab, const __grid_constant__ rt::XTma xt) {
+                  const int* __restrict__ tile_tab, const __grid_constant__ rt::XTma xt, int d0, int dw) {
+  // [d0, d0 + dw): the dimensions whose trace sums this launch accumulates (gpart keeps the global 2p+2 layout; entries 0, 1
+  // and the K alpha partials are written by every launch with identical values)
   // xt.on (never together with tile_tab): the X tiles of the NEXT tile of this persistent CTA are fetched by TMA into a
   // second pair of buffers while the current tile is being processed (grad_smem_bytes(p, true))
   // tile_tab != null (distributed mode): nblk is the number of table entries
@@ -377,7 +390,8 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
   CS_BS(X); CS_BS(z); CS_BS(params); CS_BS(Cinv); CS_BS(alpha); CS_BS(sc); CS_BS(gpart); CS_BS(kal_part);
   CS_DYN_SMEM(double, sm_);
   const int p = lay.p;
-  const int nacc = 2 * p + 2;
+  const int nacc = 2 * dw + 2;          // accumulated here; the global layout has 2p + 2 entries per CTA
+  const int nacc_all = 2 * p + 2;
   double* acc = sm_;                    // [nacc][ETH]
   double* xr = acc + nacc * ETH;        // [p][TB]
   double* xc = xr + p * TB;
@@ -523,20 +537,20 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
       oa = (ga[0] + ga[1]) + (ga[2] + ga[3]);
     };
     int i = 0;
-    for (; i + 1 < p; i += 2) {
+    for (; i + 1 < dw; i += 2) {
       double m0, a0, m1, a1;
-      one_dim(i, m0, a0);
-      one_dim(i + 1, m1, a1);
+      one_dim(d0 + i, m0, a0);
+      one_dim(d0 + i + 1, m1, a1);
       acc[(2 + i) * ETH + tid] += wgt * m0;
-      acc[(2 + p + i) * ETH + tid] += wgt * a0;
+      acc[(2 + dw + i) * ETH + tid] += wgt * a0;
       acc[(3 + i) * ETH + tid] += wgt * m1;
-      acc[(3 + p + i) * ETH + tid] += wgt * a1;
+      acc[(3 + dw + i) * ETH + tid] += wgt * a1;
     }
-    if (i < p) {
+    if (i < dw) {
       double m0, a0;
-      one_dim(i, m0, a0);
+      one_dim(d0 + i, m0, a0);
       acc[(2 + i) * ETH + tid] += wgt * m0;
-      acc[(2 + p + i) * ETH + tid] += wgt * a0;
+      acc[(2 + dw + i) * ETH + tid] += wgt * a0;
     }
     // K*alpha partials: rows (reduce over ty) and columns (reduce over tx)
 #pragma unroll
@@ -575,7 +589,8 @@ grad_trace_kernel(const double* __restrict__ X, long long ldx, const double* __r
   __syncthreads();
   for (int k = 0; k < nacc; ++k) {
     const double v = csd::block_sum(acc[k * ETH + tid], red);
-    if (tid == 0) gpart[(long long)blockIdx.x * nacc + k] = v;
+    const int kg = k < 2 ? k : (k < 2 + dw ? 2 + d0 + (k - 2) : 2 + p + d0 + (k - 2 - dw));
+    if (tid == 0) gpart[(long long)blockIdx.x * nacc_all + kg] = v;
   }
 }
 

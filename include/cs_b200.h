@@ -41,7 +41,8 @@ extern "C" {
 #define CS_ERR_UNSUPPORTED (-5)
 #define CS_ERR_NONFINITE (-6) /* |dLML| is NaN inside the optimisation loop: R stops at `if (change < tol ...)`, R/main.R:82 */
 
-#define CS_MAX_P 40
+#define CS_MAX_P 128 /* p <= 32: tensor-path Gram / gradient kernels; p <= 43: element-wise kernels, one launch; beyond: the
+                        * gradient kernel runs one launch per window of dimensions (its accumulators live in shared memory) */
 
 typedef struct cs_fit cs_fit; /* opaque device-resident fit handle */
 

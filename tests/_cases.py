@@ -133,14 +133,20 @@ class _raises:
 def check_limits(emulib):
     """p = CS_MAX_P works, p > CS_MAX_P is refused; a non positive definite member of a batch is reported with its
     pivot (what makes arma::inv_sympd throw at src/kernel_GP_SE_cpp.cpp:56) instead of producing numbers."""
-    P = make_problem("GP", 70, 40)
-    g, st, mu = o.eval_lml_grad("GP", P["y"], P["X"], P["z"], P["w"], P["par"])
-    f = _lib.Fit(emulib, 0, P["y"], P["X"], P["z"], P["w"], o.pack_params(P["par"]))
-    g2, st2, _ = f.eval()
-    f.close()
-    assert rel(g2, o.pack_params(g), 1e-9) < TOL_GRAD and abs(st2[1] - st[1]) < TOL_LML * abs(st[1])
+    # p = 40: element-wise kernels in one launch; p = 70 and p = CS_MAX_P: the gradient kernel runs one launch per window
+    # of dimensions (its per-thread accumulators live in shared memory); p > CS_MAX_P is refused
+    for p_ in (40, 70, _lib.CS_MAX_P):
+        P = make_problem("GP", 70, p_)
+        g, st, mu = o.eval_lml_grad("GP", P["y"], P["X"], P["z"], P["w"], P["par"])
+        f = _lib.Fit(emulib, 0, P["y"], P["X"], P["z"], P["w"], o.pack_params(P["par"]))
+        g2, st2, _ = f.eval()
+        f.close()
+        gref = o.pack_params(g)
+        assert float(np.max(np.abs(g2 - gref) / np.maximum(np.abs(gref), 1e-6 * np.max(np.abs(gref))))) < TOL_GRAD, p_
+        assert abs(st2[1] - st[1]) < TOL_LML * abs(st[1])
+    pbig = _lib.CS_MAX_P + 1
     with _raises(_lib.CsError) as ei:
-        _lib.Fit(emulib, 0, np.zeros(10), np.zeros((10, 41)), np.zeros(10), None, np.zeros(86))
+        _lib.Fit(emulib, 0, np.zeros(10), np.zeros((10, pbig)), np.zeros(10), None, np.zeros(2 * pbig + 4))
     assert ei.value.code == -5
     # member 1: two identical rows and (numerically) no noise -> singular Gram matrix
     good = make_problem("GP", 40, 2)
