@@ -424,6 +424,35 @@ def measure_fits(lib, rank, world, nfit, batch=32, host_sim=False):
 GRIDS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (2, 4)}
 
 
+def measure_single_fit_configs():
+    """Configs 1-3 of BASELINE.json through the PUBLIC API (the calls a user of the reference makes): CausalStump() with the
+    reference's default settings (maxiter 5000, tol 1e-4, lr .01, Nadam) to convergence, then predict() and treatment();
+    wall clock, host buffers in and out.  config1: README example (n=120, p=1, GP); config2: Hill-shaped n=747, p=25, GP;
+    config3: the same data, Student-t process (prior=TRUE, nu=200) incl. posterior sampling of the intervals."""
+    import causalstump_b200 as cb
+    from causalstump_b200 import hill
+    out = {}
+    for name, d, kw in (("config1", hill.readme_example(120), dict(prior=False)),
+                        ("config2", hill.hill_surface_b(n=747, p=P_METRIC, replicate=3), dict(prior=False)),
+                        ("config3", hill.hill_surface_b(n=747, p=P_METRIC, replicate=3), dict(prior=True, nu=200))):
+        cb.CausalStump(d["y"], d["X"], d["z"], maxiter=3, init_draws=(0.5, 0.4), verbose=False, **kw)  # warm-up (graph capture)
+        t0 = time.perf_counter()
+        fit = cb.CausalStump(d["y"], d["X"], d["z"], init_draws=(0.5, 0.4), verbose=False, **kw)
+        t_fit = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        pr = cb.predict(fit)
+        tr = cb.treatment(fit)
+        t_pt = time.perf_counter() - t0
+        pehe = float(np.sqrt(np.mean((d["tau"] - tr["map"]) ** 2)))
+        out[name] = {"n": int(len(d["y"])), "p": int(np.atleast_2d(d["X"].T).shape[0]), "prior": bool(kw["prior"]), "iterations": int(fit.iters),
+                     "fit_seconds": t_fit, "ms_per_iteration": 1e3 * t_fit / max(int(fit.iters), 1), "predict_plus_treatment_seconds": t_pt,
+                     "lml": float(fit.stats[1, -1]), "pehe_train": pehe, "ate": float(tr["ate"]),
+                     "finite": bool(np.isfinite(pr["map"]).all() and np.isfinite(tr["map"]).all())}
+    out["what"] = ("BASELINE.json configs 1-3 through the public API (CausalStump / predict / treatment, reference defaults: maxiter 5000, "
+                   "tol 1e-4, lr .01, Nadam), wall clock incl. host<->device copies; the whole optimisation loop is one device-side loop")
+    return out
+
+
 def measure_stateless_boundary(sizes=((747, 3), (8192, 1))):
     """What a user gets who swaps the library in but leaves the R package untouched (INTEGRATION.md step 2 without step 3):
     the RefClass methods keep issuing the 8 stateless `.Call`s of one GP iteration (R/kernel_GP_SE_class.R:45-60: kernmat,
@@ -803,9 +832,10 @@ def run_ours(args, rank, world, local_rank):
         if world in GRIDS:
             c5_obj = measure_config5(lib, torch, dev, rank, world, dist, barrier)
 
-    stateless_obj = None
+    stateless_obj = single_obj = None
     if rank == 0 and world == 1 and not args.no_fits:
         stateless_obj = measure_stateless_boundary()
+        single_obj = measure_single_fit_configs()
 
     if rank == 0 and fits_obj and world == 1 and not args.no_cpu:
         # the same fit on the host: one reference-faithful optimizer iteration of the oracle port (para_update, which
@@ -868,6 +898,8 @@ def run_ours(args, rank, world, local_rank):
             line["student_t"] = tp_obj
         if stateless_obj:
             line["boundary_stateless"] = stateless_obj
+        if single_obj:
+            line["configs_1_2_3"] = single_obj
         if c4_obj:
             line["config4"] = c4_obj
         if c5_obj:

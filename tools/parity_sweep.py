@@ -32,7 +32,7 @@ def main():
         kind = "GP" if rng.random() < 0.6 else "TP"
         sizes = [2, 3, 17, 63, 64, 65, 127, 128, 129, 200, 333, 512, 640, 747] + ([] if use_ref else [1000, 1300, 1537])
         n = int(rng.choice(sizes))
-        p = int(rng.choice([1, 2, 5, 13, 25, 26, 40]))
+        p = int(rng.choice([1, 2, 5, 13, 25, 26, 32, 33, 40, 60, 100]))
         tile = int(rng.choice([0, 0, 64, 128]))
         pipe = int(rng.integers(0, 2))
         weights = bool(rng.random() < 0.5)
