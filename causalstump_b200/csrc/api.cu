@@ -1011,7 +1011,7 @@ int cs_debug_timeline(cs_fit* f, int cap, int* n_out, float* rows) {
   size_t e = 0;
   auto emit = [&](const std::vector<csdense::Launch>& sq) {
     for (const csdense::Launch& L : sq) {
-      if (L.is_leaf != csdense::OP_LEAF && L.is_leaf != csdense::OP_GEMM && L.is_leaf != csdense::OP_COPY) continue;
+      if (L.is_leaf != csdense::OP_LEAF && L.is_leaf != csdense::OP_GEMM && L.is_leaf != csdense::OP_COPY && L.is_leaf != csdense::OP_TRSM) continue;
       if (e + 1 >= evs.size()) break;
       float t0 = 0.f, t1 = 0.f;
       rt::event_elapsed(&t0, base, evs[e]);
@@ -1019,9 +1019,9 @@ int cs_debug_timeline(cs_fit* f, int cap, int* n_out, float* rows) {
       e += 2;
       if (n < cap) {
         float* r = rows + 6 * (size_t)n;
-        r[0] = (float)L.stream; r[1] = (float)L.is_leaf;
+        r[0] = (float)L.stream; r[1] = (float)((L.is_leaf == csdense::OP_LEAF && L.leaf_mode == 2) ? 6 : L.is_leaf);  // 6: tile inverse (leaf mode 2), 5: triangular solve
         r[2] = (float)(L.is_leaf == csdense::OP_GEMM ? L.ntiles : 1);
-        r[3] = (float)(L.is_leaf == csdense::OP_LEAF ? L.blk : (L.is_leaf == csdense::OP_COPY ? 0 : f->eng.probs[L.first_prob].K));
+        r[3] = (float)((L.is_leaf == csdense::OP_LEAF || L.is_leaf == csdense::OP_TRSM) ? L.blk : (L.is_leaf == csdense::OP_COPY ? 0 : f->eng.probs[L.first_prob].K));
         r[4] = t0; r[5] = t1;
         ++n;
       }

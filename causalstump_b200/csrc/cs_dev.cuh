@@ -42,6 +42,15 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
 #endif
 }
+// 8-byte variant (element-granular staging of a packed triangle)
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+#ifdef CS_EMU
+  std::memcpy(smem_dst, gmem_src, 8);
+#else
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem_src));
+#endif
+}
 __device__ __forceinline__ void cp_async_commit() {
 #ifndef CS_EMU
   asm volatile("cp.async.commit_group;\n" ::);

@@ -46,7 +46,7 @@ inline int set_device(int) { return 0; }
 inline int sm_count() { return 4; }
 inline int host_alloc(void** p, size_t b) { *p = std::malloc(b ? b : 1); return *p ? 0 : 2; }
 inline int host_free(void* p) { std::free(p); return 0; }
-inline int partition_streams(int, cudaStream_t*, cudaStream_t*, cudaStream_t**, const int*, int, int*, int*) { return 1; }
+inline int partition_streams(int, cudaStream_t*, cudaStream_t*, cudaStream_t*, cudaStream_t**, const int*, int, int*, int*) { return 1; }
 inline int copy2d(double* dst, long long ldd, const double* src, long long lds, long long rows, long long cols, cudaStream_t) {
   for (long long c = 0; c < cols; ++c) std::memmove(dst + c * ldd, src + c * lds, sizeof(double) * rows);
   return 0;
@@ -148,8 +148,8 @@ inline int copy2d(double* dst, long long ldd, const double* src, long long lds, 
   return (int)cudaMemcpy2DAsync(dst, sizeof(double) * ldd, src, sizeof(double) * lds, sizeof(double) * rows, (size_t)cols,
                                 cudaMemcpyDeviceToDevice, s);
 }
-inline int partition_streams(int sm_crit, cudaStream_t* crit_hi, cudaStream_t* crit_hi2, cudaStream_t** bulk, const int* level, int nbulk,
-                             int* sm_a, int* sm_b) {
+inline int partition_streams(int sm_crit, cudaStream_t* crit_hi, cudaStream_t* crit_hi2, cudaStream_t* crit_hi3, cudaStream_t** bulk,
+                             const int* level, int nbulk, int* sm_a, int* sm_b) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 1;
   static std::mutex mu;  // handles may be created from several host threads
@@ -190,6 +190,9 @@ inline int partition_streams(int sm_crit, cudaStream_t* crit_hi, cudaStream_t* c
   CUstream s0b = nullptr;
   if (f_gstream(&s0b, P.a, CU_STREAM_NON_BLOCKING, prio_of_level(0)) != CUDA_SUCCESS) return 1;
   *crit_hi2 = (cudaStream_t)s0b;
+  CUstream s0c = nullptr;
+  if (f_gstream(&s0c, P.a, CU_STREAM_NON_BLOCKING, prio_of_level(0)) != CUDA_SUCCESS) return 1;
+  *crit_hi3 = (cudaStream_t)s0c;
   for (int i = 0; i < nbulk; ++i) {
     CUstream sb = nullptr;
     if (f_gstream(&sb, P.b, CU_STREAM_NON_BLOCKING, prio_of_level(level[i])) != CUDA_SUCCESS) return 1;

@@ -35,7 +35,9 @@ template <int TILE>
 __global__ void __launch_bounds__(LEAF_THREADS)
 leaf_kernel(double* __restrict__ Gt, long long ldg, double* __restrict__ Xt, long long ldx, int pivot_base,
             double* __restrict__ logdet_out, int* __restrict__ status, int n_real,
-            const int* __restrict__ skip, long long bstride) {
+            const int* __restrict__ skip, long long bstride, int mode) {
+  // mode 0: factor and invert (L into Gt, L^-1 into Xt); 1: factor only; 2: invert only (L is read back from Gt) -- the
+  // split lets the inversion leave the critical chain of the Cholesky (plan v2: chain = factor + triangular solve)
   // Gt / Xt point at the diagonal tile; pivot_base is its first global row (for LAPACK `info`)
   skip = csd::bshift(skip, bstride);
   if (skip && *skip) return;
@@ -57,7 +59,9 @@ leaf_kernel(double* __restrict__ Gt, long long ldg, double* __restrict__ Xt, lon
     for (int a = 0; a < NA; ++a) {
       const int r = tx + 16 * a, c = ty + 16 * b;
       reg[a][b] = (r >= c) ? Gt[r + c * ldg] : 0.0;
+      if (mode == 2 && r == c) dinv[c] = 1.0 / reg[a][b];   // L_cc read back: the same 1 / sqrt(pivot) as in mode 0
     }
+  if (mode != 2) {
 
   // ---- phase 1: right-looking Cholesky; columns stay unscaled (L[r][j] = S[r][j] / sqrt(d_j)) ----
   // Split by the 16-column block bj so every register index / loop bound is a compile-time
@@ -137,6 +141,10 @@ leaf_kernel(double* __restrict__ Gt, long long ldg, double* __restrict__ Xt, lon
   }
   const double ldsum = csd::block_sum(tid < TILE ? 0.5 * log(piv[tid < TILE ? tid : 0]) : 0.0, red);
   if (tid == 0) *logdet_out = ldsum;  // block_sum ends with a barrier: dinv is visible
+  if (mode == 1) return;
+  } else {
+    __syncthreads();  // dinv visible
+  }
 
   // ---- phase 2: in-place inverse X = L^-1, row by row with rank-1 updates of the rows below ----
   // Same software pipelining: at step i the owners of row i+1 apply step i's update to their
@@ -233,13 +241,86 @@ leaf_kernel(double* __restrict__ Gt, long long ldg, double* __restrict__ Xt, lon
 }
 
 // ---------------------------------------------------------------------------------
+// Triangular solve of the in-panel block rows: X L_kk^T = A, in place (L_ik = A_ik L_kk^-T), one warp per row of A.
+// Replaces "multiply by the explicit inverse X_kk" on the critical chain, so that the inversion of the diagonal tile
+// (the second half of the leaf) no longer sits between the factorization of tile k and the panel below it.
+// Column-oriented forward substitution: x_j = a_j / L_jj is broadcast from its owner lane, then a_l -= x_j L_lj for l > j
+// (column j of L is contiguous; every warp of the device reads the same 128 KB tile, which stays in L1 / L2).
+// ---------------------------------------------------------------------------------
+constexpr int TRSM_THREADS = 128;
+constexpr int TRSM_ROWS = 4;   // rows of A per warp: every column of L read from shared memory serves 4 rows
+// the lower triangle of the tile, packed by columns: element (l, j), l >= j, at j * TILE - j (j + 1) / 2 + l
+template <int TILE> constexpr int trsm_smem_bytes() { return TILE * (TILE + 1) / 2 * (int)sizeof(double); }
+
+// Measured on the B200 (tools/trsm_bench.cu, tools/lat_bench.cu): one substitution step is a 43-cycle dependent chain
+// (SHFL + DMUL + DFMA) but about 14 issue slots per row, so the kernel is issue-bound as soon as an SM sub-partition holds more
+// than one warp of it: 16 warps per CTA took 31 us whatever the row count.  Hence small CTAs (4 warps x 4 rows) spread over all
+// SMs of the partition, with the packed triangle (66 KB at TILE = 128) leaving room for three of them per SM.  The tile of L is
+// staged with cp.async, all copies in flight at once: reading the columns from global memory inside the loop cost one L2 round
+// trip per column on every SM.
+template <int TILE>
+__global__ void __launch_bounds__(TRSM_THREADS)
+trsm_kernel(const double* __restrict__ Lkk, long long ldl, double* __restrict__ A, long long lda, int nrows,
+            const int* __restrict__ skip, long long bstride) {
+  skip = csd::bshift(skip, bstride);
+  if (skip && *skip) return;
+  Lkk = csd::bshift(Lkk, bstride); A = csd::bshift(A, bstride);
+  constexpr int NS = TILE / 32, R = TRSM_ROWS, NW = TRSM_THREADS / 32;
+  CS_DYN_SMEM(double, Ls);
+  __shared__ double rinv[TILE];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int c = wid; c < TILE; c += NW) {
+    double* dst = Ls + c * TILE - c * (c + 1) / 2;
+    const double* src = Lkk + (long long)c * ldl;
+    for (int r = c + lane; r < TILE; r += 32) csd::cp_async8(dst + r, src + r);
+  }
+  csd::cp_async_commit();
+  const int r0 = ((int)blockIdx.x * NW + wid) * R;   // nrows is a multiple of the tile, hence of R
+  const bool live = r0 < nrows;
+  double a[R][NS];
+#pragma unroll
+  for (int q = 0; q < R; ++q)
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2) a[q][s2] = live ? A[r0 + q + (long long)(lane + 32 * s2) * lda] : 0.0;
+  csd::cp_async_wait<0>();
+  __syncthreads();
+  if (tid < TILE) rinv[tid] = 1.0 / Ls[tid * TILE - tid * (tid + 1) / 2 + tid];
+  __syncthreads();
+  if (!live) return;
+#pragma unroll
+  for (int s0 = 0; s0 < NS; ++s0) {
+#pragma unroll 4
+    for (int jj = 0; jj < 32; ++jj) {
+      const int j = 32 * s0 + jj;
+      const double* col = Ls + j * TILE - j * (j + 1) / 2;
+      double lc[NS];
+#pragma unroll
+      for (int s2 = 0; s2 < NS; ++s2) lc[s2] = (s2 >= s0 && lane + 32 * s2 > j) ? col[lane + 32 * s2] : 0.0;
+      const double ri = rinv[j];
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const double xj = __shfl_sync(0xffffffffu, a[q][s0], jj) * ri;
+        if (lane == jj) a[q][s0] = xj;
+#pragma unroll
+        for (int s2 = 0; s2 < NS; ++s2)
+          if (s2 >= s0) a[q][s2] = fma(-xj, lc[s2], a[q][s2]);   // lc is zero at and above the diagonal
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < R; ++q)
+#pragma unroll
+    for (int s2 = 0; s2 < NS; ++s2) A[r0 + q + (long long)(lane + 32 * s2) * lda] = a[q][s2];
+}
+
+// ---------------------------------------------------------------------------------
 // Host-side plan
 // ---------------------------------------------------------------------------------
 enum GemmKind { GK_NT = 0, GK_NN = 1, GK_TN = 2 };
 
 static std::atomic<long long> g_launches{0};  // kernels launched by this library (claimed count for bench.py)
 
-enum OpType { OP_GEMM = 0, OP_LEAF = 1, OP_RECORD = 2, OP_WAIT = 3, OP_COPY = 4 };
+enum OpType { OP_GEMM = 0, OP_LEAF = 1, OP_RECORD = 2, OP_WAIT = 3, OP_COPY = 4, OP_TRSM = 5 };
 
 struct Launch {
   int is_leaf;     // OpType (1: leaf_kernel(blk), 0: gemm group, 2/3: event record / wait)
@@ -251,6 +332,8 @@ struct Launch {
   int stream;      // 0: main (critical path, high priority)   1: auxiliary (bulk updates)
   int ev;          // event index for OP_RECORD / OP_WAIT
   int gtile;       // CTA tile of this launch (0 = engine default gt)
+  int leaf_mode;   // OP_LEAF: 0 factor + invert, 1 factor only, 2 invert only
+  int r0, nb;      // OP_TRSM: block rows r0 .. r0+nb-1 of block column blk
   // OP_COPY: 2-D device copy of `rows` x `cols` doubles (leading dimension np on both sides)
   double* cp_dst; const double* cp_src; long long cp_rows, cp_cols, cp_ldd, cp_lds;
 };
@@ -302,15 +385,26 @@ inline void configure_kernels() {
   { auto k = csg::gemm_kernel<64, 2, 2, true, true, 16, 2>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<64, true, true, 16, 2>())); }
   { auto k = leaf_kernel<128>; CS_SET_SMEM(k, leaf_smem_bytes<128>()); }
   { auto k = leaf_kernel<64>; CS_SET_SMEM(k, leaf_smem_bytes<64>()); }
+  { auto k = trsm_kernel<128>; CS_SET_SMEM(k, trsm_smem_bytes<128>()); }
 }
 
 inline void launch_leaf(int tile, double* Gt, long long ldg, double* Xt, long long ldx, int pivot_base,
                         double* logdet_out, int* status, int n_real, cudaStream_t s, const int* skip, int nbatch = 1,
-                        long long bstride = 0) {
+                        long long bstride = 0, int mode = 0) {
   ++g_launches;
   const dim3 grid(1, 1, nbatch);
-  if (tile == 128) { auto k = leaf_kernel<128>; CS_LAUNCH(k, grid, LEAF_THREADS, leaf_smem_bytes<128>(), s, Gt, ldg, Xt, ldx, pivot_base, logdet_out, status, n_real, skip, bstride); }
-  else { auto k = leaf_kernel<64>; CS_LAUNCH(k, grid, LEAF_THREADS, leaf_smem_bytes<64>(), s, Gt, ldg, Xt, ldx, pivot_base, logdet_out, status, n_real, skip, bstride); }
+  if (tile == 128) { auto k = leaf_kernel<128>; CS_LAUNCH(k, grid, LEAF_THREADS, leaf_smem_bytes<128>(), s, Gt, ldg, Xt, ldx, pivot_base, logdet_out, status, n_real, skip, bstride, mode); }
+  else { auto k = leaf_kernel<64>; CS_LAUNCH(k, grid, LEAF_THREADS, leaf_smem_bytes<64>(), s, Gt, ldg, Xt, ldx, pivot_base, logdet_out, status, n_real, skip, bstride, mode); }
+}
+
+inline void launch_trsm(int tile, const double* Lkk, long long ldl, double* A, long long lda, int nrows, cudaStream_t s,
+                        const int* skip, int nbatch = 1, long long bstride = 0) {
+  if (nrows <= 0) return;
+  ++g_launches;
+  const int per_cta = (TRSM_THREADS / 32) * TRSM_ROWS;
+  const dim3 grid((nrows + per_cta - 1) / per_cta, 1, nbatch);
+  if (tile == 128) { auto k = trsm_kernel<128>; CS_LAUNCH(k, grid, TRSM_THREADS, trsm_smem_bytes<128>(), s, Lkk, ldl, A, lda, nrows, skip, bstride); }
+  else { auto k = trsm_kernel<64>; CS_LAUNCH(k, grid, TRSM_THREADS, trsm_smem_bytes<64>(), s, Lkk, ldl, A, lda, nrows, skip, bstride); }
 }
 
 struct DenseEngine {
@@ -343,6 +437,9 @@ struct DenseEngine {
   std::vector<int> bounds;          // plan v2: panel boundaries in blocks (graded: narrow first and last panels)
   int n_events = 0;
   std::vector<cudaEvent_t> events;
+  cudaStream_t aux8{};  // S8: inversion of the diagonal tiles (leaf mode 2), partition A, off the critical chain
+  bool aux8_ok = false;
+  bool split_leaf = false;  // plan v2: chain = factor (leaf mode 1) + triangular solve; the tile inverses run on S8
   cudaStream_t aux{}, aux2{}, aux3{}, aux4{}, aux5{}, aux6{}, aux7{};  // S7: U2b-rest (bulk trailing update behind the look-ahead);  // S6: second chain stream (X_PP), partition A;  // S4: K^-1 accumulation (lowest); S5: Acc rows below the next panel; S1: bulk trailing updates (low); S2: panel rest (high); S3: pipelined inverse (low)
   bool aux_ok = false, aux2_ok = false, aux3_ok = false, aux4_ok = false, aux5_ok = false, aux6_ok = false, aux7_ok = false;
   // SM partition (rt::partition_streams): the critical chain of the Cholesky (leaf + one-tile GEMMs, plan
@@ -609,6 +706,7 @@ struct DenseEngine {
       o.cp_ldd = ldd; o.cp_lds = lds; seq.push_back(o);
     };
     int last_aux_ev = -1, last_inv_ev = -1, last_inv3_ev = -1, last_rest_ev = -1, ev_u1top_prev = -1, last_s6_ev = -1, last_u2b_ev = -1, last_u2brest_ev = -1;
+    int last_s8_ev = -1;
     auto push_panel = [&](int k, int r0, int nb, int stream) {  // in-place L = A X_kk^T for nb block rows of column k
       if (nb <= 0) return;
       double* pan = G + (long long)r0 * T + (long long)k * T * ld;
@@ -634,12 +732,22 @@ struct DenseEngine {
       if (ev_u1top_prev >= 0) op(OP_WAIT, 0, ev_u1top_prev);
       if (last_s6_ev >= 0) op(OP_WAIT, 0, last_s6_ev);   // keeps the happens-before relation of S6 simple
       for (int k = p0; k < p1; ++k) {
-        { Launch L{}; L.is_leaf = OP_LEAF; L.blk = k; seq.push_back(L); }
+        { Launch L{}; L.is_leaf = OP_LEAF; L.blk = k; L.leaf_mode = split_leaf ? 1 : 0; seq.push_back(L); }
         const int ev_leaf = nev++;
         op(OP_RECORD, 0, ev_leaf);
+        int ev_inv = -1;
+        if (split_leaf) {  // X_kk = L_kk^-1 on S8, beside the chain
+          op(OP_WAIT, 8, ev_leaf);
+          { Launch L{}; L.is_leaf = OP_LEAF; L.blk = k; L.leaf_mode = 2; L.stream = 8; seq.push_back(L); }
+          ev_inv = nev++;
+          op(OP_RECORD, 8, ev_inv);
+          last_s8_ev = ev_inv;
+          if (k == p0) op(OP_WAIT, 6, ev_inv);  // S6 (and everything ordered behind its ev_xpp) sees the first tile inverse
+        }
         const int nb = p1 - 1 - k;
         if (nb > 0) {
-          push_panel(k, k + 1, nb, 0);
+          if (split_leaf) { Launch L{}; L.is_leaf = OP_TRSM; L.blk = k; L.r0 = k + 1; L.nb = nb; seq.push_back(L); }
+          else push_panel(k, k + 1, nb, 0);
           double* col = G + (long long)(k + 1) * T + (long long)k * T * ld;  // L_{k+1..p1-1, k}
           grp.push_back(mk(col, ld, col, ld, G + (long long)(k + 1) * T * (ld + 1), ld, nb * rr, nb * rr, tile, csg::KM_FULL, csg::ORD_LOWER, 0, -1.0, 1.0));
           add_group(seq, GK_NT, grp);
@@ -651,6 +759,7 @@ struct DenseEngine {
           op(OP_WAIT, 6, ev_leaf);
           grp.push_back(mk(G + (long long)k * T + (long long)p0 * T * ld, ld, Xpp, ld, rowk, ld, rr, q * rr, q * tile, csg::KM_GE_J, csg::ORD_COL, 0, 1.0, 0.0));
           add_group(seq, GK_NN, grp); seq.back().stream = 6;
+          if (ev_inv >= 0) op(OP_WAIT, 6, ev_inv);
           grp.push_back(mk(X + (long long)k * T * (ld + 1), ld, rowk, ld, rowk, ld, 1, q, tile, csg::KM_FULL, csg::ORD_COL, 0, -1.0, 0.0));
           add_group(seq, GK_NN, grp); seq.back().stream = 6; seq.back().gtile = tile;
         }
@@ -817,7 +926,7 @@ struct DenseEngine {
     }
     tail_pieces.clear();
     // the chain stream rejoins every other stream before anything reads the results
-    for (int ev : {last_aux_ev, last_u2b_ev, last_u2brest_ev, last_inv_ev, last_inv3_ev, last_rest_ev, last_s6_ev, ev_u1top_prev})
+    for (int ev : {last_aux_ev, last_u2b_ev, last_u2brest_ev, last_inv_ev, last_inv3_ev, last_rest_ev, last_s6_ev, ev_u1top_prev, last_s8_ev})
       if (ev >= 0) op(OP_WAIT, 0, ev);
     };
     // ---- left-looking plan for batched small-n handles: block column k is first brought up to date with ONE multiply whose
@@ -853,6 +962,11 @@ struct DenseEngine {
     plan_version = 2;
     if (const char* pv = std::getenv("CS_PLAN")) plan_version = std::atoi(pv);
     left_looking = nbatch > 1 && !inv_pipeline && N > 1 && std::getenv("CS_PLAN") == nullptr && std::getenv("CS_BATCH_RIGHT") == nullptr;
+    // Split leaf: below np = 8192 a single evaluation is bound by the chain of leaves, so the inversion of the diagonal
+    // tiles leaves the chain (S8) and the panel below a tile comes from a triangular solve.  From np = 8192 on the run is bound
+    // by the bulk streams and the chain partition's idle time is sold to the tail share, which is sized for the fused leaf
+    // (measured at n = 8192: split 20.3 ms vs fused 19.5 ms; n = 4096: 4.5 vs 5.2 ms).  CS_SPLIT_LEAF=1 / CS_NO_SPLIT_LEAF=1 force it.
+    split_leaf = nbatch == 1 && N > 1 && !std::getenv("CS_NO_SPLIT_LEAF") && (np < 8192 || std::getenv("CS_SPLIT_LEAF") != nullptr);
     top32 = tile == 128 && gt == 64 && nbatch == 1 && !std::getenv("CS_NO_TOP32");
     split_u2b = nbatch == 1 && !std::getenv("CS_NO_U2B_SPLIT");
     {
@@ -960,8 +1074,10 @@ struct DenseEngine {
     cudaStream_t* bulk[6] = {&aux, &aux2, &aux3, &aux4, &aux5, &aux7};
     int level[6] = {2, 0, 1, 5, 5, 3};  // 0 = highest (swept on the B200: tools/gpu_sweep.sh); last: S7
     if (const char* ev = std::getenv("CS_PRIO")) std::sscanf(ev, "%d,%d,%d,%d,%d,%d", &level[0], &level[1], &level[2], &level[3], &level[4], &level[5]);
-    if (want_part && rt::partition_streams(8, &crit, &aux6, bulk, level, 6, &sm_crit, &sm_bulk) == 0) {
-      crit_ok = aux_ok = aux2_ok = aux3_ok = aux4_ok = aux5_ok = aux6_ok = aux7_ok = true;
+    int crit_sms = 8;   // swept on the B200 (CS_CRIT_SMS): see profiles/r02_split_leaf.md
+    if (const char* ev = std::getenv("CS_CRIT_SMS")) crit_sms = std::max(4, std::min(64, std::atoi(ev)));
+    if (want_part && rt::partition_streams(crit_sms, &crit, &aux6, &aux8, bulk, level, 6, &sm_crit, &sm_bulk) == 0) {
+      crit_ok = aux_ok = aux2_ok = aux3_ok = aux4_ok = aux5_ok = aux6_ok = aux7_ok = aux8_ok = true;
       if ((e = rt::event_create_fast(&ev_in))) return e;
       if ((e = rt::event_create_fast(&ev_out))) return e;
     } else {
@@ -979,6 +1095,8 @@ struct DenseEngine {
       aux6_ok = true;
       if ((e = rt::stream_create_level(&aux7, level[5]))) return e;
       aux7_ok = true;
+      if ((e = rt::stream_create_level(&aux8, 0))) return e;
+      aux8_ok = true;
     }
     if ((e = rt::event_create_fast(&ev_gram))) return e;
     ev_gram_ok = true;
@@ -1008,6 +1126,7 @@ struct DenseEngine {
     if (aux5_ok) { rt::stream_sync(aux5); rt::stream_destroy(aux5); aux5_ok = false; }
     if (aux6_ok) { rt::stream_sync(aux6); rt::stream_destroy(aux6); aux6_ok = false; }
     if (aux7_ok) { rt::stream_sync(aux7); rt::stream_destroy(aux7); aux7_ok = false; }
+    if (aux8_ok) { rt::stream_sync(aux8); rt::stream_destroy(aux8); aux8_ok = false; }
     if (crit_ok) { rt::stream_sync(crit); rt::stream_destroy(crit); rt::event_destroy(ev_in); rt::event_destroy(ev_out); crit_ok = false; }
     G = X = C = logdet_part = nullptr; status = nullptr; d_probs = nullptr;
   }
@@ -1027,12 +1146,15 @@ struct DenseEngine {
       s0 = crit;
     }
     for (const Launch& L : seq) {
-      cudaStream_t s = L.stream == 1 ? aux : (L.stream == 2 ? aux2 : (L.stream == 3 ? aux3 : (L.stream == 4 ? aux4 : (L.stream == 5 ? aux5 : (L.stream == 6 ? aux6 : (L.stream == 7 ? aux7 : s0))))));
-      const bool timed = tl && (L.is_leaf == OP_LEAF || L.is_leaf == OP_GEMM || L.is_leaf == OP_COPY);
+      cudaStream_t s = L.stream == 1 ? aux : (L.stream == 2 ? aux2 : (L.stream == 3 ? aux3 : (L.stream == 4 ? aux4 : (L.stream == 5 ? aux5 : (L.stream == 6 ? aux6 : (L.stream == 7 ? aux7 : (L.stream == 8 ? aux8 : s0)))))));
+      const bool timed = tl && (L.is_leaf == OP_LEAF || L.is_leaf == OP_GEMM || L.is_leaf == OP_COPY || L.is_leaf == OP_TRSM);
       if (timed) { cudaEvent_t e0; rt::event_create(&e0); rt::event_record(e0, s); tl->push_back(e0); }
       if (L.is_leaf == OP_LEAF) {
         launch_leaf(tile, G + (long long)L.blk * tile * ((long long)np + 1), np, X + (long long)L.blk * tile * ((long long)np + 1), np,
-                    L.blk * tile, logdet_part + L.blk, status, n, s, skip, nbatch, bstride);
+                    L.blk * tile, logdet_part + L.blk, status, n, s, skip, nbatch, bstride, L.leaf_mode);
+      } else if (L.is_leaf == OP_TRSM) {
+        launch_trsm(tile, G + (long long)L.blk * tile * ((long long)np + 1), np, G + (long long)L.r0 * tile + (long long)L.blk * tile * np, np,
+                    L.nb * tile, s, skip, nbatch, bstride);
       } else if (L.is_leaf == OP_COPY) {
         launch_copy(L, s, skip);
       } else if (L.is_leaf == OP_RECORD) {
@@ -1074,8 +1196,15 @@ struct DenseEngine {
     out.clear();
     if (L.is_leaf == OP_LEAF) {
       const long long o = (long long)L.blk * tile;
-      out.push_back(Rect{0, o, o + tile, o, o + tile, true});
-      out.push_back(Rect{1, o, o + tile, o, o + tile, true});
+      if (L.leaf_mode != 2) out.push_back(Rect{0, o, o + tile, o, o + tile, true});
+      else out.push_back(Rect{0, o, o + tile, o, o + tile, false});
+      if (L.leaf_mode != 1) out.push_back(Rect{1, o, o + tile, o, o + tile, true});
+      return;
+    }
+    if (L.is_leaf == OP_TRSM) {
+      const long long o = (long long)L.blk * tile, r0 = (long long)L.r0 * tile;
+      out.push_back(Rect{0, o, o + tile, o, o + tile, false});
+      out.push_back(Rect{0, r0, r0 + (long long)L.nb * tile, o, o + tile, true});
       return;
     }
     if (L.is_leaf == OP_COPY) {
@@ -1099,7 +1228,7 @@ struct DenseEngine {
     const int n_ops = (int)seq.size();
     const int words = (n_ops + 63) / 64;
     std::vector<std::vector<unsigned long long>> anc(n_ops, std::vector<unsigned long long>(words, 0ULL));
-    int last_on_stream[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+    int last_on_stream[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
     std::vector<int> last_record(n_events + 1, -1);
     auto add_pred = [&](int j, int i) {
       if (i < 0) return;
