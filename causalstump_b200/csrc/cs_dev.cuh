@@ -42,6 +42,14 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
 #endif
 }
+// L2 prefetch of the 128-byte line holding p
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifndef CS_EMU
+  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
 // 8-byte variant (element-granular staging of a packed triangle)
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
 #ifdef CS_EMU

@@ -340,6 +340,10 @@ struct Launch {
 
 inline int pick_tile(int n) { return n <= 1536 ? 64 : 128; }
 
+// CTAs per SM the 64 x 64 kernels are compiled for (__launch_bounds__ register cap: 4 -> 128 registers, 5 -> 96 with a few
+// spilled descriptor fields)
+constexpr int GEMM64_MINB = 4;
+
 template <int TILE>
 inline void launch_gemm_t(int kind, const GemmProblem* dprobs, int nprob, int ntiles_, cudaStream_t st,
                           const int* skip, int nbatch) {
@@ -350,11 +354,13 @@ inline void launch_gemm_t(int kind, const GemmProblem* dprobs, int nprob, int nt
     else if (kind == GK_NN) { auto k = csg::gemm_kernel<128, 2, 4, false, true>; CS_LAUNCH(k, ntiles, 256, (csg::gemm_smem_bytes<128, false, true>()), st, dprobs, nprob, skip); }
     else { auto k = csg::gemm_kernel<128, 2, 4, true, true>; CS_LAUNCH(k, ntiles, 256, (csg::gemm_smem_bytes<128, true, true>()), st, dprobs, nprob, skip); }
   } else {
-    // 64 x 64 CTA tiles, 128 registers/thread: 3-4 CTAs per SM hide the prologue / epilogue
-    // of one tile behind the main loop of another (stage counts from tools/gemm_bench on B200)
-    if (kind == GK_NT) { auto k = csg::gemm_kernel<64, 2, 2, false, false, 16, 3>; CS_LAUNCH(k, ntiles, 128, (csg::gemm_smem_bytes<64, false, false, 16, 3>()), st, dprobs, nprob, skip); }
-    else if (kind == GK_NN) { auto k = csg::gemm_kernel<64, 2, 2, false, true, 16, 3>; CS_LAUNCH(k, ntiles, 128, (csg::gemm_smem_bytes<64, false, true, 16, 3>()), st, dprobs, nprob, skip); }
-    else { auto k = csg::gemm_kernel<64, 2, 2, true, true, 16, 2>; CS_LAUNCH(k, ntiles, 128, (csg::gemm_smem_bytes<64, true, true, 16, 2>()), st, dprobs, nprob, skip); }
+    // 64 x 64 CTA tiles, 128 registers/thread: 4 CTAs per SM hide the prologue / epilogue of one tile behind the main loop
+    // of another.  Two stages everywhere: with the CTA count fixed by the registers, every extra stage was slower on the
+    // B200 (K = 512 whole waves, NT: 2 stages 32.6, 3 stages 32.0, 4 stages 31.5 TFLOP/s; tools/gemm_bench)
+    // (keeping three stages for the chain's one-to-twelve-tile launches made no measurable difference: n = 4096 4.5 vs 4.6 ms)
+    if (kind == GK_NT) { auto k = csg::gemm_kernel<64, 2, 2, false, false, 16, 2, GEMM64_MINB>; CS_LAUNCH(k, ntiles, 128, (csg::gemm_smem_bytes<64, false, false, 16, 2>()), st, dprobs, nprob, skip); }
+    else if (kind == GK_NN) { auto k = csg::gemm_kernel<64, 2, 2, false, true, 16, 2, GEMM64_MINB>; CS_LAUNCH(k, ntiles, 128, (csg::gemm_smem_bytes<64, false, true, 16, 2>()), st, dprobs, nprob, skip); }
+    else { auto k = csg::gemm_kernel<64, 2, 2, true, true, 16, 2, GEMM64_MINB>; CS_LAUNCH(k, ntiles, 128, (csg::gemm_smem_bytes<64, true, true, 16, 2>()), st, dprobs, nprob, skip); }
   }
 }
 
@@ -380,9 +386,9 @@ inline void configure_kernels() {
   { auto k = csg::gemm_kernel<128, 2, 4, false, false>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<128, false, false>())); }
   { auto k = csg::gemm_kernel<128, 2, 4, false, true>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<128, false, true>())); }
   { auto k = csg::gemm_kernel<128, 2, 4, true, true>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<128, true, true>())); }
-  { auto k = csg::gemm_kernel<64, 2, 2, false, false, 16, 3>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<64, false, false, 16, 3>())); }
-  { auto k = csg::gemm_kernel<64, 2, 2, false, true, 16, 3>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<64, false, true, 16, 3>())); }
-  { auto k = csg::gemm_kernel<64, 2, 2, true, true, 16, 2>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<64, true, true, 16, 2>())); }
+  { auto k = csg::gemm_kernel<64, 2, 2, false, false, 16, 2, GEMM64_MINB>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<64, false, false, 16, 2>())); }
+  { auto k = csg::gemm_kernel<64, 2, 2, false, true, 16, 2, GEMM64_MINB>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<64, false, true, 16, 2>())); }
+  { auto k = csg::gemm_kernel<64, 2, 2, true, true, 16, 2, GEMM64_MINB>; CS_SET_SMEM(k, (csg::gemm_smem_bytes<64, true, true, 16, 2>())); }
   { auto k = leaf_kernel<128>; CS_SET_SMEM(k, leaf_smem_bytes<128>()); }
   { auto k = leaf_kernel<64>; CS_SET_SMEM(k, leaf_smem_bytes<64>()); }
   { auto k = trsm_kernel<128>; CS_SET_SMEM(k, trsm_smem_bytes<128>()); }

@@ -108,10 +108,9 @@ constexpr int gemm_smem_bytes() {
   return NS * (OperandSmem<TILE, AK, KC>::SIZE + OperandSmem<TILE, BK_, KC>::SIZE) * (int)sizeof(double);
 }
 
-// copy one TILE x GEMM_BK operand chunk into a stage buffer
+// copy one TILE x KC operand chunk into a stage buffer; g points at the chunk's first element (tile row 0, first k)
 template <int TILE, bool KMAJ, int THREADS, int KC>
-__device__ __forceinline__ void load_operand(double* __restrict__ s, const double* __restrict__ g, long long ld,
-                                             int row0, int k0, int tid) {
+__device__ __forceinline__ void load_operand(double* __restrict__ s, const double* __restrict__ g, long long ld, int tid) {
   using S = OperandSmem<TILE, KMAJ, KC>;
   constexpr int NCOPY = TILE * KC / 2;
   static_assert(NCOPY % THREADS == 0, "copy count must divide");
@@ -120,16 +119,59 @@ __device__ __forceinline__ void load_operand(double* __restrict__ s, const doubl
     const int idx = tid + it * THREADS;
     if (KMAJ) {
       const int i = idx / (KC / 2), kc = idx - i * (KC / 2);
-      csd::cp_async16(s + i * S::LD + 2 * kc, g + (long long)(row0 + i) * ld + k0 + 2 * kc);
+      csd::cp_async16(s + i * S::LD + 2 * kc, g + (long long)i * ld + 2 * kc);
     } else {
       const int kk = idx / (TILE / 2), ic = idx - kk * (TILE / 2);
-      csd::cp_async16(s + kk * S::LD + 2 * ic, g + (long long)(k0 + kk) * ld + row0 + 2 * ic);
+      csd::cp_async16(s + kk * S::LD + 2 * ic, g + (long long)kk * ld + 2 * ic);
     }
   }
 }
 
-template <int TILE, int WM, int WN, bool AK, bool BK_, int KC = GEMM_BK, int NS = GEMM_STAGES>
-__global__ void __launch_bounds__(WM * WN * 32)
+// What one CTA needs to know about its tile.  Decoded by ONE thread (descriptor search, tile decode, k-range, operand
+// bases) and handed to the others through shared memory: 128 threads each walking the descriptor list in global memory
+// and decoding the same tile cost 3 % at K = 512 and 12-18 % at K = 64-128 (tools/gemm_bench, profiles/r02_gemm_experiments.md §6).
+struct TileCtx {
+  const double* A;   // operand bases already at (row0, kbeg)
+  const double* B;
+  double* C;         // at (i0, j0)
+  double* Cm;        // mirrored tile base at (j0, i0), or nullptr
+  long long lda, ldb, ldc;
+  int nchunks;
+  unsigned neg;
+  int beta_one;
+  int pad;
+};
+
+template <int TILE, bool AK, bool BK_, int KC>
+__device__ inline void tile_setup(const GemmProblem* __restrict__ probs, int nprob, int bt, int& pi, TileCtx& c) {
+  while (pi + 1 < nprob && bt >= probs[pi + 1].tile_base) ++pi;
+  const GemmProblem& P = probs[pi];
+  const double* A = csd::bshift(P.A, P.bstride);
+  const double* B = csd::bshift(P.B, P.bstride);
+  double* C = csd::bshift(P.C, P.bstride);
+  double* Cm = csd::bshift(P.Cm, P.bstride);
+  int I = 0, J = 0, kbeg = 0, kend = P.K;
+  if (P.table) {
+    const long long* te = P.table + 3LL * (bt - P.tile_base);
+    A += te[0]; B += te[1]; C += te[2];
+  } else {
+    decode_tile(P.order, P.mt, P.nt, bt - P.tile_base, I, J);
+    tile_krange(P.kmode, P.K, TILE, I, J, kbeg, kend);
+  }
+  const long long i0 = (long long)I * TILE, j0 = (long long)J * TILE;
+  c.lda = P.lda; c.ldb = P.ldb; c.ldc = P.ldc;
+  c.A = AK ? A + i0 * P.lda + kbeg : A + (long long)kbeg * P.lda + i0;
+  c.B = BK_ ? B + j0 * P.ldb + kbeg : B + (long long)kbeg * P.ldb + j0;
+  c.C = C + i0 + j0 * P.ldc;
+  c.Cm = (P.mirror == 2 || (P.mirror == 1 && I != J)) ? (Cm ? Cm : C) + j0 + i0 * P.ldc : nullptr;
+  c.nchunks = (kend - kbeg) / KC;
+  c.neg = P.neg_mask;
+  c.beta_one = P.beta_one;
+  c.pad = 0;
+}
+
+template <int TILE, int WM, int WN, bool AK, bool BK_, int KC = GEMM_BK, int NS = GEMM_STAGES, int MINB = 1>
+__global__ void __launch_bounds__(WM * WN * 32, MINB)
 gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restrict__ skip) {
   skip = csd::bshift(skip, probs[0].bstride);
   if (skip && *skip) return;
@@ -140,26 +182,15 @@ gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restr
   CS_DYN_SMEM(double, smem);
   double* sA = smem;
   double* sB = smem + NS * SA::SIZE;
+  __shared__ TileCtx sctx;
 
   const int tid = threadIdx.x;
-  // locate the problem this CTA belongs to (uniform across the CTA)
-  int pi = 0;
-  const int bt = (int)blockIdx.x;
-  while (pi + 1 < nprob && bt >= probs[pi + 1].tile_base) ++pi;
-  GemmProblem P = probs[pi];
-  P.A = csd::bshift(P.A, P.bstride); P.B = csd::bshift(P.B, P.bstride); P.C = csd::bshift(P.C, P.bstride);
-  P.Cm = csd::bshift(P.Cm, P.bstride);
-  int I = 0, J = 0;
-  int kbeg = 0, kend = P.K;
-  if (P.table) {
-    const long long* te = P.table + 3LL * (bt - P.tile_base);
-    P.A += te[0]; P.B += te[1]; P.C += te[2];
-  } else {
-    decode_tile(P.order, P.mt, P.nt, bt - P.tile_base, I, J);
-    tile_krange(P.kmode, P.K, TILE, I, J, kbeg, kend);
-  }
-  const int nchunks = (kend - kbeg) / KC;
-  const int i0 = I * TILE, j0 = J * TILE;
+  if (tid == 0) { int pi = 0; tile_setup<TILE, AK, BK_, KC>(probs, nprob, (int)blockIdx.x, pi, sctx); }
+  __syncthreads();
+  const TileCtx cur = sctx;
+  const int nchunks = cur.nchunks;
+  const long long achunk = AK ? (long long)KC : (long long)KC * cur.lda;   // per-chunk advance of the operand bases
+  const long long bchunk = BK_ ? (long long)KC : (long long)KC * cur.ldb;
 
   const int lane = tid & 31, wid = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -168,16 +199,16 @@ gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restr
   // Accumulators start from (beta/alpha)*C so the read of C overlaps the pipeline fill and
   // the epilogue is store-only:  C = alpha * ((beta/alpha) C + sum_k A B^T).
   double acc[FM][FN][2];
-  const unsigned neg = P.neg_mask;
-  if (P.beta_one) {  // acc = (beta / alpha) C = +-C
+  const unsigned neg = cur.neg;
+  if (cur.beta_one) {  // acc = (beta / alpha) C = +-C
 #pragma unroll
     for (int a = 0; a < FM; ++a) {
-      const long long r = i0 + wm + a * 8 + g;
+      const int r = wm + a * 8 + g;
 #pragma unroll
       for (int b = 0; b < FN; ++b) {
-        const double* p0 = P.C + r + (long long)(j0 + wn + b * 8 + 2 * t) * P.ldc;
+        const double* p0 = cur.C + r + (long long)(wn + b * 8 + 2 * t) * cur.ldc;
         acc[a][b][0] = flip_sign(p0[0], neg);
-        acc[a][b][1] = flip_sign(p0[P.ldc], neg);
+        acc[a][b][1] = flip_sign(p0[cur.ldc], neg);
       }
     }
   } else {
@@ -191,8 +222,8 @@ gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restr
 #pragma unroll
   for (int s = 0; s < NS - 1; ++s) {
     if (s < nchunks) {
-      load_operand<TILE, AK, Cfg::THREADS, KC>(sA + s * SA::SIZE, P.A, P.lda, i0, kbeg + s * KC, tid);
-      load_operand<TILE, BK_, Cfg::THREADS, KC>(sB + s * SB::SIZE, P.B, P.ldb, j0, kbeg + s * KC, tid);
+      load_operand<TILE, AK, Cfg::THREADS, KC>(sA + s * SA::SIZE, cur.A + s * achunk, cur.lda, tid);
+      load_operand<TILE, BK_, Cfg::THREADS, KC>(sB + s * SB::SIZE, cur.B + s * bchunk, cur.ldb, tid);
     }
     csd::cp_async_commit();
   }
@@ -204,8 +235,8 @@ gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restr
       const int cn = c + NS - 1;
       if (cn < nchunks) {
         const int sn = cn % NS;
-        load_operand<TILE, AK, Cfg::THREADS, KC>(sA + sn * SA::SIZE, P.A, P.lda, i0, kbeg + cn * KC, tid);
-        load_operand<TILE, BK_, Cfg::THREADS, KC>(sB + sn * SB::SIZE, P.B, P.ldb, j0, kbeg + cn * KC, tid);
+        load_operand<TILE, AK, Cfg::THREADS, KC>(sA + sn * SA::SIZE, cur.A + cn * achunk, cur.lda, tid);
+        load_operand<TILE, BK_, Cfg::THREADS, KC>(sB + sn * SB::SIZE, cur.B + cn * bchunk, cur.ldb, tid);
       }
       csd::cp_async_commit();
     }
@@ -231,16 +262,15 @@ gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restr
   // epilogue: C = alpha*acc = +-acc (+ mirrored store)
 #pragma unroll
   for (int a = 0; a < FM; ++a) {
-    const long long r = i0 + wm + a * 8 + g;
+    const int r = wm + a * 8 + g;
 #pragma unroll
     for (int b = 0; b < FN; ++b) {
-      const long long cc = j0 + wn + b * 8 + 2 * t;
-      double* p0 = P.C + r + cc * P.ldc;
-      double* p1 = p0 + P.ldc;
+      const int cc = wn + b * 8 + 2 * t;
+      double* p0 = cur.C + r + (long long)cc * cur.ldc;
       const double v0 = flip_sign(acc[a][b][0], neg), v1 = flip_sign(acc[a][b][1], neg);
-      *p0 = v0; *p1 = v1;
-      if (P.mirror == 2 || (P.mirror == 1 && I != J)) {
-        double* q = (P.Cm ? P.Cm : P.C) + cc + r * P.ldc;  // (cc, r) and (cc+1, r) are adjacent
+      p0[0] = v0; p0[cur.ldc] = v1;
+      if (cur.Cm) {
+        double* q = cur.Cm + cc + (long long)r * cur.ldc;  // (cc, r) and (cc+1, r) are adjacent
         q[0] = v0; q[1] = v1;
       }
     }
