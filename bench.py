@@ -46,8 +46,8 @@ METRIC = "fp64 LML+gradient evals/sec at n=8192,p=25"
 UNIT = "evals/s"
 # time-weighted DMMA sub-pipe activity of the K = 512 bulk launches of the timed plan (ncu --set full over every GEMM launch
 # of one evaluation, plain priority streams -- ncu cannot attach to green-context streams); updated with each capture
-DMMA_ACTIVE_K512 = {"pct": 86.3, "all_gemm_launches_pct": 77.9,
-                    "source": "profiles/r02_gemm_launches.md (71 launches with >= 592 CTA tiles, time-weighted; 77.9 % over all 460 GEMM launches)"}
+DMMA_ACTIVE_K512 = {"pct": 88.0, "all_gemm_launches_pct": 78.2,
+                    "source": "profiles/r02_gemm_launches.md (71 launches with >= 592 CTA tiles, time-weighted; 78.2 % over all 460 GEMM launches)"}
 
 
 def workload_config():
