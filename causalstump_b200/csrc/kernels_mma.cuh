@@ -36,11 +36,29 @@ __device__ __forceinline__ void stage_x_coop(double* __restrict__ xs, const doub
 }
 
 #ifndef CS_EMU
-// one thread: p bulk copies of one 512-byte dimension row each, completing on `bar`
-__device__ __forceinline__ void stage_x_bulk(double* xs, const double* X, long long ldx, int row0, int p, unsigned long long* bar) {
-  for (int d = 0; d < p; ++d) {
+// One warp: lane d issues the two bulk copies (one 512-byte dimension row of the row tile, one of the column tile) of
+// dimension d, completing on `bar`; lane 0 posts the byte count first.  (Issued by a single thread, the 2p copies of a tile
+// were a serial chain of about 1000 instructions that the seven other warps waited for at the next barrier: 17 % of all stall
+// samples of the gradient kernel, profiles/r02_ncu_grad_source.md.)
+// za != nullptr: lanes 0..3 also fetch z[row0..], z[col0..], alpha[row0..], alpha[col0..] into za[0..4 TB).
+__device__ __forceinline__ void stage_x_bulk_warp(double* xr, double* xc, const double* X, long long ldx, int row0, int col0, int p,
+                                                  unsigned long long* bar, int lane, double* za = nullptr,
+                                                  const double* z = nullptr, const double* alpha = nullptr) {
+  if (lane == 0) csd::mbar_expect_tx(bar, (2u * (unsigned)p + (za ? 4u : 0u)) * TB * (unsigned)sizeof(double));
+  __syncwarp();
+  if (za && lane < 4) {
+    const double* src = ((lane & 2) ? alpha : z) + ((lane & 1) ? col0 : row0);
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                 ::"r"(csd::smem_u32(xs + d * XS)), "l"(X + (long long)d * ldx + row0), "r"((unsigned)(TB * sizeof(double))),
+                 ::"r"(csd::smem_u32(za + lane * TB)), "l"(src), "r"((unsigned)(TB * sizeof(double))),
+                   "r"(csd::smem_u32(bar)) : "memory");
+  }
+  if (lane < p) {
+    const double* src = X + (long long)lane * ldx;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(csd::smem_u32(xr + lane * XS)), "l"(src + row0), "r"((unsigned)(TB * sizeof(double))),
+                   "r"(csd::smem_u32(bar)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(csd::smem_u32(xc + lane * XS)), "l"(src + col0), "r"((unsigned)(TB * sizeof(double))),
                    "r"(csd::smem_u32(bar)) : "memory");
   }
 }
@@ -84,7 +102,7 @@ __device__ __forceinline__ void pass1_mma(const double* __restrict__ xr, const d
 // ---------------------------------------------------------------------------------
 // K1 on the tensor path
 // ---------------------------------------------------------------------------------
-inline int gram_mma_smem_bytes() { return (2 * XT + 2 * XD + 4 * TB + 3 * TB) * (int)sizeof(double); }
+inline int gram_mma_smem_bytes() { return (2 * XT + 2 * XD + 4 * TB + 3 * TB + csd::EXP_TAB) * (int)sizeof(double); }
 
 __global__ void __launch_bounds__(ETH, 3)
 gram_train_mma_kernel(const double* __restrict__ X, long long ldx, const double* __restrict__ z, const double* __restrict__ w,
@@ -103,7 +121,9 @@ gram_train_mma_kernel(const double* __restrict__ X, long long ldx, const double*
   double* zr = uv + 4 * TB;
   double* zc = zr + TB;
   double* wr = zc + TB;
+  double* etab = wr + TB;        // 2^(j/64), see csd::exp_tab
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+  csd::exp_tab_fill(etab, tid);
   const int tl = (int)blockIdx.x + tile0;
   const int I = csg_lower_row(tl), J = tl - I * (I + 1) / 2;
   const int r0 = I * TB, c0 = J * TB;
@@ -111,12 +131,10 @@ gram_train_mma_kernel(const double* __restrict__ X, long long ldx, const double*
 #ifndef CS_EMU
   __shared__ unsigned long long xbar;
   if (use_bulk) {
-    if (tid == 0) {
-      csd::mbar_init(&xbar, 1);
-      csd::mbar_fence_init();
-      csd::mbar_expect_tx(&xbar, 2u * (unsigned)p * TB * (unsigned)sizeof(double));
-      stage_x_bulk(xr, X, ldx, r0, p, &xbar);
-      stage_x_bulk(xc, X, ldx, c0, p, &xbar);
+    if (wid == 0) {
+      if (lane == 0) { csd::mbar_init(&xbar, 1); csd::mbar_fence_init(); }
+      __syncwarp();
+      stage_x_bulk_warp(xr, xc, X, ldx, r0, c0, p, &xbar, lane);
     }
   } else
 #endif
@@ -153,7 +171,7 @@ gram_train_mma_kernel(const double* __restrict__ X, long long ldx, const double*
       else {
         const double em = fma(-2.0, Dm[cb][i], umr + uv[2 * TB + cl]);
         const double ea_ = fma(-2.0, Da[cb][i], uar + uv[3 * TB + cl]);
-        v = exp(lam_m - em) + exp(lam_a - ea_) * zrr * zc[cl];
+        v = csd::exp_tab(lam_m - em, etab) + csd::exp_tab(lam_a - ea_, etab) * zrr * zc[cl];
         if (gr == gc) v += esig / wr[r];
       }
       G[(long long)gc * ldg + gr] = v;
@@ -164,7 +182,7 @@ gram_train_mma_kernel(const double* __restrict__ X, long long ldx, const double*
 // K3 / K4 on the tensor path
 // ---------------------------------------------------------------------------------
 inline int grad_mma_smem_bytes() {
-  return (4 * XT + 2 * XD + 8 * TB + 24 * TB + 3 * TB + 16 * XD + 32) * (int)sizeof(double);
+  return (4 * XT + 2 * XD + 12 * TB + 24 * TB + 3 * TB + 16 * XD + 32 + csd::EXP_TAB) * (int)sizeof(double);
 }
 
 // column sums over the 8 rows of a warp (lanes that differ in g) of a 16-vector indexed e = 2cb + i: recursive halving, after
@@ -210,16 +228,15 @@ grad_trace_mma_kernel(const double* __restrict__ X, long long ldx, const double*
   double* ea = xbuf + 4 * XT;
   double* eb = ea + XD;
   double* uv = eb + XD;                // um | ua | vm | va
-  double* zr = uv + 4 * TB;
-  double* zc = zr + TB;
-  double* ar = zc + TB;                // alpha rows
-  double* ac = ar + TB;                // alpha cols
-  double* colred = ac + TB;            // [8 warps][3][TB]: column sums of T o Km, T o Ka, K alpha_r per warp
+  double* zabuf = uv + 4 * TB;         // [2 buffers][z rows | z cols | alpha rows | alpha cols][TB]
+  double* colred = zabuf + 8 * TB;     // [8 warps][3][TB]: column sums of T o Km, T o Ka, K alpha_r per warp
   double* colsum = colred + 24 * TB;   // [3][TB]
   double* fin = colsum + 3 * TB;       // [8][2][XD] final reduction scratch
   double* red = fin + 16 * XD;         // [32]
+  double* etab = red + 32;             // 2^(j/64), see csd::exp_tab
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
   for (int idx = tid; idx < 4 * XT; idx += ETH) xbuf[idx] = 0.0;   // rows >= p stay zero for the whole kernel
+  csd::exp_tab_fill(etab, tid);
 #ifndef CS_EMU
   csd::fence_proxy_async();   // these generic-proxy writes precede the bulk copies into the same buffers
 #endif
@@ -234,18 +251,19 @@ grad_trace_mma_kernel(const double* __restrict__ X, long long ldx, const double*
 #ifndef CS_EMU
   __shared__ unsigned long long xbar[2];
   const bool bulk = use_bulk && !tile_tab;
-  if (bulk && tid == 0) {
-    csd::mbar_init(&xbar[0], 1);
-    csd::mbar_init(&xbar[1], 1);
-    csd::mbar_fence_init();
+  if (bulk && wid == 0) {
+    if (lane == 0) {
+      csd::mbar_init(&xbar[0], 1);
+      csd::mbar_init(&xbar[1], 1);
+      csd::mbar_fence_init();
+    }
     csd::fence_proxy_async();
+    __syncwarp();
     const int t0 = (int)blockIdx.x;
     if (t0 < ntiles) {
       int I0, J0;
       lower_tile_of(t0, I0, J0);
-      csd::mbar_expect_tx(&xbar[0], 2u * (unsigned)p * TB * (unsigned)sizeof(double));
-      stage_x_bulk(xbuf, X, ldx, I0 * TB, p, &xbar[0]);
-      stage_x_bulk(xbuf + XT, X, ldx, J0 * TB, p, &xbar[0]);
+      stage_x_bulk_warp(xbuf, xbuf + XT, X, ldx, I0 * TB, J0 * TB, p, &xbar[0], lane, zabuf, z, alpha);
     }
   }
   int local_tile = 0;
@@ -277,18 +295,19 @@ grad_trace_mma_kernel(const double* __restrict__ X, long long ldx, const double*
     __syncthreads();  // previous tile fully consumed
     double* xr = xbuf;
     double* xc = xbuf + XT;
+    double* zr = zabuf;                  // z rows | z cols | alpha rows | alpha cols of this tile
 #ifndef CS_EMU
     if (bulk) {
       const int b = local_tile & 1;
-      if (tid == 0) {
+      zr = zabuf + b * 4 * TB;
+      if (wid == 0) {
         const int tn = tl + (int)gridDim.x;
         if (tn < ntiles) {
           int In, Jn;
           lower_tile_of(tn, In, Jn);
           csd::fence_proxy_async();
-          csd::mbar_expect_tx(&xbar[b ^ 1], 2u * (unsigned)p * TB * (unsigned)sizeof(double));
-          stage_x_bulk(xbuf + (b ^ 1) * 2 * XT, X, ldx, In * TB, p, &xbar[b ^ 1]);
-          stage_x_bulk(xbuf + (b ^ 1) * 2 * XT + XT, X, ldx, Jn * TB, p, &xbar[b ^ 1]);
+          stage_x_bulk_warp(xbuf + (b ^ 1) * 2 * XT, xbuf + (b ^ 1) * 2 * XT + XT, X, ldx, In * TB, Jn * TB, p, &xbar[b ^ 1], lane,
+                            zabuf + (b ^ 1) * 4 * TB, z, alpha);
         }
       }
       xr = xbuf + b * 2 * XT; xc = xr + XT;
@@ -297,8 +316,11 @@ grad_trace_mma_kernel(const double* __restrict__ X, long long ldx, const double*
     {
       stage_x_coop(xr, X, ldx, r0, p, tid);
       stage_x_coop(xc, X, ldx, c0, p, tid);
+      if (tid < TB) { zr[tid] = z[r0 + tid]; zr[TB + tid] = z[c0 + tid]; zr[2 * TB + tid] = alpha[r0 + tid]; zr[3 * TB + tid] = alpha[c0 + tid]; }
     }
-    if (tid < TB) { zr[tid] = z[r0 + tid]; zc[tid] = z[c0 + tid]; ar[tid] = alpha[r0 + tid]; ac[tid] = alpha[c0 + tid]; }
+    const double* zc = zr + TB;
+    const double* ar = zr + 2 * TB;
+    const double* ac = zr + 3 * TB;
     // the K^-1 entries of this tile are requested before anything waits (HBM latency hides behind the staging and pass 1)
     const int gr = r0 + r;
     double tv[16];
@@ -335,8 +357,8 @@ grad_trace_mma_kernel(const double* __restrict__ X, long long ldx, const double*
             vka = Ka_in[(long long)gc * ldc + gr];
             kfull = Kmat_in[(long long)gc * ldc + gr];
           } else {
-            vkm = exp(lam_m - fma(-2.0, Wm[e], umr + uv[2 * TB + cl]));
-            vka = exp(lam_a - fma(-2.0, Wa[e], uar + uv[3 * TB + cl])) * zrr * zc[cl];
+            vkm = csd::exp_tab(lam_m - fma(-2.0, Wm[e], umr + uv[2 * TB + cl]), etab);
+            vka = csd::exp_tab(lam_a - fma(-2.0, Wa[e], uar + uv[3 * TB + cl]), etab) * zrr * zc[cl];
             kfull = vkm + vka;
           }
           T = tv[e] - coef * arr * ac[cl];

@@ -150,3 +150,34 @@ def test_oracle_reproduces_golden_fixtures():
         assert cs.rel(o.pack_params(g), G[nm + "/grad"], 1e-12) < 1e-9
         assert cs.rel(st, G[nm + "/stats"]) < 1e-11
         assert abs(mu - float(G[nm + "/mu_sol"])) < 1e-12
+
+
+def test_table_exp():
+    """csd::exp_tab (cs_dev.cuh) restated in NumPy: 64-entry table of 2^(j/64) + degree-5 polynomial, against 50-digit
+    arithmetic on the argument range of the Gram / gradient kernels."""
+    from decimal import Decimal, getcontext
+    getcontext().prec = 50
+    T = np.array([float(Decimal(2) ** (Decimal(j) / 64)) for j in range(64)])
+    inv, hi, lo, magic = 92.33248261689366, 0.01083042469326756, 2.9815858269852933e-12, 6755399441055744.0
+
+    def exp_tab(x):
+        t = x * inv + magic
+        kd = t - magic
+        k = kd.astype(np.int64)
+        r = (x - kd * hi) - kd * lo
+        p = r / 120.0 + 1.0 / 24.0
+        for c in (1.0 / 6.0, 0.5, 1.0, 1.0):
+            p = p * r + c
+        return np.where(x < -700.0, 0.0, np.ldexp(T[k & 63] * p, (k >> 6).astype(np.int64)))
+
+    rng = np.random.default_rng(7)
+    x = np.concatenate([rng.uniform(-700, 5, 4000), rng.uniform(-40, 3, 4000), rng.uniform(-1e-3, 1e-3, 500), [0.0, -745.0]])
+    ref = np.array([float(Decimal(float(v)).exp()) for v in x])
+    got = exp_tab(x)
+    ok = ref > 1e-300
+    assert np.max(np.abs(got[ok] - ref[ok]) / ref[ok]) < 1e-15
+    assert got[-1] == 0.0 and got[-2] == 1.0
+    # the split of ln2/64 used by the kernel: kd * hi must be exact for |kd| < 2^17
+    import math
+    assert (math.frexp(hi)[0] * 2.0 ** 33).is_integer()
+    assert abs(Decimal(hi) + Decimal(lo) - Decimal(2).ln() / 64) < Decimal(10) ** -26
