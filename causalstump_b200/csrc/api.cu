@@ -212,6 +212,7 @@ struct cs_fit {
   cudaStream_t st{};
   DenseEngine eng;
   double *X = nullptr, *y = nullptr, *z = nullptr, *w = nullptr, *ones = nullptr;
+  double* Xt = nullptr;  // packed covariate tiles of the tensor-path Gram / gradient kernels (csk::pack_x_tiles_kernel), or nullptr
   rt::XTma xt{};  // TMA descriptor of X over all members (kernels stage their covariate tiles with it); on == 0: plain loads
   double *params = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr;
   double *alpha = nullptr, *u = nullptr, *s = nullptr;
@@ -309,13 +310,21 @@ static int use_bulk_copies() {
   static const int on = std::getenv("CS_NO_TMA") == nullptr ? 1 : 0;
   return on;
 }
+// The packed tiles follow X, z, w of the handle: rebuilt in front of every evaluation (18 KB per 64 observations; the data
+// may have been rewritten by the caller or by the simulation driver since the last one).
+static void pack_tiles(cs_fit* f, cudaStream_t st, const int* skip, unsigned B) {
+  if (!f->Xt || !use_mma_kernels(f->p)) return;
+  auto k = csk::pack_x_tiles_kernel;
+  ++g_launches;
+  CS_LAUNCH(k, dim3(f->nblk, 1, B), csk::ETH, 0, st, f->X, (long long)f->np, f->z, f->w, f->lay, f->Xt, skip);
+}
 static void launch_gram_train(cs_fit* f, cudaStream_t st, const int* skip, int tile0, int ntiles, unsigned B) {
   const long long ld = f->np;
   ++g_launches;
   if (use_mma_kernels(f->p)) {
     auto k = csk::gram_train_mma_kernel;
     CS_LAUNCH(k, dim3(ntiles, 1, B), csk::ETH, csk::gram_mma_smem_bytes(), st, f->X, ld, f->z, f->w, f->params, f->lay, f->n, f->eng.G, ld,
-              skip, tile0, use_bulk_copies());
+              skip, tile0, (const double*)f->Xt);
   } else {
     auto k = csk::gram_train_kernel;
     CS_LAUNCH(k, dim3(ntiles, 1, B), csk::ETH, csk::gram_smem_bytes(f->p), st, f->X, ld, f->z, f->w, f->params, f->lay, f->n, f->eng.G, ld,
@@ -329,7 +338,7 @@ static void launch_grad_trace(cs_fit* f, cudaStream_t st, const int* skip, unsig
   if (use_mma_kernels(f->p)) {
     auto k = csk::grad_trace_mma_kernel<false>;
     CS_LAUNCH(k, dim3(f->ncta_grad, 1, B), csk::ETH, csk::grad_mma_smem_bytes(), st, f->X, ld, f->z, f->params, f->lay, f->n, f->nblk,
-              f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, nul, nul, nul, skip, (const int*)nullptr, use_bulk_copies());
+              f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, nul, nul, nul, skip, (const int*)nullptr, (const double*)f->Xt);
   } else {
     // element-wise kernel; p beyond what its shared-memory accumulators hold runs as several launches, one dimension window each
     auto k = csk::grad_trace_kernel<false>;
@@ -355,6 +364,7 @@ static int fit_enqueue_eval(cs_fit* f, const int* skip, cudaEvent_t* phase_ev) {
   // inside the optimisation loop (skip = the member's `done` flag) the status word is not reset per iteration: a
   // non positive definite matrix at ANY iteration of a chunk must reach the host (the reference throws there)
   f->eng.reset_status = (skip == nullptr);
+  pack_tiles(f, st, skip, B);
   if (phase_ev) rt::event_record(phase_ev[ph++], st);
   {  // K1.  With the v2 plan the build is split: the tiles of the first diagonal block (rows < W*TILE) on the
      // handle's stream, the rest on the panel stream S2, which every other consumer of G is ordered behind
@@ -500,6 +510,7 @@ static int fit_create_impl(const cs_fit_config* cfg, int nbatch, int n, int p, c
   f->want((void**)&E.status, sizeof(int));
   f->want((void**)&f->X, vb * p); f->want((void**)&f->y, vb); f->want((void**)&f->z, vb); f->want((void**)&f->w, vb);
   f->want((void**)&f->ones, vb);
+  if (csk::mma_kernels_ok(p) && use_bulk_copies()) f->want((void**)&f->Xt, sizeof(double) * csk::XT * f->nblk);
   f->want((void**)&f->params, sizeof(double) * NP); f->want((void**)&f->grad, sizeof(double) * NP);
   f->want((void**)&f->m, sizeof(double) * NP); f->want((void**)&f->v, sizeof(double) * NP);
   f->want((void**)&f->alpha, vb); f->want((void**)&f->u, vb); f->want((void**)&f->s, vb);
@@ -995,6 +1006,7 @@ int cs_debug_timeline(cs_fit* f, int cap, int* n_out, float* rows) {
   if (!f || !n_out || !rows) return fail(CS_ERR_ARG, "null argument");
   cudaStream_t st = f->st;
   std::vector<cudaEvent_t> evs;
+  pack_tiles(f, st, nullptr, (unsigned)f->nbatch);
   launch_gram_train(f, st, nullptr, 0, csg::lower_tiles(f->nblk), (unsigned)f->nbatch);  // Gram first so the factorization sees a valid matrix
   RT(rt::stream_sync(st));
   cudaEvent_t base;
@@ -1441,6 +1453,7 @@ static int grad_stats_common(int kind, int n, int p, const double* y, const doub
     ++g_launches; CS_LAUNCH(k, (unsigned)((tot + 255) / 256), 256, 0, st, f->eng.G, ld, n, np);
   }
   f->eng.factor(st);  // logdet_part now holds log det(invK)/2 per block; sign flipped below
+  pack_tiles(f, st, nullptr, 1u);
   DevBuf dK, dM, dA;
   const size_t mb = sizeof(double) * (size_t)np * np;
   const bool from_mem = Kmat && Km && Ka;
@@ -1468,7 +1481,7 @@ static int grad_stats_common(int kind, int n, int p, const double* y, const doub
         auto k3 = csk::grad_trace_mma_kernel<true>;
         CS_LAUNCH(k3, f->ncta_grad, csk::ETH, csk::grad_mma_smem_bytes(), st, f->X, ld, f->z, f->params, f->lay, n, f->nblk,
                   f->eng.C, ld, f->alpha, f->sc, f->gpart, f->kal_part, ld, (const double*)dK.d(), (const double*)dM.d(),
-                  (const double*)dA.d(), (const int*)nullptr, (const int*)nullptr, use_bulk_copies());
+                  (const double*)dA.d(), (const int*)nullptr, (const int*)nullptr, (const double*)f->Xt);
       } else {
         auto k3 = csk::grad_trace_kernel<true>;
         const int dwmax = csk::grad_window(p);

@@ -23,7 +23,8 @@ namespace csk {
 
 constexpr int XS = 68;         // doubles per staged dimension row
 constexpr int XD = 32;         // staged dimensions
-constexpr int XT = XD * XS;    // doubles per staged tile
+constexpr int XROWS = XD + 2;  // staged rows of a tile: the dimensions, then z, then the observation weights
+constexpr int XT = XROWS * XS; // doubles per staged tile
 
 inline bool mma_kernels_ok(int p) { return p <= XD; }
 
@@ -35,32 +36,43 @@ __device__ __forceinline__ void stage_x_coop(double* __restrict__ xs, const doub
   }
 }
 
+// Packed tiles: Xt[blk][XROWS][XS] holds, for the 64 observations of block blk, the p covariate rows (zero up to XD), z and
+// w, already in the padded shared-memory layout, so that a kernel stages a whole operand tile with ONE bulk copy.  (A tile
+// used to arrive as 2p bulk copies of 512 bytes; the copy engine takes them one at a time, about 100 cycles each, and the
+// seven other warps waited for the issuing warp at the next barrier: 18 % of all stall samples of the gradient kernel.)
+// Rebuilt at the start of every evaluation (X, z, w live in the handle and may have been rewritten): 18 KB per block.
+__global__ void __launch_bounds__(ETH)
+pack_x_tiles_kernel(const double* __restrict__ X, long long ldx, const double* __restrict__ z, const double* __restrict__ w, Layout lay,
+                    double* __restrict__ Xt, const int* __restrict__ skip) {
+  CS_BS(skip);
+  if (skip && *skip) return;
+  CS_BS(X); CS_BS(z); CS_BS(w); CS_BS(Xt);
+  const int p = lay.p, blk = (int)blockIdx.x;
+  for (int idx = (int)threadIdx.x; idx < XT; idx += ETH) {
+    const int row = idx / XS, c = idx - row * XS;
+    double v = 0.0;
+    if (c < TB) {
+      const long long gi = (long long)blk * TB + c;
+      if (row < p) v = X[(long long)row * ldx + gi];
+      else if (row == XD) v = z[gi];
+      else if (row == XD + 1) v = w[gi];
+    }
+    Xt[(long long)blk * XT + idx] = v;
+  }
+}
+
+// cooperative staging of the same layout (emulator, table-driven tiles of the distributed engine, CS_NO_TMA)
+__device__ __forceinline__ void stage_tile_coop(double* __restrict__ xs, const double* __restrict__ X, long long ldx,
+                                                const double* __restrict__ z, const double* __restrict__ w, int row0, int p, int tid) {
+  stage_x_coop(xs, X, ldx, row0, p, tid);
+  if (tid < TB) { xs[XD * XS + tid] = z[row0 + tid]; xs[(XD + 1) * XS + tid] = w ? w[row0 + tid] : 0.0; }
+}
+
 #ifndef CS_EMU
-// One warp: lane d issues the two bulk copies (one 512-byte dimension row of the row tile, one of the column tile) of
-// dimension d, completing on `bar`; lane 0 posts the byte count first.  (Issued by a single thread, the 2p copies of a tile
-// were a serial chain of about 1000 instructions that the seven other warps waited for at the next barrier: 17 % of all stall
-// samples of the gradient kernel, profiles/r02_ncu_grad_source.md.)
-// za != nullptr: lanes 0..3 also fetch z[row0..], z[col0..], alpha[row0..], alpha[col0..] into za[0..4 TB).
-__device__ __forceinline__ void stage_x_bulk_warp(double* xr, double* xc, const double* X, long long ldx, int row0, int col0, int p,
-                                                  unsigned long long* bar, int lane, double* za = nullptr,
-                                                  const double* z = nullptr, const double* alpha = nullptr) {
-  if (lane == 0) csd::mbar_expect_tx(bar, (2u * (unsigned)p + (za ? 4u : 0u)) * TB * (unsigned)sizeof(double));
-  __syncwarp();
-  if (za && lane < 4) {
-    const double* src = ((lane & 2) ? alpha : z) + ((lane & 1) ? col0 : row0);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                 ::"r"(csd::smem_u32(za + lane * TB)), "l"(src), "r"((unsigned)(TB * sizeof(double))),
-                   "r"(csd::smem_u32(bar)) : "memory");
-  }
-  if (lane < p) {
-    const double* src = X + (long long)lane * ldx;
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                 ::"r"(csd::smem_u32(xr + lane * XS)), "l"(src + row0), "r"((unsigned)(TB * sizeof(double))),
-                   "r"(csd::smem_u32(bar)) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                 ::"r"(csd::smem_u32(xc + lane * XS)), "l"(src + col0), "r"((unsigned)(TB * sizeof(double))),
-                   "r"(csd::smem_u32(bar)) : "memory");
-  }
+// one thread: one bulk copy of `bytes` completing on `bar` (the byte count has been posted by mbar_expect_tx)
+__device__ __forceinline__ void bulk_copy(double* dst, const double* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(csd::smem_u32(dst)), "l"(src), "r"(bytes), "r"(csd::smem_u32(bar)) : "memory");
 }
 #endif
 
@@ -102,54 +114,57 @@ __device__ __forceinline__ void pass1_mma(const double* __restrict__ xr, const d
 // ---------------------------------------------------------------------------------
 // K1 on the tensor path
 // ---------------------------------------------------------------------------------
-inline int gram_mma_smem_bytes() { return (2 * XT + 2 * XD + 4 * TB + 3 * TB + csd::EXP_TAB) * (int)sizeof(double); }
+inline int gram_mma_smem_bytes() { return (2 * XT + 2 * XD + 4 * TB + csd::EXP_TAB) * (int)sizeof(double); }
 
 __global__ void __launch_bounds__(ETH, 3)
 gram_train_mma_kernel(const double* __restrict__ X, long long ldx, const double* __restrict__ z, const double* __restrict__ w,
                       const double* __restrict__ params, Layout lay, int n, double* __restrict__ G, long long ldg,
-                      const int* __restrict__ skip, int tile0, int use_bulk) {
+                      const int* __restrict__ skip, int tile0, const double* __restrict__ Xt) {
+  // Xt != nullptr: packed tiles (pack_x_tiles_kernel), one bulk copy per operand tile; nullptr: cooperative staging
   CS_BS(skip);
   if (skip && *skip) return;
-  CS_BS(X); CS_BS(z); CS_BS(w); CS_BS(params); CS_BS(G);
+  CS_BS(X); CS_BS(z); CS_BS(w); CS_BS(params); CS_BS(G); CS_BS(Xt);
   CS_DYN_SMEM(double, sm_);
   const int p = lay.p;
-  double* xr = sm_;
-  double* xc = xr + XT;
+  double* xr = sm_;              // row tile: dimensions | z | w
+  double* xc = xr + XT;          // column tile
   double* ea = xc + XT;
   double* eb = ea + XD;
   double* uv = eb + XD;          // um | ua | vm | va
-  double* zr = uv + 4 * TB;
-  double* zc = zr + TB;
-  double* wr = zc + TB;
-  double* etab = wr + TB;        // 2^(j/64), see csd::exp_tab
+  double* etab = uv + 4 * TB;    // 2^(j/64), see csd::exp_tab
+  const double* zr = xr + XD * XS;
+  const double* zc = xc + XD * XS;
+  const double* wr = xr + (XD + 1) * XS;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
   csd::exp_tab_fill(etab, tid);
   const int tl = (int)blockIdx.x + tile0;
   const int I = csg_lower_row(tl), J = tl - I * (I + 1) / 2;
   const int r0 = I * TB, c0 = J * TB;
-  for (int idx = tid; idx < (XD - p) * XS; idx += ETH) { xr[p * XS + idx] = 0.0; xc[p * XS + idx] = 0.0; }
 #ifndef CS_EMU
   __shared__ unsigned long long xbar;
-  if (use_bulk) {
-    if (wid == 0) {
-      if (lane == 0) { csd::mbar_init(&xbar, 1); csd::mbar_fence_init(); }
-      __syncwarp();
-      stage_x_bulk_warp(xr, xc, X, ldx, r0, c0, p, &xbar, lane);
+  const bool bulk = Xt != nullptr;
+  if (bulk) {
+    if (tid == 0) {
+      csd::mbar_init(&xbar, 1);
+      csd::mbar_fence_init();
+      csd::mbar_expect_tx(&xbar, 2u * XT * (unsigned)sizeof(double));
+      bulk_copy(xr, Xt + (long long)I * XT, XT * (unsigned)sizeof(double), &xbar);
+      bulk_copy(xc, Xt + (long long)J * XT, XT * (unsigned)sizeof(double), &xbar);
     }
   } else
 #endif
   {
-    stage_x_coop(xr, X, ldx, r0, p, tid);
-    stage_x_coop(xc, X, ldx, c0, p, tid);
+    for (int idx = tid; idx < (XD - p) * XS; idx += ETH) { xr[p * XS + idx] = 0.0; xc[p * XS + idx] = 0.0; }
+    stage_tile_coop(xr, X, ldx, z, w, r0, p, tid);
+    stage_tile_coop(xc, X, ldx, z, w, c0, p, tid);
   }
   if (tid < XD) {
     ea[tid] = tid < p ? exp(-params[lay.i_Lm() + tid]) : 0.0;
     eb[tid] = tid < p ? exp(-params[lay.i_La() + tid]) : 0.0;
   }
-  if (tid < TB) { zr[tid] = z[r0 + tid]; zc[tid] = z[c0 + tid]; wr[tid] = w[r0 + tid]; }
   __syncthreads();
 #ifndef CS_EMU
-  if (use_bulk) csd::mbar_wait(&xbar, 0);
+  if (bulk) csd::mbar_wait(&xbar, 0);
 #endif
   tile_norms(xr, xc, ea, eb, p, tid, uv);
   const int r = 8 * wid + g;
@@ -182,7 +197,7 @@ gram_train_mma_kernel(const double* __restrict__ X, long long ldx, const double*
 // K3 / K4 on the tensor path
 // ---------------------------------------------------------------------------------
 inline int grad_mma_smem_bytes() {
-  return (4 * XT + 2 * XD + 12 * TB + 24 * TB + 3 * TB + 16 * XD + 32 + csd::EXP_TAB) * (int)sizeof(double);
+  return (4 * XT + 2 * XD + 8 * TB + 24 * TB + 3 * TB + 16 * XD + 32 + csd::EXP_TAB) * (int)sizeof(double);
 }
 
 // column sums over the 8 rows of a warp (lanes that differ in g) of a 16-vector indexed e = 2cb + i: recursive halving, after
@@ -216,11 +231,12 @@ grad_trace_mma_kernel(const double* __restrict__ X, long long ldx, const double*
                       const EvalScalars* __restrict__ sc, double* __restrict__ gpart, double* __restrict__ kal_part,
                       long long kal_stride, const double* __restrict__ Kmat_in, const double* __restrict__ Km_in,
                       const double* __restrict__ Ka_in, const int* __restrict__ skip,
-                      const int* __restrict__ tile_tab, int use_bulk) {
+                      const int* __restrict__ tile_tab, const double* __restrict__ Xt) {
   // outputs and the tile_tab (distributed) mode exactly as grad_trace_kernel (kernels.cuh)
+  // Xt != nullptr: packed tiles (pack_x_tiles_kernel): every operand tile is one bulk copy, prefetched one tile ahead
   CS_BS(skip);
   if (skip && *skip) return;
-  CS_BS(X); CS_BS(z); CS_BS(params); CS_BS(Cinv); CS_BS(alpha); CS_BS(sc); CS_BS(gpart); CS_BS(kal_part);
+  CS_BS(X); CS_BS(z); CS_BS(params); CS_BS(Cinv); CS_BS(alpha); CS_BS(sc); CS_BS(gpart); CS_BS(kal_part); CS_BS(Xt);
   CS_DYN_SMEM(double, sm_);
   const int p = lay.p;
   const int nacc = 2 * p + 2;
@@ -228,18 +244,21 @@ grad_trace_mma_kernel(const double* __restrict__ X, long long ldx, const double*
   double* ea = xbuf + 4 * XT;
   double* eb = ea + XD;
   double* uv = eb + XD;                // um | ua | vm | va
-  double* zabuf = uv + 4 * TB;         // [2 buffers][z rows | z cols | alpha rows | alpha cols][TB]
-  double* colred = zabuf + 8 * TB;     // [8 warps][3][TB]: column sums of T o Km, T o Ka, K alpha_r per warp
+  double* abuf = uv + 4 * TB;          // [2 buffers][alpha rows | alpha cols][TB]
+  double* colred = abuf + 4 * TB;      // [8 warps][3][TB]: column sums of T o Km, T o Ka, K alpha_r per warp
   double* colsum = colred + 24 * TB;   // [3][TB]
   double* fin = colsum + 3 * TB;       // [8][2][XD] final reduction scratch
   double* red = fin + 16 * XD;         // [32]
   double* etab = red + 32;             // 2^(j/64), see csd::exp_tab
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
-  for (int idx = tid; idx < 4 * XT; idx += ETH) xbuf[idx] = 0.0;   // rows >= p stay zero for the whole kernel
-  csd::exp_tab_fill(etab, tid);
 #ifndef CS_EMU
-  csd::fence_proxy_async();   // these generic-proxy writes precede the bulk copies into the same buffers
+  const bool bulk = Xt != nullptr && !tile_tab;
+#else
+  const bool bulk = false;
 #endif
+  if (!bulk)
+    for (int idx = tid; idx < 4 * XT; idx += ETH) xbuf[idx] = 0.0;   // cooperative staging: rows >= p stay zero for the whole kernel
+  csd::exp_tab_fill(etab, tid);
   if (tid < XD) {
     ea[tid] = tid < p ? exp(-params[lay.i_Lm() + tid]) : 0.0;
     eb[tid] = tid < p ? exp(-params[lay.i_La() + tid]) : 0.0;
@@ -250,25 +269,23 @@ grad_trace_mma_kernel(const double* __restrict__ X, long long ldx, const double*
   __syncthreads();
 #ifndef CS_EMU
   __shared__ unsigned long long xbar[2];
-  const bool bulk = use_bulk && !tile_tab;
-  if (bulk && wid == 0) {
-    if (lane == 0) {
-      csd::mbar_init(&xbar[0], 1);
-      csd::mbar_init(&xbar[1], 1);
-      csd::mbar_fence_init();
-    }
-    csd::fence_proxy_async();
-    __syncwarp();
+  constexpr unsigned TILE_TX = (2u * XT + 2u * TB) * (unsigned)sizeof(double);   // two operand tiles + alpha rows / cols
+  if (bulk && tid == 0) {
+    csd::mbar_init(&xbar[0], 1);
+    csd::mbar_init(&xbar[1], 1);
+    csd::mbar_fence_init();
     const int t0 = (int)blockIdx.x;
     if (t0 < ntiles) {
       int I0, J0;
       lower_tile_of(t0, I0, J0);
-      stage_x_bulk_warp(xbuf, xbuf + XT, X, ldx, I0 * TB, J0 * TB, p, &xbar[0], lane, zabuf, z, alpha);
+      csd::mbar_expect_tx(&xbar[0], TILE_TX);
+      bulk_copy(xbuf, Xt + (long long)I0 * XT, XT * (unsigned)sizeof(double), &xbar[0]);
+      bulk_copy(xbuf + XT, Xt + (long long)J0 * XT, XT * (unsigned)sizeof(double), &xbar[0]);
+      bulk_copy(abuf, alpha + I0 * TB, TB * (unsigned)sizeof(double), &xbar[0]);
+      bulk_copy(abuf + TB, alpha + J0 * TB, TB * (unsigned)sizeof(double), &xbar[0]);
     }
   }
   int local_tile = 0;
-#else
-  const bool bulk = false;
 #endif
   // per-thread accumulators over all tiles of this CTA: dims 8nb + 2t + ii of the row-side terms, one (matrix, dim,
   // column quarter) of the column-side term, and the two plain traces
@@ -295,32 +312,38 @@ grad_trace_mma_kernel(const double* __restrict__ X, long long ldx, const double*
     __syncthreads();  // previous tile fully consumed
     double* xr = xbuf;
     double* xc = xbuf + XT;
-    double* zr = zabuf;                  // z rows | z cols | alpha rows | alpha cols of this tile
+    double* ar_ = abuf;                  // alpha rows | alpha cols of this tile
 #ifndef CS_EMU
     if (bulk) {
       const int b = local_tile & 1;
-      zr = zabuf + b * 4 * TB;
-      if (wid == 0) {
+      if (tid == 0) {
         const int tn = tl + (int)gridDim.x;
         if (tn < ntiles) {
           int In, Jn;
           lower_tile_of(tn, In, Jn);
-          csd::fence_proxy_async();
-          stage_x_bulk_warp(xbuf + (b ^ 1) * 2 * XT, xbuf + (b ^ 1) * 2 * XT + XT, X, ldx, In * TB, Jn * TB, p, &xbar[b ^ 1], lane,
-                            zabuf + (b ^ 1) * 4 * TB, z, alpha);
+          double* xn = xbuf + (b ^ 1) * 2 * XT;
+          double* an = abuf + (b ^ 1) * 2 * TB;
+          csd::fence_proxy_async();   // the generic-proxy reads of the tile before last (barrier above) precede the refill
+          csd::mbar_expect_tx(&xbar[b ^ 1], TILE_TX);
+          bulk_copy(xn, Xt + (long long)In * XT, XT * (unsigned)sizeof(double), &xbar[b ^ 1]);
+          bulk_copy(xn + XT, Xt + (long long)Jn * XT, XT * (unsigned)sizeof(double), &xbar[b ^ 1]);
+          bulk_copy(an, alpha + In * TB, TB * (unsigned)sizeof(double), &xbar[b ^ 1]);
+          bulk_copy(an + TB, alpha + Jn * TB, TB * (unsigned)sizeof(double), &xbar[b ^ 1]);
         }
       }
       xr = xbuf + b * 2 * XT; xc = xr + XT;
+      ar_ = abuf + b * 2 * TB;
     } else
 #endif
     {
-      stage_x_coop(xr, X, ldx, r0, p, tid);
-      stage_x_coop(xc, X, ldx, c0, p, tid);
-      if (tid < TB) { zr[tid] = z[r0 + tid]; zr[TB + tid] = z[c0 + tid]; zr[2 * TB + tid] = alpha[r0 + tid]; zr[3 * TB + tid] = alpha[c0 + tid]; }
+      stage_tile_coop(xr, X, ldx, z, nullptr, r0, p, tid);
+      stage_tile_coop(xc, X, ldx, z, nullptr, c0, p, tid);
+      if (tid < TB) { ar_[tid] = alpha[r0 + tid]; ar_[TB + tid] = alpha[c0 + tid]; }
     }
-    const double* zc = zr + TB;
-    const double* ar = zr + 2 * TB;
-    const double* ac = zr + 3 * TB;
+    const double* zr = xr + XD * XS;
+    const double* zc = xc + XD * XS;
+    const double* ar = ar_;
+    const double* ac = ar_ + TB;
     // the K^-1 entries of this tile are requested before anything waits (HBM latency hides behind the staging and pass 1)
     const int gr = r0 + r;
     double tv[16];
