@@ -316,15 +316,15 @@ static void pack_tiles(cs_fit* f, cudaStream_t st, const int* skip, unsigned B) 
   if (!f->Xt || !use_mma_kernels(f->p)) return;
   auto k = csk::pack_x_tiles_kernel;
   ++g_launches;
-  CS_LAUNCH(k, dim3(f->nblk, 1, B), csk::ETH, 0, st, f->X, (long long)f->np, f->z, f->w, f->lay, f->Xt, skip);
+  CS_LAUNCH(k, dim3(f->nblk, 1, B), csk::ETH, 0, st, f->X, (long long)f->np, f->z, f->w, f->params, f->lay, f->nblk, f->Xt, skip);
 }
 static void launch_gram_train(cs_fit* f, cudaStream_t st, const int* skip, int tile0, int ntiles, unsigned B) {
   const long long ld = f->np;
   ++g_launches;
   if (use_mma_kernels(f->p)) {
     auto k = csk::gram_train_mma_kernel;
-    CS_LAUNCH(k, dim3(ntiles, 1, B), csk::ETH, csk::gram_mma_smem_bytes(), st, f->X, ld, f->z, f->w, f->params, f->lay, f->n, f->eng.G, ld,
-              skip, tile0, (const double*)f->Xt);
+    CS_LAUNCH(k, dim3(ntiles, 1, B), csk::ETH, csk::gram_mma_smem_bytes(), st, f->X, ld, f->z, f->w, f->params, f->lay, f->n, f->nblk,
+              f->eng.G, ld, skip, tile0, (const double*)f->Xt);
   } else {
     auto k = csk::gram_train_kernel;
     CS_LAUNCH(k, dim3(ntiles, 1, B), csk::ETH, csk::gram_smem_bytes(f->p), st, f->X, ld, f->z, f->w, f->params, f->lay, f->n, f->eng.G, ld,
@@ -510,7 +510,7 @@ static int fit_create_impl(const cs_fit_config* cfg, int nbatch, int n, int p, c
   f->want((void**)&E.status, sizeof(int));
   f->want((void**)&f->X, vb * p); f->want((void**)&f->y, vb); f->want((void**)&f->z, vb); f->want((void**)&f->w, vb);
   f->want((void**)&f->ones, vb);
-  if (csk::mma_kernels_ok(p) && use_bulk_copies()) f->want((void**)&f->Xt, sizeof(double) * csk::XT * f->nblk);
+  if (csk::mma_kernels_ok(p) && use_bulk_copies()) f->want((void**)&f->Xt, sizeof(double) * ((size_t)csk::XT * f->nblk + csk::CST_N));
   f->want((void**)&f->params, sizeof(double) * NP); f->want((void**)&f->grad, sizeof(double) * NP);
   f->want((void**)&f->m, sizeof(double) * NP); f->want((void**)&f->v, sizeof(double) * NP);
   f->want((void**)&f->alpha, vb); f->want((void**)&f->u, vb); f->want((void**)&f->s, vb);

@@ -23,8 +23,12 @@ namespace csk {
 
 constexpr int XS = 68;         // doubles per staged dimension row
 constexpr int XD = 32;         // staged dimensions
-constexpr int XROWS = XD + 2;  // staged rows of a tile: the dimensions, then z, then the observation weights
+constexpr int XROWS = XD + 4;  // staged rows of a tile: the dimensions, then z, the observation weights and the two scaled norms
 constexpr int XT = XROWS * XS; // doubles per staged tile
+constexpr int ROW_Z = XD, ROW_W = XD + 1, ROW_UM = XD + 2, ROW_UA = XD + 3;
+// per-evaluation constants of the two kernels, computed once by the pack kernel instead of by every CTA:
+// exp(-Lm_k) | exp(-La_k) | 2^(j/64) (csd::exp_tab) | lambda_m, lambda_a, exp(sigma), 5 x padding
+constexpr int CST_EA = 0, CST_EB = XD, CST_TAB = 2 * XD, CST_SC = 2 * XD + csd::EXP_TAB, CST_N = CST_SC + 8;
 
 inline bool mma_kernels_ok(int p) { return p <= XD; }
 
@@ -36,36 +40,73 @@ __device__ __forceinline__ void stage_x_coop(double* __restrict__ xs, const doub
   }
 }
 
-// Packed tiles: Xt[blk][XROWS][XS] holds, for the 64 observations of block blk, the p covariate rows (zero up to XD), z and
-// w, already in the padded shared-memory layout, so that a kernel stages a whole operand tile with ONE bulk copy.  (A tile
-// used to arrive as 2p bulk copies of 512 bytes; the copy engine takes them one at a time, about 100 cycles each, and the
-// seven other warps waited for the issuing warp at the next barrier: 18 % of all stall samples of the gradient kernel.)
-// Rebuilt at the start of every evaluation (X, z, w live in the handle and may have been rewritten): 18 KB per block.
+// Packed tiles: Xt[blk][XROWS][XS] holds, for the 64 observations of block blk, the p covariate rows (zero up to XD), z, w
+// and the scaled norms u_m[i] = sum_k exp(-Lm_k) x_ik^2, u_a[i] (same with La), already in the padded shared-memory layout, so
+// that a kernel stages a whole operand tile with ONE bulk copy; behind the nblk tiles sit the CST_N per-evaluation constants.
+// (A tile used to arrive as 2p bulk copies of 512 bytes; the copy engine takes them one at a time, about 100 cycles each, and
+// the seven other warps waited for the issuing warp at the next barrier: 18 % of all stall samples of the gradient kernel.
+// The constants -- 2p + 1 library exp, the 64-entry exp2 table -- and the norms were recomputed by every CTA: with one tile
+// per CTA that was a quarter of the Gram kernel, profiles/r02_ncu_grad_source.md.)
+// Rebuilt at the start of every evaluation: the parameters change with every iteration, X, z, w may have been rewritten.
+__device__ __forceinline__ void eval_constants(const double* __restrict__ params, const Layout& lay, int tid, double* __restrict__ cst) {
+  const int p = lay.p;
+  if (tid < XD) {
+    cst[CST_EA + tid] = tid < p ? exp(-params[lay.i_Lm() + tid]) : 0.0;
+    cst[CST_EB + tid] = tid < p ? exp(-params[lay.i_La() + tid]) : 0.0;
+  }
+  csd::exp_tab_fill(cst + CST_TAB, tid);
+  if (tid == 0) {
+    cst[CST_SC + 0] = params[lay.i_lm()];
+    cst[CST_SC + 1] = params[lay.i_la()];
+    cst[CST_SC + 2] = exp(params[lay.i_sigma()]);
+#pragma unroll
+    for (int q = 3; q < 8; ++q) cst[CST_SC + q] = 0.0;
+  }
+}
+
 __global__ void __launch_bounds__(ETH)
-pack_x_tiles_kernel(const double* __restrict__ X, long long ldx, const double* __restrict__ z, const double* __restrict__ w, Layout lay,
-                    double* __restrict__ Xt, const int* __restrict__ skip) {
+pack_x_tiles_kernel(const double* __restrict__ X, long long ldx, const double* __restrict__ z, const double* __restrict__ w,
+                    const double* __restrict__ params, Layout lay, int nblk, double* __restrict__ Xt, const int* __restrict__ skip) {
   CS_BS(skip);
   if (skip && *skip) return;
-  CS_BS(X); CS_BS(z); CS_BS(w); CS_BS(Xt);
-  const int p = lay.p, blk = (int)blockIdx.x;
-  for (int idx = (int)threadIdx.x; idx < XT; idx += ETH) {
+  CS_BS(X); CS_BS(z); CS_BS(w); CS_BS(params); CS_BS(Xt);
+  __shared__ double cst[CST_N];
+  const int p = lay.p, blk = (int)blockIdx.x, tid = (int)threadIdx.x;
+  eval_constants(params, lay, tid, cst);
+  __syncthreads();
+  double* T = Xt + (long long)blk * XT;
+  for (int idx = tid; idx < ROW_UM * XS; idx += ETH) {
     const int row = idx / XS, c = idx - row * XS;
     double v = 0.0;
     if (c < TB) {
       const long long gi = (long long)blk * TB + c;
       if (row < p) v = X[(long long)row * ldx + gi];
-      else if (row == XD) v = z[gi];
-      else if (row == XD + 1) v = w[gi];
+      else if (row == ROW_Z) v = z[gi];
+      else if (row == ROW_W) v = w[gi];
     }
-    Xt[(long long)blk * XT + idx] = v;
+    T[idx] = v;
   }
+  if (tid < 2 * XS) {   // norms: thread = (matrix, observation)
+    const int which = tid / XS, c = tid - which * XS;
+    double sacc = 0.0;
+    if (c < TB) {
+      const double* e = cst + (which ? CST_EB : CST_EA);
+      const long long gi = (long long)blk * TB + c;
+      for (int k = 0; k < p; ++k) {
+        const double x = X[(long long)k * ldx + gi];
+        sacc = fma(e[k] * x, x, sacc);
+      }
+    }
+    T[(ROW_UM + which) * XS + c] = sacc;
+  }
+  if (blk == 0 && tid < CST_N) Xt[(long long)nblk * XT + tid] = cst[tid];
 }
 
 // cooperative staging of the same layout (emulator, table-driven tiles of the distributed engine, CS_NO_TMA)
 __device__ __forceinline__ void stage_tile_coop(double* __restrict__ xs, const double* __restrict__ X, long long ldx,
                                                 const double* __restrict__ z, const double* __restrict__ w, int row0, int p, int tid) {
   stage_x_coop(xs, X, ldx, row0, p, tid);
-  if (tid < TB) { xs[XD * XS + tid] = z[row0 + tid]; xs[(XD + 1) * XS + tid] = w ? w[row0 + tid] : 0.0; }
+  if (tid < TB) { xs[ROW_Z * XS + tid] = z[row0 + tid]; xs[ROW_W * XS + tid] = w ? w[row0 + tid] : 0.0; }
 }
 
 #ifndef CS_EMU
@@ -76,18 +117,19 @@ __device__ __forceinline__ void bulk_copy(double* dst, const double* src, unsign
 }
 #endif
 
-// u[idx] = sum_k e_k x[k][idx]^2 for the row tile (ea, eb) and the column tile (ea, eb): 4 x 64 values, one per thread
-__device__ __forceinline__ void tile_norms(const double* __restrict__ xr, const double* __restrict__ xc, const double* __restrict__ ea,
-                                           const double* __restrict__ eb, int p, int tid, double* __restrict__ uv) {
+// cooperative staging only: the norm rows of the row tile and of the column tile (packed tiles bring them along), one value
+// per thread; a barrier separates the staging before and the readers behind
+__device__ __forceinline__ void tile_norms(double* __restrict__ xr, double* __restrict__ xc, const double* __restrict__ ea,
+                                           const double* __restrict__ eb, int p, int tid) {
   const int which = tid >> 6, idx = tid & 63;
-  const double* xs = which < 2 ? xr : xc;
+  double* xs = which < 2 ? xr : xc;
   const double* e = (which & 1) ? eb : ea;
   double s = 0.0;
   for (int k = 0; k < p; ++k) {
     const double x = xs[k * XS + idx];
     s = fma(e[k] * x, x, s);
   }
-  uv[which * TB + idx] = s;   // um | ua | vm | va
+  xs[(ROW_UM + (which & 1)) * XS + idx] = s;
 }
 
 // D[cb][i] = sum_k e_k x_rk x_ck for the thread's row and 16 columns, both scalings at once
@@ -114,29 +156,22 @@ __device__ __forceinline__ void pass1_mma(const double* __restrict__ xr, const d
 // ---------------------------------------------------------------------------------
 // K1 on the tensor path
 // ---------------------------------------------------------------------------------
-inline int gram_mma_smem_bytes() { return (2 * XT + 2 * XD + 4 * TB + csd::EXP_TAB) * (int)sizeof(double); }
+inline int gram_mma_smem_bytes() { return (2 * XT + CST_N) * (int)sizeof(double); }
 
 __global__ void __launch_bounds__(ETH, 3)
 gram_train_mma_kernel(const double* __restrict__ X, long long ldx, const double* __restrict__ z, const double* __restrict__ w,
-                      const double* __restrict__ params, Layout lay, int n, double* __restrict__ G, long long ldg,
+                      const double* __restrict__ params, Layout lay, int n, int nblk, double* __restrict__ G, long long ldg,
                       const int* __restrict__ skip, int tile0, const double* __restrict__ Xt) {
-  // Xt != nullptr: packed tiles (pack_x_tiles_kernel), one bulk copy per operand tile; nullptr: cooperative staging
+  // Xt != nullptr: packed tiles + constants (pack_x_tiles_kernel), three bulk copies per CTA; nullptr: cooperative staging
   CS_BS(skip);
   if (skip && *skip) return;
   CS_BS(X); CS_BS(z); CS_BS(w); CS_BS(params); CS_BS(G); CS_BS(Xt);
   CS_DYN_SMEM(double, sm_);
   const int p = lay.p;
-  double* xr = sm_;              // row tile: dimensions | z | w
+  double* xr = sm_;              // row tile: dimensions | z | w | u_m | u_a
   double* xc = xr + XT;          // column tile
-  double* ea = xc + XT;
-  double* eb = ea + XD;
-  double* uv = eb + XD;          // um | ua | vm | va
-  double* etab = uv + 4 * TB;    // 2^(j/64), see csd::exp_tab
-  const double* zr = xr + XD * XS;
-  const double* zc = xc + XD * XS;
-  const double* wr = xr + (XD + 1) * XS;
+  double* cst = xc + XT;         // exp(-Lm) | exp(-La) | exp table | lambda_m, lambda_a, exp(sigma)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
-  csd::exp_tab_fill(etab, tid);
   const int tl = (int)blockIdx.x + tile0;
   const int I = csg_lower_row(tl), J = tl - I * (I + 1) / 2;
   const int r0 = I * TB, c0 = J * TB;
@@ -147,34 +182,36 @@ gram_train_mma_kernel(const double* __restrict__ X, long long ldx, const double*
     if (tid == 0) {
       csd::mbar_init(&xbar, 1);
       csd::mbar_fence_init();
-      csd::mbar_expect_tx(&xbar, 2u * XT * (unsigned)sizeof(double));
+      csd::mbar_expect_tx(&xbar, (2u * XT + CST_N) * (unsigned)sizeof(double));
       bulk_copy(xr, Xt + (long long)I * XT, XT * (unsigned)sizeof(double), &xbar);
       bulk_copy(xc, Xt + (long long)J * XT, XT * (unsigned)sizeof(double), &xbar);
+      bulk_copy(cst, Xt + (long long)nblk * XT, CST_N * (unsigned)sizeof(double), &xbar);
     }
+    __syncthreads();   // the barrier object is initialised
+    csd::mbar_wait(&xbar, 0);
   } else
 #endif
   {
     for (int idx = tid; idx < (XD - p) * XS; idx += ETH) { xr[p * XS + idx] = 0.0; xc[p * XS + idx] = 0.0; }
     stage_tile_coop(xr, X, ldx, z, w, r0, p, tid);
     stage_tile_coop(xc, X, ldx, z, w, c0, p, tid);
+    eval_constants(params, lay, tid, cst);
+    __syncthreads();
+    tile_norms(xr, xc, cst + CST_EA, cst + CST_EB, p, tid);
+    __syncthreads();
   }
-  if (tid < XD) {
-    ea[tid] = tid < p ? exp(-params[lay.i_Lm() + tid]) : 0.0;
-    eb[tid] = tid < p ? exp(-params[lay.i_La() + tid]) : 0.0;
-  }
-  __syncthreads();
-#ifndef CS_EMU
-  if (bulk) csd::mbar_wait(&xbar, 0);
-#endif
-  tile_norms(xr, xc, ea, eb, p, tid, uv);
+  const double* zr = xr + ROW_Z * XS;
+  const double* zc = xc + ROW_Z * XS;
+  const double* wr = xr + ROW_W * XS;
+  const double* vm = xc + ROW_UM * XS;
+  const double* va = xc + ROW_UA * XS;
+  const double* etab = cst + CST_TAB;
   const int r = 8 * wid + g;
   double Dm[8][2], Da[8][2];
-  pass1_mma(xr, xc, ea, eb, p, r, g, t, Dm, Da);
-  __syncthreads();
-  const double lam_m = params[lay.i_lm()], lam_a = params[lay.i_la()];
-  const double esig = exp(params[lay.i_sigma()]);
+  pass1_mma(xr, xc, cst + CST_EA, cst + CST_EB, p, r, g, t, Dm, Da);
+  const double lam_m = cst[CST_SC], lam_a = cst[CST_SC + 1], esig = cst[CST_SC + 2];
   const int gr = r0 + r;
-  const double umr = uv[r], uar = uv[TB + r], zrr = zr[r];
+  const double umr = xr[ROW_UM * XS + r], uar = xr[ROW_UA * XS + r], zrr = zr[r];
 #pragma unroll
   for (int cb = 0; cb < 8; ++cb)
 #pragma unroll
@@ -184,8 +221,8 @@ gram_train_mma_kernel(const double* __restrict__ X, long long ldx, const double*
       if (gr >= n || gc >= n) v = (gr == gc) ? 1.0 : 0.0;
       else if (gr < gc) v = 0.0;
       else {
-        const double em = fma(-2.0, Dm[cb][i], umr + uv[2 * TB + cl]);
-        const double ea_ = fma(-2.0, Da[cb][i], uar + uv[3 * TB + cl]);
+        const double em = fma(-2.0, Dm[cb][i], umr + vm[cl]);
+        const double ea_ = fma(-2.0, Da[cb][i], uar + va[cl]);
         v = csd::exp_tab(lam_m - em, etab) + csd::exp_tab(lam_a - ea_, etab) * zrr * zc[cl];
         if (gr == gc) v += esig / wr[r];
       }
@@ -197,7 +234,7 @@ gram_train_mma_kernel(const double* __restrict__ X, long long ldx, const double*
 // K3 / K4 on the tensor path
 // ---------------------------------------------------------------------------------
 inline int grad_mma_smem_bytes() {
-  return (4 * XT + 2 * XD + 8 * TB + 24 * TB + 3 * TB + 16 * XD + 32 + csd::EXP_TAB) * (int)sizeof(double);
+  return (4 * XT + CST_N + 4 * TB + 24 * TB + 3 * TB + 16 * XD + 32) * (int)sizeof(double);
 }
 
 // column sums over the 8 rows of a warp (lanes that differ in g) of a 16-vector indexed e = 2cb + i: recursive halving, after
@@ -241,27 +278,24 @@ grad_trace_mma_kernel(const double* __restrict__ X, long long ldx, const double*
   const int p = lay.p;
   const int nacc = 2 * p + 2;
   double* xbuf = sm_;                  // [2 buffers][row tile | column tile][XT]
-  double* ea = xbuf + 4 * XT;
-  double* eb = ea + XD;
-  double* uv = eb + XD;                // um | ua | vm | va
-  double* abuf = uv + 4 * TB;          // [2 buffers][alpha rows | alpha cols][TB]
+  double* cst = xbuf + 4 * XT;         // exp(-Lm) | exp(-La) | exp table | scalars (pack_x_tiles_kernel / eval_constants)
+  double* abuf = cst + CST_N;          // [2 buffers][alpha rows | alpha cols][TB]
   double* colred = abuf + 4 * TB;      // [8 warps][3][TB]: column sums of T o Km, T o Ka, K alpha_r per warp
   double* colsum = colred + 24 * TB;   // [3][TB]
   double* fin = colsum + 3 * TB;       // [8][2][XD] final reduction scratch
   double* red = fin + 16 * XD;         // [32]
-  double* etab = red + 32;             // 2^(j/64), see csd::exp_tab
+  const double* ea = cst + CST_EA;
+  const double* eb = cst + CST_EB;
+  const double* etab = cst + CST_TAB;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
 #ifndef CS_EMU
   const bool bulk = Xt != nullptr && !tile_tab;
 #else
   const bool bulk = false;
 #endif
-  if (!bulk)
+  if (!bulk) {
     for (int idx = tid; idx < 4 * XT; idx += ETH) xbuf[idx] = 0.0;   // cooperative staging: rows >= p stay zero for the whole kernel
-  csd::exp_tab_fill(etab, tid);
-  if (tid < XD) {
-    ea[tid] = tid < p ? exp(-params[lay.i_Lm() + tid]) : 0.0;
-    eb[tid] = tid < p ? exp(-params[lay.i_La() + tid]) : 0.0;
+    eval_constants(params, lay, tid, cst);
   }
   const double lam_m = params[lay.i_lm()], lam_a = params[lay.i_la()];
   const double coef = sc->coef;
@@ -278,7 +312,8 @@ grad_trace_mma_kernel(const double* __restrict__ X, long long ldx, const double*
     if (t0 < ntiles) {
       int I0, J0;
       lower_tile_of(t0, I0, J0);
-      csd::mbar_expect_tx(&xbar[0], TILE_TX);
+      csd::mbar_expect_tx(&xbar[0], TILE_TX + CST_N * (unsigned)sizeof(double));
+      bulk_copy(cst, Xt + (long long)nblk * XT, CST_N * (unsigned)sizeof(double), &xbar[0]);
       bulk_copy(xbuf, Xt + (long long)I0 * XT, XT * (unsigned)sizeof(double), &xbar[0]);
       bulk_copy(xbuf + XT, Xt + (long long)J0 * XT, XT * (unsigned)sizeof(double), &xbar[0]);
       bulk_copy(abuf, alpha + I0 * TB, TB * (unsigned)sizeof(double), &xbar[0]);
@@ -340,8 +375,8 @@ grad_trace_mma_kernel(const double* __restrict__ X, long long ldx, const double*
       stage_tile_coop(xc, X, ldx, z, nullptr, c0, p, tid);
       if (tid < TB) { ar_[tid] = alpha[r0 + tid]; ar_[TB + tid] = alpha[c0 + tid]; }
     }
-    const double* zr = xr + XD * XS;
-    const double* zc = xc + XD * XS;
+    const double* zr = xr + ROW_Z * XS;
+    const double* zc = xc + ROW_Z * XS;
     const double* ar = ar_;
     const double* ac = ar_ + TB;
     // the K^-1 entries of this tile are requested before anything waits (HBM latency hides behind the staging and pass 1)
@@ -358,18 +393,22 @@ grad_trace_mma_kernel(const double* __restrict__ X, long long ldx, const double*
 #endif
     double Wm[16], Wa[16];   // pass-1 products, then T o Km and T o Ka
     if (!FROM_MEM) {
-      tile_norms(xr, xc, ea, eb, p, tid, uv);
+      if (!bulk) {   // packed tiles bring their norm rows along
+        tile_norms(xr, xc, ea, eb, p, tid);
+        __syncthreads();
+      }
       double Dm[8][2], Da[8][2];
       pass1_mma(xr, xc, ea, eb, p, r, g, t, Dm, Da);
 #pragma unroll
       for (int e = 0; e < 16; ++e) { Wm[e] = Dm[e >> 1][e & 1]; Wa[e] = Da[e >> 1][e & 1]; }
-      __syncthreads();  // u / v visible
     }
+    const double* vm = xc + ROW_UM * XS;
+    const double* va = xc + ROW_UA * XS;
     // ---- per entry: Km, Ka, T = K^-1 - coef alpha alpha^T, W = T o K; row / column pieces of K alpha
     double kc[16];           // K[r,c] alpha_r: column partials of K alpha
     double rm = 0.0, ra = 0.0, rk = 0.0;
     {
-      const double umr = uv[r], uar = uv[TB + r], zrr = zr[r], arr = ar[r];
+      const double umr = xr[ROW_UM * XS + r], uar = xr[ROW_UA * XS + r], zrr = zr[r], arr = ar[r];
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int cl = 8 * (e >> 1) + 2 * t + (e & 1), gc = c0 + cl;
@@ -380,8 +419,8 @@ grad_trace_mma_kernel(const double* __restrict__ X, long long ldx, const double*
             vka = Ka_in[(long long)gc * ldc + gr];
             kfull = Kmat_in[(long long)gc * ldc + gr];
           } else {
-            vkm = csd::exp_tab(lam_m - fma(-2.0, Wm[e], umr + uv[2 * TB + cl]), etab);
-            vka = csd::exp_tab(lam_a - fma(-2.0, Wa[e], uar + uv[3 * TB + cl]), etab) * zrr * zc[cl];
+            vkm = csd::exp_tab(lam_m - fma(-2.0, Wm[e], umr + vm[cl]), etab);
+            vka = csd::exp_tab(lam_a - fma(-2.0, Wa[e], uar + va[cl]), etab) * zrr * zc[cl];
             kfull = vkm + vka;
           }
           T = tv[e] - coef * arr * ac[cl];
