@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "libcausalstump_b200.so")
 SOURCES = ["api.cu"]
-DEPS = ["api.cu", "cs_rt.h", "cs_dev.cuh", "gemm.cuh", "dense.cuh", "kernels.cuh", "predict.cuh", "dist.cuh",
-        os.path.join("..", "..", "include", "cs_b200.h")]
+# every source of the library: a header missing here means edits to it are silently not rebuilt
+DEPS = sorted(f for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".h"))) + [os.path.join("..", "..", "include", "cs_b200.h")]
 
 
 def nvcc_path():
