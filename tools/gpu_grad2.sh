@@ -6,7 +6,7 @@ cd "${GRAFT_REPO_ROOT:-.}"
 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_golden_8192.py -m gpu -x -q -k "not nccl and not distributed" > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest_exit=$?"; tail -2 gpurun_out/pytest_gpu.log
 for c in ${GRAD_CTAS_LIST:-2 1}; do
-  export CS_GRAD_CTAS=$c
+  true
   echo "== CS_GRAD_CTAS=$c"
   timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-configs --no-fits > gpurun_out/bench_g.json 2> gpurun_out/bench_g.err
   python - <<'PY'
