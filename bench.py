@@ -39,9 +39,9 @@ if ROOT not in sys.path:
 N_METRIC, P_METRIC = 8192, 25
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
 # `ncu --set full` capture (per launch; None until a capture of the current kernel exists)
-XTX_TRAFFIC_BYTES = 4.086840e9 + 485.787392e6
+XTX_TRAFFIC_BYTES = 4.555720e9 + 486.406912e6
 XTX_TRAFFIC_SOURCE = ("profiles/r02_ncu_xtx.txt: ncu --set full of this kernel in `bench.py --inv-pipeline 0` "
-                      "(dram__bytes_read.sum 4.087 GB + dram__bytes_write.sum 485.8 MB per launch)")
+                      "(dram__bytes_read.sum 4.556 GB + dram__bytes_write.sum 486.4 MB per launch, final round-2 build)")
 METRIC = "fp64 LML+gradient evals/sec at n=8192,p=25"
 UNIT = "evals/s"
 # time-weighted DMMA sub-pipe activity of the K = 512 bulk launches of the timed plan (ncu --set full over every GEMM launch
