@@ -307,8 +307,12 @@ static bool use_mma_kernels(int p) {
   return csk::mma_kernels_ok(p) && !old_k;
 }
 static int use_bulk_copies() {
+#ifdef CS_EMU
+  return std::getenv("CS_NO_TMA") == nullptr ? 1 : 0;   // read at every handle creation: the CPU tests run both staging paths
+#else
   static const int on = std::getenv("CS_NO_TMA") == nullptr ? 1 : 0;
   return on;
+#endif
 }
 // The packed tiles follow X, z, w of the handle: rebuilt in front of every evaluation (18 KB per 64 observations; the data
 // may have been rewritten by the caller or by the simulation driver since the last one).

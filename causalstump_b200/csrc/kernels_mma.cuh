@@ -190,6 +190,15 @@ gram_train_mma_kernel(const double* __restrict__ X, long long ldx, const double*
     __syncthreads();   // the barrier object is initialised
     csd::mbar_wait(&xbar, 0);
   } else
+#else
+  if (Xt != nullptr) {   // emulator: the three bulk copies as plain copies, so that the CPU tests consume the packed layout too
+    if (tid == 0) {
+      std::memcpy(xr, Xt + (long long)I * XT, XT * sizeof(double));
+      std::memcpy(xc, Xt + (long long)J * XT, XT * sizeof(double));
+      std::memcpy(cst, Xt + (long long)nblk * XT, CST_N * sizeof(double));
+    }
+    __syncthreads();
+  } else
 #endif
   {
     for (int idx = tid; idx < (XD - p) * XS; idx += ETH) { xr[p * XS + idx] = 0.0; xc[p * XS + idx] = 0.0; }
@@ -288,15 +297,14 @@ grad_trace_mma_kernel(const double* __restrict__ X, long long ldx, const double*
   const double* eb = cst + CST_EB;
   const double* etab = cst + CST_TAB;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
-#ifndef CS_EMU
   const bool bulk = Xt != nullptr && !tile_tab;
-#else
-  const bool bulk = false;
-#endif
   if (!bulk) {
     for (int idx = tid; idx < 4 * XT; idx += ETH) xbuf[idx] = 0.0;   // cooperative staging: rows >= p stay zero for the whole kernel
     eval_constants(params, lay, tid, cst);
   }
+#ifdef CS_EMU
+  else if (tid == 0) std::memcpy(cst, Xt + (long long)nblk * XT, CST_N * sizeof(double));   // emulator: copies instead of bulk copies
+#endif
   const double lam_m = params[lay.i_lm()], lam_a = params[lay.i_la()];
   const double coef = sc->coef;
   const int ntiles = tile_tab ? nblk : nblk * (nblk + 1) / 2;
@@ -368,6 +376,15 @@ grad_trace_mma_kernel(const double* __restrict__ X, long long ldx, const double*
       }
       xr = xbuf + b * 2 * XT; xc = xr + XT;
       ar_ = abuf + b * 2 * TB;
+    } else
+#else
+    if (bulk) {   // emulator: the tile of THIS iteration, copied by one thread (no prefetch)
+      if (tid == 0) {
+        std::memcpy(xr, Xt + (long long)I * XT, XT * sizeof(double));
+        std::memcpy(xc, Xt + (long long)J * XT, XT * sizeof(double));
+        std::memcpy(ar_, alpha + r0, TB * sizeof(double));
+        std::memcpy(ar_ + TB, alpha + c0, TB * sizeof(double));
+      }
     } else
 #endif
     {

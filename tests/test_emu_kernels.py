@@ -220,3 +220,28 @@ def test_kernel_handle_cache_follows_the_data(emulib):
         assert K._fit is None
     finally:
         rx.use_library(None)
+
+
+@pytest.mark.parametrize("kind,n,p", [("GP", 200, 25), ("TP", 131, 7), ("GP", 70, 32)])
+def test_packed_tiles_and_cooperative_staging_agree(emulib, monkeypatch, kind, n, p):
+    """The tensor-path Gram / gradient kernels read either the packed tiles written by pack_x_tiles_kernel (covariates, z, w,
+    the scaled norms and the per-evaluation constants; on the GPU one bulk copy per operand tile, here plain copies) or stage
+    the same layout cooperatively (CS_NO_TMA=1).  Same arithmetic on both routes: identical results, and both match the oracle."""
+    P = cs.make_problem(kind, n, p, weights=True)
+    g, st, mu = o.eval_lml_grad(kind, P["y"], P["X"], P["z"], P["w"], P["par"])
+    out = []
+    for no_tma in (False, True):
+        if no_tma:
+            monkeypatch.setenv("CS_NO_TMA", "1")
+        else:
+            monkeypatch.delenv("CS_NO_TMA", raising=False)
+        f = _lib.Fit(emulib, cs.kcode(kind), P["y"], P["X"], P["z"], P["w"], o.pack_params(P["par"]))
+        try:
+            out.append(f.eval())
+        finally:
+            f.close()
+    (g1, st1, mu1), (g2, st2, mu2) = out
+    assert np.array_equal(g1, g2) and np.array_equal(st1, st2) and mu1 == mu2
+    gref = o.pack_params(g)   # entries that are ~0 by cancellation are compared against the largest one (as cs.check_eval)
+    gerr = float(np.max(np.abs(g1 - gref) / np.maximum(np.abs(gref), 1e-6 * np.max(np.abs(gref)))))
+    assert gerr < cs.TOL_GRAD and abs(st1[1] - st[1]) < cs.TOL_LML * abs(st[1])
