@@ -73,7 +73,7 @@ void run_mt(const char* name, GemmProblem P, double flops, int tpc) {
   run<128, 2, 4, AK, BK_, 32, 3>(tag " 128 2x4 kc32 s3", MK(128), FL);               \
   run<64, 2, 2, AK, BK_, 16, 4>(tag " 64 2x2 kc16 s4 (2 CTA/SM)", MK(64), FL);       \
   run<64, 2, 2, AK, BK_, 16, 3>(tag " 64 2x2 kc16 s3 (3 CTA/SM)", MK(64), FL);       \
-  run<64, 2, 2, AK, BK_, 16, 2>(tag " 64 2x2 kc16 s2 (5 CTA/SM)", MK(64), FL);       \
+  run<64, 2, 2, AK, BK_, 16, 2, 4>(tag " 64 2x2 kc16 s2 minb4 (shipped)", MK(64), FL); \
   run<64, 2, 2, AK, BK_, 32, 3>(tag " 64 2x2 kc32 s3 (2 CTA/SM)", MK(64), FL);       \
   run<64, 2, 2, AK, BK_, 32, 2>(tag " 64 2x2 kc32 s2 (3 CTA/SM)", MK(64), FL);       \
   run<64, 1, 4, AK, BK_, 16, 3>(tag " 64 1x4 kc16 s3", MK(64), FL);                  \
