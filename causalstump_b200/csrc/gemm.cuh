@@ -127,6 +127,27 @@ __device__ __forceinline__ void load_operand(double* __restrict__ s, const doubl
   }
 }
 
+// The same copies with the per-thread part of the addresses computed ONCE per tile: thread tid moves the 16-byte pieces
+// idx = tid + it * THREADS, whose row (m-major: k row, k-major: tile row) advances by a constant ROWS per `it` while the position
+// inside the row stays, so piece `it` sits at a fixed stride behind piece 0 in global and in shared memory.  (Recomputing
+// row, column and the 64-bit product per copy was 60 of the ~250 instructions a thread issues per chunk: ncu source page of a
+// K = 512 launch, profiles/r02_ncu_nt512.md.)
+template <int TILE, bool KMAJ, int THREADS, int KC>
+struct OperandCopy {
+  using S = OperandSmem<TILE, KMAJ, KC>;
+  static constexpr int PER_ROW = KMAJ ? KC / 2 : TILE / 2;      // 16-byte pieces per row
+  static constexpr int NCOPY = TILE * KC / 2 / THREADS;         // pieces per thread and chunk
+  static constexpr int ROWS = THREADS / PER_ROW;                // rows between consecutive pieces of a thread
+  static_assert(THREADS % PER_ROW == 0 && (TILE * KC / 2) % THREADS == 0, "copy layout must divide");
+  __device__ __forceinline__ static int soff0(int tid) { return (tid / PER_ROW) * S::LD + 2 * (tid % PER_ROW); }
+  __device__ __forceinline__ static long long goff0(int tid, long long ld) { return (long long)(tid / PER_ROW) * ld + 2 * (tid % PER_ROW); }
+  // s, g: stage buffer / chunk origin already advanced by soff0 / goff0; gstep = ROWS * ld
+  __device__ __forceinline__ static void copy(double* __restrict__ s, const double* __restrict__ g, long long gstep) {
+#pragma unroll
+    for (int it = 0; it < NCOPY; ++it) csd::cp_async16(s + it * ROWS * S::LD, g + it * gstep);
+  }
+};
+
 // What one CTA needs to know about its tile.  Decoded by ONE thread (descriptor search, tile decode, k-range, operand
 // bases) and handed to the others through shared memory: 128 threads each walking the descriptor list in global memory
 // and decoding the same tile cost 3 % at K = 512 and 12-18 % at K = 64-128 (tools/gemm_bench, profiles/r02_gemm_experiments.md §6).
@@ -191,6 +212,16 @@ gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restr
   const int nchunks = cur.nchunks;
   const long long achunk = AK ? (long long)KC : (long long)KC * cur.lda;   // per-chunk advance of the operand bases
   const long long bchunk = BK_ ? (long long)KC : (long long)KC * cur.ldb;
+  // measured (tools/gemm_bench, 8880 tiles, K = 512): NT 33.5 -> 34.5, NN 33.5 -> 34.8 TFLOP/s with the precomputed offsets, which
+  // closes the gap of the m-major operands; with both operands k-major the plain form stays ahead (34.7 vs 34.4)
+  constexpr bool PLAN = !(AK && BK_);
+  using CA = OperandCopy<TILE, AK, Cfg::THREADS, KC>;
+  using CB = OperandCopy<TILE, BK_, Cfg::THREADS, KC>;
+  const double* gA = cur.A + CA::goff0(tid, cur.lda);    // this thread's first piece of chunk 0
+  const double* gB = cur.B + CB::goff0(tid, cur.ldb);
+  const long long gsA = CA::ROWS * cur.lda, gsB = CB::ROWS * cur.ldb;
+  double* sAt = sA + CA::soff0(tid);
+  double* sBt = sB + CB::soff0(tid);
 
   const int lane = tid & 31, wid = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -222,8 +253,13 @@ gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restr
 #pragma unroll
   for (int s = 0; s < NS - 1; ++s) {
     if (s < nchunks) {
-      load_operand<TILE, AK, Cfg::THREADS, KC>(sA + s * SA::SIZE, cur.A + s * achunk, cur.lda, tid);
-      load_operand<TILE, BK_, Cfg::THREADS, KC>(sB + s * SB::SIZE, cur.B + s * bchunk, cur.ldb, tid);
+      if (PLAN) {
+        CA::copy(sAt + s * SA::SIZE, gA + s * achunk, gsA);
+        CB::copy(sBt + s * SB::SIZE, gB + s * bchunk, gsB);
+      } else {
+        load_operand<TILE, AK, Cfg::THREADS, KC>(sA + s * SA::SIZE, cur.A + s * achunk, cur.lda, tid);
+        load_operand<TILE, BK_, Cfg::THREADS, KC>(sB + s * SB::SIZE, cur.B + s * bchunk, cur.ldb, tid);
+      }
     }
     csd::cp_async_commit();
   }
@@ -235,8 +271,13 @@ gemm_kernel(const GemmProblem* __restrict__ probs, int nprob, const int* __restr
       const int cn = c + NS - 1;
       if (cn < nchunks) {
         const int sn = cn % NS;
-        load_operand<TILE, AK, Cfg::THREADS, KC>(sA + sn * SA::SIZE, cur.A + cn * achunk, cur.lda, tid);
-        load_operand<TILE, BK_, Cfg::THREADS, KC>(sB + sn * SB::SIZE, cur.B + cn * bchunk, cur.ldb, tid);
+        if (PLAN) {
+          CA::copy(sAt + sn * SA::SIZE, gA + cn * achunk, gsA);
+          CB::copy(sBt + sn * SB::SIZE, gB + cn * bchunk, gsB);
+        } else {
+          load_operand<TILE, AK, Cfg::THREADS, KC>(sA + sn * SA::SIZE, cur.A + cn * achunk, cur.lda, tid);
+          load_operand<TILE, BK_, Cfg::THREADS, KC>(sB + sn * SB::SIZE, cur.B + cn * bchunk, cur.ldb, tid);
+        }
       }
       csd::cp_async_commit();
     }
