@@ -47,7 +47,7 @@ UNIT = "evals/s"
 # time-weighted DMMA sub-pipe activity of the K = 512 bulk launches of the timed plan (ncu --set full over every GEMM launch
 # of one evaluation, plain priority streams -- ncu cannot attach to green-context streams); updated with each capture
 DMMA_ACTIVE_K512 = {"pct": 88.0, "all_gemm_launches_pct": 78.2,
-                    "source": "profiles/r02_gemm_launches.md (71 launches with >= 592 CTA tiles, time-weighted; 78.2 % over all 460 GEMM launches)"}
+                    "source": "profiles/r02_gemm_launches.md (71 launches with >= 592 CTA tiles, time-weighted; 78.2 % over all 460 GEMM launches; ncu pass taken before the last GEMM change of the round -- fixed per-thread copy offsets -- which lifted a K = 512 NT launch from 33.5 to 34.5 TFLOP/s)"}
 
 
 def workload_config():
